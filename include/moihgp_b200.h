@@ -1,0 +1,131 @@
+/* moihgp_b200.h - C ABI of libmoihgp.so, the B200-native (sm_100a) drop-in for the hot path of
+ * lim271/MultiOutputIHGP: the OILMM-decoupled steady-state Kalman filter, smoother and
+ * negative-log-likelihood / gradient evaluation.
+ *
+ * Two groups of entry points:
+ *
+ *  (1) LEGACY symbols - exactly the 26 symbols of the reference's moihgp/src/wrapper.cpp
+ *      (gp32_* at wrapper.cpp:31-326, gp52_* at :329-624) with the same signatures, argument
+ *      layouts and (absent) error convention, so that the reference's moihgp/pywrapper.py
+ *      (ctypes bindings at pywrapper.py:28-145) loads this library unchanged.  One observation
+ *      per call; each call is one small kernel launch on the GPU.
+ *
+ *  (2) WHOLE-SEQUENCE symbols (moihgp_cuda_*) - the device boundary moved up to where the
+ *      reference's callers loop over observations:
+ *        RegressionObjective::operator()   moihgp/include/moihgp/moihgp_regression.h:34-52
+ *        OnlineObjective::operator()       moihgp/include/moihgp/moihgp_online.h:40-72
+ *        MOIHGPRegression::predict         moihgp/include/moihgp/moihgp_regression.h:127-139
+ *        IHGP::backwardSmoother            moihgp/include/moihgp/ihgp.h:103-114
+ *      These return an int status (0 = ok); moihgp_cuda_last_error() gives the message.
+ *
+ * All arrays are C-contiguous IEEE fp64.  Layouts (as wrapper.cpp:51-93 / pywrapper.py:146-167):
+ *   x, xnew   [L][d]            filter state per latent (d = 2 Matern-3/2, 3 Matern-5/2)
+ *   dx, dxnew [L][3][d]         its derivative w.r.t. (magnitude, lengthscale, noise)
+ *   y, yhat   [p]               one observation (NaN = missing, moihgp.h:154)
+ *   params, grad [p*L + L + 1 + 3L] = [ U row-major | S | sigma | (magnitude, lengthscale, noise) x L ]
+ *                               (moihgp.h:436-456, :721-738)
+ *   Y, Yhat   [N][T][p]         N independent sequences, time-major like the reference's vector<VectorXd>
+ *   X, Xs     [N][T][L][d]      filtered (post-update) / smoothed states
+ * There is no CPU fallback: every entry point needs a CUDA device of compute capability 10.0.
+ */
+#ifndef MOIHGP_B200_H
+#define MOIHGP_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ (1) legacy symbols */
+typedef struct moihgp_handle GP32;   /* wrapper.cpp:21 */
+typedef struct moihgp_handle GP52;   /* wrapper.cpp:22 (bound to Matern-3/2 there too; see MOIHGP_GP52_MATERN52) */
+
+#define MOIHGP_LEGACY_DECL(XX, GP)                                                                                          \
+    GP* gp##XX##_new(double dt, size_t num_output, size_t num_latent, bool threading);        /* wrapper.cpp:31  / :329 */  \
+    void gp##XX##_del(GP* gp);                                                                /* wrapper.cpp:37  / :335 */  \
+    void gp##XX##_step1(GP* gp, double* x, double* y, double* dx, double* xnew, double* yhat, double* dxnew); /* :43  / :341 */ \
+    void gp##XX##_step2(GP* gp, double* x, double* y, double* dx, double* xnew, double* dxnew);               /* :98  / :396 */ \
+    void gp##XX##_step3(GP* gp, double* x, double* y, double* xnew, double* yhat);            /* wrapper.cpp:148 / :446 */  \
+    void gp##XX##_step4(GP* gp, double* x, double* xnew, double* yhat);                       /* wrapper.cpp:187 / :485 */  \
+    void gp##XX##_update(GP* gp, double* params);                                             /* wrapper.cpp:224 / :522 */  \
+    double gp##XX##_lik1(GP* gp, double* x, double* y, double* dx, double* grad);             /* wrapper.cpp:232 / :530 */  \
+    double gp##XX##_lik2(GP* gp, double* x, double* y);                                       /* wrapper.cpp:273 / :571 */  \
+    void gp##XX##_get_params(GP* gp, double* params);                                         /* wrapper.cpp:300 / :598 */  \
+    size_t gp##XX##_igp_dim(GP* gp);                                                          /* wrapper.cpp:311 / :609 */  \
+    size_t gp##XX##_num_param(GP* gp);                                                        /* wrapper.cpp:317 / :615 */  \
+    size_t gp##XX##_num_igp_param(GP* gp);                                                    /* wrapper.cpp:323 / :621 */
+
+MOIHGP_LEGACY_DECL(32, GP32)
+MOIHGP_LEGACY_DECL(52, GP52)
+
+/* ------------------------------------------------------------------ (2) whole-sequence symbols */
+typedef struct moihgp_handle moihgp_handle;
+
+enum { MOIHGP_MATERN32 = 32, MOIHGP_MATERN52 = 52 };
+/* smoother modes: the reference's IHGP::backwardSmoother as written (ihgp.h:103-114),
+ * or the Rauch-Tung-Striebel recursion on the same steady-state quantities (our extension). */
+enum { MOIHGP_SMOOTH_NONE = -1, MOIHGP_SMOOTH_REFERENCE_LITERAL = 0, MOIHGP_SMOOTH_RTS = 1 };
+
+/* MOIHGP<StateSpace>(dt, num_output, num_latent, threading)  moihgp.h:81-136.
+ * U starts as the p x L identity block (the reference draws a random near-identity U, moihgp.h:105-125:
+ * use the legacy gpXX_new for that behaviour), S = 1, sigma = 1e-2, latents at (1, 1, 0.1).
+ * `threading` only selects the reference's loss semantics (moihgp.h:588 vs :601, forced off for L < 2). */
+int moihgp_cuda_create(moihgp_handle** out, int kernel, double dt, size_t num_output, size_t num_latent,
+                       int threading, int device);
+void moihgp_cuda_destroy(moihgp_handle* h);
+/* run every kernel of this handle on `cuda_stream` (a cudaStream_t); NULL = the handle's own stream */
+int moihgp_cuda_set_stream(moihgp_handle* h, void* cuda_stream);
+int moihgp_cuda_sync(moihgp_handle* h);
+const char* moihgp_cuda_last_error(moihgp_handle* h);
+/* kernels launched by this handle since creation (bench.py's gpu_launches) */
+long long moihgp_cuda_launch_count(moihgp_handle* h);
+
+size_t moihgp_cuda_igp_dim(moihgp_handle* h);         /* MOIHGP::getIGPDim      moihgp.h:691 */
+size_t moihgp_cuda_num_param(moihgp_handle* h);       /* MOIHGP::getNumParam    moihgp.h:709 */
+size_t moihgp_cuda_num_igp_param(moihgp_handle* h);   /* MOIHGP::getNumIGPParam moihgp.h:715 */
+
+/* MOIHGP::update(params)  moihgp.h:431-457 -> IHGP::update  ihgp.h:117-201 (K-setup kernel) */
+int moihgp_cuda_update(moihgp_handle* h, const double* params);
+/* MOIHGP::getParams()  moihgp.h:721-738 */
+int moihgp_cuda_get_params(moihgp_handle* h, double* params);
+/* U (p x L row-major), the polar factor held by the model  moihgp.h:741 */
+int moihgp_cuda_get_U(moihgp_handle* h, double* U);
+/* IHGP public members of latent l after update (ihgp.h:243-254), flat:
+ *   A[d*d] Q[d*d] K[d] S PF[d*d] HA[d] AKHA[d*d], then for k = 0..2: dS dA[d*d] dK[d] dAKHA[d*d] HdA[d]
+ * (matrices row-major).  Returns the number of doubles written (<= cap) or a negative status. */
+long long moihgp_cuda_latent_consts(moihgp_handle* h, size_t l, double* out, size_t cap);
+/* iteration counts / converged flags the reference discards (ihgp.h:125,187):
+ * out[0] DARE iterations, out[1..3] DLyap iterations, out[4] DARE converged, out[5..7] DLyap converged */
+int moihgp_cuda_latent_iters(moihgp_handle* h, size_t l, int* out8);
+/* smoother gain G and smoothed covariance P of latent l (IHGP::backwardSmoother outputs, ihgp.h:105-107), d x d row-major */
+int moihgp_cuda_smoother_consts(moihgp_handle* h, size_t l, int mode, double* G, double* P);
+
+/* The fused pass on N independent sequences, HOST buffers (copies inside the call):
+ *   filter  : X[n][t] = state after observation t   (loop of MOIHGP::step v3, moihgp_regression.h:127-139)
+ *   Yhat    : U sqrt(S) X[.][0]                     (moihgp.h:222-225)
+ *   nll[n]  : sum_t MOIHGP::negLogLikelihood(x_t, y_t) on the pre-update state (moihgp.h:614-688)
+ *   smoother: Xs per `smoother_mode`                (IHGP::backwardSmoother, ihgp.h:103-114)
+ * x0 [N][L][d] carried-in state (NULL = zeros); X, Xs, Yhat, nll, xT may each be NULL. */
+int moihgp_cuda_filter_smoother_nll(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0,
+                                    int smoother_mode, double* X, double* Xs, double* Yhat, double* nll, double* xT);
+/* same, DEVICE buffers already resident in HBM; asynchronous on the handle's stream */
+int moihgp_cuda_filter_smoother_nll_dev(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0,
+                                        int smoother_mode, double* X, double* Xs, double* Yhat, double* nll, double* xT);
+
+/* RegressionObjective::operator() / OnlineObjective::operator() window loop over N sequences
+ * (moihgp_regression.h:42-50, moihgp_online.h:61-70): loss = sum_n sum_t negLogLikelihood(x, y, dx, grad)
+ * with MOIHGP::step v2 advancing (x, dx); grad[num_param] summed the same way.  x0 [N][L][d] and
+ * dx0 [N][L][3][d] are the carried-in state (NULL = zeros); xT / dxT receive the final state (may be NULL).
+ * HOST buffers. */
+int moihgp_cuda_objective(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0, const double* dx0,
+                          double* loss, double* grad, double* xT, double* dxT);
+/* same, DEVICE buffers (loss[1], grad[num_param] on the device); asynchronous on the handle's stream */
+int moihgp_cuda_objective_dev(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0, const double* dx0,
+                              double* loss, double* grad, double* xT, double* dxT);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOIHGP_B200_H */

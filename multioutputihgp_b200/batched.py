@@ -1,0 +1,166 @@
+"""Whole-sequence interface to the B200 library (the moihgp_cuda_* entry points).
+
+``MOIHGPSequences`` keeps the reference's model vocabulary (``update(params)``, ``params``,
+``negLogLikelihood``) but takes whole sequences ``Y[N][T][p]`` where the reference's callers loop
+over observations (RegressionObjective::operator(), moihgp_regression.h:34-52; OnlineObjective,
+moihgp_online.h:40-72; MOIHGPRegression::predict, moihgp_regression.h:127-139).
+
+NumPy arrays go through the host entry points (copies inside the call); torch CUDA tensors go
+through the ``*_dev`` entry points on torch's current stream and stay resident in HBM.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+SMOOTH_NONE, SMOOTH_REFERENCE_LITERAL, SMOOTH_RTS = -1, 0, 1
+_KERNELS = {"Matern32": 32, "Matern52": 52}
+
+
+def _np(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    return a.data_ptr()  # torch tensor
+
+
+class MOIHGPSequences(object):
+
+    def __init__(self, dt, num_output, num_latent, kernel="Matern32", threading=False, device=-1):
+        self._lib = _lib.load()
+        h = ctypes.c_void_p()
+        rc = self._lib.moihgp_cuda_create(ctypes.byref(h), _KERNELS[kernel], dt, num_output, num_latent, int(threading), device)
+        if rc != 0 or not h:
+            raise RuntimeError("moihgp_cuda_create failed (no B200-class CUDA device? there is no CPU fallback)")
+        self._h = h
+        self.dt, self.num_output, self.num_latent, self.kernel = dt, num_output, num_latent, kernel
+        self.igp_dim = int(self._lib.moihgp_cuda_igp_dim(h))
+        self.num_param = int(self._lib.moihgp_cuda_num_param(h))
+        self.num_igp_param = int(self._lib.moihgp_cuda_num_igp_param(h))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.moihgp_cuda_destroy(self._h)
+            self._h = None
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError("libmoihgp: " + self._lib.moihgp_cuda_last_error(self._h).decode())
+
+    # ---- model ------------------------------------------------------------------------------
+    def update(self, params):
+        params = _np(params)
+        assert params.size == self.num_param
+        self._check(self._lib.moihgp_cuda_update(self._h, params.ctypes.data_as(_lib.c_double_p)))
+
+    @property
+    def params(self):
+        out = np.zeros(self.num_param)
+        self._check(self._lib.moihgp_cuda_get_params(self._h, out.ctypes.data_as(_lib.c_double_p)))
+        return out
+
+    @property
+    def U(self):
+        out = np.zeros((self.num_output, self.num_latent))
+        self._check(self._lib.moihgp_cuda_get_U(self._h, out.ctypes.data_as(_lib.c_double_p)))
+        return out
+
+    def latent_consts(self, l):
+        flat = np.zeros(256)
+        n = self._lib.moihgp_cuda_latent_consts(self._h, l, flat.ctypes.data_as(_lib.c_double_p), flat.size)
+        if n < 0:
+            raise RuntimeError("moihgp_cuda_latent_consts failed")
+        d, out, o = self.igp_dim, {}, 0
+        lay = [("A", (d, d)), ("Q", (d, d)), ("K", (d,)), ("S", ()), ("PF", (d, d)), ("HA", (d,)), ("AKHA", (d, d))]
+        for k in range(3):
+            lay += [("dS%d" % k, ()), ("dA%d" % k, (d, d)), ("dK%d" % k, (d,)), ("dAKHA%d" % k, (d, d)), ("HdA%d" % k, (d,))]
+        for name, shp in lay:
+            m = int(np.prod(shp)) if shp else 1
+            out[name] = flat[o:o + m].reshape(shp).copy() if shp else float(flat[o])
+            o += m
+        return out
+
+    def latent_iters(self, l):
+        out = (ctypes.c_int * 8)()
+        self._check(self._lib.moihgp_cuda_latent_iters(self._h, l, out))
+        return list(out)
+
+    def smoother_consts(self, l, mode):
+        d = self.igp_dim
+        G, P = np.zeros((d, d)), np.zeros((d, d))
+        self._check(self._lib.moihgp_cuda_smoother_consts(self._h, l, mode, G.ctypes.data_as(_lib.c_double_p), P.ctypes.data_as(_lib.c_double_p)))
+        return G, P
+
+    @property
+    def launch_count(self):
+        return int(self._lib.moihgp_cuda_launch_count(self._h))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self._lib.moihgp_cuda_set_stream(self._h, cuda_stream_ptr))
+
+    def synchronize(self):
+        self._check(self._lib.moihgp_cuda_sync(self._h))
+
+    # ---- fused pass: filter + smoother + NLL ----------------------------------------------------
+    def filter_smoother_nll(self, Y, x0=None, smoother_mode=SMOOTH_RTS, want_states=True, want_yhat=False, want_nll=True):
+        """Y: [N,T,p] (or [T,p]) NumPy array -> dict of NumPy arrays X, Xs, Yhat, nll, xT."""
+        Y = _np(Y)
+        if Y.ndim == 2:
+            Y = Y[None]
+        N, T, p = Y.shape
+        assert p == self.num_output
+        L, d = self.num_latent, self.igp_dim
+        x0 = None if x0 is None else _np(x0).reshape(N, L, d)
+        X = np.empty((N, T, L, d)) if want_states else None
+        Xs = np.empty((N, T, L, d)) if (want_states and smoother_mode >= 0) else None
+        Yhat = np.empty((N, T, p)) if want_yhat else None
+        nll = np.empty(N) if want_nll else None
+        xT = np.empty((N, L, d))
+        self._check(self._lib.moihgp_cuda_filter_smoother_nll(self._h, _ptr(Y), N, T, _ptr(x0), smoother_mode, _ptr(X), _ptr(Xs),
+                                                              _ptr(Yhat), _ptr(nll), _ptr(xT)))
+        return {"X": X, "Xs": Xs, "Yhat": Yhat, "nll": nll, "xT": xT}
+
+    def filter_smoother_nll_device(self, Y, x0=None, smoother_mode=SMOOTH_RTS, X=None, Xs=None, Yhat=None, nll=None, xT=None):
+        """Device-resident variant: all arguments are torch CUDA float64 tensors (outputs pre-allocated by the
+        caller, any may be None); runs asynchronously on torch's current stream."""
+        import torch
+        assert Y.is_cuda and Y.dtype == torch.float64 and Y.is_contiguous() and Y.dim() == 3
+        N, T, _ = Y.shape
+        self.set_stream(torch.cuda.current_stream(Y.device).cuda_stream)
+        self._check(self._lib.moihgp_cuda_filter_smoother_nll_dev(self._h, _ptr(Y), N, T, _ptr(x0), smoother_mode, _ptr(X), _ptr(Xs),
+                                                                  _ptr(Yhat), _ptr(nll), _ptr(xT)))
+
+    # ---- objective: NLL + gradient ----------------------------------------------------------------
+    def objective(self, Y, x0=None, dx0=None, want_state=False):
+        """sum over sequences and time of negLogLikelihood(x, y, dx, grad) with step v2 advancing the state
+        (RegressionObjective::operator(), moihgp_regression.h:42-50).  Returns (loss, grad[, xT, dxT])."""
+        Y = _np(Y)
+        if Y.ndim == 2:
+            Y = Y[None]
+        N, T, p = Y.shape
+        assert p == self.num_output
+        L, d = self.num_latent, self.igp_dim
+        x0 = None if x0 is None else _np(x0).reshape(N, L, d)
+        dx0 = None if dx0 is None else _np(dx0).reshape(N, L, 3, d)
+        loss = np.zeros(1)
+        grad = np.zeros(self.num_param)
+        xT = np.empty((N, L, d)) if want_state else None
+        dxT = np.empty((N, L, 3, d)) if want_state else None
+        self._check(self._lib.moihgp_cuda_objective(self._h, _ptr(Y), N, T, _ptr(x0), _ptr(dx0), _ptr(loss), _ptr(grad), _ptr(xT), _ptr(dxT)))
+        if want_state:
+            return float(loss[0]), grad, xT, dxT
+        return float(loss[0]), grad
+
+    def objective_device(self, Y, loss, grad, x0=None, dx0=None, xT=None, dxT=None):
+        import torch
+        assert Y.is_cuda and Y.dtype == torch.float64 and Y.is_contiguous() and Y.dim() == 3
+        N, T, _ = Y.shape
+        self.set_stream(torch.cuda.current_stream(Y.device).cuda_stream)
+        self._check(self._lib.moihgp_cuda_objective_dev(self._h, _ptr(Y), N, T, _ptr(x0), _ptr(dx0), _ptr(loss), _ptr(grad), _ptr(xT), _ptr(dxT)))

@@ -1,0 +1,525 @@
+// C ABI of libmoihgp.so (declared in include/moihgp_b200.h): the model handle, its device
+// workspace, and the host-side glue between the reference-facing entry points and the kernels.
+//
+// Host-side pieces of the reference that live here:
+//   MOIHGP::MOIHGP      moihgp.h:81-136   construction (random near-identity U for the legacy symbols)
+//   MOIHGP::update      moihgp.h:431-457  polar factor of the U block (host one-sided Jacobi; the
+//                                         per-latent steady-state solve is the K-setup kernel)
+//   MOIHGP::getParams   moihgp.h:721-738
+//   src/wrapper.cpp:31-624                the 26 legacy symbols (argument marshalling only)
+// Everything numerical on the hot path runs on the device; there is no CPU fallback.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <random>
+#include <string>
+#include <vector>
+#include "../../include/moihgp_b200.h"
+#include "launch.h"
+
+using namespace moihgp;
+
+namespace {
+
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct moihgp_handle {
+    int kernel = 32, dim = 2, p = 0, L = 0, threading = 0, device = 0, num_param = 0;
+    double dt = 0.0, sigma = 1e-2;
+    std::vector<double> U, S, igp;            // host copies: [p*L], [L], [L*3]
+    std::vector<LatentConsts> consts;         // host copy of the per-latent constants
+    double *d_U = nullptr, *d_S = nullptr, *d_igp = nullptr;
+    LatentConsts* d_consts = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::map<std::string, Buf> ws;            // grow-only device workspace
+    double* h_stage = nullptr;                // pinned host staging for the per-observation calls
+    double* d_stage = nullptr;
+    size_t stage_cap = 0;
+    long long launches = 0;
+    std::string err;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return -1;                                                                             \
+        }                                                                                          \
+    } while (0)
+
+int fail(moihgp_handle* h, const std::string& m) {
+    h->err = m;
+    return -2;
+}
+
+template <typename T>
+int ws_get(moihgp_handle* h, const char* name, size_t count, T** out) {
+    Buf& b = h->ws[name];
+    const size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+    if (b.cap < bytes) {
+        if (b.p) cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+        CK(cudaMalloc(&b.p, bytes));
+        b.cap = bytes;
+    }
+    *out = static_cast<T*>(b.p);
+    return 0;
+}
+
+// Polar factor U = W V' of a (p x L, row-major, p >= L) via one-sided Jacobi: a V = W diag(s).
+// (MOIHGP::update forms svd.matrixU() * svd.matrixV().transpose(), moihgp.h:439,446.)
+void polar_factor(const double* a, int p, int L, double* out) {
+    std::vector<double> W(a, a + (size_t)p * L), V((size_t)L * L, 0.0);
+    for (int i = 0; i < L; ++i) V[(size_t)i * L + i] = 1.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0;
+        for (int i = 0; i < L - 1; ++i)
+            for (int j = i + 1; j < L; ++j) {
+                double al = 0.0, be = 0.0, ga = 0.0;
+                for (int r = 0; r < p; ++r) {
+                    const double wi = W[(size_t)r * L + i], wj = W[(size_t)r * L + j];
+                    al += wi * wi; be += wj * wj; ga += wi * wj;
+                }
+                if (ga == 0.0) continue;
+                off = std::max(off, std::fabs(ga) / std::sqrt(al * be));
+                const double zeta = (be - al) / (2.0 * ga);
+                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+                const double c = 1.0 / std::sqrt(1.0 + t * t), s = c * t;
+                for (int r = 0; r < p; ++r) {
+                    const double wi = W[(size_t)r * L + i], wj = W[(size_t)r * L + j];
+                    W[(size_t)r * L + i] = c * wi - s * wj;
+                    W[(size_t)r * L + j] = s * wi + c * wj;
+                }
+                for (int r = 0; r < L; ++r) {
+                    const double vi = V[(size_t)r * L + i], vj = V[(size_t)r * L + j];
+                    V[(size_t)r * L + i] = c * vi - s * vj;
+                    V[(size_t)r * L + j] = s * vi + c * vj;
+                }
+            }
+        if (off < 1e-15) break;
+    }
+    for (int j = 0; j < L; ++j) {
+        double q = 0.0;
+        for (int r = 0; r < p; ++r) q += W[(size_t)r * L + j] * W[(size_t)r * L + j];
+        const double s = std::sqrt(q);
+        for (int r = 0; r < p; ++r) W[(size_t)r * L + j] = s > 0.0 ? W[(size_t)r * L + j] / s : 0.0;
+    }
+    for (int r = 0; r < p; ++r)
+        for (int c = 0; c < L; ++c) {
+            double s = 0.0;
+            for (int k = 0; k < L; ++k) s += W[(size_t)r * L + k] * V[(size_t)c * L + k];
+            out[(size_t)r * L + c] = s;
+        }
+}
+
+int push_model(moihgp_handle* h) {
+    CK(cudaMemcpyAsync(h->d_U, h->U.data(), sizeof(double) * h->U.size(), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_S, h->S.data(), sizeof(double) * h->S.size(), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_igp, h->igp.data(), sizeof(double) * h->igp.size(), cudaMemcpyHostToDevice, h->stream));
+    CK(launch_setup(h->dim, h->d_igp, h->dt, h->L, h->d_consts, h->stream));
+    h->launches += 1;
+    CK(cudaMemcpyAsync(h->consts.data(), h->d_consts, sizeof(LatentConsts) * h->L, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int create(moihgp_handle** out, int kernel, double dt, size_t p, size_t L, int threading, int device, bool random_U) {
+    if (!out) return -2;
+    *out = nullptr;
+    moihgp_handle* h = new moihgp_handle();
+    auto bail = [&](const std::string& m) {
+        std::fprintf(stderr, "libmoihgp (B200): %s\n", m.c_str());
+        delete h;
+        return -1;
+    };
+    if (kernel != 32 && kernel != 52) return bail("kernel must be 32 (Matern-3/2) or 52 (Matern-5/2)");
+    if (p == 0 || L == 0 || L > p) return bail("need 1 <= num_latent <= num_output");
+    if (L > 64) return bail("num_latent > 64 is not supported by the per-observation kernels");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return bail("no CUDA device: this library has no CPU fallback");
+    if (device < 0) cudaGetDevice(&device);
+    if (device >= ndev) return bail("bad device index");
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major != 10) return bail(std::string("device '") + prop.name + "' is not compute capability 10.x (built for sm_100a only)");
+    cudaSetDevice(device);
+    h->kernel = kernel; h->dim = kernel == 32 ? 2 : 3; h->p = (int)p; h->L = (int)L; h->dt = dt; h->device = device;
+    h->threading = L < 2 ? 0 : (threading ? 1 : 0);                       // moihgp.h:128-135
+    h->num_param = (int)(p * L + L + 1 + 3 * L);                          // moihgp.h:93
+    h->U.assign(p * L, 0.0);
+    if (random_U) {                                                       // moihgp.h:103-125
+        std::random_device rd;
+        std::mt19937 gen(rd());
+        std::normal_distribution<> distr(0.0, 1e-3);
+        std::vector<double> raw(p * L, 0.0);
+        for (size_t r = 0; r < p; ++r) for (size_t c = 0; c < L; ++c) raw[r * L + c] = (r == c ? 1.0 : 0.0) + distr(gen);
+        polar_factor(raw.data(), (int)p, (int)L, h->U.data());
+    } else {
+        for (size_t i = 0; i < L; ++i) h->U[i * L + i] = 1.0;
+    }
+    h->S.assign(L, 1.0);                                                  // moihgp.h:126
+    h->sigma = 1e-2;                                                      // moihgp.h:127
+    h->igp.resize(3 * L);
+    for (size_t l = 0; l < L; ++l) { h->igp[3 * l] = 1.0; h->igp[3 * l + 1] = 1.0; h->igp[3 * l + 2] = 0.1; }   // matern32ss.h:35
+    h->consts.resize(L);
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate failed");
+    h->stream = h->own_stream;
+    bool ok = cudaMalloc(&h->d_U, sizeof(double) * p * L) == cudaSuccess && cudaMalloc(&h->d_S, sizeof(double) * L) == cudaSuccess &&
+              cudaMalloc(&h->d_igp, sizeof(double) * 3 * L) == cudaSuccess && cudaMalloc(&h->d_consts, sizeof(LatentConsts) * L) == cudaSuccess;
+    if (!ok) return bail("cudaMalloc failed");
+    h->stage_cap = (size_t)(2 * (L * 3 + L * 9) + 2 * p + 2 * h->num_param + 16);
+    if (cudaMallocHost(&h->h_stage, sizeof(double) * h->stage_cap) != cudaSuccess || cudaMalloc(&h->d_stage, sizeof(double) * h->stage_cap) != cudaSuccess)
+        return bail("staging allocation failed");
+    if (push_model(h) != 0) return bail(h->err);
+    *out = h;
+    return 0;
+}
+
+// ---- one observation: marshalling for the legacy symbols -------------------------------------------
+struct StageLayout {
+    size_t x, dx, y, xnew, dxnew, yhat, loss, grad, total_in;
+};
+StageLayout stage_layout(const moihgp_handle* h) {
+    StageLayout s;
+    const size_t Ld = (size_t)h->L * h->dim;
+    s.x = 0; s.dx = s.x + Ld; s.y = s.dx + 3 * Ld; s.total_in = s.y + h->p;
+    s.xnew = s.total_in; s.dxnew = s.xnew + Ld; s.yhat = s.dxnew + 3 * Ld; s.loss = s.yhat + h->p; s.grad = s.loss + 2;
+    return s;
+}
+
+int step_call(moihgp_handle* h, const double* x, const double* y, const double* dx, double* xnew, double* yhat, double* dxnew) {
+    cudaSetDevice(h->device);
+    const StageLayout s = stage_layout(h);
+    const size_t Ld = (size_t)h->L * h->dim;
+    std::memcpy(h->h_stage + s.x, x, sizeof(double) * Ld);
+    if (dx) std::memcpy(h->h_stage + s.dx, dx, sizeof(double) * 3 * Ld);
+    if (y) std::memcpy(h->h_stage + s.y, y, sizeof(double) * h->p);
+    CK(cudaMemcpyAsync(h->d_stage, h->h_stage, sizeof(double) * s.total_in, cudaMemcpyHostToDevice, h->stream));
+    StepArgs a;
+    a.consts = h->d_consts; a.U = h->d_U; a.S = h->d_S; a.sigma = h->sigma; a.p = h->p; a.L = h->L; a.dim = h->dim; a.threading = h->threading;
+    a.x = h->d_stage + s.x; a.y = y ? h->d_stage + s.y : nullptr; a.dx = dx ? h->d_stage + s.dx : nullptr;
+    a.xnew = h->d_stage + s.xnew; a.yhat = yhat ? h->d_stage + s.yhat : nullptr; a.dxnew = (dx && dxnew) ? h->d_stage + s.dxnew : nullptr;
+    a.scratch = nullptr;
+    CK(launch_step(a, h->stream));
+    h->launches += 1;
+    CK(cudaMemcpyAsync(h->h_stage + s.xnew, h->d_stage + s.xnew, sizeof(double) * (s.loss - s.xnew), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    std::memcpy(xnew, h->h_stage + s.xnew, sizeof(double) * Ld);
+    if (dx && dxnew) std::memcpy(dxnew, h->h_stage + s.dxnew, sizeof(double) * 3 * Ld);
+    if (yhat) std::memcpy(yhat, h->h_stage + s.yhat, sizeof(double) * h->p);
+    return 0;
+}
+
+int lik_call(moihgp_handle* h, const double* x, const double* y, const double* dx, double* loss, double* grad) {
+    cudaSetDevice(h->device);
+    const StageLayout s = stage_layout(h);
+    const size_t Ld = (size_t)h->L * h->dim;
+    std::memcpy(h->h_stage + s.x, x, sizeof(double) * Ld);
+    if (dx) std::memcpy(h->h_stage + s.dx, dx, sizeof(double) * 3 * Ld);
+    std::memcpy(h->h_stage + s.y, y, sizeof(double) * h->p);
+    CK(cudaMemcpyAsync(h->d_stage, h->h_stage, sizeof(double) * s.total_in, cudaMemcpyHostToDevice, h->stream));
+    LikArgs a;
+    a.consts = h->d_consts; a.U = h->d_U; a.S = h->d_S; a.sigma = h->sigma; a.p = h->p; a.L = h->L; a.dim = h->dim; a.threading = h->threading;
+    a.x = h->d_stage + s.x; a.y = h->d_stage + s.y; a.dx = dx ? h->d_stage + s.dx : nullptr;
+    a.loss = h->d_stage + s.loss; a.grad = (dx && grad) ? h->d_stage + s.grad : nullptr; a.scratch = nullptr;
+    CK(launch_lik(a, h->stream));
+    h->launches += 1;
+    const size_t nout = 2 + ((dx && grad) ? (size_t)h->num_param : 0);
+    CK(cudaMemcpyAsync(h->h_stage + s.loss, h->d_stage + s.loss, sizeof(double) * nout, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *loss = h->h_stage[s.loss];
+    if (dx && grad) std::memcpy(grad, h->h_stage + s.grad, sizeof(double) * h->num_param);
+    return 0;
+}
+
+void legacy_fatal(moihgp_handle* h, const char* where) {
+    // The reference's C ABI has no error channel (all void / value returns).  A CUDA failure here
+    // cannot be reported to the caller, so fail loudly rather than return garbage.
+    std::fprintf(stderr, "libmoihgp (B200): %s failed: %s\n", where, h ? h->err.c_str() : "null handle");
+    std::abort();
+}
+
+moihgp_handle* legacy_new(int kernel, double dt, size_t p, size_t L, bool threading) {
+    moihgp_handle* h = nullptr;
+    if (create(&h, kernel, dt, p, L, threading ? 1 : 0, -1, /*random_U=*/true) != 0) {
+        std::fprintf(stderr, "libmoihgp (B200): gpXX_new failed (no CPU fallback)\n");
+        std::abort();
+    }
+    return h;
+}
+
+int kernel_for_gp52() {
+    // wrapper.cpp:22 typedefs GP52 to the Matern-3/2 class; the drop-in keeps that
+    // behaviour unless MOIHGP_GP52_MATERN52=1 asks for the kernel the name promises.
+    const char* e = std::getenv("MOIHGP_GP52_MATERN52");
+    return (e && e[0] == '1') ? 52 : 32;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int moihgp_cuda_create(moihgp_handle** out, int kernel, double dt, size_t p, size_t L, int threading, int device) {
+    return create(out, kernel, dt, p, L, threading, device, /*random_U=*/false);
+}
+
+void moihgp_cuda_destroy(moihgp_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (auto& kv : h->ws) if (kv.second.p) cudaFree(kv.second.p);
+    cudaFree(h->d_U); cudaFree(h->d_S); cudaFree(h->d_igp); cudaFree(h->d_consts); cudaFree(h->d_stage);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+int moihgp_cuda_set_stream(moihgp_handle* h, void* s) {
+    if (!h) return -2;
+    cudaStreamSynchronize(h->stream);
+    h->stream = s ? static_cast<cudaStream_t>(s) : h->own_stream;
+    return 0;
+}
+
+int moihgp_cuda_sync(moihgp_handle* h) {
+    if (!h) return -2;
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+const char* moihgp_cuda_last_error(moihgp_handle* h) { return h ? h->err.c_str() : "null handle"; }
+long long moihgp_cuda_launch_count(moihgp_handle* h) { return h ? h->launches : 0; }
+size_t moihgp_cuda_igp_dim(moihgp_handle* h) { return (size_t)h->dim; }
+size_t moihgp_cuda_num_param(moihgp_handle* h) { return (size_t)h->num_param; }
+size_t moihgp_cuda_num_igp_param(moihgp_handle* h) { return 3; }
+
+int moihgp_cuda_update(moihgp_handle* h, const double* params) {
+    if (!h || !params) return -2;
+    cudaSetDevice(h->device);
+    const int p = h->p, L = h->L;
+    polar_factor(params, p, L, h->U.data());                               // moihgp.h:436-446
+    for (int l = 0; l < L; ++l) h->S[l] = params[p * L + l];               // moihgp.h:448
+    h->sigma = params[p * L + L];                                          // moihgp.h:449
+    for (int i = 0; i < 3 * L; ++i) h->igp[i] = params[p * L + L + 1 + i]; // moihgp.h:450-456
+    return push_model(h);
+}
+
+int moihgp_cuda_get_params(moihgp_handle* h, double* params) {
+    if (!h || !params) return -2;
+    const int p = h->p, L = h->L;
+    std::copy(h->U.begin(), h->U.end(), params);
+    std::copy(h->S.begin(), h->S.end(), params + p * L);
+    params[p * L + L] = h->sigma;
+    std::copy(h->igp.begin(), h->igp.end(), params + p * L + L + 1);
+    return 0;
+}
+
+int moihgp_cuda_get_U(moihgp_handle* h, double* U) {
+    if (!h || !U) return -2;
+    std::copy(h->U.begin(), h->U.end(), U);
+    return 0;
+}
+
+long long moihgp_cuda_latent_consts(moihgp_handle* h, size_t l, double* out, size_t cap) {
+    if (!h || !out || l >= (size_t)h->L) return -2;
+    const LatentConsts& c = h->consts[l];
+    const int d = h->dim;
+    std::vector<double> v;
+    auto mat = [&](const double* m) { for (int i = 0; i < d; ++i) for (int j = 0; j < d; ++j) v.push_back(m[i * 3 + j]); };
+    auto vec = [&](const double* m) { for (int i = 0; i < d; ++i) v.push_back(m[i]); };
+    mat(c.A); mat(c.Q); vec(c.K); v.push_back(c.S); mat(c.PF); vec(c.HA); mat(c.AKHA);
+    for (int k = 0; k < 3; ++k) { v.push_back(c.dS[k]); mat(c.dA[k]); vec(c.dK[k]); mat(c.dAKHA[k]); vec(c.HdA[k]); }
+    if (v.size() > cap) return -3;
+    std::copy(v.begin(), v.end(), out);
+    return (long long)v.size();
+}
+
+int moihgp_cuda_latent_iters(moihgp_handle* h, size_t l, int* out8) {
+    if (!h || !out8 || l >= (size_t)h->L) return -2;
+    for (int i = 0; i < 4; ++i) { out8[i] = h->consts[l].iters[i]; out8[4 + i] = h->consts[l].conv[i]; }
+    return 0;
+}
+
+int moihgp_cuda_smoother_consts(moihgp_handle* h, size_t l, int mode, double* G, double* P) {
+    if (!h || l >= (size_t)h->L || mode < 0 || mode > 1) return -2;
+    const int d = h->dim;
+    for (int i = 0; i < d; ++i) for (int j = 0; j < d; ++j) {
+        if (G) G[i * d + j] = h->consts[l].G[mode][i * 3 + j];
+        if (P) P[i * d + j] = h->consts[l].Ps[mode][i * 3 + j];
+    }
+    return 0;
+}
+
+int moihgp_cuda_filter_smoother_nll_dev(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0, int mode,
+                                        double* X, double* Xs, double* Yhat, double* nll, double* xT) {
+    if (!h || !Y) return -2;
+    if (N == 0 || T == 0) return fail(h, "N and T must be positive");
+    if (mode < -1 || mode > 1) return fail(h, "smoother_mode must be -1, 0 or 1");
+    if (mode < 0 && Xs) return fail(h, "Xs requested with smoother_mode = none");
+    cudaSetDevice(h->device);
+    const int L = h->L, D = h->dim;
+    const size_t nC = scan_chunks((long long)T);
+    double *u, *rho, *fsum, *bsum, *xin, *bin, *Bx, *vsq, *Xtmp = nullptr;
+    int* nanf;
+    if (ws_get(h, "u", N * L * T, &u) || ws_get(h, "rho", N * T, &rho) || ws_get(h, "fsum", nC * N * L * D, &fsum) ||
+        ws_get(h, "bsum", nC * N * L * D, &bsum) || ws_get(h, "xin", nC * N * L * D, &xin) || ws_get(h, "bin", nC * N * L * D, &bin) ||
+        ws_get(h, "Bx", (size_t)L * 2 * 9, &Bx) || ws_get(h, "vsq", nC * N * L, &vsq) || ws_get(h, "nanf", 4, &nanf))
+        return -1;
+    if (Yhat && !X) { if (ws_get(h, "Xtmp", N * T * L * D, &Xtmp)) return -1; X = Xtmp; }
+    CK(cudaMemsetAsync(nanf, 0, sizeof(int), h->stream));
+    CK(launch_project(Y, h->d_U, h->d_S, h->p, L, (long long)N, (long long)T, u, nullptr, nullptr, nll ? rho : nullptr, nanf, h->stream));
+    ScanArgs a;
+    a.u = u; a.consts = h->d_consts; a.L = L; a.N = (long long)N; a.T = (long long)T; a.x0 = x0;
+    a.fsum = fsum; a.bsum = bsum; a.xin = xin; a.bin = bin; a.Bx = Bx; a.X = X; a.Xs = Xs; a.vsq = vsq; a.xT = xT;
+    CK(launch_scan(D, mode < 0 ? 1 : mode, a, h->stream));
+    h->launches += 1 + scan_launch_count((long long)T);
+    if (nll) { CK(launch_nll_reduce(rho, vsq, h->d_consts, h->d_S, h->sigma, h->p, L, (long long)N, (long long)T, nll, h->stream)); h->launches += 1; }
+    if (Yhat) { CK(launch_backproject(X, h->d_U, h->d_S, h->p, L, D, (long long)N, (long long)T, Yhat, h->stream)); h->launches += 1; }
+    return 0;
+}
+
+int moihgp_cuda_filter_smoother_nll(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0, int mode, double* X,
+                                    double* Xs, double* Yhat, double* nll, double* xT) {
+    if (!h || !Y) return -2;
+    if (N == 0 || T == 0) return fail(h, "N and T must be positive");
+    cudaSetDevice(h->device);
+    const size_t L = h->L, D = h->dim, p = h->p;
+    double *dY, *dx0 = nullptr, *dX = nullptr, *dXs = nullptr, *dYh = nullptr, *dnll = nullptr, *dxT = nullptr;
+    if (ws_get(h, "hY", N * T * p, &dY)) return -1;
+    if (x0 && ws_get(h, "hx0", N * L * D, &dx0)) return -1;
+    if ((X || Yhat) && ws_get(h, "hX", N * T * L * D, &dX)) return -1;
+    if (Xs && ws_get(h, "hXs", N * T * L * D, &dXs)) return -1;
+    if (Yhat && ws_get(h, "hYh", N * T * p, &dYh)) return -1;
+    if (nll && ws_get(h, "hnll", N, &dnll)) return -1;
+    if (xT && ws_get(h, "hxT", N * L * D, &dxT)) return -1;
+    CK(cudaMemcpyAsync(dY, Y, sizeof(double) * N * T * p, cudaMemcpyHostToDevice, h->stream));
+    if (x0) CK(cudaMemcpyAsync(dx0, x0, sizeof(double) * N * L * D, cudaMemcpyHostToDevice, h->stream));
+    const int rc = moihgp_cuda_filter_smoother_nll_dev(h, dY, N, T, dx0, mode, dX, dXs, dYh, dnll, dxT);
+    if (rc) return rc;
+    if (X) CK(cudaMemcpyAsync(X, dX, sizeof(double) * N * T * L * D, cudaMemcpyDeviceToHost, h->stream));
+    if (Xs) CK(cudaMemcpyAsync(Xs, dXs, sizeof(double) * N * T * L * D, cudaMemcpyDeviceToHost, h->stream));
+    if (Yhat) CK(cudaMemcpyAsync(Yhat, dYh, sizeof(double) * N * T * p, cudaMemcpyDeviceToHost, h->stream));
+    if (nll) CK(cudaMemcpyAsync(nll, dnll, sizeof(double) * N, cudaMemcpyDeviceToHost, h->stream));
+    if (xT) CK(cudaMemcpyAsync(xT, dxT, sizeof(double) * N * L * D, cudaMemcpyDeviceToHost, h->stream));
+    int flag = 0;
+    int* nanf;
+    if (ws_get(h, "nanf", 4, &nanf)) return -1;
+    CK(cudaMemcpyAsync(&flag, nanf, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (flag) return fail(h, "Y contains NaN (missing observations): not supported by the whole-sequence pass yet; use gpXX_step*");
+    return 0;
+}
+
+int moihgp_cuda_objective_dev(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0, const double* dx0,
+                              double* loss, double* grad, double* xT, double* dxT) {
+    if (!h || !Y || !loss || !grad) return -2;
+    if (N == 0 || T == 0) return fail(h, "N and T must be positive");
+    cudaSetDevice(h->device);
+    const int L = h->L, D = h->dim, p = h->p;
+    const size_t nC = obj_chunks((long long)T), nsplit = obj_gu_splits((long long)N, (long long)T);
+    double *u, *w, *yl, *rho, *zsum, *zin, *part, *gU, *Ek, *lat;
+    int* nanf;
+    if (ws_get(h, "u", N * L * T, &u) || ws_get(h, "w", N * L * T, &w) || ws_get(h, "yl", N * L * T, &yl) || ws_get(h, "rho", N * T, &rho) ||
+        ws_get(h, "zsum", nC * N * L * 4 * D, &zsum) || ws_get(h, "zin", nC * N * L * 4 * D, &zin) || ws_get(h, "part", nC * N * L * 8, &part) ||
+        ws_get(h, "gU", nsplit * p * L, &gU) || ws_get(h, "Ek", (size_t)L * 27, &Ek) || ws_get(h, "lat", ((size_t)L + 1) * 8, &lat) ||
+        ws_get(h, "nanf", 4, &nanf))
+        return -1;
+    CK(cudaMemsetAsync(nanf, 0, sizeof(int), h->stream));
+    CK(launch_project(Y, h->d_U, h->d_S, p, L, (long long)N, (long long)T, u, w, yl, rho, nanf, h->stream));
+    ObjArgs a;
+    a.Y = Y; a.u = u; a.w = w; a.yl = yl; a.rho = rho; a.wgt = w;   // the weights overwrite w in place (same thread, same index)
+    a.consts = h->d_consts; a.U = h->d_U; a.S = h->d_S; a.sigma = h->sigma; a.p = p; a.L = L; a.threading = h->threading;
+    a.N = (long long)N; a.T = (long long)T; a.x0 = x0; a.dx0 = dx0; a.zsum = zsum; a.zin = zin; a.part = part; a.gU_part = gU;
+    a.Ek = Ek; a.lat_sums = lat; a.loss = loss; a.grad = grad; a.xT = xT; a.dxT = dxT;
+    CK(launch_objective(D, a, h->stream));
+    h->launches += 1 + obj_launch_count((long long)T);
+    return 0;
+}
+
+int moihgp_cuda_objective(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0, const double* dx0, double* loss,
+                          double* grad, double* xT, double* dxT) {
+    if (!h || !Y || !loss || !grad) return -2;
+    if (N == 0 || T == 0) return fail(h, "N and T must be positive");
+    cudaSetDevice(h->device);
+    const size_t L = h->L, D = h->dim, p = h->p, np = h->num_param;
+    double *dY, *dx = nullptr, *ddx = nullptr, *dout, *dxT_ = nullptr, *ddxT = nullptr;
+    if (ws_get(h, "hY", N * T * p, &dY) || ws_get(h, "hout", np + 2, &dout)) return -1;
+    if (x0 && ws_get(h, "hx0", N * L * D, &dx)) return -1;
+    if (dx0 && ws_get(h, "hdx0", N * L * 3 * D, &ddx)) return -1;
+    if (xT && ws_get(h, "hxT", N * L * D, &dxT_)) return -1;
+    if (dxT && ws_get(h, "hdxT", N * L * 3 * D, &ddxT)) return -1;
+    CK(cudaMemcpyAsync(dY, Y, sizeof(double) * N * T * p, cudaMemcpyHostToDevice, h->stream));
+    if (x0) CK(cudaMemcpyAsync(dx, x0, sizeof(double) * N * L * D, cudaMemcpyHostToDevice, h->stream));
+    if (dx0) CK(cudaMemcpyAsync(ddx, dx0, sizeof(double) * N * L * 3 * D, cudaMemcpyHostToDevice, h->stream));
+    const int rc = moihgp_cuda_objective_dev(h, dY, N, T, dx, ddx, dout, dout + 2, dxT_, ddxT);
+    if (rc) return rc;
+    std::vector<double> host(np + 2);
+    CK(cudaMemcpyAsync(host.data(), dout, sizeof(double) * (np + 2), cudaMemcpyDeviceToHost, h->stream));
+    if (xT) CK(cudaMemcpyAsync(xT, dxT_, sizeof(double) * N * L * D, cudaMemcpyDeviceToHost, h->stream));
+    if (dxT) CK(cudaMemcpyAsync(dxT, ddxT, sizeof(double) * N * L * 3 * D, cudaMemcpyDeviceToHost, h->stream));
+    int flag = 0;
+    int* nanf;
+    if (ws_get(h, "nanf", 4, &nanf)) return -1;
+    CK(cudaMemcpyAsync(&flag, nanf, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *loss = host[0];
+    std::copy(host.begin() + 2, host.end(), grad);
+    if (flag) return fail(h, "Y contains NaN (missing observations): not supported by the whole-sequence pass yet; use gpXX_lik*");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// legacy symbols (src/wrapper.cpp:31-624).  Same signatures; errors cannot be returned, so they abort.
+#define LEGACY_DEF(XX, KERNEL_EXPR)                                                                                        \
+    moihgp_handle* gp##XX##_new(double dt, size_t num_output, size_t num_latent, bool threading) {                          \
+        return legacy_new(KERNEL_EXPR, dt, num_output, num_latent, threading);                                              \
+    }                                                                                                                       \
+    void gp##XX##_del(moihgp_handle* gp) { moihgp_cuda_destroy(gp); }                                                       \
+    void gp##XX##_step1(moihgp_handle* gp, double* x, double* y, double* dx, double* xnew, double* yhat, double* dxnew) {   \
+        if (step_call(gp, x, y, dx, xnew, yhat, dxnew)) legacy_fatal(gp, "gp" #XX "_step1");                                \
+    }                                                                                                                       \
+    void gp##XX##_step2(moihgp_handle* gp, double* x, double* y, double* dx, double* xnew, double* dxnew) {                 \
+        if (step_call(gp, x, y, dx, xnew, nullptr, dxnew)) legacy_fatal(gp, "gp" #XX "_step2");                             \
+    }                                                                                                                       \
+    void gp##XX##_step3(moihgp_handle* gp, double* x, double* y, double* xnew, double* yhat) {                              \
+        if (step_call(gp, x, y, nullptr, xnew, yhat, nullptr)) legacy_fatal(gp, "gp" #XX "_step3");                         \
+    }                                                                                                                       \
+    void gp##XX##_step4(moihgp_handle* gp, double* x, double* xnew, double* yhat) {                                         \
+        if (step_call(gp, x, nullptr, nullptr, xnew, yhat, nullptr)) legacy_fatal(gp, "gp" #XX "_step4");                   \
+    }                                                                                                                       \
+    void gp##XX##_update(moihgp_handle* gp, double* params) {                                                               \
+        if (moihgp_cuda_update(gp, params)) legacy_fatal(gp, "gp" #XX "_update");                                           \
+    }                                                                                                                       \
+    double gp##XX##_lik1(moihgp_handle* gp, double* x, double* y, double* dx, double* grad) {                               \
+        double loss = 0.0;                                                                                                  \
+        if (lik_call(gp, x, y, dx, &loss, grad)) legacy_fatal(gp, "gp" #XX "_lik1");                                        \
+        return loss;                                                                                                        \
+    }                                                                                                                       \
+    double gp##XX##_lik2(moihgp_handle* gp, double* x, double* y) {                                                         \
+        double loss = 0.0;                                                                                                  \
+        if (lik_call(gp, x, y, nullptr, &loss, nullptr)) legacy_fatal(gp, "gp" #XX "_lik2");                                \
+        return loss;                                                                                                        \
+    }                                                                                                                       \
+    void gp##XX##_get_params(moihgp_handle* gp, double* params) { moihgp_cuda_get_params(gp, params); }                     \
+    size_t gp##XX##_igp_dim(moihgp_handle* gp) { return (size_t)gp->dim; }                                                  \
+    size_t gp##XX##_num_param(moihgp_handle* gp) { return (size_t)gp->num_param; }                                          \
+    size_t gp##XX##_num_igp_param(moihgp_handle* gp) { return 3; }
+
+LEGACY_DEF(32, 32)
+LEGACY_DEF(52, kernel_for_gp52())
+
+}  // extern "C"

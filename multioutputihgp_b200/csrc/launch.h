@@ -1,0 +1,84 @@
+// Host-side launchers of the MOIHGP kernels (internal to libmoihgp.so; the public boundary is
+// include/moihgp_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include "moihgp_device.cuh"
+
+namespace moihgp {
+
+// setup.cu
+cudaError_t launch_setup(int dim, const double* d_igp_params, double dt, int L, LatentConsts* d_out, cudaStream_t stream);
+
+// project.cu
+cudaError_t launch_project(const double* Y, const double* U, const double* S, int p, int L, long long N, long long T,
+                           double* u, double* w, double* yl, double* rho, int* nan_flag, cudaStream_t stream);
+cudaError_t launch_backproject(const double* X, const double* U, const double* S, int p, int L, int d, long long N,
+                               long long T, double* Yhat, cudaStream_t stream);
+
+// scan.cu
+struct ScanArgs {
+    const double* u;              // [N][L][T] projected observations
+    const LatentConsts* consts;   // [L]
+    int L;
+    long long N, T;
+    const double* x0;             // [N][L][D] carried-in filter state or null (zeros)
+    double *fsum, *bsum, *xin, *bin;   // [nC][N][L][D] chunk summaries / carries (workspace)
+    double* Bx;                   // [L][2][D*D] chunk responses (workspace)
+    double *X, *Xs;               // [N][T][L][D] outputs (either may be null)
+    double* vsq;                  // [nC][N][L] sum of squared innovations (workspace)
+    double* xT;                   // [N][L][D] final filtered state or null
+};
+size_t scan_chunks(long long T);
+int scan_launch_count(long long T);
+cudaError_t launch_scan(int dim, int mode, const ScanArgs& a, cudaStream_t st);
+cudaError_t launch_nll_reduce(const double* rho, const double* vsq, const LatentConsts* consts, const double* S, double sigma,
+                              int p, int L, long long N, long long T, double* nll, cudaStream_t st);
+
+// objective.cu
+struct ObjArgs {
+    const double* Y;              // [N][T][p]
+    const double *u, *w, *yl, *rho;   // [N][L][T] x3, [N][T]   (from k_project)
+    double* wgt;                  // [N][L][T] workspace: per-step weights of the dU contraction
+    const LatentConsts* consts;
+    const double *U, *S;
+    double sigma;
+    int p, L, threading;
+    long long N, T;
+    const double *x0, *dx0;       // [N][L][D], [N][L][3][D] carried-in state or null
+    double *zsum, *zin;           // [nC][N][L][4*D] chunk summaries / carries
+    double* part;                 // [nC][N][L][8] per-chunk partial sums
+    double* gU_part;              // [nSplit][p][L] split-K partials of dU
+    double* Ek;                   // [L][3][D*D] cross-chunk coupling matrices (workspace)
+    double* lat_sums;             // [L+1][8] per-latent reduced sums (workspace)
+    double *loss, *grad;          // [1], [num_param] outputs (device)
+    double *xT, *dxT;             // final state or null
+};
+size_t obj_chunks(long long T);
+size_t obj_gu_splits(long long N, long long T);
+int obj_launch_count(long long T);
+cudaError_t launch_objective(int dim, const ObjArgs& a, cudaStream_t st);
+
+// step.cu  (one observation per call: the legacy gpXX_* entry points)
+struct StepArgs {
+    const LatentConsts* consts;
+    const double *U, *S;
+    double sigma;
+    int p, L, dim, threading;
+    const double *x, *y, *dx;     // device staging: [L][D], [p] (null = predict only), [L][3][D] (may be null)
+    double *xnew, *yhat, *dxnew;  // outputs (yhat/dxnew may be null)
+    double* scratch;              // >= L*L + 3*L doubles
+};
+cudaError_t launch_step(const StepArgs& a, cudaStream_t st);
+struct LikArgs {
+    const LatentConsts* consts;
+    const double *U, *S;
+    double sigma;
+    int p, L, dim, threading;
+    const double *x, *y, *dx;     // dx null => lik2 (no gradient)
+    double* loss;                 // [1]
+    double* grad;                 // [num_param] or null
+    double* scratch;
+};
+cudaError_t launch_lik(const LikArgs& a, cudaStream_t st);
+
+}  // namespace moihgp

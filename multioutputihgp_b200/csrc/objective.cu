@@ -1,0 +1,461 @@
+// K-objective: negative log-likelihood and its hyper-parameter gradient over whole sequences (sm_100a).
+//
+// Replaces the per-observation loop of RegressionObjective::operator() (moihgp_regression.h:42-50)
+// and OnlineObjective::operator() (moihgp_online.h:61-70):
+//     for each y_t:  MOIHGP::step v2 (moihgp.h:229-301)  +  MOIHGP::negLogLikelihood(x, y, dx, grad) (moihgp.h:460-611)
+// i.e. per latent the sensitivity recursion ihgp.h:60-78
+//     x+ = AKHA x + K u,      dx_k+ = dAKHA_k x + AKHA dx_k + dK_k u
+// and the per-step loss / gradient ihgp.h:212-222, with the mixing terms of moihgp.h:499-609.
+//
+// The reference's O(p^3 L^2)-per-step dU loop (moihgp.h:538-552) is the rank-1 update
+// y_r * ( -(U'y)_c / sigma + pv_c / sqrt(S_c) ) (oracle test_rank1), so summed over
+// time it is ONE dense contraction  dU = Y' W  (k_gradU, split over time and reduced in fixed order).
+//
+// Scan structure: as scan.cu.  The dx_k chains are LTI recurrences with the SAME transition AKHA
+// and a drive dAKHA_k x_t + dK_k u_t that depends on the true filtered state, so inside a warp
+// the x chain is resolved first and each dx_k chain is then scanned with the same AKHA powers;
+// across chunks the coupling is the constant matrix E_k = sum_i AKHA^(CH-1-i) dAKHA_k AKHA^i.
+//
+// Quirks kept for parity: Q5 (per-latent loss terms only when `threading`),
+// Q8 (pv uses the RAW y(l)), Q9 (norm not squared; 1/2 log(sum S)), Q20 (dv_k uses HdA_k(0) x(0)).
+#include <cuda_runtime.h>
+#include <math.h>
+#include "moihgp_device.cuh"
+#include "launch.h"
+
+namespace moihgp {
+
+namespace {
+
+constexpr int SUB = 8;
+constexpr int CH = 32 * SUB;
+constexpr int LOG2_SUB = 3;
+constexpr int LOG2_CH = 8;
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int NPART = 8;          // per-chunk partial sums: loss, g0, g1, g2, pv*w (3 spare)
+
+template <int D> __device__ __forceinline__ void load_mat(const double* src9, double* dst) {
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) dst[i * D + j] = __ldg(src9 + i * 3 + j);
+}
+template <int D> __device__ __forceinline__ void load_vec(const double* src3, double* dst) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) dst[i] = __ldg(src3 + i);
+}
+template <int D> __device__ __forceinline__ void mv(const double* M, const double* x, double* y) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        double s = M[i * D] * x[0];
+#pragma unroll
+        for (int j = 1; j < D; ++j) s = fma(M[i * D + j], x[j], s);
+        y[i] = s;
+    }
+}
+template <int D> __device__ __forceinline__ void mv_acc(const double* M, const double* x, double* y) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        double s = y[i];
+#pragma unroll
+        for (int j = 0; j < D; ++j) s = fma(M[i * D + j], x[j], s);
+        y[i] = s;
+    }
+}
+
+// Warp-level LTI scan  z+ = M z + r_i  over this lane's SUB steps: returns, per step, the state BEFORE
+// the step (pre[i]) and the lane's end state after the inclusive scan (z_end; lane 31 = chunk end).
+template <int D>
+__device__ __forceinline__ void lti_scan(const double (&M)[D * D], const LatentConsts* lc, const double (&r)[SUB][D],
+                                         const double (&z_in)[D], int lane, double (&pre)[SUB][D], double (&z_end)[D]) {
+    double z[D];
+#pragma unroll
+    for (int q = 0; q < D; ++q) z[q] = lane == 0 ? z_in[q] : 0.0;
+#pragma unroll
+    for (int i = 0; i < SUB; ++i) {
+        double zn[D];
+        mv<D>(M, z, zn);
+#pragma unroll
+        for (int q = 0; q < D; ++q) z[q] = zn[q] + r[i][q];
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int o = 1 << k;
+        double zo[D], P[D * D];
+#pragma unroll
+        for (int q = 0; q < D; ++q) zo[q] = __shfl_up_sync(FULL, z[q], o);
+        load_mat<D>(lc->powM[LOG2_SUB + k], P);
+        if (lane >= o) mv_acc<D>(P, zo, z);
+    }
+#pragma unroll
+    for (int q = 0; q < D; ++q) z_end[q] = z[q];
+    double x[D];
+#pragma unroll
+    for (int q = 0; q < D; ++q) {
+        const double up = __shfl_up_sync(FULL, z[q], 1);
+        x[q] = lane == 0 ? z_in[q] : up;
+    }
+#pragma unroll
+    for (int i = 0; i < SUB; ++i) {
+#pragma unroll
+        for (int q = 0; q < D; ++q) pre[i][q] = x[q];
+        double xn[D];
+        mv<D>(M, x, xn);
+#pragma unroll
+        for (int q = 0; q < D; ++q) x[q] = xn[q] + r[i][q];
+    }
+}
+
+// grid: N * nC * L warps, 4 warps per CTA (one warp = one (sequence, chunk, latent)); arrays [c][n][l][...]
+template <int D, bool FINAL>
+__global__ void __launch_bounds__(128) k_obj_scan(const double* __restrict__ u, const double* __restrict__ w,
+                                                 const double* __restrict__ yl, const LatentConsts* __restrict__ consts,
+                                                 const double* __restrict__ S, double sigma, int L, long long N, long long T,
+                                                 long long nC, const double* __restrict__ zin, double* __restrict__ zsum,
+                                                 double* __restrict__ wgt, double* __restrict__ part,
+                                                 double* __restrict__ xT, double* __restrict__ dxT) {
+    const int lane = threadIdx.x & 31;
+    const long long wid = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (wid >= N * nC * L) return;
+    const int l = (int)(wid % L);
+    const long long c = (wid / L) % nC;
+    const long long n = wid / ((long long)L * nC);
+    const LatentConsts* lc = consts + l;
+    const long long tf = c * CH + (long long)lane * SUB;
+    const size_t so = ((size_t)n * L + l) * T;
+
+    double M[D * D], K[D], HA[D];
+    load_mat<D>(lc->AKHA, M);
+    load_vec<D>(lc->K, K);
+    load_vec<D>(lc->HA, HA);
+    double uu[SUB];
+#pragma unroll
+    for (int i = 0; i < SUB; ++i) uu[i] = tf + i < T ? __ldg(u + so + tf + i) : 0.0;
+
+    const size_t ci = (((size_t)c * N + n) * L + l) * 4 * D;
+    double zi[4][D];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int q = 0; q < D; ++q) zi[a][q] = FINAL ? zin[ci + a * D + q] : 0.0;
+
+    // ---- x chain ----------------------------------------------------------------------------------
+    double r[SUB][D], xpre[SUB][D], zend[D];
+#pragma unroll
+    for (int i = 0; i < SUB; ++i)
+#pragma unroll
+        for (int q = 0; q < D; ++q) r[i][q] = K[q] * uu[i];
+    lti_scan<D>(M, lc, r, zi[0], lane, xpre, zend);
+    if (!FINAL && lane == 31) {
+#pragma unroll
+        for (int q = 0; q < D; ++q) zsum[ci + q] = zend[q];
+    }
+    const bool last_lane = FINAL && (T - 1 >= tf && T - 1 < tf + SUB);    // this lane owns step T-1
+    const int ilast = (int)(T - 1 - tf);
+    if (last_lane && xT) {
+        // state after step T-1: one more literal step from the pre-step state
+#pragma unroll
+        for (int i = 0; i < SUB; ++i)
+            if (i == ilast) {
+                double xn[D];
+                mv<D>(M, xpre[i], xn);
+#pragma unroll
+                for (int q = 0; q < D; ++q) xT[((size_t)n * L + l) * D + q] = xn[q] + r[i][q];
+            }
+    }
+
+    double v[SUB];
+    double acc_loss = 0.0, acc_g[3] = {0.0, 0.0, 0.0}, acc_pvw = 0.0;
+    const double Si = __ldg(&lc->S), logSi = __ldg(&lc->logS), hak = __ldg(&lc->hak);
+    if (FINAL) {
+        const double Sl = __ldg(S + l);
+        const double rsS = 1.0 / sqrt(Sl);
+#pragma unroll
+        for (int i = 0; i < SUB; ++i) {
+            double hax = HA[0] * xpre[i][0];
+#pragma unroll
+            for (int q = 1; q < D; ++q) hax = fma(HA[q], xpre[i][q], hax);
+            v[i] = uu[i] - hax;                                                     // ihgp.h:214
+            if (tf + i < T) {
+                const double wt = __ldg(w + so + tf + i);
+                const double yr = __ldg(yl + so + tf + i);
+                const double pv = (yr - hax) * (1 - hak) / Si;                      // moihgp.h:510-511 (raw y(l), Q8)
+                acc_loss += 0.5 * (v[i] * v[i] / Si + logSi);                       // ihgp.h:215
+                acc_pvw = fma(pv, wt, acc_pvw);                                     // moihgp.h:558-560
+                wgt[so + tf + i] = -wt / sigma + pv * rsS;                          // moihgp.h:546-550 (rank-1 form)
+            }
+        }
+    }
+
+    // ---- dx_k chains ------------------------------------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double dM[D * D], dK[D], pre[SUB][D];
+        load_mat<D>(lc->dAKHA[k], dM);
+        load_vec<D>(lc->dK[k], dK);
+#pragma unroll
+        for (int i = 0; i < SUB; ++i) {
+            double t1[D];
+            mv<D>(dM, xpre[i], t1);
+#pragma unroll
+            for (int q = 0; q < D; ++q) r[i][q] = fma(dK[q], uu[i], t1[q]);         // ihgp.h:75
+        }
+        lti_scan<D>(M, lc, r, zi[1 + k], lane, pre, zend);
+        if (!FINAL) {
+            if (lane == 31) {
+#pragma unroll
+                for (int q = 0; q < D; ++q) zsum[ci + (1 + k) * D + q] = zend[q];
+            }
+        } else {
+            const double hda0 = __ldg(&lc->HdA[k][0]), dSk = __ldg(&lc->dS[k]);
+#pragma unroll
+            for (int i = 0; i < SUB; ++i) {
+                if (tf + i < T) {
+                    double hd = HA[0] * pre[i][0];
+#pragma unroll
+                    for (int q = 1; q < D; ++q) hd = fma(HA[q], pre[i][q], hd);
+                    const double dv = -hda0 * xpre[i][0] - hd;                      // ihgp.h:218 (Q20 de facto)
+                    acc_g[k] += (v[i] * dv - 0.5 * (v[i] * v[i] / Si - 1) * dSk) / Si;   // ihgp.h:219
+                }
+            }
+            if (last_lane && dxT) {
+#pragma unroll
+                for (int i = 0; i < SUB; ++i)
+                    if (i == ilast) {
+                        double xn[D];
+                        mv<D>(M, pre[i], xn);
+#pragma unroll
+                        for (int q = 0; q < D; ++q) dxT[(((size_t)n * L + l) * 3 + k) * D + q] = xn[q] + r[i][q];
+                    }
+            }
+        }
+    }
+    if (FINAL) {
+        double s[5] = {acc_loss, acc_g[0], acc_g[1], acc_g[2], acc_pvw};
+#pragma unroll
+        for (int j = 0; j < 5; ++j)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s[j] += __shfl_xor_sync(FULL, s[j], o);
+        if (lane == 0) {
+            double* pp = part + (((size_t)c * N + n) * L + l) * NPART;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) pp[j] = s[j];
+        }
+    }
+}
+
+// Cross-chunk coupling matrices E_k = sum_i M^(CH-1-i) dM_k M^i by doubling: E(2n) = E(n) M^n + M^n E(n).
+// One thread per (latent, k).  Ek layout [l][3][D*D].
+template <int D>
+__global__ void k_obj_coupling(const LatentConsts* __restrict__ consts, int L, double* __restrict__ Ek) {
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= 3 * L) return;
+    const int l = id / 3, k = id % 3;
+    const LatentConsts* lc = consts + l;
+    double E[D * D], Mn[D * D];
+    load_mat<D>(lc->dAKHA[k], E);
+    for (int lev = 0; lev < LOG2_CH; ++lev) {
+        load_mat<D>(lc->powM[lev], Mn);
+        double a[D * D];
+        for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) {
+            double s = 0.0;
+            for (int q = 0; q < D; ++q) s += E[i * D + q] * Mn[q * D + j] + Mn[i * D + q] * E[q * D + j];
+            a[i * D + j] = s;
+        }
+        for (int i = 0; i < D * D; ++i) E[i] = a[i];
+    }
+    for (int i = 0; i < D * D; ++i) Ek[((size_t)l * 3 + k) * D * D + i] = E[i];
+}
+
+// zin[c+1] = Z^CH zin[c] + zsum[c], one thread per (sequence, latent)
+template <int D>
+__global__ void __launch_bounds__(128) k_obj_carry(const LatentConsts* __restrict__ consts, const double* __restrict__ Ek, int L,
+                                                  long long N, long long nC, const double* __restrict__ x0,
+                                                  const double* __restrict__ dx0, const double* __restrict__ zsum,
+                                                  double* __restrict__ zin) {
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= N * L) return;
+    const int l = (int)(id % L);
+    double MC[D * D], E[3][D * D];
+    load_mat<D>(consts[l].powM[LOG2_CH], MC);
+    for (int k = 0; k < 3; ++k) for (int i = 0; i < D * D; ++i) E[k][i] = Ek[((size_t)l * 3 + k) * D * D + i];
+    double z[4][D];
+    for (int q = 0; q < D; ++q) {
+        z[0][q] = x0 ? x0[(size_t)id * D + q] : 0.0;
+        for (int k = 0; k < 3; ++k) z[1 + k][q] = dx0 ? dx0[((size_t)id * 3 + k) * D + q] : 0.0;
+    }
+    const size_t stride = (size_t)N * L * 4 * D, base = (size_t)id * 4 * D;
+    for (long long c = 0; c < nC; ++c) {
+        for (int a = 0; a < 4; ++a) for (int q = 0; q < D; ++q) zin[c * stride + base + a * D + q] = z[a][q];
+        if (c + 1 < nC) {
+            double zn[4][D];
+            mv<D>(MC, z[0], zn[0]);
+            for (int k = 0; k < 3; ++k) { mv<D>(MC, z[1 + k], zn[1 + k]); mv_acc<D>(E[k], z[0], zn[1 + k]); }
+            for (int a = 0; a < 4; ++a) for (int q = 0; q < D; ++q) z[a][q] = zn[a][q] + zsum[c * stride + base + a * D + q];
+        }
+    }
+}
+
+// dU partials: gU_part[split][r][c] = sum over the split's (n, t) range of Y[n][t][r] * wgt[n][c][t].
+// CTA tile: 64 x 64 outputs, 16 x 16 threads, 4 x 4 outputs per thread, K panels of 16 steps.
+constexpr int GT = 64, GK = 16;
+__global__ void __launch_bounds__(256) k_gradU(const double* __restrict__ Y, const double* __restrict__ wgt, int p, int L,
+                                              long long N, long long T, long long slabs_per_split, double* __restrict__ gU_part) {
+    __shared__ double ys[GK][GT + 1];
+    __shared__ double wsm[GK][GT + 1];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int rt = blockIdx.x, ct = blockIdx.y, split = blockIdx.z;
+    const int r0 = rt * GT, c0 = ct * GT;
+    const long long slabs_per_seq = (T + GK - 1) / GK;
+    const long long total = N * slabs_per_seq;
+    const long long s_begin = (long long)split * slabs_per_split;
+    const long long s_end = min(total, s_begin + slabs_per_split);
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (long long s = s_begin; s < s_end; ++s) {
+        const long long n = s / slabs_per_seq;
+        const long long t0 = (s - n * slabs_per_seq) * GK;
+        __syncthreads();
+        for (int i = threadIdx.x; i < GK * GT; i += 256) {
+            const int kk = i / GT, rr = i - kk * GT;          // consecutive threads -> consecutive outputs r (contiguous in Y)
+            const long long t = t0 + kk;
+            ys[kk][rr] = (t < T && r0 + rr < p) ? Y[((size_t)n * T + t) * p + r0 + rr] : 0.0;
+        }
+        for (int i = threadIdx.x; i < GK * GT; i += 256) {
+            const int cc = i / GK, kk = i - cc * GK;          // consecutive threads -> consecutive t (contiguous in wgt)
+            const long long t = t0 + kk;
+            wsm[kk][cc] = (t < T && c0 + cc < L) ? wgt[((size_t)n * L + c0 + cc) * T + t] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GK; ++kk) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = ys[kk][ty + 16 * i]; b[i] = wsm[kk][tx + 16 * i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+    }
+    double* out = gU_part + (size_t)split * p * L;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = r0 + ty + 16 * i, c = c0 + tx + 16 * j;
+            if (r < p && c < L) out[(size_t)r * L + c] = acc[i][j];
+        }
+}
+
+// Per-latent reduction of the chunk partials (blocks 0..L-1) and of rho (block L): fixed order.
+__global__ void __launch_bounds__(256) k_obj_reduce(const double* __restrict__ part, const double* __restrict__ rho, int L,
+                                                   long long N, long long T, long long nC, double* __restrict__ lat_sums /*[L+1][8]*/) {
+    __shared__ double red[256][5];
+    const int tid = threadIdx.x;
+    const int l = blockIdx.x;
+    double s[5] = {0, 0, 0, 0, 0};
+    if (l < L) {
+        for (long long i = tid; i < nC * N; i += 256) {
+            const double* pp = part + ((size_t)i * L + l) * NPART;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) s[j] += pp[j];
+        }
+    } else {
+        for (long long i = tid; i < N * T; i += 256) s[0] += rho[i];
+    }
+#pragma unroll
+    for (int j = 0; j < 5; ++j) red[tid][j] = s[j];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) red[tid][j] += red[tid + o][j];
+        }
+        __syncthreads();
+    }
+    if (tid < 5) lat_sums[(size_t)l * 8 + tid] = red[0][tid];
+}
+
+// Assemble loss and gradient [U (p*L row-major) | S (L) | sigma | (mag, len, noise) x L]  (moihgp.h:553-609)
+__global__ void __launch_bounds__(256) k_obj_finish(const double* __restrict__ lat_sums, const double* __restrict__ gU_part,
+                                                   int nsplit, const double* __restrict__ S, double sigma, int p, int L,
+                                                   long long N, long long T, int threading, double* __restrict__ loss,
+                                                   double* __restrict__ grad) {
+    const int tid = threadIdx.x;
+    const int sizeU = p * L;
+    for (int i = tid; i < sizeU; i += 256) {
+        double s = 0.0;
+        for (int k = 0; k < nsplit; ++k) s += gU_part[(size_t)k * sizeU + i];
+        grad[i] = s;
+    }
+    if (tid == 0) {
+        const double steps = (double)N * (double)T;
+        const double rho_sum = lat_sums[(size_t)L * 8];
+        const double m_n = fmax((double)(p - L), 0.0);                                     // moihgp.h:502
+        double Ssum = 0.0;
+        for (int l = 0; l < L; ++l) Ssum += S[l];
+        double ls = steps * (0.5 * log(Ssum) + 0.5 * m_n * log(sigma)) + 0.5 * rho_sum / sigma;   // moihgp.h:503
+        double gsig = 0.5 * (steps * m_n - rho_sum / sigma) / sigma;                       // moihgp.h:563
+        for (int l = 0; l < L; ++l) {
+            const double* q = lat_sums + (size_t)l * 8;
+            if (threading) ls += q[0];                                                     // moihgp.h:588 vs :601 (Q5)
+            const double Sl = S[l], rs = sqrt(Sl);
+            const double g2 = q[3];
+            grad[sizeU + l] = steps * 0.5 / Sl - 0.5 * (1.0 / rs / rs / rs) * q[4] - g2 * sigma / Sl / Sl;   // :555-562, :591
+            gsig += g2 / Sl;                                                               // :592
+            for (int k = 0; k < 3; ++k) grad[sizeU + L + 1 + 3 * l + k] = q[1 + k];        // :608-609
+        }
+        grad[sizeU + L] = gsig;
+        *loss = ls;
+    }
+}
+
+template <int D>
+cudaError_t run_objective(const ObjArgs& a, cudaStream_t st) {
+    const long long nC = (a.T + CH - 1) / CH;
+    const long long warps = a.N * nC * a.L;
+    const unsigned grid = (unsigned)((warps + 3) / 4);
+    double* Ek = a.Ek;
+    if (nC > 1) {
+        k_obj_scan<D, false><<<grid, 128, 0, st>>>(a.u, a.w, a.yl, a.consts, a.S, a.sigma, a.L, a.N, a.T, nC, nullptr, a.zsum,
+                                                   nullptr, nullptr, nullptr, nullptr);
+        k_obj_coupling<D><<<(3 * a.L + 63) / 64, 64, 0, st>>>(a.consts, a.L, Ek);
+    }
+    k_obj_carry<D><<<(unsigned)((a.N * a.L + 127) / 128), 128, 0, st>>>(a.consts, Ek, a.L, a.N, nC, a.x0, a.dx0, a.zsum, a.zin);
+    k_obj_scan<D, true><<<grid, 128, 0, st>>>(a.u, a.w, a.yl, a.consts, a.S, a.sigma, a.L, a.N, a.T, nC, a.zin, nullptr, a.wgt,
+                                              a.part, a.xT, a.dxT);
+    const size_t nsplit = obj_gu_splits(a.N, a.T);
+    const long long slabs = a.N * ((a.T + GK - 1) / GK);
+    const long long per = (slabs + (long long)nsplit - 1) / (long long)nsplit;
+    dim3 gg((a.p + GT - 1) / GT, (a.L + GT - 1) / GT, (unsigned)nsplit);
+    k_gradU<<<gg, 256, 0, st>>>(a.Y, a.wgt, a.p, a.L, a.N, a.T, per, a.gU_part);
+    double* lat_sums = a.lat_sums;
+    k_obj_reduce<<<a.L + 1, 256, 0, st>>>(a.part, a.rho, a.L, a.N, a.T, nC, lat_sums);
+    k_obj_finish<<<1, 256, 0, st>>>(lat_sums, a.gU_part, (int)nsplit, a.S, a.sigma, a.p, a.L, a.N, a.T, a.threading, a.loss, a.grad);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+size_t obj_chunks(long long T) { return (size_t)((T + CH - 1) / CH); }
+
+// number of split-K partial buffers of the dU contraction: enough CTAs to fill the GPU, never more than slabs
+size_t obj_gu_splits(long long N, long long T) {
+    const long long slabs = N * ((T + GK - 1) / GK);
+    long long s = 296;   // 2 x 148 SMs
+    if (s > slabs) s = slabs;
+    if (s < 1) s = 1;
+    return (size_t)s;
+}
+
+int obj_launch_count(long long T) { return (T + CH - 1) / CH > 1 ? 7 : 5; }
+
+cudaError_t launch_objective(int dim, const ObjArgs& a, cudaStream_t st) {
+    return dim == 2 ? run_objective<2>(a, st) : run_objective<3>(a, st);
+}
+
+}  // namespace moihgp

@@ -1,0 +1,464 @@
+// K-scan: the steady-state Kalman filter, the backward smoother and the per-step innovation
+// log-likelihood as ONE chunked parallel scan over time (sm_100a).
+//
+// Replaces (reference, /root/reference/moihgp/include/moihgp):
+//   ihgp.h:81-93     IHGP::step             x+ = AKHA x + K y        (the LTI-affine recursion)
+//   ihgp.h:204-209   IHGP::negLogLikelihood v = y - HA x; 1/2 (v^2/S + log S)   on the PRE-step state
+//   ihgp.h:108-113   IHGP::backwardSmoother recursion (reference_literal mode, Q3)
+//   moihgp_regression.h:127-139 / :42-50    the per-observation driver loops
+// plus the rts_correct smoother mode (our extension).
+//
+// Parallel structure.  The recursion has constant matrices, so a chunk of c steps maps its
+// carry-in affinely:  x_end = M^c x_in + f,  and likewise backwards.  One WARP owns one
+// (sequence, latent, chunk of CH = 256 steps); lane s owns SUB = 8 consecutive steps:
+//   1. every lane runs its 8 steps from zero (lane 0 from the chunk carry-in),
+//   2. a Kogge-Stone warp-shuffle scan with the precomputed powers M^(8*2^k) turns the lane
+//      end states into true lane start states,
+//   3. every lane re-runs its 8 steps from the true start state - this is the literal
+//      recurrence of the reference, so per-step values differ from the sequential loop only
+//      through the ~1e-16 rounding of the carry,
+//   4. the same three steps run backwards for the smoother, fused in the same kernel.
+// Across chunks: k_scan<.., FINAL=false> produces per-chunk summaries from zero carries,
+// k_response the (constant) linear response of a chunk to its carry-in, k_carry chains them
+// (a length T/256 recurrence per (sequence, latent)), and k_scan<.., FINAL=true> produces the
+// outputs from the true carries.  The input series u[n][l][t] is read with unit stride; the
+// outputs X/Xs [n][t][l][d] are staged in shared memory and written as contiguous rows.
+#include <cuda_runtime.h>
+#include <math.h>
+#include "moihgp_device.cuh"
+#include "launch.h"
+
+namespace moihgp {
+
+namespace {
+
+constexpr int SUB = 8;            // steps per lane
+constexpr int CH = 32 * SUB;      // steps per warp-chunk
+constexpr int LOG2_SUB = 3;       // powM[LOG2_SUB + k] = M^(SUB * 2^k)
+constexpr int LOG2_CH = 8;        // powM[LOG2_CH]     = M^CH
+constexpr int LGMAX = 8;          // latents (warps) per CTA
+constexpr unsigned FULL = 0xffffffffu;
+
+template <int D>
+struct LC {                       // per-warp register copy of the latent's constants
+    double M[D * D], K[D], HA[D], G[D * D], drv[D * D];
+};
+
+template <int D> __device__ __forceinline__ void load_mat(const double* src9, double* dst) {
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) dst[i * D + j] = __ldg(src9 + i * 3 + j);
+}
+template <int D> __device__ __forceinline__ void load_vec(const double* src3, double* dst) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) dst[i] = __ldg(src3 + i);
+}
+template <int D, int MODE>
+__device__ __forceinline__ void load_lc(const LatentConsts* c, LC<D>& o) {
+    load_mat<D>(c->AKHA, o.M);
+    load_vec<D>(c->K, o.K);
+    load_vec<D>(c->HA, o.HA);
+    load_mat<D>(c->G[MODE], o.G);
+    if (MODE == 0) load_mat<D>(c->ImA, o.drv);
+    else load_vec<D>(c->GK, o.drv);
+}
+template <int D> __device__ __forceinline__ void mv(const double* M, const double* x, double* y) {  // y = M x
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        double s = M[i * D] * x[0];
+#pragma unroll
+        for (int j = 1; j < D; ++j) s = fma(M[i * D + j], x[j], s);
+        y[i] = s;
+    }
+}
+template <int D> __device__ __forceinline__ void mv_acc(const double* M, const double* x, double* y) {  // y += M x
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        double s = y[i];
+#pragma unroll
+        for (int j = 0; j < D; ++j) s = fma(M[i * D + j], x[j], s);
+        y[i] = s;
+    }
+}
+
+// Where a lane's steps live in the CTA's shared-memory output tile:
+// tile[t][lw][dd], rows of RS = lg*D doubles, each group of SUB rows padded by 2 doubles so that the
+// 32 lanes of a warp (row stride SUB*RS+2) spread over the banks.
+__host__ __device__ __forceinline__ int tile_group_stride(int RS) { return SUB * RS + 2; }
+
+// One warp, one (sequence, latent, chunk).  uu[i] = u at global step tf + i (0 beyond T), u_next = u at the first
+// step of the next chunk (0 if none), tf = global index of this lane's first step.
+//   FINAL = false: x_in / b_in are zero (or a unit vector for k_response); returns f_end (lane 31) and beta (lane 0).
+//   FINAL = true : additionally stores X / Xs rows into the shared tiles and returns sum v^2 (per lane).
+template <int D, int MODE, bool FINAL>
+__device__ __forceinline__ void chunk_pass(const LC<D>& c, const LatentConsts* lc, const double (&uu)[SUB], double u_next,
+                                           long long tf, long long T, const double (&x_in)[D], const double (&b_in)[D],
+                                           int lane, double (&f_end)[D], double (&beta)[D], double& vsq,
+                                           double* tX, double* tXs, int RS, double (&x_last_out)[D]) {
+    // ---- forward, local --------------------------------------------------------------------
+    double z[D];
+#pragma unroll
+    for (int q = 0; q < D; ++q) z[q] = lane == 0 ? x_in[q] : 0.0;
+#pragma unroll
+    for (int i = 0; i < SUB; ++i) {
+        double zn[D];
+        mv<D>(c.M, z, zn);
+#pragma unroll
+        for (int q = 0; q < D; ++q) z[q] = fma(c.K[q], uu[i], zn[q]);      // ihgp.h:90
+    }
+    // ---- forward, inclusive scan over lanes ------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int o = 1 << k;
+        double zo[D], P[D * D];
+#pragma unroll
+        for (int q = 0; q < D; ++q) zo[q] = __shfl_up_sync(FULL, z[q], o);
+        load_mat<D>(lc->powM[LOG2_SUB + k], P);
+        if (lane >= o) mv_acc<D>(P, zo, z);
+    }
+#pragma unroll
+    for (int q = 0; q < D; ++q) f_end[q] = z[q];
+    // ---- forward, final: the literal recurrence from the true start state --------------------
+    double x[D];
+#pragma unroll
+    for (int q = 0; q < D; ++q) {
+        const double up = __shfl_up_sync(FULL, z[q], 1);
+        x[q] = lane == 0 ? x_in[q] : up;
+    }
+    double v[SUB], X[SUB][D];
+    vsq = 0.0;
+#pragma unroll
+    for (int i = 0; i < SUB; ++i) {
+        double hax = c.HA[0] * x[0];
+#pragma unroll
+        for (int q = 1; q < D; ++q) hax = fma(c.HA[q], x[q], hax);
+        v[i] = uu[i] - hax;                                                  // ihgp.h:206
+        double xn[D];
+        mv<D>(c.M, x, xn);
+#pragma unroll
+        for (int q = 0; q < D; ++q) { x[q] = fma(c.K[q], uu[i], xn[q]); X[i][q] = x[q]; }   // ihgp.h:90
+        if (FINAL && tf + i < T) {
+            vsq = fma(v[i], v[i], vsq);
+#pragma unroll
+            for (int q = 0; q < D; ++q) tX[i * RS + q] = x[q];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < D; ++q) x_last_out[q] = x[q];
+    // ---- what the step after this lane's last one looks like (drive of the backward pass) --------
+    double v_next = 0.0, X_next[D];
+    if (MODE == 1) {
+        double hax = c.HA[0] * x[0];
+#pragma unroll
+        for (int q = 1; q < D; ++q) hax = fma(c.HA[q], x[q], hax);
+        const double mine = u_next - hax;
+        const double dn = __shfl_down_sync(FULL, v[0], 1);
+        v_next = lane == 31 ? mine : dn;
+    } else {
+        double xn[D];
+        mv<D>(c.M, x, xn);
+#pragma unroll
+        for (int q = 0; q < D; ++q) {
+            const double mine = fma(c.K[q], u_next, xn[q]);
+            const double dn = __shfl_down_sync(FULL, X[0][q], 1);
+            X_next[q] = lane == 31 ? mine : dn;
+        }
+    }
+    // drive g_i of the backward recursion b[j] = G b[j+1] + g[j]:
+    //   rts_correct      : g[j] = G K v[j+1]            (j < T-1), 0 at j = T-1;   Xs[j] = X[j] + b[j]
+    //   reference_literal: g[j] = (I - A) X[j+1]        (j < T-1), X[T-1] at j = T-1 (ihgp.h:108,111);  Xs[j] = b[j]
+    auto drive = [&](int i, double (&g)[D]) {
+        const long long t = tf + i;
+        if (MODE == 1) {
+            const double vn = (i + 1 < SUB) ? v[(i + 1) % SUB] : v_next;
+            const double s = t < T - 1 ? vn : 0.0;
+#pragma unroll
+            for (int q = 0; q < D; ++q) g[q] = c.drv[q] * s;
+        } else {
+            double xn[D];
+#pragma unroll
+            for (int q = 0; q < D; ++q) xn[q] = (i + 1 < SUB) ? X[(i + 1) % SUB][q] : X_next[q];
+            double im[D];
+            mv<D>(c.drv, xn, im);
+#pragma unroll
+            for (int q = 0; q < D; ++q) g[q] = t < T - 1 ? im[q] : (t == T - 1 ? X[i][q] : 0.0);
+        }
+    };
+    // ---- backward, local --------------------------------------------------------------------
+    double b[D];
+#pragma unroll
+    for (int q = 0; q < D; ++q) b[q] = lane == 31 ? b_in[q] : 0.0;
+#pragma unroll
+    for (int i = SUB - 1; i >= 0; --i) {
+        double g[D], bn[D];
+        drive(i, g);
+        mv<D>(c.G, b, bn);
+#pragma unroll
+        for (int q = 0; q < D; ++q) b[q] = bn[q] + g[q];
+    }
+    // ---- backward, inclusive scan (towards lane 0) --------------------------------------------
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int o = 1 << k;
+        double bo[D], P[D * D];
+#pragma unroll
+        for (int q = 0; q < D; ++q) bo[q] = __shfl_down_sync(FULL, b[q], o);
+        load_mat<D>(lc->powG[MODE][LOG2_SUB + k], P);
+        if (lane + o < 32) mv_acc<D>(P, bo, b);
+    }
+#pragma unroll
+    for (int q = 0; q < D; ++q) beta[q] = b[q];
+    if (!FINAL) return;
+    // ---- backward, final ----------------------------------------------------------------------
+#pragma unroll
+    for (int q = 0; q < D; ++q) {
+        const double dn = __shfl_down_sync(FULL, b[q], 1);
+        b[q] = lane == 31 ? b_in[q] : dn;
+    }
+#pragma unroll
+    for (int i = SUB - 1; i >= 0; --i) {
+        double g[D], bn[D];
+        drive(i, g);
+        mv<D>(c.G, b, bn);
+#pragma unroll
+        for (int q = 0; q < D; ++q) b[q] = bn[q] + g[q];
+        if (tf + i < T) {
+#pragma unroll
+            for (int q = 0; q < D; ++q) tXs[i * RS + q] = MODE == 1 ? X[i][q] + b[q] : b[q];
+        }
+    }
+}
+
+// grid: N * nC * nLG CTAs (latent-group minor), block: 32 * lg threads (lg = latents in the group, <= LGMAX).
+// Per-chunk arrays are laid out [c][n][l][D].
+template <int D, int MODE, bool FINAL>
+__global__ void __launch_bounds__(32 * LGMAX) k_scan(const double* __restrict__ u, const LatentConsts* __restrict__ consts,
+                                                    int L, long long N, long long T, long long nC, int nLG,
+                                                    const double* __restrict__ xin, const double* __restrict__ bin,
+                                                    double* __restrict__ fsum, double* __restrict__ bsum,
+                                                    double* __restrict__ X, double* __restrict__ Xs,
+                                                    double* __restrict__ vsq_out, double* __restrict__ xT) {
+    extern __shared__ double tile[];
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const long long bid = blockIdx.x;
+    const int lgi = (int)(bid % nLG);
+    const long long c = (bid / nLG) % nC;
+    const long long n = bid / ((long long)nLG * nC);
+    const int l0 = lgi * LGMAX;
+    const int lg = min(LGMAX, L - l0);          // == blockDim.x / 32 for all but a ragged last group
+    const int l = l0 + wi;
+    const bool active = wi < lg;
+    const long long t0 = c * CH;
+    const int RS = lg * D;
+    const int GS = tile_group_stride(RS);
+    double* tileX = tile;
+    double* tileXs = tile + 32 * GS;
+
+    if (active) {
+        const LatentConsts* lc = consts + l;
+        LC<D> cst;
+        load_lc<D, MODE>(lc, cst);
+        const long long tf = t0 + (long long)lane * SUB;
+        const double* up = u + ((size_t)n * L + l) * T;
+        double uu[SUB];
+#pragma unroll
+        for (int i = 0; i < SUB; ++i) uu[i] = tf + i < T ? __ldg(up + tf + i) : 0.0;
+        const double u_next = t0 + CH < T ? __ldg(up + t0 + CH) : 0.0;
+        double x_in[D], b_in[D], f_end[D], beta[D], x_last[D], vsq;
+        const size_t ci = (((size_t)c * N + n) * L + l) * D;
+#pragma unroll
+        for (int q = 0; q < D; ++q) {
+            x_in[q] = FINAL ? xin[ci + q] : 0.0;
+            b_in[q] = FINAL ? bin[ci + q] : 0.0;
+        }
+        double* tX = tileX + lane * GS + wi * D;
+        double* tXs = tileXs + lane * GS + wi * D;
+        chunk_pass<D, MODE, FINAL>(cst, lc, uu, u_next, tf, T, x_in, b_in, lane, f_end, beta, vsq, tX, tXs, RS, x_last);
+        if (!FINAL) {
+            if (lane == 31) {
+#pragma unroll
+                for (int q = 0; q < D; ++q) fsum[ci + q] = f_end[q];
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < D; ++q) bsum[ci + q] = beta[q];
+            }
+        } else {
+            // deterministic warp reduction of sum v^2
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) vsq += __shfl_xor_sync(FULL, vsq, o);
+            if (lane == 0) vsq_out[((size_t)c * N + n) * L + l] = vsq;
+            // final filtered state of the sequence: X[T-1]
+            if (xT && T - 1 >= tf && T - 1 < tf + SUB) {
+                const int i = (int)(T - 1 - tf);
+#pragma unroll
+                for (int q = 0; q < D; ++q) xT[((size_t)n * L + l) * D + q] = tX[i * RS + q];
+            }
+        }
+    }
+    if (!FINAL) return;
+    __syncthreads();
+    // ---- coalesced copy-out of the staged rows ----------------------------------------------------
+    const int rows = (int)min((long long)CH, T - t0);
+    const size_t grow = (size_t)L * D;                       // global row pitch (doubles)
+    const size_t gbase = ((size_t)n * T + t0) * grow + (size_t)l0 * D;
+    for (int i = threadIdx.x; i < rows * RS; i += blockDim.x) {
+        const int row = i / RS, col = i - row * RS;
+        const int so = (row / SUB) * GS + (row % SUB) * RS + col;
+        const size_t go = gbase + (size_t)row * grow + col;
+        if (X) X[go] = tileX[so];
+        if (Xs) Xs[go] = tileXs[so];
+    }
+}
+
+// Linear response of a chunk's backward summary to its forward carry-in: column k of Bx is beta(u = 0, x_in = e_k).
+// kind 0: interior chunk (CH steps, a next chunk exists); kind 1: last chunk of the sequence (r_last steps).
+// grid: L * 2 * D blocks of one warp.  Bx layout [l][kind][D*D] row-major.
+template <int D, int MODE>
+__global__ void __launch_bounds__(32) k_response(const LatentConsts* __restrict__ consts, long long r_last, double* __restrict__ Bx) {
+    const int lane = threadIdx.x;
+    const int k = blockIdx.x % D;
+    const int kind = (blockIdx.x / D) % 2;
+    const int l = blockIdx.x / (2 * D);
+    const LatentConsts* lc = consts + l;
+    LC<D> cst;
+    load_lc<D, MODE>(lc, cst);
+    double uu[SUB];
+#pragma unroll
+    for (int i = 0; i < SUB; ++i) uu[i] = 0.0;
+    double x_in[D], b_in[D], f_end[D], beta[D], x_last[D], vsq;
+#pragma unroll
+    for (int q = 0; q < D; ++q) { x_in[q] = q == k ? 1.0 : 0.0; b_in[q] = 0.0; }
+    const long long T = kind == 0 ? (1LL << 60) : r_last;
+    chunk_pass<D, MODE, false>(cst, lc, uu, 0.0, (long long)lane * SUB, T, x_in, b_in, lane, f_end, beta, vsq, nullptr, nullptr, 0, x_last);
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < D; ++q) Bx[((size_t)l * 2 + kind) * D * D + q * D + k] = beta[q];
+    }
+}
+
+// Chain the chunk summaries: one thread per (sequence, latent).
+//   forward : xin[c+1] = M^CH xin[c] + f[c]
+//   backward: bin[c-1] = beta0[c] + Bx(kind c) xin[c] + G^CH bin[c]
+template <int D, int MODE>
+__global__ void __launch_bounds__(128) k_carry(const LatentConsts* __restrict__ consts, const double* __restrict__ Bx, int L,
+                                              long long N, long long nC, const double* __restrict__ x0,
+                                              const double* __restrict__ fsum, const double* __restrict__ bsum,
+                                              double* __restrict__ xin, double* __restrict__ bin) {
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= N * L) return;
+    const int l = (int)(id % L);
+    const LatentConsts* lc = consts + l;
+    double MC[D * D], GC[D * D], Bf[D * D], Bl[D * D];
+    load_mat<D>(lc->powM[LOG2_CH], MC);
+    load_mat<D>(lc->powG[MODE][LOG2_CH], GC);
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) { Bf[i] = Bx[((size_t)l * 2 + 0) * D * D + i]; Bl[i] = Bx[((size_t)l * 2 + 1) * D * D + i]; }
+    const size_t stride = (size_t)N * L * D;   // between consecutive chunks
+    const size_t base = (size_t)id * D;
+    double x[D];
+#pragma unroll
+    for (int q = 0; q < D; ++q) x[q] = x0 ? x0[base + q] : 0.0;
+    for (long long c = 0; c < nC; ++c) {
+#pragma unroll
+        for (int q = 0; q < D; ++q) xin[c * stride + base + q] = x[q];
+        if (c + 1 < nC) {
+            double xn[D];
+            mv<D>(MC, x, xn);
+#pragma unroll
+            for (int q = 0; q < D; ++q) x[q] = xn[q] + fsum[c * stride + base + q];
+        }
+    }
+    double b[D];
+#pragma unroll
+    for (int q = 0; q < D; ++q) b[q] = 0.0;
+    for (long long c = nC - 1; c >= 0; --c) {
+#pragma unroll
+        for (int q = 0; q < D; ++q) bin[c * stride + base + q] = b[q];
+        if (c > 0) {
+            double xi[D], bn[D];
+#pragma unroll
+            for (int q = 0; q < D; ++q) { xi[q] = xin[c * stride + base + q]; bn[q] = bsum[c * stride + base + q]; }
+            mv_acc<D>(c == nC - 1 ? Bl : Bf, xi, bn);
+            if (c < nC - 1) mv_acc<D>(GC, b, bn);
+#pragma unroll
+            for (int q = 0; q < D; ++q) b[q] = bn[q];
+        }
+    }
+}
+
+// nll[n] = sum_t [ 1/2 log(sum S) + 1/2 m_n log(sigma) + 1/2 rho_t / sigma ]            moihgp.h:653
+//        + sum_l sum_t 1/2 ( v^2 / S_l + log S_l )                                       ihgp.h:207, moihgp.h:675,684
+// One CTA per sequence; fixed-order (deterministic) reduction.
+__global__ void __launch_bounds__(256) k_nll_reduce(const double* __restrict__ rho, const double* __restrict__ vsq,
+                                                   const LatentConsts* __restrict__ consts, const double* __restrict__ S,
+                                                   double sigma, int p, int L, long long N, long long T, long long nC,
+                                                   double* __restrict__ nll) {
+    __shared__ double red[256];
+    const long long n = blockIdx.x;
+    const int tid = threadIdx.x;
+    double acc = 0.0;
+    for (long long t = tid; t < T; t += 256) acc += rho[(size_t)n * T + t];
+    acc *= 0.5 / sigma;
+    for (long long i = tid; i < nC * L; i += 256) {
+        const long long c = i / L;
+        const int l = (int)(i - c * L);
+        acc += 0.5 * vsq[((size_t)c * N + n) * L + l] / consts[l].S;
+    }
+    red[tid] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) red[tid] += red[tid + o];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        double Ssum = 0.0, logs = 0.0;
+        for (int l = 0; l < L; ++l) { Ssum += S[l]; logs += consts[l].logS; }
+        const double m_n = fmax((double)(p - L), 0.0);                       // moihgp.h:652
+        nll[n] = red[0] + (double)T * (0.5 * log(Ssum) + 0.5 * m_n * log(sigma) + 0.5 * logs);
+    }
+}
+
+template <int D, int MODE>
+cudaError_t run_scan(const ScanArgs& a, cudaStream_t st) {
+    const long long nC = (a.T + CH - 1) / CH;
+    const int nLG = (a.L + LGMAX - 1) / LGMAX;
+    const int lg = a.L < LGMAX ? a.L : LGMAX;
+    const long long r_last = a.T - (nC - 1) * CH;
+    const unsigned grid = (unsigned)(a.N * nC * nLG);
+    const int RS = lg * D;
+    const size_t smem = sizeof(double) * 2 * 32 * (size_t)tile_group_stride(RS);
+    if (smem > 48 * 1024) {
+        cudaFuncSetAttribute(k_scan<D, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    if (nC > 1) {
+        k_scan<D, MODE, false><<<grid, 32 * lg, 0, st>>>(a.u, a.consts, a.L, a.N, a.T, nC, nLG, nullptr, nullptr, a.fsum, a.bsum,
+                                                         nullptr, nullptr, nullptr, nullptr);
+        k_response<D, MODE><<<a.L * 2 * D, 32, 0, st>>>(a.consts, r_last, a.Bx);
+    }
+    k_carry<D, MODE><<<(unsigned)((a.N * a.L + 127) / 128), 128, 0, st>>>(a.consts, a.Bx, a.L, a.N, nC, a.x0, a.fsum, a.bsum, a.xin, a.bin);
+    k_scan<D, MODE, true><<<grid, 32 * lg, smem, st>>>(a.u, a.consts, a.L, a.N, a.T, nC, nLG, a.xin, a.bin, nullptr, nullptr, a.X, a.Xs,
+                                                       a.vsq, a.xT);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+size_t scan_chunks(long long T) { return (size_t)((T + CH - 1) / CH); }
+
+int scan_launch_count(long long T) { return (T + CH - 1) / CH > 1 ? 4 : 2; }
+
+cudaError_t launch_scan(int dim, int mode, const ScanArgs& a, cudaStream_t st) {
+    if (dim == 2) return mode == 0 ? run_scan<2, 0>(a, st) : run_scan<2, 1>(a, st);
+    return mode == 0 ? run_scan<3, 0>(a, st) : run_scan<3, 1>(a, st);
+}
+
+cudaError_t launch_nll_reduce(const double* rho, const double* vsq, const LatentConsts* consts, const double* S, double sigma,
+                              int p, int L, long long N, long long T, double* nll, cudaStream_t st) {
+    const long long nC = (T + CH - 1) / CH;
+    k_nll_reduce<<<(unsigned)N, 256, 0, st>>>(rho, vsq, consts, S, sigma, p, L, N, T, nC, nll);
+    return cudaGetLastError();
+}
+
+}  // namespace moihgp

@@ -1,0 +1,236 @@
+// One observation per call: the kernels behind the legacy gp32_* / gp52_* entry points (sm_100a).
+//
+// Replaces (reference, /root/reference/moihgp/include/moihgp):
+//   moihgp.h:148-428   the four MOIHGP::step overloads, incl. the missing-data (NaN) least-squares
+//                      projection  Ty = S^-1/2 (U0'U0)^-1 U0' y_obs  (:167-178)
+//   moihgp.h:460-688   the two MOIHGP::negLogLikelihood overloads
+//   ihgp.h:37-100, :204-222   the per-latent step / NLL they call
+// These are latency-bound by construction (one tiny launch per observation); the whole-sequence
+// kernels (project.cu / scan.cu / objective.cu) are the throughput path.  One CTA does the call.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <float.h>
+#include "moihgp_device.cuh"
+#include "launch.h"
+
+namespace moihgp {
+
+namespace {
+
+constexpr int ST = 128;
+
+// Ty for one observation.  sh: Ty[L] (out), G[L*L], b[L], work[L*L + 2L] in shared memory.
+// Full observation: Ty = (S^-1/2 U') y (moihgp.h:181).  With NaNs: LS projection on the observed rows,
+// solved like Eigen's LDLT::solve (symmetric pivoting on the largest |diagonal|, pseudo-inverse of D:
+// an exactly-zero pivot gives 0, so an all-NaN observation yields Ty = 0).
+__device__ void project_one(const double* __restrict__ U, const double* __restrict__ S, const double* __restrict__ y, int p, int L,
+                            double* Ty, double* G, double* b, double* Lm, int* perm, int* s_nmiss) {
+    const int tid = threadIdx.x;
+    if (tid == 0) *s_nmiss = 0;
+    __syncthreads();
+    int miss = 0;
+    for (int r = tid; r < p; r += ST) miss += isnan(y[r]) ? 1 : 0;
+    if (miss) atomicAdd(s_nmiss, miss);
+    __syncthreads();
+    if (*s_nmiss == 0) {
+        for (int l = tid; l < L; l += ST) {
+            const double si = 1 / sqrt(S[l]);
+            double s = 0.0;
+            for (int r = 0; r < p; ++r) s += (si * U[(size_t)r * L + l]) * y[r];
+            Ty[l] = s;
+        }
+        __syncthreads();
+        return;
+    }
+    for (int i = tid; i < L * L; i += ST) {                                 // U0'U0   (moihgp.h:176-177)
+        const int a = i / L, c = i - a * L;
+        double s = 0.0;
+        for (int r = 0; r < p; ++r) if (!isnan(y[r])) s += U[(size_t)r * L + a] * U[(size_t)r * L + c];
+        G[i] = s;
+        Lm[i] = a == c ? 1.0 : 0.0;
+    }
+    for (int a = tid; a < L; a += ST) {                                     // U0' y_obs
+        double s = 0.0;
+        for (int r = 0; r < p; ++r) if (!isnan(y[r])) s += U[(size_t)r * L + a] * y[r];
+        b[a] = s;
+        perm[a] = a;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int n = L;
+        double* D = Lm + (size_t)L * L;          // [L]
+        double* yv = D + L;                      // [L]
+        for (int k = 0; k < n; ++k) {
+            int piv = k;
+            for (int i = k + 1; i < n; ++i) if (fabs(G[i * n + i]) > fabs(G[piv * n + piv])) piv = i;
+            if (piv != k) {
+                for (int j = 0; j < n; ++j) { double t = G[k * n + j]; G[k * n + j] = G[piv * n + j]; G[piv * n + j] = t; }
+                for (int i = 0; i < n; ++i) { double t = G[i * n + k]; G[i * n + k] = G[i * n + piv]; G[i * n + piv] = t; }
+                for (int j = 0; j < k; ++j) { double t = Lm[k * n + j]; Lm[k * n + j] = Lm[piv * n + j]; Lm[piv * n + j] = t; }
+                int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t;
+            }
+            const double dk = G[k * n + k];
+            D[k] = dk;
+            if (dk == 0.0) continue;
+            for (int i = k + 1; i < n; ++i) Lm[i * n + k] = G[i * n + k] / dk;
+            for (int j = k + 1; j < n; ++j)
+                for (int i = j; i < n; ++i) { G[i * n + j] -= Lm[i * n + k] * dk * Lm[j * n + k]; G[j * n + i] = G[i * n + j]; }
+        }
+        for (int i = 0; i < n; ++i) yv[i] = b[perm[i]];
+        for (int i = 0; i < n; ++i) for (int j = 0; j < i; ++j) yv[i] -= Lm[i * n + j] * yv[j];
+        for (int i = 0; i < n; ++i) yv[i] = fabs(D[i]) > DBL_MIN ? yv[i] / D[i] : 0.0;
+        for (int i = n - 1; i >= 0; --i) for (int j = i + 1; j < n; ++j) yv[i] -= Lm[j * n + i] * yv[j];
+        for (int i = 0; i < n; ++i) Ty[perm[i]] = (1 / sqrt(S[perm[i]])) * yv[i];
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(ST) k_step(StepArgs a) {
+    extern __shared__ double sm[];
+    const int L = a.L, p = a.p, d = a.dim, tid = threadIdx.x;
+    double* Ty = sm;                 // [L]
+    double* Tyhat = Ty + L;          // [L]
+    double* b = Tyhat + L;           // [L]
+    double* G = b + L;               // [L*L]
+    double* Lm = G + (size_t)L * L;  // [L*L + 2L]
+    int* perm = (int*)(Lm + (size_t)L * L + 2 * L);   // [L]
+    int* s_nmiss = perm + L;
+    if (a.y) project_one(a.U, a.S, a.y, p, L, Ty, G, b, Lm, perm, s_nmiss);
+    for (int l = tid; l < L; l += ST) {
+        const LatentConsts& c = a.consts[l];
+        const double* x = a.x + (size_t)l * d;
+        double* xn = a.xnew + (size_t)l * d;
+        const bool predict = a.y == nullptr || isnan(Ty[l]);                // ihgp.h:96-100 / :39
+        const double yy = predict ? 0.0 : Ty[l];
+        const double* M = predict ? c.A : c.AKHA;
+        for (int i = 0; i < d; ++i) {
+            double s = 0.0;
+            for (int j = 0; j < d; ++j) s += M[i * 3 + j] * x[j];
+            xn[i] = predict ? s : s + c.K[i] * yy;                          // ihgp.h:41 / :50
+        }
+        Tyhat[l] = xn[0];                                                   // ihgp.h:42 / :51
+        if (a.dx && a.dxnew) {
+            for (int k = 0; k < 3; ++k) {
+                const double* dM = predict ? c.dA[k] : c.dAKHA[k];
+                const double* dxk = a.dx + ((size_t)l * 3 + k) * d;
+                double* dxn = a.dxnew + ((size_t)l * 3 + k) * d;
+                for (int i = 0; i < d; ++i) {
+                    double s1 = 0.0, s2 = 0.0;
+                    for (int j = 0; j < d; ++j) { s1 += dM[i * 3 + j] * x[j]; s2 += M[i * 3 + j] * dxk[j]; }
+                    dxn[i] = predict ? s1 + s2 : s1 + s2 + c.dK[k][i] * yy; // ihgp.h:45 / :54
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (a.yhat) {
+        for (int r = tid; r < p; r += ST) {                                 // moihgp.h:222-225
+            double s = 0.0;
+            for (int l = 0; l < L; ++l) s += (a.U[(size_t)r * L + l] * sqrt(a.S[l])) * Tyhat[l];
+            a.yhat[r] = s;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(ST) k_lik(LikArgs a) {
+    extern __shared__ double sm[];
+    const int L = a.L, p = a.p, d = a.dim, tid = threadIdx.x;
+    double* Ty = sm;                 // [L]
+    double* w = Ty + L;              // [L]   U'y
+    double* b = w + L;               // [L]
+    double* pv = b + L;              // [L]
+    double* li = pv + L;             // [L]   per-latent loss
+    double* gi = li + L;             // [3L]  per-latent grads
+    double* red = gi + 3 * L;        // [ST]
+    double* G = red + ST;            // [L*L]
+    double* Lm = G + (size_t)L * L;  // [L*L + 2L]
+    int* perm = (int*)(Lm + (size_t)L * L + 2 * L);
+    int* s_nmiss = perm + L;
+    project_one(a.U, a.S, a.y, p, L, Ty, G, b, Lm, perm, s_nmiss);
+    for (int l = tid; l < L; l += ST) {
+        double s = 0.0;
+        for (int r = 0; r < p; ++r) s += a.U[(size_t)r * L + l] * a.y[r];
+        w[l] = s;
+    }
+    __syncthreads();
+    double q = 0.0;
+    for (int r = tid; r < p; r += ST) {                                     // moihgp.h:501 / :651
+        double e = a.y[r];
+        for (int l = 0; l < L; ++l) e -= a.U[(size_t)r * L + l] * w[l];
+        q += e * e;
+    }
+    red[tid] = q;
+    __syncthreads();
+    for (int o = ST / 2; o > 0; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+    const double yu = sqrt(red[0]);
+    for (int l = tid; l < L; l += ST) {
+        const LatentConsts& c = a.consts[l];
+        const double* x = a.x + (size_t)l * d;
+        double hax = 0.0;
+        for (int j = 0; j < d; ++j) hax += c.HA[j] * x[j];
+        const double v = Ty[l] - hax;                                       // ihgp.h:206 / :214
+        li[l] = 0.5 * (v * v / c.S + log(c.S));                             // ihgp.h:207 / :215
+        if (a.dx) {
+            pv[l] = (a.y[l] - hax) * (1 - c.hak) / c.S;                     // moihgp.h:510-511 (raw y(l), Q8)
+            for (int k = 0; k < 3; ++k) {
+                const double* dxk = a.dx + ((size_t)l * 3 + k) * d;
+                double hd = 0.0;
+                for (int j = 0; j < d; ++j) hd += c.HA[j] * dxk[j];
+                const double dv = -c.HdA[k][0] * x[0] - hd;                 // ihgp.h:218 (Q20 de facto)
+                gi[3 * l + k] = (v * dv - 0.5 * (v * v / c.S - 1) * c.dS[k]) / c.S;   // ihgp.h:219
+            }
+        }
+    }
+    __syncthreads();
+    const int sizeU = p * L;
+    if (a.dx && a.grad) {
+        for (int i = tid; i < sizeU; i += ST) {                             // moihgp.h:538-552 in its rank-1 form
+            const int r = i / L, c = i - r * L;
+            a.grad[i] = a.y[r] * (-w[c] / a.sigma + pv[c] * (1 / sqrt(a.S[c])));
+        }
+    }
+    if (tid == 0) {
+        const double m_n = fmax((double)(p - L), 0.0);                      // moihgp.h:502
+        double Ssum = 0.0;
+        for (int l = 0; l < L; ++l) Ssum += a.S[l];
+        double loss = 0.5 * log(Ssum) + 0.5 * m_n * log(a.sigma) + 0.5 * yu / a.sigma;   // moihgp.h:503
+        if (a.dx && a.grad) {
+            double gsig = 0.5 * (m_n - yu / a.sigma) / a.sigma;             // moihgp.h:563
+            for (int l = 0; l < L; ++l) {
+                const double Sl = a.S[l], rs = sqrt(Sl);
+                double gS = 0.5 / Sl + pv[l] * (-0.5 * (1 / rs / rs / rs) * w[l]);   // moihgp.h:555-561
+                if (a.threading) loss += li[l];                             // moihgp.h:588 vs :601 (Q5)
+                const double dn = gi[3 * l + 2];
+                gS -= dn * a.sigma / Sl / Sl;                               // moihgp.h:591 / :604
+                gsig += dn / Sl;                                            // moihgp.h:592 / :605
+                a.grad[sizeU + l] = gS;
+                for (int k = 0; k < 3; ++k) a.grad[sizeU + L + 1 + 3 * l + k] = gi[3 * l + k];   // moihgp.h:608-609
+            }
+            a.grad[sizeU + L] = gsig;
+        } else {
+            for (int l = 0; l < L; ++l) loss += li[l];                      // moihgp.h:675 / :684 (always)
+        }
+        *a.loss = loss;
+    }
+}
+
+size_t step_smem(int L) { return sizeof(double) * (3 * (size_t)L + 2 * (size_t)L * L + 2 * L) + sizeof(int) * ((size_t)L + 2); }
+size_t lik_smem(int L) { return sizeof(double) * (8 * (size_t)L + ST + 2 * (size_t)L * L + 2 * L) + sizeof(int) * ((size_t)L + 2); }
+
+}  // namespace
+
+cudaError_t launch_step(const StepArgs& a, cudaStream_t st) {
+    const size_t smem = step_smem(a.L);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_step<<<1, ST, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lik(const LikArgs& a, cudaStream_t st) {
+    const size_t smem = lik_smem(a.L);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_lik, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_lik<<<1, ST, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace moihgp

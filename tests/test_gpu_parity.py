@@ -1,0 +1,213 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against
+  * the golden fixtures generated from the reference itself (tests/golden),
+  * the CPU oracle on the same seeded inputs at sizes it finishes in seconds,
+  * size-independent properties at larger sizes (chunk invariance, carried state, linearity).
+Tolerance: 1e-9 norm-wise relative in fp64 (BASELINE.json north_star), written as conftest.TOL."""
+import numpy as np
+import pytest
+
+from conftest import TOL, golden_cases, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _models(g):
+    from multioutputihgp_b200 import MOIHGPSequences
+    m = MOIHGPSequences(float(g["dt"]), int(g["p"]), int(g["L"]), str(g["kernel"]), bool(g["threading"]))
+    m.update(g["params"])
+    return m
+
+
+def _close(a, b, tol=TOL):
+    return abs(a - b) <= tol * abs(b)
+
+
+@pytest.mark.parametrize("path", golden_cases(), ids=lambda p: p.split("/")[-1][:-4])
+def test_cuda_matches_reference_golden(cuda_lib, path):
+    g = load_golden(path)
+    m = _models(g)
+    p, L, T = int(g["p"]), int(g["L"]), int(g["T"])
+    assert rel_err(m.params, g["params_after_update"]) < 1e-12
+    # K-setup: steady-state members of every latent (ihgp.h:243-254)
+    for l in range(L):
+        c = m.latent_consts(l)
+        for k, v in c.items():
+            ref = g["c%d_%s" % (l, k)]
+            if np.max(np.abs(ref)) > 0:
+                assert rel_err(np.asarray(v), np.asarray(ref)) < TOL, (l, k)
+            else:
+                assert np.max(np.abs(v)) == 0, (l, k)
+        G, P = m.smoother_consts(l, 0)
+        assert rel_err(G, g["sm%d_G" % l]) < TOL
+    # objective = RegressionObjective loop (moihgp_regression.h:42-50)
+    loss, grad, xT, dxT = m.objective(g["Y"], want_state=True)
+    assert _close(loss, g["obj_loss"])
+    assert rel_err(grad, g["obj_grad"]) < TOL
+    assert rel_err(xT[0], g["obj_xT"]) < TOL and rel_err(dxT[0], g["obj_dxT"]) < TOL
+    n2 = max(T // 3, 2)
+    loss, grad, xT, dxT = m.objective(g["Y"][:n2], g["x0"], g["dx0"], want_state=True)
+    assert _close(loss, g["obj2_loss"]) and rel_err(grad, g["obj2_grad"]) < TOL
+    assert rel_err(xT[0], g["obj2_xT"]) < TOL and rel_err(dxT[0], g["obj2_dxT"]) < TOL
+    # filter + NLL (+ back-projection)
+    r = m.filter_smoother_nll(g["Y"], smoother_mode=1, want_yhat=True)
+    assert rel_err(r["X"][0], g["flt_X"]) < TOL
+    assert rel_err(r["Yhat"][0], g["flt_Yhat"]) < TOL
+    assert _close(r["nll"][0], g["flt_nll"])
+    assert rel_err(r["xT"][0], g["flt_X"][-1]) < TOL
+    # literal smoother (IHGP::backwardSmoother) on the first 40 filtered states, where the reference is finite
+    n = min(T, 40)
+    r0 = m.filter_smoother_nll(g["Y"][:n], smoother_mode=0)
+    for l in range(L):
+        ref = g["sm%d_Xs" % l]
+        if np.all(np.isfinite(ref)) and np.max(np.abs(ref)) < 1e100:
+            assert rel_err(r0["Xs"][0][:, l, :], ref) < 1e-7, l
+
+
+@pytest.mark.parametrize("path", golden_cases(), ids=lambda p: p.split("/")[-1][:-4])
+def test_legacy_symbols_match_reference_golden(cuda_lib, path, monkeypatch):
+    """gp32_* / gp52_* one observation per call (src/wrapper.cpp), incl. missing data and predict-only."""
+    g = load_golden(path)
+    if str(g["kernel"]) == "Matern52":
+        monkeypatch.setenv("MOIHGP_GP52_MATERN52", "1")
+    from multioutputihgp_b200 import MOIHGP
+    m = MOIHGP(float(g["dt"]), int(g["p"]), int(g["L"]), kernel=str(g["kernel"]), threading=bool(g["threading"]))
+    m.update(g["params"])
+    assert rel_err(m.params, g["params_after_update"]) < 1e-12
+    for i in range(3):
+        xn, yh, dxn = m.step(g["one_x"], g["nan%d_y" % i], g["one_dx"])
+        assert rel_err(xn, g["nan%d_xn" % i]) < TOL and rel_err(yh, g["nan%d_yh" % i]) < TOL and rel_err(dxn, g["nan%d_dxn" % i]) < TOL
+    xn, yh = m.step(g["one_x"])
+    assert rel_err(xn, g["pred_xn"]) < TOL and rel_err(yh, g["pred_yh"]) < TOL
+    l1, g1 = m.negLogLikelihood(g["one_x"], g["one_y"], g["one_dx"])
+    assert _close(l1, g["one_lik1"]) and rel_err(g1, g["one_grad"]) < TOL
+    assert _close(m.negLogLikelihood(g["one_x"], g["one_y"]), g["one_lik2"])
+    # the reference's own driver loop through the per-observation symbols (online_learning.py:83-89)
+    T = min(int(g["T"]), 25)
+    x = np.zeros((int(g["L"]), m.igp_dim))
+    dx = np.zeros((int(g["L"]), 3, m.igp_dim))
+    X = []
+    for y in g["Y"][:T]:
+        x, yh, dx = m.step(x, y, dx)
+        X.append(x)
+    assert rel_err(np.array(X), g["flt_X"][:T]) < TOL
+
+
+CONFIGS = [
+    # kernel, threading, p, L, N, T, seed           (shapes after BASELINE configs 1-5, oracle-sized)
+    ("Matern32", True, 2, 1, 1, 63, 1),
+    ("Matern32", False, 8, 4, 3, 700, 2),
+    ("Matern52", True, 16, 8, 5, 1037, 3),
+    ("Matern32", True, 64, 32, 1, 2100, 4),
+    ("Matern32", True, 40, 12, 2, 300, 5),           # ragged latent group (12 = 8 + 4)
+    ("Matern52", False, 3, 3, 4, 256, 6),            # p == L (no residual), exactly one chunk
+    ("Matern52", True, 5, 2, 2, 257, 7),             # one step into the second chunk
+]
+
+
+@pytest.mark.parametrize("kernel,threading,p,L,N,T,seed", CONFIGS)
+def test_cuda_matches_oracle(cuda_lib, kernel, threading, p, L, N, T, seed):
+    from multioutputihgp_b200 import MOIHGPSequences
+    from oracle.binding import OracleMOIHGP
+    from oracle.gen_golden import make_data, make_params
+    rng = np.random.default_rng(seed)
+    params = make_params(rng, p, L, kernel)
+    Y = np.stack([make_data(rng, p, L, T) for _ in range(N)])
+    m = MOIHGPSequences(0.1, p, L, kernel, threading)
+    o = OracleMOIHGP(0.1, p, L, kernel, threading)
+    m.update(params)
+    o.update(params)
+    d = m.igp_dim
+    x0 = 0.2 * rng.standard_normal((N, L, d))
+    dx0 = 0.1 * rng.standard_normal((N, L, 3, d))
+    for mode in (1, 0):
+        r = m.filter_smoother_nll(Y, x0=x0, smoother_mode=mode, want_yhat=True)
+        ro = o.filter_smoother_nll(Y, x0=x0, smoother_mode=mode, want_yhat=True)
+        assert rel_err(r["X"], ro["X"]) < TOL
+        assert rel_err(r["Yhat"], ro["Yhat"]) < TOL
+        assert rel_err(r["nll"], ro["nll"]) < TOL
+        assert rel_err(r["xT"], ro["xT"]) < TOL
+        if mode == 1 or np.max(np.abs(ro["Xs"])) < 1e100:
+            assert rel_err(r["Xs"], ro["Xs"]) < (TOL if mode == 1 else 1e-7), mode
+    loss, grad, xT, dxT = m.objective(Y, x0=x0, dx0=dx0, want_state=True)
+    lo, go, xo, dxo = o.objective(Y, x0=x0, dx0=dx0)
+    assert _close(loss, lo)
+    assert rel_err(grad, go) < TOL
+    assert rel_err(xT, xo) < TOL and rel_err(dxT, dxo) < TOL
+
+
+def test_chunk_and_carry_invariance(cuda_lib):
+    """Splitting a sequence in two calls with the carried state equals one call (filter state, NLL, objective)."""
+    from multioutputihgp_b200 import MOIHGPSequences
+    from oracle.gen_golden import make_data, make_params
+    rng = np.random.default_rng(9)
+    p, L, T, cut = 16, 8, 5000, 1777
+    params = make_params(rng, p, L, "Matern52")
+    Y = make_data(rng, p, L, T)[None]
+    m = MOIHGPSequences(0.1, p, L, "Matern52", True)
+    m.update(params)
+    full = m.filter_smoother_nll(Y, smoother_mode=-1)
+    a = m.filter_smoother_nll(Y[:, :cut], smoother_mode=-1)
+    b = m.filter_smoother_nll(Y[:, cut:], x0=a["xT"], smoother_mode=-1)
+    assert rel_err(np.concatenate([a["X"], b["X"]], axis=1), full["X"]) < TOL
+    assert _close(a["nll"][0] + b["nll"][0], full["nll"][0])
+    lf, gf = m.objective(Y)
+    la, ga, xa, dxa = m.objective(Y[:, :cut], want_state=True)
+    lb, gb = m.objective(Y[:, cut:], x0=xa, dx0=dxa)
+    assert _close(la + lb, lf) and rel_err(ga + gb, gf) < TOL
+
+
+def test_filter_is_linear_in_the_observations(cuda_lib):
+    """x is an LTI-affine function of y with x0 = 0: X(a Y1 + b Y2) = a X(Y1) + b X(Y2); same for the smoother."""
+    from multioutputihgp_b200 import MOIHGPSequences
+    from oracle.gen_golden import make_params
+    rng = np.random.default_rng(10)
+    p, L, N, T = 8, 4, 6, 3000
+    m = MOIHGPSequences(0.1, p, L, "Matern32", True)
+    m.update(make_params(rng, p, L, "Matern32"))
+    Y1, Y2 = rng.standard_normal((N, T, p)), rng.standard_normal((N, T, p))
+    r1, r2 = m.filter_smoother_nll(Y1), m.filter_smoother_nll(Y2)
+    r3 = m.filter_smoother_nll(0.7 * Y1 - 1.9 * Y2)
+    for k in ("X", "Xs"):
+        assert rel_err(r3[k], 0.7 * r1[k] - 1.9 * r2[k]) < 1e-11
+
+
+def test_device_resident_entry_points(cuda_lib):
+    """torch CUDA tensors through the *_dev symbols give the same results as host buffers."""
+    import torch
+    from multioutputihgp_b200 import MOIHGPSequences
+    from oracle.gen_golden import make_data, make_params
+    rng = np.random.default_rng(12)
+    p, L, N, T = 16, 8, 4, 1500
+    m = MOIHGPSequences(0.1, p, L, "Matern52", True)
+    m.update(make_params(rng, p, L, "Matern52"))
+    Y = np.stack([make_data(rng, p, L, T) for _ in range(N)])
+    host = m.filter_smoother_nll(Y)
+    dev = torch.device("cuda:0")
+    Yd = torch.from_numpy(Y).to(dev)
+    X = torch.empty((N, T, L, 3), dtype=torch.float64, device=dev)
+    Xs = torch.empty_like(X)
+    nll = torch.empty(N, dtype=torch.float64, device=dev)
+    m.filter_smoother_nll_device(Yd, X=X, Xs=Xs, nll=nll)
+    torch.cuda.synchronize()
+    assert rel_err(X.cpu().numpy(), host["X"]) == 0.0
+    assert rel_err(Xs.cpu().numpy(), host["Xs"]) == 0.0
+    assert rel_err(nll.cpu().numpy(), host["nll"]) == 0.0
+    loss = torch.zeros(1, dtype=torch.float64, device=dev)
+    grad = torch.zeros(m.num_param, dtype=torch.float64, device=dev)
+    m.objective_device(Yd, loss, grad)
+    torch.cuda.synchronize()
+    lh, gh = m.objective(Y)
+    assert float(loss.item()) == lh and rel_err(grad.cpu().numpy(), gh) == 0.0
+
+
+def test_online_learner_runs_like_the_reference_example(cuda_lib):
+    """example.py / online_learning.py protocol: 8 outputs, 4 latents, window 2 (BASELINE config 2 shape)."""
+    from multioutputihgp_b200 import MOIHGPOnlineLearning
+    rng = np.random.default_rng(5)
+    gp = MOIHGPOnlineLearning(0.1, 8, 4, gamma=0.9, windowsize=2, threading=False)
+    t = np.arange(12) * 0.1
+    data = np.stack([np.sin((1 + i % 3) * t) for i in range(8)], axis=1) + 0.05 * rng.standard_normal((12, 8))
+    for y in data:
+        yhat = gp.step(y)
+        assert yhat.shape == (8,) and np.all(np.isfinite(yhat))
+    assert np.all(np.isfinite(gp.params)) and gp.covariance.shape == (8, 8)
