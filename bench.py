@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py - latent time-steps/s of the fused filter + smoother + NLL pass (fp64) on B200.
+
+Contract (one JSON line on stdout from rank 0):
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun, one rank per GPU)
+    python bench.py --impl reference ...                      (the CPU implementation of the same path, host cores)
+
+Workload (BASELINE.json configs[2], the configuration its metric and SURVEY 8(d)'s >= 50 % target are
+quoted on): 4096 independent sequences x T = 16384, p = 16 outputs, L = 8 latents, Matern-5/2 (state
+dim 3), dt = 0.1, synthetic data.  One "step" = one fused pass over the whole batch: projection, steady-state
+Kalman filter, RTS smoother and NLL, writing the filtered states X, the smoothed states Xs and nll[n].
+Multi-GPU: sequences are sharded over ranks (weak scaling: 4096 sequences PER GPU), no data-path collective;
+the only exchange is the fp64 all-reduce of the summed NLL.
+
+  value    : N*T*L / time with Y, X, Xs resident in HBM (CUDA events around K steps, max over ranks)
+  e2e      : same metric through the host-buffer C-ABI call (moihgp_cuda_filter_smoother_nll), pinned host
+             memory, H2D of Y and D2H of X, Xs, nll inside the timed region
+  roofline : algorithmic bytes (8*(p/L + 2d) per latent-step) / device time, vs the measured HBM peak
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (kernel, p, L, N per GPU, T)
+    "c3": ("Matern52", 16, 8, 4096, 16384),
+}
+WORKLOAD_DESC = {
+    "c3": "BASELINE configs[2]: batched filter+smoother, 4096 sequences x T=16384, p=16, L=8, Matern-5/2 (d=3), dt=0.1",
+}
+# per-latent (magnitude, lengthscale, noise), cycled; filter- and smoother-stable under the reference's semantics
+# (SURVEY 8(d)); checked at setup (rho(AKHA) < 1, rho(G) < 1)
+IGP_TABLE = {
+    "Matern32": [(1, 1, .1), (.5, .5, .1), (2, .3, .05), (.5, .3, .5)],
+    "Matern52": [(1, 1, .1), (.5, .5, .1), (.5, .3, .05), (.5, .5, .5)],
+}
+DT = 0.1
+METRIC = "latent time-steps/sec (filter+smoother+NLL, fp64)"
+UNIT = "latent-steps/s"
+
+
+def model_params(p, L, kernel, seed):
+    rng = np.random.default_rng(seed)
+    Hmix = rng.standard_normal((p, L)) / np.sqrt(L)
+    tbl = IGP_TABLE[kernel]
+    igp = np.array([tbl[l % len(tbl)] for l in range(L)], dtype=np.float64).ravel()
+    # U = polar(Hmix) is formed by update(); S = 1, sigma = 1e-2 are the reference's defaults (moihgp.h:126-127)
+    return np.concatenate([Hmix.ravel(), np.ones(L), [1e-2], igp]), Hmix
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def alg_bytes_per_latent_step(p, L, d):
+    return 8.0 * (p / L + 2 * d)   # read y share, write filtered x (d) and smoothed xs (d)
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if val.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def make_data_device(torch, dev, Hmix, N, T, p, L, seed, rank):
+    """Synthetic observations after example_regression.cpp:18-28: sinusoidal latents sin(w_l t + phi_n), mixed by Hmix,
+    plus 0.1 * U(-1, 1) noise.  Built block-wise on the device."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed + 7919 * rank)
+    Y = torch.empty((N, T, p), dtype=torch.float64, device=dev)
+    t = torch.arange(T, dtype=torch.float64, device=dev) * DT
+    w = 1.0 + 3.0 * torch.arange(L, dtype=torch.float64, device=dev) / max(L - 1, 1)
+    H = torch.from_numpy(Hmix).to(dev)
+    nb = 128
+    for n0 in range(0, N, nb):
+        n1 = min(N, n0 + nb)
+        phi = 2.0 * np.pi * (torch.arange(n0, n1, dtype=torch.float64, device=dev) + rank * N) / N
+        F = torch.sin(t[None, :, None] * w[None, None, :] + phi[:, None, None])
+        noise = 0.1 * (2.0 * torch.rand((n1 - n0, T, p), dtype=torch.float64, device=dev, generator=g) - 1.0)
+        Y[n0:n1] = F @ H.T + noise
+    return Y
+
+
+def check_stability(model, L):
+    worst = {"rho_AKHA": 0.0, "rho_G_rts": 0.0}
+    for l in range(L):
+        c = model.latent_consts(l)
+        G, _ = model.smoother_consts(l, 1)
+        worst["rho_AKHA"] = max(worst["rho_AKHA"], float(np.max(np.abs(np.linalg.eigvals(c["AKHA"])))))
+        worst["rho_G_rts"] = max(worst["rho_G_rts"], float(np.max(np.abs(np.linalg.eigvals(G)))))
+    if worst["rho_AKHA"] >= 1.0 or worst["rho_G_rts"] >= 1.0:
+        raise SystemExit("benchmark hyper-parameters are unstable under the reference's semantics: %s" % worst)
+    return worst
+
+
+def cpu_reference_rate(kernel, p, L, T, seed, budget_s, nthreads):
+    """Time the CPU implementation of the same pass (the oracle port, -O3, std::thread over sequences) on a
+    bounded sample of the workload: as many full-length sequences as fit in ~budget_s seconds."""
+    from oracle.binding import OracleMOIHGP
+    from oracle.gen_golden import make_data
+    params, Hmix = model_params(p, L, kernel, seed)
+    o = OracleMOIHGP(DT, p, L, kernel, threading=True)
+    o.update(params)
+    rng = np.random.default_rng(seed)
+    base = make_data(rng, p, L, T, DT)
+
+    def run(nseq):
+        Y = np.ascontiguousarray(np.broadcast_to(base, (nseq, T, p))) + 0.01 * rng.standard_normal((nseq, 1, p))
+        t0 = time.perf_counter()
+        o.filter_smoother_nll(Y, smoother_mode=1, nthreads=nthreads)
+        return time.perf_counter() - t0
+
+    n0 = max(nthreads, 1)
+    t_cal = run(n0)
+    nseq = int(max(n0, min(4096, n0 * budget_s / max(t_cal, 1e-3))))
+    nseq = (nseq // n0) * n0
+    dt_ = run(nseq)
+    return nseq * T * L / dt_, nseq, dt_
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--nseq", type=int, default=0, help="override sequences per GPU (debug only: not the benchmark config)")
+    ap.add_argument("--tlen", type=int, default=0, help="override T (debug only)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    kernel, p, L, N, T = WORKLOADS[a.workload]
+    if a.nseq:
+        N = a.nseq
+    if a.tlen:
+        T = a.tlen
+    d = 3 if kernel == "Matern52" else 2
+    seed = 1234 + 2   # 1234 + config index
+    steps, warmup = max(a.steps, 1), max(a.warmup, 3)
+    cfg = {"workload": WORKLOAD_DESC[a.workload], "kernel": kernel, "p": p, "L": L, "d": d, "sequences_per_gpu": N, "T": T,
+           "dt": DT, "smoother": "rts", "sharding": "sequences over ranks, no data-path collective; all-reduce of the summed NLL only",
+           "l2": "inputs (%.1f GB/GPU) larger than L2, no flush needed" % (8.0 * N * T * p / 1e9)}
+    cores = len(os.sched_getaffinity(0))
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        t0 = time.perf_counter()
+        rates, samples = [], []
+        for i in range(warmup + steps):
+            r, nseq, dt_ = cpu_reference_rate(kernel, p, L, T, seed, budget_s=max(2.0, 60.0 / (warmup + steps)), nthreads=cores)
+            if i >= warmup:
+                rates.append(r)
+                samples.append((nseq, dt_))
+        value = float(np.mean(rates))
+        nseq = samples[-1][0]
+        sample = "%d full-length sequences (of %d per GPU) x T=%d per step, all host cores" % (nseq, N, T)
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": warmup,
+                "ms_per_step": 1e3 * float(np.mean([s[1] for s in samples])), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "CPU oracle port of the reference path (oracle/moihgp_oracle.cpp, -O3, std::thread over sequences); the reference "
+                        "itself needs Eigen, absent from the image; wall %.0f s" % (time.perf_counter() - t0)}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm (B200)
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from multioutputihgp_b200 import MOIHGPSequences
+    model = MOIHGPSequences(DT, p, L, kernel, threading=True, device=local_rank)
+    params, Hmix = model_params(p, L, kernel, seed)
+    model.update(params)
+    stab = check_stability(model, L)
+
+    Y = make_data_device(torch, dev, Hmix, N, T, p, L, seed, rank)
+    X = torch.empty((N, T, L, d), dtype=torch.float64, device=dev)
+    Xs = torch.empty_like(X)
+    nll = torch.empty(N, dtype=torch.float64, device=dev)
+    nll_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def step():
+        model.filter_smoother_nll_device(Y, smoother_mode=1, X=X, Xs=Xs, nll=nll)
+        torch.sum(nll, dim=0, keepdim=True, out=nll_sum)
+        if world > 1:
+            dist.all_reduce(nll_sum)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(warmup):
+        step()
+    sync_all()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = model.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    sync_all()
+    launches = model.launch_count - l0
+    clocks = sampler.stop() if sampler else None
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item())
+    units = float(N) * T * L * world
+    value = units / (ms_per_step * 1e-3)
+    nll_total = float(nll_sum.item())
+
+    # per-kernel device times (events on the launching stream, separate run of the same steps)
+    model.profile(True)
+    for _ in range(steps):
+        model.filter_smoother_nll_device(Y, smoother_mode=1, X=X, Xs=Xs, nll=nll)
+    prof = model.profile_read()
+    model.profile(False)
+    kern = {k: v[0] / v[1] for k, v in prof.items()}
+    pass_ms = sum(kern.values())
+    peak, peak_src = measured_peak()
+    balg = alg_bytes_per_latent_step(p, L, d)
+    dom = max(kern, key=kern.get)
+    # bytes each kernel must move by construction (its own compulsory traffic, per launch)
+    own = {"k_project": 8.0 * N * T * (p + L + 1), "k_scan_summaries": 8.0 * N * T * L, "k_scan_final": 8.0 * N * T * L * (1 + 2 * d)}
+    roof = {"bound": "hbm", "kernel": "fused pass = " + " + ".join(kern.keys()),
+            "achieved": balg * N * T * L / (pass_ms * 1e-3) / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+            "traffic": None, "algorithmic_bytes_per_latent_step": balg, "pass_ms": pass_ms,
+            "kernels_ms": {k: round(v, 4) for k, v in kern.items()},
+            "dominant": {"kernel": dom, "ms": kern[dom], "share": kern[dom] / pass_ms,
+                         "own_bytes": own.get(dom), "own_GBps": (own[dom] / (kern[dom] * 1e-3) / 1e9) if dom in own else None}}
+    roof["frac"] = roof["achieved"] / peak
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            roof["traffic"] = json.load(f).get("fused_pass_dram_bytes_per_step")
+    except Exception:
+        pass
+
+    # ------------------------------------------------------------------ e2e: host buffers through the C ABI
+    e2e = None
+    if not a.no_e2e:
+        import psutil
+        need = 8.0 * N * T * (p + 2 * L * d) * 1.05
+        avail = psutil.virtual_memory().available / max(world, 1)
+        Ne = N if need < 0.7 * avail else max(1, int(N * 0.7 * avail / need))
+        del X, Xs
+        torch.cuda.empty_cache()
+        Yh = torch.empty((Ne, T, p), dtype=torch.float64, pin_memory=True)
+        Yh.copy_(Y[:Ne])
+        Xh = torch.empty((Ne, T, L, d), dtype=torch.float64, pin_memory=True)
+        Xsh = torch.empty((Ne, T, L, d), dtype=torch.float64, pin_memory=True)
+        nllh = torch.empty(Ne, dtype=torch.float64, pin_memory=True)
+        lib, h = model._lib, model._h
+        model.set_stream(None)
+
+        def e2e_step():
+            rc = lib.moihgp_cuda_filter_smoother_nll(h, Yh.data_ptr(), Ne, T, None, 1, Xh.data_ptr(), Xsh.data_ptr(), None, nllh.data_ptr(), None)
+            if rc != 0:
+                raise SystemExit("e2e call failed: " + lib.moihgp_cuda_last_error(h).decode())
+
+        ke = max(2, min(steps, 3))
+        e2e_step()   # warm-up (allocates the call's device buffers)
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            e2e_step()
+        sync_all()
+        te = torch.tensor([(time.perf_counter() - t0) / ke], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": float(Ne) * T * L * world / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(8 * Ne * T * p),
+               "d2h_bytes_per_step": int(8 * Ne * (2 * T * L * d + 1)), "ms_per_step": 1e3 * float(te.item()), "sequences_per_gpu": Ne,
+               "api": "moihgp_cuda_filter_smoother_nll (host buffers, pinned)", "steps": ke,
+               "nll_check": abs(float(nllh.sum().item()) - float(nll[:Ne].sum().item())) <= 1e-9 * abs(float(nll[:Ne].sum().item()))}
+
+    # ------------------------------------------------------------------ CPU baseline beside it (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        r, nseq, dt_ = cpu_reference_rate(kernel, p, L, T, seed, budget_s=a.cpu_seconds, nthreads=cores)
+        cpu = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d full-length sequences of the workload (T=%d), %.1f s, oracle/moihgp_oracle.cpp -O3, std::thread over sequences" % (nseq, T, dt_)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "hbm_GBps_alg": balg * units / world / (ms_per_step * 1e-3) / 1e9, "nll_total": nll_total, "stability": stab}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

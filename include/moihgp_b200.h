@@ -79,6 +79,11 @@ void moihgp_cuda_destroy(moihgp_handle* h);
 int moihgp_cuda_set_stream(moihgp_handle* h, void* cuda_stream);
 int moihgp_cuda_sync(moihgp_handle* h);
 const char* moihgp_cuda_last_error(moihgp_handle* h);
+/* per-kernel device timing: while enabled, a CUDA event is recorded on the launching stream after every kernel of
+ * the whole-sequence entry points; _read() returns "name total_ms launches" lines accumulated since it was enabled
+ * (and clears the record).  Used by bench.py for the roofline figures; off by default. */
+int moihgp_cuda_profile(moihgp_handle* h, int enable);
+const char* moihgp_cuda_profile_read(moihgp_handle* h);
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 long long moihgp_cuda_launch_count(moihgp_handle* h);
 

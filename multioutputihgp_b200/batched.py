@@ -102,6 +102,17 @@ class MOIHGPSequences(object):
     def launch_count(self):
         return int(self._lib.moihgp_cuda_launch_count(self._h))
 
+    def profile(self, enable):
+        self._check(self._lib.moihgp_cuda_profile(self._h, int(enable)))
+
+    def profile_read(self):
+        """{kernel name: (total ms, launches)} since profile(True); clears the record."""
+        out = {}
+        for line in self._lib.moihgp_cuda_profile_read(self._h).decode().splitlines():
+            name, ms, cnt = line.split()
+            out[name] = (float(ms), int(cnt))
+        return out
+
     def set_stream(self, cuda_stream_ptr):
         self._check(self._lib.moihgp_cuda_set_stream(self._h, cuda_stream_ptr))
 

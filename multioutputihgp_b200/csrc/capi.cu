@@ -45,6 +45,9 @@ struct moihgp_handle {
     double* d_stage = nullptr;
     size_t stage_cap = 0;
     long long launches = 0;
+    Marker marker;                            // per-kernel events, only while profiling is on
+    bool profiling = false;
+    std::string prof_text;
     std::string err;
 };
 
@@ -301,6 +304,41 @@ int moihgp_cuda_sync(moihgp_handle* h) {
     return 0;
 }
 
+int moihgp_cuda_profile(moihgp_handle* h, int enable) {
+    if (!h) return -2;
+    cudaStreamSynchronize(h->stream);
+    for (auto& e : h->marker.ev) cudaEventDestroy(e.second);
+    h->marker.ev.clear();
+    h->profiling = enable != 0;
+    return 0;
+}
+
+// "name total_ms launches" per line, accumulated since moihgp_cuda_profile(h, 1); resets the record
+const char* moihgp_cuda_profile_read(moihgp_handle* h) {
+    if (!h) return "";
+    cudaStreamSynchronize(h->stream);
+    std::vector<std::string> order;
+    std::map<std::string, std::pair<double, long long>> acc;
+    auto& ev = h->marker.ev;
+    for (size_t i = 1; i < ev.size(); ++i) {
+        if (ev[i].first == "begin") continue;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second);
+        if (!acc.count(ev[i].first)) order.push_back(ev[i].first);
+        acc[ev[i].first].first += ms;
+        acc[ev[i].first].second += 1;
+    }
+    h->prof_text.clear();
+    char line[256];
+    for (auto& n : order) {
+        std::snprintf(line, sizeof(line), "%s %.6f %lld\n", n.c_str(), acc[n].first, acc[n].second);
+        h->prof_text += line;
+    }
+    for (auto& e : ev) cudaEventDestroy(e.second);
+    ev.clear();
+    return h->prof_text.c_str();
+}
+
 const char* moihgp_cuda_last_error(moihgp_handle* h) { return h ? h->err.c_str() : "null handle"; }
 long long moihgp_cuda_launch_count(moihgp_handle* h) { return h ? h->launches : 0; }
 size_t moihgp_cuda_igp_dim(moihgp_handle* h) { return (size_t)h->dim; }
@@ -381,14 +419,18 @@ int moihgp_cuda_filter_smoother_nll_dev(moihgp_handle* h, const double* Y, size_
         return -1;
     if (Yhat && !X) { if (ws_get(h, "Xtmp", N * T * L * D, &Xtmp)) return -1; X = Xtmp; }
     CK(cudaMemsetAsync(nanf, 0, sizeof(int), h->stream));
+    Marker* mk = h->profiling ? &h->marker : nullptr;
+    if (mk) { mk->st = h->stream; mk->mark("begin"); }
     CK(launch_project(Y, h->d_U, h->d_S, h->p, L, (long long)N, (long long)T, u, nullptr, nullptr, nll ? rho : nullptr, nanf, h->stream));
+    mark(mk, "k_project");
     ScanArgs a;
+    a.mk = mk;
     a.u = u; a.consts = h->d_consts; a.L = L; a.N = (long long)N; a.T = (long long)T; a.x0 = x0;
     a.fsum = fsum; a.bsum = bsum; a.xin = xin; a.bin = bin; a.Bx = Bx; a.X = X; a.Xs = Xs; a.vsq = vsq; a.xT = xT;
     CK(launch_scan(D, mode < 0 ? 1 : mode, a, h->stream));
     h->launches += 1 + scan_launch_count((long long)T);
-    if (nll) { CK(launch_nll_reduce(rho, vsq, h->d_consts, h->d_S, h->sigma, h->p, L, (long long)N, (long long)T, nll, h->stream)); h->launches += 1; }
-    if (Yhat) { CK(launch_backproject(X, h->d_U, h->d_S, h->p, L, D, (long long)N, (long long)T, Yhat, h->stream)); h->launches += 1; }
+    if (nll) { CK(launch_nll_reduce(rho, vsq, h->d_consts, h->d_S, h->sigma, h->p, L, (long long)N, (long long)T, nll, h->stream)); h->launches += 1; mark(mk, "k_nll_reduce"); }
+    if (Yhat) { CK(launch_backproject(X, h->d_U, h->d_S, h->p, L, D, (long long)N, (long long)T, Yhat, h->stream)); h->launches += 1; mark(mk, "k_backproject"); }
     return 0;
 }
 
@@ -439,8 +481,12 @@ int moihgp_cuda_objective_dev(moihgp_handle* h, const double* Y, size_t N, size_
         ws_get(h, "nanf", 4, &nanf))
         return -1;
     CK(cudaMemsetAsync(nanf, 0, sizeof(int), h->stream));
+    Marker* mk = h->profiling ? &h->marker : nullptr;
+    if (mk) { mk->st = h->stream; mk->mark("begin"); }
     CK(launch_project(Y, h->d_U, h->d_S, p, L, (long long)N, (long long)T, u, w, yl, rho, nanf, h->stream));
+    mark(mk, "k_project");
     ObjArgs a;
+    a.mk = mk;
     a.Y = Y; a.u = u; a.w = w; a.yl = yl; a.rho = rho; a.wgt = w;   // the weights overwrite w in place (same thread, same index)
     a.consts = h->d_consts; a.U = h->d_U; a.S = h->d_S; a.sigma = h->sigma; a.p = p; a.L = L; a.threading = h->threading;
     a.N = (long long)N; a.T = (long long)T; a.x0 = x0; a.dx0 = dx0; a.zsum = zsum; a.zin = zin; a.part = part; a.gU_part = gU;

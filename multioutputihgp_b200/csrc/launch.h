@@ -2,9 +2,26 @@
 // include/moihgp_b200.h).
 #pragma once
 #include <cuda_runtime.h>
+#include <string>
+#include <utility>
+#include <vector>
 #include "moihgp_device.cuh"
 
 namespace moihgp {
+
+// Optional per-kernel timing: one CUDA event recorded on the launching stream after every kernel
+// (bench.py's roofline figures come from these, measured live, never under a profiler).
+struct Marker {
+    cudaStream_t st = nullptr;
+    std::vector<std::pair<std::string, cudaEvent_t>> ev;
+    void mark(const char* name) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        ev.emplace_back(name, e);
+    }
+};
+inline void mark(Marker* m, const char* name) { if (m) m->mark(name); }
 
 // setup.cu
 cudaError_t launch_setup(int dim, const double* d_igp_params, double dt, int L, LatentConsts* d_out, cudaStream_t stream);
@@ -27,6 +44,7 @@ struct ScanArgs {
     double *X, *Xs;               // [N][T][L][D] outputs (either may be null)
     double* vsq;                  // [nC][N][L] sum of squared innovations (workspace)
     double* xT;                   // [N][L][D] final filtered state or null
+    Marker* mk = nullptr;
 };
 size_t scan_chunks(long long T);
 int scan_launch_count(long long T);
@@ -52,6 +70,7 @@ struct ObjArgs {
     double* lat_sums;             // [L+1][8] per-latent reduced sums (workspace)
     double *loss, *grad;          // [1], [num_param] outputs (device)
     double *xT, *dxT;             // final state or null
+    Marker* mk = nullptr;
 };
 size_t obj_chunks(long long T);
 size_t obj_gu_splits(long long N, long long T);

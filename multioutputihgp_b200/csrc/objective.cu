@@ -423,19 +423,24 @@ cudaError_t run_objective(const ObjArgs& a, cudaStream_t st) {
     if (nC > 1) {
         k_obj_scan<D, false><<<grid, 128, 0, st>>>(a.u, a.w, a.yl, a.consts, a.S, a.sigma, a.L, a.N, a.T, nC, nullptr, a.zsum,
                                                    nullptr, nullptr, nullptr, nullptr);
+        mark(a.mk, "k_obj_scan_summaries");
         k_obj_coupling<D><<<(3 * a.L + 63) / 64, 64, 0, st>>>(a.consts, a.L, Ek);
     }
     k_obj_carry<D><<<(unsigned)((a.N * a.L + 127) / 128), 128, 0, st>>>(a.consts, Ek, a.L, a.N, nC, a.x0, a.dx0, a.zsum, a.zin);
+    mark(a.mk, "k_obj_carry");
     k_obj_scan<D, true><<<grid, 128, 0, st>>>(a.u, a.w, a.yl, a.consts, a.S, a.sigma, a.L, a.N, a.T, nC, a.zin, nullptr, a.wgt,
                                               a.part, a.xT, a.dxT);
+    mark(a.mk, "k_obj_scan_final");
     const size_t nsplit = obj_gu_splits(a.N, a.T);
     const long long slabs = a.N * ((a.T + GK - 1) / GK);
     const long long per = (slabs + (long long)nsplit - 1) / (long long)nsplit;
     dim3 gg((a.p + GT - 1) / GT, (a.L + GT - 1) / GT, (unsigned)nsplit);
     k_gradU<<<gg, 256, 0, st>>>(a.Y, a.wgt, a.p, a.L, a.N, a.T, per, a.gU_part);
+    mark(a.mk, "k_gradU");
     double* lat_sums = a.lat_sums;
     k_obj_reduce<<<a.L + 1, 256, 0, st>>>(a.part, a.rho, a.L, a.N, a.T, nC, lat_sums);
     k_obj_finish<<<1, 256, 0, st>>>(lat_sums, a.gU_part, (int)nsplit, a.S, a.sigma, a.p, a.L, a.N, a.T, a.threading, a.loss, a.grad);
+    mark(a.mk, "k_obj_reduce");
     return cudaGetLastError();
 }
 

@@ -435,11 +435,15 @@ cudaError_t run_scan(const ScanArgs& a, cudaStream_t st) {
     if (nC > 1) {
         k_scan<D, MODE, false><<<grid, 32 * lg, 0, st>>>(a.u, a.consts, a.L, a.N, a.T, nC, nLG, nullptr, nullptr, a.fsum, a.bsum,
                                                          nullptr, nullptr, nullptr, nullptr);
+        mark(a.mk, "k_scan_summaries");
         k_response<D, MODE><<<a.L * 2 * D, 32, 0, st>>>(a.consts, r_last, a.Bx);
+        mark(a.mk, "k_response");
     }
     k_carry<D, MODE><<<(unsigned)((a.N * a.L + 127) / 128), 128, 0, st>>>(a.consts, a.Bx, a.L, a.N, nC, a.x0, a.fsum, a.bsum, a.xin, a.bin);
+    mark(a.mk, "k_carry");
     k_scan<D, MODE, true><<<grid, 32 * lg, smem, st>>>(a.u, a.consts, a.L, a.N, a.T, nC, nLG, a.xin, a.bin, nullptr, nullptr, a.X, a.Xs,
                                                        a.vsq, a.xT);
+    mark(a.mk, "k_scan_final");
     return cudaGetLastError();
 }
 
