@@ -284,7 +284,8 @@ def main():
     balg = alg_bytes_per_latent_step(p, L, d)
     dom = max(kern, key=kern.get)
     # bytes each kernel must move by construction (its own compulsory traffic, per launch)
-    own = {"k_project": 8.0 * N * T * (p + L + 1), "k_scan_summaries": 8.0 * N * T * L, "k_scan_final": 8.0 * N * T * L * (1 + 2 * d)}
+    own = {"k_project": 8.0 * N * T * (p + L + 1), "k_scan_summaries": 8.0 * N * T * L, "k_scan_final": 8.0 * N * T * L * (1 + 2 * d),
+           "k_filter_chain": 8.0 * N * T * (p + L * d), "k_smooth_chain": 8.0 * N * T * 2 * L * d}
     roof = {"bound": "hbm", "kernel": "fused pass = " + " + ".join(kern.keys()),
             "achieved": balg * N * T * L / (pass_ms * 1e-3) / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
             "traffic": None, "algorithmic_bytes_per_latent_step": balg, "pass_ms": pass_ms,

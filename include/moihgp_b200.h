@@ -84,6 +84,10 @@ const char* moihgp_cuda_last_error(moihgp_handle* h);
  * (and clears the record).  Used by bench.py for the roofline figures; off by default. */
 int moihgp_cuda_profile(moihgp_handle* h, int enable);
 const char* moihgp_cuda_profile_read(moihgp_handle* h);
+/* which kernels serve the fused pass: 0 = automatic (many-chains kernels when there are enough independent
+ * (sequence, latent) chains and the shape is instantiated, else the time-parallel chunked scan), 1 = chunked scan,
+ * 2 = many-chains (fails if unavailable).  Results agree to rounding; used by the parity tests to cover both. */
+int moihgp_cuda_set_path(moihgp_handle* h, int path);
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 long long moihgp_cuda_launch_count(moihgp_handle* h);
 

@@ -102,6 +102,10 @@ class MOIHGPSequences(object):
     def launch_count(self):
         return int(self._lib.moihgp_cuda_launch_count(self._h))
 
+    def set_path(self, path):
+        """0 auto, 1 chunked scan, 2 many-chains (see moihgp_cuda_set_path)."""
+        self._check(self._lib.moihgp_cuda_set_path(self._h, {"auto": 0, "scan": 1, "chain": 2}.get(path, path)))
+
     def profile(self, enable):
         self._check(self._lib.moihgp_cuda_profile(self._h, int(enable)))
 

@@ -47,6 +47,7 @@ struct moihgp_handle {
     long long launches = 0;
     Marker marker;                            // per-kernel events, only while profiling is on
     bool profiling = false;
+    int path = 0;                             // 0 auto, 1 chunked scan, 2 many-chains
     std::string prof_text;
     std::string err;
 };
@@ -304,6 +305,12 @@ int moihgp_cuda_sync(moihgp_handle* h) {
     return 0;
 }
 
+int moihgp_cuda_set_path(moihgp_handle* h, int path) {
+    if (!h || path < 0 || path > 2) return -2;
+    h->path = path;
+    return 0;
+}
+
 int moihgp_cuda_profile(moihgp_handle* h, int enable) {
     if (!h) return -2;
     cudaStreamSynchronize(h->stream);
@@ -411,25 +418,52 @@ int moihgp_cuda_filter_smoother_nll_dev(moihgp_handle* h, const double* Y, size_
     cudaSetDevice(h->device);
     const int L = h->L, D = h->dim;
     const size_t nC = scan_chunks((long long)T);
-    double *u, *rho, *fsum, *bsum, *xin, *bin, *Bx, *vsq, *Xtmp = nullptr;
-    int* nanf;
-    if (ws_get(h, "u", N * L * T, &u) || ws_get(h, "rho", N * T, &rho) || ws_get(h, "fsum", nC * N * L * D, &fsum) ||
-        ws_get(h, "bsum", nC * N * L * D, &bsum) || ws_get(h, "xin", nC * N * L * D, &xin) || ws_get(h, "bin", nC * N * L * D, &bin) ||
-        ws_get(h, "Bx", (size_t)L * 2 * 9, &Bx) || ws_get(h, "vsq", nC * N * L, &vsq) || ws_get(h, "nanf", 4, &nanf))
-        return -1;
-    if (Yhat && !X) { if (ws_get(h, "Xtmp", N * T * L * D, &Xtmp)) return -1; X = Xtmp; }
-    CK(cudaMemsetAsync(nanf, 0, sizeof(int), h->stream));
+    double* Xtmp = nullptr;
+    if ((Yhat || Xs) && !X) { if (ws_get(h, "Xtmp", N * T * L * D, &Xtmp)) return -1; X = Xtmp; }
     Marker* mk = h->profiling ? &h->marker : nullptr;
     if (mk) { mk->st = h->stream; mk->mark("begin"); }
-    CK(launch_project(Y, h->d_U, h->d_S, h->p, L, (long long)N, (long long)T, u, nullptr, nullptr, nll ? rho : nullptr, nanf, h->stream));
-    mark(mk, "k_project");
-    ScanArgs a;
-    a.mk = mk;
-    a.u = u; a.consts = h->d_consts; a.L = L; a.N = (long long)N; a.T = (long long)T; a.x0 = x0;
-    a.fsum = fsum; a.bsum = bsum; a.xin = xin; a.bin = bin; a.Bx = Bx; a.X = X; a.Xs = Xs; a.vsq = vsq; a.xT = xT;
-    CK(launch_scan(D, mode < 0 ? 1 : mode, a, h->stream));
-    h->launches += 1 + scan_launch_count((long long)T);
-    if (nll) { CK(launch_nll_reduce(rho, vsq, h->d_consts, h->d_S, h->sigma, h->p, L, (long long)N, (long long)T, nll, h->stream)); h->launches += 1; mark(mk, "k_nll_reduce"); }
+    auto aligned16 = [](const void* q) { return (reinterpret_cast<size_t>(q) & 15) == 0; };
+    const size_t chain_warps = (N * (size_t)L + 31) / 32;
+    bool use_chain = chain_supported(h->p, L, D) && aligned16(Y) && aligned16(X) && aligned16(Xs) && chain_warps >= 148;
+    if (h->path == 1) use_chain = false;
+    if (h->path == 2) {
+        if (!(chain_supported(h->p, L, D) && aligned16(Y) && aligned16(X) && aligned16(Xs))) return fail(h, "many-chains path not available for this shape/alignment");
+        use_chain = true;
+    }
+    if (use_chain) {
+        // one thread per (sequence, latent) chain, sequential in time: chain.cu
+        int* nanf;
+        if (ws_get(h, "nanf", 4, &nanf)) return -1;
+        CK(cudaMemsetAsync(nanf, 0, sizeof(int), h->stream));
+        double Ssum = 0.0, logs = 0.0;
+        for (int l = 0; l < L; ++l) { Ssum += h->S[l]; logs += h->consts[l].logS; }
+        const double m_n = std::max((double)(h->p - L), 0.0);
+        ChainArgs c;
+        c.Y = Y; c.U_host = h->U.data(); c.S_host = h->S.data(); c.consts = h->d_consts; c.sigma = h->sigma;
+        c.nll_const = (double)T * (0.5 * std::log(Ssum) + 0.5 * m_n * std::log(h->sigma) + 0.5 * logs);
+        c.N = (long long)N; c.T = (long long)T; c.mode = mode < 0 ? 1 : mode; c.x0 = x0; c.X = X; c.Xs = Xs; c.nll = nll; c.xT = xT; c.mk = mk;
+        CK(launch_chain(h->p, L, D, c, h->stream));
+        h->launches += Xs ? 2 : 1;
+    } else {
+        // time-parallel chunked scan: project.cu + scan.cu
+        const size_t nC = scan_chunks((long long)T);
+        double *u, *rho, *fsum, *bsum, *xin, *bin, *Bx, *vsq;
+        int* nanf;
+        if (ws_get(h, "u", N * L * T, &u) || ws_get(h, "rho", N * T, &rho) || ws_get(h, "fsum", nC * N * L * D, &fsum) ||
+            ws_get(h, "bsum", nC * N * L * D, &bsum) || ws_get(h, "xin", nC * N * L * D, &xin) || ws_get(h, "bin", nC * N * L * D, &bin) ||
+            ws_get(h, "Bx", (size_t)L * 2 * 9, &Bx) || ws_get(h, "vsq", nC * N * L, &vsq) || ws_get(h, "nanf", 4, &nanf))
+            return -1;
+        CK(cudaMemsetAsync(nanf, 0, sizeof(int), h->stream));
+        CK(launch_project(Y, h->d_U, h->d_S, h->p, L, (long long)N, (long long)T, u, nullptr, nullptr, nll ? rho : nullptr, nanf, h->stream));
+        mark(mk, "k_project");
+        ScanArgs a;
+        a.mk = mk;
+        a.u = u; a.consts = h->d_consts; a.L = L; a.N = (long long)N; a.T = (long long)T; a.x0 = x0;
+        a.fsum = fsum; a.bsum = bsum; a.xin = xin; a.bin = bin; a.Bx = Bx; a.X = X; a.Xs = Xs; a.vsq = vsq; a.xT = xT;
+        CK(launch_scan(D, mode < 0 ? 1 : mode, a, h->stream));
+        h->launches += 1 + scan_launch_count((long long)T);
+        if (nll) { CK(launch_nll_reduce(rho, vsq, h->d_consts, h->d_S, h->sigma, h->p, L, (long long)N, (long long)T, nll, h->stream)); h->launches += 1; mark(mk, "k_nll_reduce"); }
+    }
     if (Yhat) { CK(launch_backproject(X, h->d_U, h->d_S, h->p, L, D, (long long)N, (long long)T, Yhat, h->stream)); h->launches += 1; mark(mk, "k_backproject"); }
     return 0;
 }

@@ -52,6 +52,21 @@ cudaError_t launch_scan(int dim, int mode, const ScanArgs& a, cudaStream_t st);
 cudaError_t launch_nll_reduce(const double* rho, const double* vsq, const LatentConsts* consts, const double* S, double sigma,
                               int p, int L, long long N, long long T, double* nll, cudaStream_t st);
 
+// chain.cu  (many-chains path: thread per (sequence, latent), sequential in time)
+struct ChainArgs {
+    const double* Y;              // [N][T][p], 16-byte aligned
+    const double *U_host, *S_host;    // host copies (become constant-bank kernel parameters)
+    const LatentConsts* consts;   // device
+    double sigma, nll_const;      // nll_const = T * (1/2 log sum S + 1/2 m_n log sigma + 1/2 sum_l log S_l)
+    long long N, T;
+    int mode;                     // smoother mode 0 / 1 (used when Xs != null)
+    const double* x0;
+    double *X, *Xs, *nll, *xT;    // X must be non-null when Xs is requested
+    Marker* mk = nullptr;
+};
+bool chain_supported(int p, int L, int dim);
+cudaError_t launch_chain(int p, int L, int dim, const ChainArgs& a, cudaStream_t st);
+
 // objective.cu
 struct ObjArgs {
     const double* Y;              // [N][T][p]

@@ -135,6 +135,73 @@ def test_cuda_matches_oracle(cuda_lib, kernel, threading, p, L, N, T, seed):
     assert rel_err(xT, xo) < TOL and rel_err(dxT, dxo) < TOL
 
 
+CHAIN_CONFIGS = [
+    # kernel, p, L, N, T, seed      shapes instantiated for the many-chains kernels (chain.cu); ragged N and T on purpose
+    ("Matern52", 16, 8, 9, 1037, 21),
+    ("Matern32", 16, 8, 4, 64, 22),
+    ("Matern32", 8, 4, 11, 333, 23),
+    ("Matern52", 8, 4, 1, 7, 24),
+    ("Matern52", 16, 8, 6, 1, 25),
+]
+
+
+@pytest.mark.parametrize("kernel,p,L,N,T,seed", CHAIN_CONFIGS)
+def test_many_chains_path_matches_oracle_and_scan_path(cuda_lib, kernel, p, L, N, T, seed):
+    from multioutputihgp_b200 import MOIHGPSequences
+    from oracle.binding import OracleMOIHGP
+    from oracle.gen_golden import make_data, make_params
+    rng = np.random.default_rng(seed)
+    params = make_params(rng, p, L, kernel)
+    Y = np.stack([make_data(rng, p, L, T) for _ in range(N)])
+    m = MOIHGPSequences(0.1, p, L, kernel, True)
+    o = OracleMOIHGP(0.1, p, L, kernel, True)
+    m.update(params)
+    o.update(params)
+    x0 = 0.2 * rng.standard_normal((N, L, m.igp_dim))
+    for mode in (1, 0):
+        ro = o.filter_smoother_nll(Y, x0=x0, smoother_mode=mode, want_yhat=True)
+        res = {}
+        for path in ("chain", "scan"):
+            m.set_path(path)
+            res[path] = r = m.filter_smoother_nll(Y, x0=x0, smoother_mode=mode, want_yhat=True)
+            assert rel_err(r["X"], ro["X"]) < TOL, path
+            assert rel_err(r["Yhat"], ro["Yhat"]) < TOL, path
+            assert rel_err(r["nll"], ro["nll"]) < TOL, path
+            assert rel_err(r["xT"], ro["xT"]) < TOL, path
+            if mode == 1 or np.max(np.abs(ro["Xs"])) < 1e100:
+                assert rel_err(r["Xs"], ro["Xs"]) < (TOL if mode == 1 else 1e-7), (path, mode)
+        assert rel_err(res["chain"]["X"], res["scan"]["X"]) < 1e-12
+    # smoother-only request (no filtered states wanted) and NLL-only request
+    m.set_path("chain")
+    r = m.filter_smoother_nll(Y, x0=x0, smoother_mode=-1, want_states=False)
+    assert rel_err(r["nll"], ro["nll"]) < TOL
+
+
+def test_many_chains_path_full_T_properties(cuda_lib):
+    """BASELINE config 3 at full T = 16384 (fewer sequences): chunk/carry invariance and linearity on the many-chains path."""
+    from multioutputihgp_b200 import MOIHGPSequences
+    from oracle.gen_golden import make_params
+    rng = np.random.default_rng(31)
+    p, L, N, T, cut = 16, 8, 12, 16384, 5003
+    m = MOIHGPSequences(0.1, p, L, "Matern52", True)
+    m.update(make_params(rng, p, L, "Matern52"))
+    m.set_path("chain")
+    Y1, Y2 = rng.standard_normal((N, T, p)), rng.standard_normal((N, T, p))
+    full = m.filter_smoother_nll(Y1)
+    a = m.filter_smoother_nll(Y1[:, :cut], smoother_mode=-1)
+    b = m.filter_smoother_nll(Y1[:, cut:], x0=a["xT"], smoother_mode=-1)
+    assert rel_err(np.concatenate([a["X"], b["X"]], axis=1), full["X"]) < TOL
+    assert rel_err(a["nll"] + b["nll"], full["nll"]) < TOL
+    r2 = m.filter_smoother_nll(Y2)
+    r3 = m.filter_smoother_nll(0.7 * Y1 - 1.9 * Y2)
+    for k in ("X", "Xs"):
+        assert rel_err(r3[k], 0.7 * full[k] - 1.9 * r2[k]) < 1e-11
+    m.set_path("scan")
+    rs = m.filter_smoother_nll(Y1)
+    for k in ("X", "Xs", "nll"):
+        assert rel_err(rs[k], full[k]) < 1e-11, k
+
+
 def test_chunk_and_carry_invariance(cuda_lib):
     """Splitting a sequence in two calls with the carried state equals one call (filter state, NLL, objective)."""
     from multioutputihgp_b200 import MOIHGPSequences
