@@ -36,6 +36,7 @@ struct LatentConsts {
     double Ps[2][9];      // smoothed covariance: [0] literal DLyap iterate (ihgp.h:107), [1] exact
     double GK[3];         // G[1] K   (drive of the rts_correct error recursion)
     double ImA[9];        // I - A    (drive of the literal recursion, ihgp.h:111)
+    double Bs[9];         // I - G[1] A   (rts_correct written as Xs[j] = Bs X[j] + G Xs[j+1])
     double params[3];     // magnitude, lengthscale, noise
     double powM[NPOW][9]; // AKHA^(2^k)
     double powG[2][NPOW][9];  // G[mode]^(2^k)

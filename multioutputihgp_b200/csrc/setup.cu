@@ -432,7 +432,10 @@ __global__ void __launch_bounds__(128) k_setup(const double* __restrict__ igp_pa
         double GK[D];
         for (int i = 0; i < D; ++i) { double s = 0.0; for (int k = 0; k < D; ++k) s += G[i * D + k] * w.K[k]; GK[i] = s; }
         cpy<DD>(G, w.G[1]);
-        store_mat<D>(G, o.G[1]); store_mat<D>(pv, o.Ps[1]); store_vec<D>(GK, o.GK);
+        double GA[DD], Bs[DD];
+        mm<D, D, D>(G, w.A, GA);
+        for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) Bs[i * D + j] = (i == j ? 1.0 : 0.0) - GA[i * D + j];
+        store_mat<D>(G, o.G[1]); store_mat<D>(pv, o.Ps[1]); store_vec<D>(GK, o.GK); store_mat<D>(Bs, o.Bs);
     }
     __syncwarp();
     // ---- 2^k power tables for the chunked scans ---------------------------------------------------
