@@ -31,11 +31,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (kernel, p, L, N per GPU, T)
-    "c3": ("Matern52", 16, 8, 4096, 16384),
+    # name: (kind, kernel, p, L, N per GPU, T)      kind "fsn" = filter + smoother + NLL, "obj" = NLL + gradient
+    "c3": ("fsn", "Matern52", 16, 8, 4096, 16384),
+    "c4": ("fsn", "Matern32", 64, 32, 1, 10000000),
+    "c5": ("obj", "Matern32", 256, 64, 1, 1000000),
 }
 WORKLOAD_DESC = {
     "c3": "BASELINE configs[2]: batched filter+smoother, 4096 sequences x T=16384, p=16, L=8, Matern-5/2 (d=3), dt=0.1",
+    "c4": "BASELINE configs[3]: long-horizon single sequence, p=64, L=32, Matern-3/2 (d=2), T=1e7, dt=0.1 (parallel-scan stress test)",
+    "c5": "BASELINE configs[4]: L-BFGS objective (NLL + gradient), p=256, L=64, Matern-3/2 (d=2), T=1e6, dt=0.1",
 }
 # per-latent (magnitude, lengthscale, noise), cycled; filter- and smoother-stable under the reference's semantics
 # (SURVEY 8(d)); checked at setup (rho(AKHA) < 1, rho(G) < 1)
@@ -65,8 +69,10 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def alg_bytes_per_latent_step(p, L, d):
-    return 8.0 * (p / L + 2 * d)   # read y share, write filtered x (d) and smoothed xs (d)
+def alg_bytes_per_latent_step(kind, p, L, d):
+    if kind == "obj":
+        return 8.0 * p / L             # the objective reads Y once and writes O(num_param)
+    return 8.0 * (p / L + 2 * d)       # read y share, write filtered x (d) and smoothed xs (d)
 
 
 class ClockSampler:
@@ -139,29 +145,39 @@ def check_stability(model, L):
     return worst
 
 
-def cpu_reference_rate(kernel, p, L, T, seed, budget_s, nthreads):
+def cpu_reference_rate(kind, kernel, p, L, N, T, seed, budget_s, nthreads):
     """Time the CPU implementation of the same pass (the oracle port, -O3, std::thread over sequences) on a
-    bounded sample of the workload: as many full-length sequences as fit in ~budget_s seconds."""
+    bounded sample of the workload: as many sequences (full length when the workload has many, a T-prefix when it is
+    one long sequence) as fit in ~budget_s seconds.  Returns (latent-steps/s, description, seconds)."""
     from oracle.binding import OracleMOIHGP
     from oracle.gen_golden import make_data
     params, Hmix = model_params(p, L, kernel, seed)
     o = OracleMOIHGP(DT, p, L, kernel, threading=True)
     o.update(params)
     rng = np.random.default_rng(seed)
-    base = make_data(rng, p, L, T, DT)
+    many = N >= nthreads
+    Ts = T if many else min(T, 20000 if kind == "fsn" else 2000)
+    base = make_data(rng, p, L, Ts, DT)
 
     def run(nseq):
-        Y = np.ascontiguousarray(np.broadcast_to(base, (nseq, T, p))) + 0.01 * rng.standard_normal((nseq, 1, p))
+        Y = np.ascontiguousarray(np.broadcast_to(base, (nseq, Ts, p))) + 0.01 * rng.standard_normal((nseq, 1, p))
         t0 = time.perf_counter()
-        o.filter_smoother_nll(Y, smoother_mode=1, nthreads=nthreads)
+        if kind == "fsn":
+            o.filter_smoother_nll(Y, smoother_mode=1, nthreads=nthreads)
+        else:
+            o.objective(Y)       # single thread: the reference's objective loop is sequential (moihgp_regression.h:42-50)
         return time.perf_counter() - t0
 
-    n0 = max(nthreads, 1)
+    n0 = max(nthreads, 1) if kind == "fsn" else 1
     t_cal = run(n0)
-    nseq = int(max(n0, min(4096, n0 * budget_s / max(t_cal, 1e-3))))
+    cap = 4096 if many else 64 * n0
+    nseq = int(max(n0, min(cap, n0 * budget_s / max(t_cal, 1e-3))))
     nseq = (nseq // n0) * n0
     dt_ = run(nseq)
-    return nseq * T * L / dt_, nseq, dt_
+    what = ("%d full-length sequences of the workload (T=%d)" % (nseq, Ts)) if many else \
+           ("%d copies of a T=%d prefix of the workload's single sequence (T=%d)" % (nseq, Ts, T))
+    used = nthreads if kind == "fsn" else 1
+    return nseq * Ts * L / dt_, what, dt_, used
 
 
 def main():
@@ -173,6 +189,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--nseq", type=int, default=0, help="override sequences per GPU (debug only: not the benchmark config)")
     ap.add_argument("--tlen", type=int, default=0, help="override T (debug only)")
+    ap.add_argument("--path", default="auto", choices=["auto", "scan", "chain"], help="force a kernel path (debug only)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -181,17 +198,21 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    kernel, p, L, N, T = WORKLOADS[a.workload]
+    kind, kernel, p, L, N, T = WORKLOADS[a.workload]
     if a.nseq:
         N = a.nseq
     if a.tlen:
         T = a.tlen
     d = 3 if kernel == "Matern52" else 2
-    seed = 1234 + 2   # 1234 + config index
+    seed = 1234 + {"c3": 2, "c4": 3, "c5": 4}[a.workload]   # 1234 + config index
     steps, warmup = max(a.steps, 1), max(a.warmup, 3)
+    metric = METRIC if kind == "fsn" else "latent time-steps/sec (NLL+gradient objective, fp64)"
+    ybytes = 8.0 * N * T * p
     cfg = {"workload": WORKLOAD_DESC[a.workload], "kernel": kernel, "p": p, "L": L, "d": d, "sequences_per_gpu": N, "T": T,
-           "dt": DT, "smoother": "rts", "sharding": "sequences over ranks, no data-path collective; all-reduce of the summed NLL only",
-           "l2": "inputs (%.1f GB/GPU) larger than L2, no flush needed" % (8.0 * N * T * p / 1e9)}
+           "dt": DT, "pass": "filter + RTS smoother + NLL (writes X, Xs, nll)" if kind == "fsn" else "NLL + gradient (writes loss, grad[num_param])",
+           "sharding": "sequences over ranks, no data-path collective; all-reduce of the summed NLL only" if kind == "fsn"
+                       else "independent sequences over ranks; fp64 all-reduce of [loss, grad]",
+           "l2": "inputs (%.1f GB/GPU) larger than L2 (126 MB), no flush needed" % (ybytes / 1e9)}
     cores = len(os.sched_getaffinity(0))
 
     # ------------------------------------------------------------------ reference arm (CPU)
@@ -201,20 +222,20 @@ def main():
         t0 = time.perf_counter()
         rates, samples = [], []
         for i in range(warmup + steps):
-            r, nseq, dt_ = cpu_reference_rate(kernel, p, L, T, seed, budget_s=max(2.0, 60.0 / (warmup + steps)), nthreads=cores)
+            r, what, dt_, used = cpu_reference_rate(kind, kernel, p, L, N, T, seed, budget_s=max(2.0, 60.0 / (warmup + steps)), nthreads=cores)
             if i >= warmup:
                 rates.append(r)
-                samples.append((nseq, dt_))
+                samples.append((what, dt_))
         value = float(np.mean(rates))
-        nseq = samples[-1][0]
-        sample = "%d full-length sequences (of %d per GPU) x T=%d per step, all host cores" % (nseq, N, T)
-        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": warmup,
+        sample = samples[-1][0] + " per step"
+        line = {"impl": "reference", "metric": metric, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": warmup,
                 "ms_per_step": 1e3 * float(np.mean([s[1] for s in samples])), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "note": "CPU oracle port of the reference path (oracle/moihgp_oracle.cpp, -O3, std::thread over sequences); the reference "
-                        "itself needs Eigen, absent from the image; wall %.0f s" % (time.perf_counter() - t0)}
+                "note": "CPU oracle port of the reference path (oracle/moihgp_oracle.cpp, -O3, std::thread over sequences); the reference's "
+                        "own classes have no whole-sequence filter+smoother entry point (backwardSmoother has no caller) and need Eigen, "
+                        "absent from the image; wall %.0f s" % (time.perf_counter() - t0)}
         print(json.dumps(line))
         return
 
@@ -231,19 +252,34 @@ def main():
     model = MOIHGPSequences(DT, p, L, kernel, threading=True, device=local_rank)
     params, Hmix = model_params(p, L, kernel, seed)
     model.update(params)
+    model.set_path(a.path)
     stab = check_stability(model, L)
 
     Y = make_data_device(torch, dev, Hmix, N, T, p, L, seed, rank)
-    X = torch.empty((N, T, L, d), dtype=torch.float64, device=dev)
-    Xs = torch.empty_like(X)
-    nll = torch.empty(N, dtype=torch.float64, device=dev)
-    nll_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+    if kind == "fsn":
+        X = torch.empty((N, T, L, d), dtype=torch.float64, device=dev)
+        Xs = torch.empty_like(X)
+        nll = torch.empty(N, dtype=torch.float64, device=dev)
+        out = torch.zeros(1, dtype=torch.float64, device=dev)       # summed NLL (all-reduced)
 
-    def step():
-        model.filter_smoother_nll_device(Y, smoother_mode=1, X=X, Xs=Xs, nll=nll)
-        torch.sum(nll, dim=0, keepdim=True, out=nll_sum)
-        if world > 1:
-            dist.all_reduce(nll_sum)
+        def device_pass():
+            model.filter_smoother_nll_device(Y, smoother_mode=1, X=X, Xs=Xs, nll=nll)
+
+        def step():
+            device_pass()
+            torch.sum(nll, dim=0, keepdim=True, out=out)
+            if world > 1:
+                dist.all_reduce(out)
+    else:
+        out = torch.zeros(2 + model.num_param, dtype=torch.float64, device=dev)   # [loss, pad, grad...] (all-reduced)
+
+        def device_pass():
+            model.objective_device(Y, out[0:1], out[2:])
+
+        def step():
+            device_pass()
+            if world > 1:
+                dist.all_reduce(out)
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -256,12 +292,15 @@ def main():
     sync_all()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     l0 = model.launch_count
+    model.profile(True)    # one CUDA event after every kernel of the library, on the launching stream, inside the timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
         step()
     e1.record()
     sync_all()
+    prof = model.profile_read()
+    model.profile(False)
     launches = model.launch_count - l0
     clocks = sampler.stop() if sampler else None
     ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
@@ -270,22 +309,22 @@ def main():
     ms_per_step = float(ms.item())
     units = float(N) * T * L * world
     value = units / (ms_per_step * 1e-3)
-    nll_total = float(nll_sum.item())
+    result_scalar = float(out[0].item())
 
-    # per-kernel device times (events on the launching stream, separate run of the same steps)
-    model.profile(True)
-    for _ in range(steps):
-        model.filter_smoother_nll_device(Y, smoother_mode=1, X=X, Xs=Xs, nll=nll)
-    prof = model.profile_read()
-    model.profile(False)
+    # per-kernel device times: the events recorded during the timed steps above
     kern = {k: v[0] / v[1] for k, v in prof.items()}
     pass_ms = sum(kern.values())
     peak, peak_src = measured_peak()
-    balg = alg_bytes_per_latent_step(p, L, d)
+    balg = alg_bytes_per_latent_step(kind, p, L, d)
     dom = max(kern, key=kern.get)
     # bytes each kernel must move by construction (its own compulsory traffic, per launch)
-    own = {"k_project": 8.0 * N * T * (p + L + 1), "k_scan_summaries": 8.0 * N * T * L, "k_scan_final": 8.0 * N * T * L * (1 + 2 * d),
-           "k_filter_chain": 8.0 * N * T * (p + L * d), "k_smooth_chain": 8.0 * N * T * 2 * L * d}
+    NT = float(N) * T
+    own = {"k_project": 8.0 * NT * (p + L + 1) if kind == "fsn" else 8.0 * NT * (p + 3 * L + 1),
+           "k_scan_summaries": 8.0 * NT * L, "k_scan_final": 8.0 * NT * L * (1 + 2 * d),
+           "k_filter_chain": 8.0 * NT * (p + L * d), "k_smooth_chain": 8.0 * NT * 2 * L * d,
+           "k_fsn_fused": 8.0 * NT * (p + 2 * L * d), "k_fwd_summaries": 8.0 * NT * p,
+           "k_obj_scan_summaries": 8.0 * NT * L, "k_obj_scan_final": 8.0 * NT * 4 * L, "k_gradU": 8.0 * NT * (p + L),
+           "k_obj_fused": 8.0 * NT * p}
     roof = {"bound": "hbm", "kernel": "fused pass = " + " + ".join(kern.keys()),
             "achieved": balg * N * T * L / (pass_ms * 1e-3) / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
             "traffic": None, "algorithmic_bytes_per_latent_step": balg, "pass_ms": pass_ms,
@@ -295,7 +334,7 @@ def main():
     roof["frac"] = roof["achieved"] / peak
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            roof["traffic"] = json.load(f).get("fused_pass_dram_bytes_per_step")
+            roof["traffic"] = json.load(f).get(a.workload, {}).get("fused_pass_dram_bytes_per_step")
     except Exception:
         pass
 
@@ -303,23 +342,37 @@ def main():
     e2e = None
     if not a.no_e2e:
         import psutil
-        need = 8.0 * N * T * (p + 2 * L * d) * 1.05
-        avail = psutil.virtual_memory().available / max(world, 1)
-        Ne = N if need < 0.7 * avail else max(1, int(N * 0.7 * avail / need))
-        del X, Xs
-        torch.cuda.empty_cache()
-        Yh = torch.empty((Ne, T, p), dtype=torch.float64, pin_memory=True)
-        Yh.copy_(Y[:Ne])
-        Xh = torch.empty((Ne, T, L, d), dtype=torch.float64, pin_memory=True)
-        Xsh = torch.empty((Ne, T, L, d), dtype=torch.float64, pin_memory=True)
-        nllh = torch.empty(Ne, dtype=torch.float64, pin_memory=True)
         lib, h = model._lib, model._h
         model.set_stream(None)
+        if kind == "fsn":
+            need = 8.0 * N * T * (p + 2 * L * d) * 1.05
+            avail = psutil.virtual_memory().available / max(world, 1)
+            Ne = N if need < 0.7 * avail else max(1, int(N * 0.7 * avail / need))
+            del X, Xs
+            torch.cuda.empty_cache()
+            Yh = torch.empty((Ne, T, p), dtype=torch.float64, pin_memory=True)
+            Yh.copy_(Y[:Ne])
+            Xh = torch.empty((Ne, T, L, d), dtype=torch.float64, pin_memory=True)
+            Xsh = torch.empty((Ne, T, L, d), dtype=torch.float64, pin_memory=True)
+            nllh = torch.empty(Ne, dtype=torch.float64, pin_memory=True)
 
-        def e2e_step():
-            rc = lib.moihgp_cuda_filter_smoother_nll(h, Yh.data_ptr(), Ne, T, None, 1, Xh.data_ptr(), Xsh.data_ptr(), None, nllh.data_ptr(), None)
-            if rc != 0:
-                raise SystemExit("e2e call failed: " + lib.moihgp_cuda_last_error(h).decode())
+            def e2e_step():
+                rc = lib.moihgp_cuda_filter_smoother_nll(h, Yh.data_ptr(), Ne, T, None, 1, Xh.data_ptr(), Xsh.data_ptr(), None, nllh.data_ptr(), None)
+                if rc != 0:
+                    raise SystemExit("e2e call failed: " + lib.moihgp_cuda_last_error(h).decode())
+            api, h2d, d2h = "moihgp_cuda_filter_smoother_nll (host buffers, pinned)", int(8 * Ne * T * p), int(8 * Ne * (2 * T * L * d + 1))
+        else:
+            Ne = N
+            Yh = torch.empty((Ne, T, p), dtype=torch.float64, pin_memory=True)
+            Yh.copy_(Y)
+            lossh = torch.zeros(1, dtype=torch.float64, pin_memory=True)
+            gradh = torch.zeros(model.num_param, dtype=torch.float64, pin_memory=True)
+
+            def e2e_step():
+                rc = lib.moihgp_cuda_objective(h, Yh.data_ptr(), Ne, T, None, None, lossh.data_ptr(), gradh.data_ptr(), None, None)
+                if rc != 0:
+                    raise SystemExit("e2e call failed: " + lib.moihgp_cuda_last_error(h).decode())
+            api, h2d, d2h = "moihgp_cuda_objective (host buffers, pinned)", int(8 * Ne * T * p), int(8 * (1 + model.num_param))
 
         ke = max(2, min(steps, 3))
         e2e_step()   # warm-up (allocates the call's device buffers)
@@ -331,23 +384,29 @@ def main():
         te = torch.tensor([(time.perf_counter() - t0) / ke], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": float(Ne) * T * L * world / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(8 * Ne * T * p),
-               "d2h_bytes_per_step": int(8 * Ne * (2 * T * L * d + 1)), "ms_per_step": 1e3 * float(te.item()), "sequences_per_gpu": Ne,
-               "api": "moihgp_cuda_filter_smoother_nll (host buffers, pinned)", "steps": ke,
-               "nll_check": abs(float(nllh.sum().item()) - float(nll[:Ne].sum().item())) <= 1e-9 * abs(float(nll[:Ne].sum().item()))}
+        if kind == "fsn":
+            ref_val, got = float(nll[:Ne].sum().item()), float(nllh.sum().item())
+        else:
+            model.objective_device(Y, out[0:1], out[2:])      # this rank's own loss (no all-reduce)
+            torch.cuda.synchronize(dev)
+            ref_val, got = float(out[0].item()), float(lossh.item())
+        e2e = {"value": float(Ne) * T * L * world / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * float(te.item()), "sequences_per_gpu": Ne,
+               "api": api, "steps": ke, "result_check": abs(got - ref_val) <= 1e-9 * abs(ref_val)}
 
     # ------------------------------------------------------------------ CPU baseline beside it (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
-        r, nseq, dt_ = cpu_reference_rate(kernel, p, L, T, seed, budget_s=a.cpu_seconds, nthreads=cores)
-        cpu = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "%d full-length sequences of the workload (T=%d), %.1f s, oracle/moihgp_oracle.cpp -O3, std::thread over sequences" % (nseq, T, dt_)}
+        r, what, dt_, used = cpu_reference_rate(kind, kernel, p, L, N, T, seed, budget_s=a.cpu_seconds, nthreads=cores)
+        cpu = {"value": r, "unit": UNIT, "cores": used, "kind": "port",
+               "sample": "%s, %.1f s, oracle/moihgp_oracle.cpp -O3%s" % (what, dt_, ", std::thread over sequences" if used > 1 else ", one thread")}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
+        line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-                "hbm_GBps_alg": balg * units / world / (ms_per_step * 1e-3) / 1e9, "nll_total": nll_total, "stability": stab}
+                "hbm_GBps_alg": balg * units / world / (ms_per_step * 1e-3) / 1e9,
+                ("nll_total" if kind == "fsn" else "loss_total"): result_scalar, "stability": stab}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
