@@ -88,6 +88,9 @@ const char* moihgp_cuda_profile_read(moihgp_handle* h);
  * (sequence, latent) chains and the shape is instantiated, else the time-parallel chunked scan), 1 = chunked scan,
  * 2 = many-chains (fails if unavailable).  Results agree to rounding; used by the parity tests to cover both. */
 int moihgp_cuda_set_path(moihgp_handle* h, int path);
+/* tuning knob of the many-chains kernels: sequences handled per warp (a power of two <= 32 / num_latent);
+ * 0 = automatic (fewer sequences per warp when the batch alone does not fill the GPU with warps) */
+int moihgp_cuda_set_chain_seqs_per_warp(moihgp_handle* h, int n);
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 long long moihgp_cuda_launch_count(moihgp_handle* h);
 

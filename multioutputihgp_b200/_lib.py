@@ -72,6 +72,8 @@ def load():
     lib.moihgp_cuda_last_error.argtypes = [vp]
     lib.moihgp_cuda_set_path.restype = ctypes.c_int
     lib.moihgp_cuda_set_path.argtypes = [vp, ctypes.c_int]
+    lib.moihgp_cuda_set_chain_seqs_per_warp.restype = ctypes.c_int
+    lib.moihgp_cuda_set_chain_seqs_per_warp.argtypes = [vp, ctypes.c_int]
     lib.moihgp_cuda_profile.restype = ctypes.c_int
     lib.moihgp_cuda_profile.argtypes = [vp, ctypes.c_int]
     lib.moihgp_cuda_profile_read.restype = ctypes.c_char_p
@@ -111,7 +113,7 @@ def load():
 # every symbol include/moihgp_b200.h declares (checked by tests/test_abi.py)
 LEGACY_NAMES = ["new", "del", "step1", "step2", "step3", "step4", "update", "lik1", "lik2", "get_params", "igp_dim",
                 "num_param", "num_igp_param"]
-CUDA_NAMES = ["create", "destroy", "set_stream", "sync", "last_error", "launch_count", "profile", "profile_read", "set_path", "igp_dim", "num_param",
+CUDA_NAMES = ["create", "destroy", "set_stream", "sync", "last_error", "launch_count", "profile", "profile_read", "set_path", "set_chain_seqs_per_warp", "igp_dim", "num_param",
               "num_igp_param", "update", "get_params", "get_U", "latent_consts", "latent_iters", "smoother_consts",
               "filter_smoother_nll", "filter_smoother_nll_dev", "objective", "objective_dev"]
 ALL_SYMBOLS = ["gp%s_%s" % (xx, n) for xx in ("32", "52") for n in LEGACY_NAMES] + ["moihgp_cuda_" + n for n in CUDA_NAMES]

@@ -106,6 +106,10 @@ class MOIHGPSequences(object):
         """0 auto, 1 chunked scan, 2 many-chains (see moihgp_cuda_set_path)."""
         self._check(self._lib.moihgp_cuda_set_path(self._h, {"auto": 0, "scan": 1, "chain": 2}.get(path, path)))
 
+    def set_chain_seqs_per_warp(self, n):
+        """Tuning knob of the many-chains kernels (0 = automatic); see moihgp_cuda_set_chain_seqs_per_warp."""
+        self._check(self._lib.moihgp_cuda_set_chain_seqs_per_warp(self._h, int(n)))
+
     def profile(self, enable):
         self._check(self._lib.moihgp_cuda_profile(self._h, int(enable)))
 

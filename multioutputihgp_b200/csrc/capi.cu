@@ -48,6 +48,7 @@ struct moihgp_handle {
     Marker marker;                            // per-kernel events, only while profiling is on
     bool profiling = false;
     int path = 0;                             // 0 auto, 1 chunked scan, 2 many-chains
+    int chain_spw = 0;                        // many-chains kernels: sequences per warp (0 = automatic)
     std::string prof_text;
     std::string err;
 };
@@ -311,6 +312,12 @@ int moihgp_cuda_set_path(moihgp_handle* h, int path) {
     return 0;
 }
 
+int moihgp_cuda_set_chain_seqs_per_warp(moihgp_handle* h, int n) {
+    if (!h || n < 0 || n > 32) return -2;
+    h->chain_spw = n;
+    return 0;
+}
+
 int moihgp_cuda_profile(moihgp_handle* h, int enable) {
     if (!h) return -2;
     cudaStreamSynchronize(h->stream);
@@ -441,7 +448,7 @@ int moihgp_cuda_filter_smoother_nll_dev(moihgp_handle* h, const double* Y, size_
         ChainArgs c;
         c.Y = Y; c.U_host = h->U.data(); c.S_host = h->S.data(); c.consts = h->d_consts; c.sigma = h->sigma;
         c.nll_const = (double)T * (0.5 * std::log(Ssum) + 0.5 * m_n * std::log(h->sigma) + 0.5 * logs);
-        c.N = (long long)N; c.T = (long long)T; c.mode = mode < 0 ? 1 : mode; c.x0 = x0; c.X = X; c.Xs = Xs; c.nll = nll; c.xT = xT; c.mk = mk;
+        c.N = (long long)N; c.T = (long long)T; c.mode = mode < 0 ? 1 : mode; c.x0 = x0; c.X = X; c.Xs = Xs; c.nll = nll; c.xT = xT; c.mk = mk; c.nan_flag = nanf; c.seqs_per_warp = h->chain_spw;
         CK(launch_chain(h->p, L, D, c, h->stream));
         h->launches += Xs ? 2 : 1;
     } else {

@@ -2,24 +2,30 @@
 //
 // When there are tens of thousands of independent (sequence, latent) recurrences (BASELINE config 3:
 // 4096 x 8), time-parallel scanning only adds redundant flops; here every recurrence is evaluated
-// exactly once, literally as the reference's loop does, and the kernels are pure HBM streams.
+// exactly once, as the reference's loop does, and the kernels are HBM streams.
 //
 // Replaces the same reference code as project.cu + scan.cu:
 //   moihgp.h:159-182, :499-501   projection and residual norm            (phase 1 of k_filter_chain)
 //   ihgp.h:81-93, :204-209       IHGP::step / IHGP::negLogLikelihood     (phase 2 of k_filter_chain)
-//   moihgp.h:614-688             MOIHGP::negLogLikelihood(x, y)          (in-warp reduction, k_filter_chain)
+//   moihgp.h:614-688             MOIHGP::negLogLikelihood(x, y)          (per-sequence reduction, k_filter_chain)
 //   ihgp.h:108-113               IHGP::backwardSmoother recursion        (k_smooth_chain; literal and RTS forms)
 //
-// k_filter_chain<P, L, D>: one WARP owns NS = 32 / L sequences for all T steps, in rounds of L steps.
-//   load   : the [NS][L rows][P] tile of Y (NS contiguous runs of L*P*8 bytes) is staged by cp.async into a
-//            ring of shared-memory stages; the 16-byte chunks of each row are XOR-swizzled with the row index so
-//            that "one row per lane" reads are bank-conflict free.
-//   phase 1: lane (s, j) projects row j of sequence s onto all L latents (U^T y, with U in the constant bank),
-//            forms the residual norm || y - U U^T y ||, and drops u = S^-1/2 U^T y into a small exchange tile.
+// k_filter_chain<P, L, D>: one WARP owns NS = 32 / L sequences for all T steps, in rounds of L steps
+// (32 rows of Y per round).
+//   load   : the [32 rows][P] tile of Y (NS contiguous runs of L*P*8 bytes) is staged by cp.async into a ring
+//            of shared-memory stages; the 16-byte chunks of each row are XOR-swizzled with the row index so
+//            that both the tensor-core fragment loads and "one row per lane" reads are bank-conflict free.
+//   phase 1: W = Ytile[32 x P] * U[P x L] on the FP64 tensor pipe (mma.sync m8n8k4: 4 row blocks x P/4 k blocks);
+//            U lives in registers as B fragments.  The residual norm || y - U U' y || comes from
+//            ||y||^2 - ||U'y||^2 (U has orthonormal columns: polar factor, moihgp.h:431-447); rows where that
+//            difference cancels (below 1e-4 ||y||^2, or NaN) take the explicit (I - U U') y evaluation instead.
+//            u = S^-1/2 U' y goes to a small exchange tile.
 //   phase 2: lane (s, l) picks latent l of the L steps out of the exchange tile and runs the recurrence
 //            x+ = AKHA x + K u, accumulating the innovation likelihood; states go to a staging tile.
-//   store  : the [NS][L rows][L*D] staging tile leaves as NS contiguous runs with 16-byte stores.
+//   store  : the staging tile leaves as NS contiguous runs of L*L*D doubles with 16-byte stores.
 // k_smooth_chain<L, D, MODE>: the same lane mapping streaming backwards over the stored X.
+// Full rounds of full sequence groups run a predicate-free fast path; the ragged last round / last CTA
+// take a clamped-and-predicated path.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <cmath>
@@ -34,7 +40,7 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int STAGES = 4;
 
 template <int P, int L>
-struct ProjConsts {          // passed by value: lives in the constant bank, uniform operands of the phase-1 FMAs
+struct ProjConsts {          // passed by value: lives in the constant bank
     double U[P][L];
     double rs[L];            // S^-1/2
 };
@@ -46,40 +52,128 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-template <int P, int L, int D>
-struct FilterSmem {
-    static constexpr int NS = 32 / L;
+// D(8x8) += A(8x4) * B(4x8), fp64 tensor pipe.  Fragments: A[lane/4][lane%4], B[lane%4][lane/4],
+// C[lane/4][2*(lane%4) + {0,1}].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// one latent's state in the staging tile: a single 16-byte access when D = 2
+template <int D> __device__ __forceinline__ void store_state(double* p, const double (&v)[D]) {
+    if (D == 2) *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+    else {
+#pragma unroll
+        for (int a = 0; a < D; ++a) p[a] = v[a];
+    }
+}
+template <int D> __device__ __forceinline__ void load_state(const double* p, double (&v)[D]) {
+    if (D == 2) { const double2 t = *reinterpret_cast<const double2*>(p); v[0] = t.x; v[1] = t.y; }
+    else {
+#pragma unroll
+        for (int a = 0; a < D; ++a) v[a] = p[a];
+    }
+}
+
+// v[rb] summed over the 4 lanes of a quad; lane q of the quad receives the total of v[q].
+__device__ __forceinline__ double quad_transpose_reduce(const double (&v)[4], int lane) {
+    const bool b0 = lane & 1, b1 = lane & 2;
+    const double k0 = b0 ? v[1] : v[0], s0 = b0 ? v[0] : v[1];
+    const double k1 = b0 ? v[3] : v[2], s1 = b0 ? v[2] : v[3];
+    const double a0 = k0 + __shfl_xor_sync(FULL, s0, 1);
+    const double a1 = k1 + __shfl_xor_sync(FULL, s1, 1);
+    const double k = b1 ? a1 : a0, s = b1 ? a0 : a1;
+    return k + __shfl_xor_sync(FULL, s, 2);
+}
+
+// Pitch (doubles) of one sequence's [L steps][L*D] staging tile such that the 8-byte state stores / loads of a
+// half-warp (lanes (s, l) -> s * pitch + l * D + a) fall into 16 distinct 8-byte bank pairs; even, so that the
+// 16-byte copy-out stays aligned.
+constexpr int staging_pitch(int L, int D) {
+    const int run = L * L * D;
+    if (D % 2 == 0) return run + 4;            // 16-byte state stores: any pitch that staggers the sequences
+    for (int pad = 0; pad < 16; pad += 2) {
+        bool ok = true;
+        for (int a = 0; a < 16 && ok; ++a)
+            for (int b = a + 1; b < 16 && ok; ++b) {
+                const int ua = (a / L) * (run + pad) + (a % L) * D, ub = (b / L) * (run + pad) + (b % L) * D;
+                if ((ua - ub) % 16 == 0) ok = false;
+            }
+        if (ok) return run + pad;
+    }
+    return run + 4;
+}
+
+template <int P, int L, int D, int NS_>
+struct FilterCfg {
+    static constexpr int NS = NS_;                     // sequences per warp (<= 32 / L)
+    static constexpr int R = NS * L;                   // rows of Y per round (8, 16 or 32)
+    static constexpr int RB = R / 8;                   // 8-row blocks of the tensor-core projection
     static constexpr int ROWB = P * 8;                 // bytes per row of Y
-    static constexpr int CH = ROWB / 16;               // 16-byte chunks per row
-    static constexpr int TILE = NS * L * ROWB;         // bytes per stage
-    static constexpr int XROW = L + 2;                 // exchange tile row pitch (doubles): conflict-free STS.128
-    static constexpr int XSEQ = L * XROW + 8;          // per-sequence pitch (doubles)
-    static constexpr int OSEQ = L * L * D + 4;         // staging tile per-sequence pitch (doubles), 16B-aligned
-    static constexpr int BYTES = STAGES * TILE + NS * XSEQ * 8 + NS * OSEQ * 8;
+    static constexpr int CH = P / 2;                   // 16-byte chunks per row
+    static constexpr int TILE = R * ROWB;              // bytes per stage
+    static constexpr int KB = P / 4;                   // k blocks of the tensor-core projection
+    static constexpr int LP = L < 8 ? 8 : L;           // latents padded to the n = 8 of m8n8k4
+    static constexpr int NB = LP / 8;
+    static constexpr int XROW = LP;                    // exchange tile row pitch (doubles): 16-byte fragment stores of two
+                                                       // adjacent rows cover one 128-byte line
+    static constexpr int XSEQ = L * XROW + L;          // per-sequence pitch (doubles): staggers the sequences of a half-warp
+    static constexpr int LD = L * D;                   // doubles per time step of X
+    static constexpr int RUN = L * LD;                 // doubles per sequence-round of X
+    static constexpr int OSEQ = staging_pitch(L, D);   // staging tile per-sequence pitch (doubles), 16B-aligned
+    static constexpr int PS = RUN / 2;                 // 16-byte pieces per sequence-round of X
+    static constexpr int RPP = 32 / CH > 0 ? 32 / CH : 1;   // rows of Y covered by one warp-wide cp.async pass
+    static constexpr int PASSES = R / RPP;             // cp.async passes per round
+    static constexpr int XCH = NS * XSEQ < 32 ? 32 : NS * XSEQ;   // exchange tile (doubles); also holds 32 partial sums at the end
+    static constexpr int BYTES = STAGES * TILE + XCH * 8 + NS * OSEQ * 8;
+    // XOR swizzle of the 16-byte chunk index within a row.  A tensor-core A-fragment load is an 8-byte access of
+    // lanes (row g, columns 4 kb + q): a half-warp covers 4 consecutive rows x 2 adjacent chunks, which this
+    // swizzle spreads over 8 distinct 16-byte bank groups.
+    __host__ __device__ static constexpr int swz(int row) { return CH >= 8 ? 2 * (row & 3) : (CH == 4 ? 2 * ((row >> 1) & 1) : 0); }
 };
 
-// grid: ceil(N / NS) CTAs of ONE warp.
-template <int P, int L, int D>
-__global__ void __launch_bounds__(32) k_filter_chain(const double* __restrict__ Y, const __grid_constant__ ProjConsts<P, L> pc,
+// grid: ceil(N / NS) CTAs of ONE warp.  NS < 32 / L leaves lanes idle in phase 2 but puts more warps in flight
+// (the recurrence is latency-bound: see DESIGN.md).
+template <int P, int L, int D, int NS_>
+__global__ void __launch_bounds__(32, 14) k_filter_chain(const double* __restrict__ Y, const __grid_constant__ ProjConsts<P, L> pc,
                                                     const LatentConsts* __restrict__ consts, double sigma, double nll_const,
                                                     long long N, long long T, const double* __restrict__ x0,
-                                                    double* __restrict__ X, double* __restrict__ nll, double* __restrict__ xT) {
-    using SM = FilterSmem<P, L, D>;
-    constexpr int NS = SM::NS, CH = SM::CH;
-    static_assert(P % 2 == 0 && CH >= 1 && (CH & (CH - 1)) == 0, "P*8 bytes must be a power-of-two number of 16B chunks");
-    static_assert(32 % L == 0, "L must divide the warp");
+                                                    double* __restrict__ X, double* __restrict__ nll, double* __restrict__ xT,
+                                                    int* __restrict__ nan_flag) {
+    using C = FilterCfg<P, L, D, NS_>;
+    constexpr int NS = C::NS, CH = C::CH, KB = C::KB, NB = C::NB, LD = C::LD, R = C::R, RB = C::RB;
+    static_assert(P % 4 == 0 && (CH & (CH - 1)) == 0 && CH <= 32, "P must be 4, 8, 16, 32 or 64");
+    static_assert(32 % L == 0 && L <= 32, "L must divide the warp");
+    static_assert(R % 8 == 0 && R <= 32 && R % C::RPP == 0, "rows per round must be 8, 16 or 32 and tile the cp.async passes");
+    static_assert(C::RPP <= L ? (L % C::RPP == 0) : (C::RPP % L == 0), "row passes must tile the sequences");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned char* ytile = smem_raw;                                           // [STAGES][NS][L][P] swizzled
-    double* xch = reinterpret_cast<double*>(smem_raw + STAGES * SM::TILE);     // [NS][L][XROW]
-    double* ost = xch + NS * SM::XSEQ;                                         // [NS][L][L*D]
+    unsigned char* ytile = smem_raw;                                           // [STAGES][32 rows][P] swizzled
+    double* xch = reinterpret_cast<double*>(smem_raw + STAGES * C::TILE);      // [NS][L][XROW]
+    double* ost = xch + C::XCH;                                                // [NS][L][L*D]
     const int lane = threadIdx.x;
-    const int s = lane / L, j = lane % L;                                      // phase 1: (sequence, row); phase 2: (sequence, latent)
+    const int s = lane / L, j = lane % L;                                      // phase 2: (sequence, latent)
     const long long n0 = (long long)blockIdx.x * NS;
+    const int nvalid = (int)(N - n0 < NS ? N - n0 : NS);                       // sequences of this warp that exist
     const long long n = n0 + s;
-    const bool seq_ok = n < N;
+    const bool active = lane < R;                                              // phase 2 lanes that own a chain
+    const bool seq_ok = s < nvalid;
     const long long rounds = (T + L - 1) / L;
 
-    // ---- per-lane latent constants (phase 2) ---------------------------------------------------
+    // ---- per-lane constants -------------------------------------------------------------------------
+    // phase 1: B fragments of U and the S^-1/2 of this lane's two output columns per n block
+    const int g4 = lane >> 2, q4 = lane & 3;
+    double bf[KB][NB];
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) bf[kb][nb] = (8 * nb + g4 < L) ? pc.U[4 * kb + q4][(8 * nb + g4) % L] : 0.0;
+    // A fragment byte offsets within a row block (rows 8 rb + g4): element (g4, 4 kb + q4)
+    int offA[KB];
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb) offA[kb] = g4 * C::ROWB + (((2 * kb + (q4 >> 1)) ^ C::swz(g4)) << 4) + ((q4 & 1) << 3);
+    // the row this lane owns after the quad transpose-reduce: row block q4, row g4 of the block
+    const int own_row = 8 * q4 + g4, own_s = own_row / L, own_i = own_row % L;
+    // phase 2: the latent's filter constants
+    const bool owner = q4 < RB;
     const LatentConsts* lc = consts + j;
     double M[D * D], K[D], HA[D];
 #pragma unroll
@@ -91,22 +185,39 @@ __global__ void __launch_bounds__(32) k_filter_chain(const double* __restrict__ 
     }
     double x[D];
 #pragma unroll
-    for (int a = 0; a < D; ++a) x[a] = (x0 && seq_ok) ? x0[((size_t)n * L + j) * D + a] : 0.0;
+    for (int a = 0; a < D; ++a) x[a] = (x0 && active && seq_ok) ? x0[((size_t)n * L + j) * D + a] : 0.0;
+    const double rs_j = pc.rs[j];                                              // S_j^-1/2  (moihgp.h:181)
     double rho_acc = 0.0, vsq_acc = 0.0;
+    bool saw_nan = false;
 
-    // ---- cp.async producer: tile of round r into stage r % STAGES --------------------------------
-    constexpr int PIECES = NS * L * CH;            // 16-byte pieces per tile
+    // ---- cp.async producer: tile of round r into stage r % STAGES ----------------------------------
+    // pass k of a round covers rows lr + RPP * k (lr = lane / CH), chunk lc16 = lane % CH of each
+    const int lr = lane / CH, lc16 = lane % CH;
+    const size_t seq_stride = (size_t)T * C::ROWB;                             // bytes between sequences of Y
+    const unsigned char* Ybytes = reinterpret_cast<const unsigned char*>(Y) + (size_t)n0 * seq_stride;
+    const size_t lane_src = (size_t)(lr / L) * seq_stride + (size_t)(lr % L) * C::ROWB + lc16 * 16;
     auto issue = [&](long long r) {
         if (r < rounds) {
-            unsigned char* st = ytile + (size_t)(r % STAGES) * SM::TILE;
+            unsigned char* st = ytile + (size_t)(r % STAGES) * C::TILE;
             const long long t0 = r * L;
+            if (nvalid == NS && t0 + L <= T) {
+                const unsigned char* src = Ybytes + (size_t)t0 * C::ROWB + lane_src;
 #pragma unroll
-            for (int k = 0; k < PIECES / 32; ++k) {
-                const int q = lane + 32 * k;
-                const int qs = q / (L * CH), qj = (q / CH) % L, qc = q % CH;
-                if (n0 + qs < N && t0 + qj < T)
-                    cp_async16(st + (size_t)(qs * L + qj) * SM::ROWB + ((qc ^ (qj % CH)) * 16),
-                               reinterpret_cast<const unsigned char*>(Y) + (((size_t)(n0 + qs) * T + t0 + qj) * P) * 8 + qc * 16);
+                for (int k = 0; k < C::PASSES; ++k) {
+                    const int row = lr + C::RPP * k;
+                    cp_async16(st + row * C::ROWB + ((lc16 ^ C::swz(row)) << 4),
+                               src + (size_t)((C::RPP * k) / L) * seq_stride + (size_t)((C::RPP * k) % L) * C::ROWB);
+                }
+            } else {
+                // ragged: rows beyond T / sequences beyond N re-read the last valid row / sequence (never used)
+                const int rows = (int)(T - t0 < L ? T - t0 : L);
+#pragma unroll
+                for (int k = 0; k < C::PASSES; ++k) {
+                    const int row = lr + C::RPP * k;
+                    const int rs_ = min(row / L, nvalid - 1), ri = min(row % L, rows - 1);
+                    cp_async16(st + row * C::ROWB + ((lc16 ^ C::swz(row)) << 4),
+                               Ybytes + (size_t)rs_ * seq_stride + (size_t)(t0 + ri) * C::ROWB + lc16 * 16);
+                }
             }
         }
         cp_async_commit();
@@ -114,55 +225,97 @@ __global__ void __launch_bounds__(32) k_filter_chain(const double* __restrict__ 
 #pragma unroll
     for (int r = 0; r < STAGES - 1; ++r) issue(r);
 
+    double* const xw = xch + (g4 / L) * C::XSEQ + (g4 % L) * C::XROW + 2 * q4;   // + row-block offset below
+    const double* const xc = xch + s * C::XSEQ + j;
+    double* const oc = ost + s * C::OSEQ + j * D;
+    double* const Xcta = X ? X + (size_t)n0 * T * LD : nullptr;
+
     for (long long r = 0; r < rounds; ++r) {
         issue(r + STAGES - 1);
         cp_async_wait<STAGES - 1>();
         __syncwarp();
         const long long t0 = r * L;
-        // ---- phase 1: project row (s, j) -----------------------------------------------------------
+        const bool fast = nvalid == NS && t0 + L <= T;
+        const unsigned char* tile = ytile + (size_t)(r % STAGES) * C::TILE;
+        // ---- phase 1: W = Ytile * U on the tensor pipe; residual norm from the two squared norms ------
         {
-            const unsigned char* row = ytile + (size_t)(r % STAGES) * SM::TILE + (size_t)(s * L + j) * SM::ROWB;
-            double y[P];
+            double sy[4] = {0.0, 0.0, 0.0, 0.0}, sw[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-            for (int c = 0; c < CH; ++c) {
-                const double2 v = *reinterpret_cast<const double2*>(row + ((c ^ (j % CH)) * 16));
-                y[2 * c] = v.x;
-                y[2 * c + 1] = v.y;
+            for (int rb = 0; rb < RB; ++rb) {
+                const unsigned char* blk = tile + rb * 8 * C::ROWB;
+                double a[KB], c[NB][2];
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) a[kb] = *reinterpret_cast<const double*>(blk + offA[kb]);
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) { c[nb][0] = 0.0; c[nb][1] = 0.0; }
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) dmma884(c[nb][0], c[nb][1], a[kb], bf[kb][nb]);   // U' y   moihgp.h:181
+                double ay = a[0] * a[0];
+#pragma unroll
+                for (int kb = 1; kb < KB; ++kb) ay = fma(a[kb], a[kb], ay);
+                double aw = c[0][0] * c[0][0];
+                aw = fma(c[0][1], c[0][1], aw);
+#pragma unroll
+                for (int nb = 1; nb < NB; ++nb) { aw = fma(c[nb][0], c[nb][0], aw); aw = fma(c[nb][1], c[nb][1], aw); }
+                sy[rb] = ay;
+                sw[rb] = aw;
+                // w = U' y of row 8 rb + g4 into the exchange tile
+                double* xr = xw + ((8 * rb) / L) * C::XSEQ + ((8 * rb) % L) * C::XROW;
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) *reinterpret_cast<double2*>(xr + 8 * nb) = make_double2(c[nb][0], c[nb][1]);
             }
-            const bool row_ok = seq_ok && (t0 + j < T);
-            if (!row_ok) {
+            const double ysq = quad_transpose_reduce(sy, lane);
+            const double wsq = quad_transpose_reduce(sw, lane);
+            double q = ysq - wsq;                                                 // || (I - U U') y ||^2
+            const bool bad = owner && !(q >= 1e-4 * ysq);                         // cancellation (or NaN): evaluate explicitly
+            if (__any_sync(FULL, bad)) {
+                // explicit  || y - U (U' y) ||^2  of row `lane` (moihgp.h:651), w read back from the exchange tile
+                __syncwarp();
+                const int rl = lane < R ? lane : R - 1;
+                const unsigned char* row = tile + rl * C::ROWB;
+                const double* Up = &pc.U[0][0];
+                asm volatile("" : "+l"(Up));      // opaque: keeps the 128 loop-invariant U loads of this cold path out of registers
+                const double* wr = xch + (rl / L) * C::XSEQ + (rl % L) * C::XROW;
+                double w[L];
 #pragma unroll
-                for (int c = 0; c < P; ++c) y[c] = 0.0;
+                for (int l = 0; l < L; l += 2) {
+                    const double2 t = *reinterpret_cast<const double2*>(wr + l);
+                    w[l] = t.x;
+                    w[l + 1] = t.y;
+                }
+                double qe = 0.0;
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    const double2 y2 = *reinterpret_cast<const double2*>(row + ((c ^ C::swz(rl)) << 4));
+                    double e0 = y2.x, e1 = y2.y;
+#pragma unroll
+                    for (int l = 0; l < L; ++l) { e0 = fma(-Up[(2 * c) * L + l], w[l], e0); e1 = fma(-Up[(2 * c + 1) * L + l], w[l], e1); }
+                    qe = fma(e0, e0, qe);
+                    qe = fma(e1, e1, qe);
+                }
+                const double mine = __shfl_sync(FULL, qe, own_row & 31);
+                if (bad) q = mine;
             }
-            double w[L];
-#pragma unroll
-            for (int l = 0; l < L; ++l) {
-                double acc = pc.U[0][l] * y[0];
-#pragma unroll
-                for (int c = 1; c < P; ++c) acc = fma(pc.U[c][l], y[c], acc);     // U' y            moihgp.h:181
-                w[l] = acc;
+            const bool own_ok = owner && (fast || (own_s < nvalid && t0 + own_i < T));
+            if (own_ok) {
+                saw_nan = saw_nan || (q != q);
+                rho_acc += sqrt(q);                                               // norm, not squared (Q9)
             }
-            double q = 0.0;
-#pragma unroll
-            for (int c = 0; c < P; ++c) {
-                double e = y[c];
-#pragma unroll
-                for (int l = 0; l < L; ++l) e = fma(-pc.U[c][l], w[l], e);        // (I - U U') y    moihgp.h:651
-                q = fma(e, e, q);
-            }
-            rho_acc += sqrt(q);                                                   // norm, not squared (Q9)
-            double* xr = xch + s * SM::XSEQ + j * SM::XROW;
-#pragma unroll
-            for (int l = 0; l < L; l += 2) *reinterpret_cast<double2*>(xr + l) = make_double2(w[l] * pc.rs[l], w[l + 1] * pc.rs[l + 1]);
         }
         __syncwarp();
         // ---- phase 2: latent (s, j) over the L steps of the round --------------------------------------
-        {
-            const double* xc = xch + s * SM::XSEQ + j;
-            double* oc = ost + s * SM::OSEQ + j * D;
+        double uu[L];
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < L; ++i) uu[i] = xc[i * C::XROW] * rs_j;
+        }
+        if (!active) {
+        } else if (fast) {
 #pragma unroll
             for (int i = 0; i < L; ++i) {
-                const double u = xc[i * SM::XROW];
+                const double u = uu[i];
                 double hax = HA[0] * x[0];
 #pragma unroll
                 for (int a = 1; a < D; ++a) hax = fma(HA[a], x[a], hax);
@@ -175,28 +328,67 @@ __global__ void __launch_bounds__(32) k_filter_chain(const double* __restrict__ 
                     for (int b = 1; b < D; ++b) acc = fma(M[a * D + b], x[b], acc);
                     xn[a] = fma(K[a], u, acc);                                    // ihgp.h:90
                 }
-                if (t0 + i < T) {
+                vsq_acc = fma(v, v, vsq_acc);
+#pragma unroll
+                for (int a = 0; a < D; ++a) x[a] = xn[a];
+                store_state<D>(oc + i * LD, xn);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < L; ++i) {
+                const double u = uu[i];
+                double hax = HA[0] * x[0];
+#pragma unroll
+                for (int a = 1; a < D; ++a) hax = fma(HA[a], x[a], hax);
+                const double v = u - hax;
+                double xn[D];
+#pragma unroll
+                for (int a = 0; a < D; ++a) {
+                    double acc = M[a * D] * x[0];
+#pragma unroll
+                    for (int b = 1; b < D; ++b) acc = fma(M[a * D + b], x[b], acc);
+                    xn[a] = fma(K[a], u, acc);
+                }
+                if (seq_ok && t0 + i < T) {
                     vsq_acc = fma(v, v, vsq_acc);
 #pragma unroll
                     for (int a = 0; a < D; ++a) x[a] = xn[a];
                 }
-#pragma unroll
-                for (int a = 0; a < D; ++a) oc[i * (L * D) + a] = x[a];
+                store_state<D>(oc + i * LD, x);
             }
         }
         __syncwarp();
         // ---- store: NS contiguous runs of L rows ------------------------------------------------------
-        if (X) {
-            constexpr int RUN16 = L * L * D / 2;                                  // 16-byte pieces per sequence-round
-            const long long rows_left = T - t0;
-            const int valid16 = (int)(rows_left >= L ? RUN16 : rows_left * (L * D / 2));
+        if (Xcta) {
+            double* Xr = Xcta + (size_t)t0 * LD;
+            if (fast) {
+                constexpr int NPASS = (NS * C::PS + 31) / 32;
+                double2 v[NPASS];
 #pragma unroll
-            for (int k = 0; k < (NS * RUN16 + 31) / 32; ++k) {
-                const int q = lane + 32 * k;
-                const int qs = q / RUN16, qo = q % RUN16;
-                if (q < NS * RUN16 && n0 + qs < N && qo < valid16) {
-                    const double2 v = *reinterpret_cast<const double2*>(ost + qs * SM::OSEQ + 2 * qo);
-                    *reinterpret_cast<double2*>(X + ((size_t)(n0 + qs) * T + t0) * (L * D) + 2 * qo) = v;
+                for (int k = 0; k < NPASS; ++k) {
+                    int qs, qo;
+                    if (C::PS % 32 == 0) { qs = k / (C::PS / 32); qo = lane + 32 * (k % (C::PS / 32)); }
+                    else { const int q = lane + 32 * k; qs = q / C::PS; qo = q % C::PS; }
+                    if ((NS * C::PS) % 32 == 0 || qs < NS) v[k] = *reinterpret_cast<const double2*>(ost + qs * C::OSEQ + 2 * qo);
+                }
+#pragma unroll
+                for (int k = 0; k < NPASS; ++k) {
+                    int qs, qo;
+                    if (C::PS % 32 == 0) { qs = k / (C::PS / 32); qo = lane + 32 * (k % (C::PS / 32)); }
+                    else { const int q = lane + 32 * k; qs = q / C::PS; qo = q % C::PS; }
+                    if ((NS * C::PS) % 32 == 0 || qs < NS) *reinterpret_cast<double2*>(Xr + (size_t)qs * T * LD + 2 * qo) = v[k];
+                }
+            } else {
+                const long long rows_left = T - t0;
+                const int valid16 = (int)(rows_left >= L ? C::PS : rows_left * (LD / 2));
+#pragma unroll
+                for (int k = 0; k < (NS * C::PS + 31) / 32; ++k) {
+                    const int q = lane + 32 * k;
+                    const int qs = q / C::PS, qo = q % C::PS;
+                    if (qs < nvalid && qo < valid16) {
+                        const double2 v = *reinterpret_cast<const double2*>(ost + qs * C::OSEQ + 2 * qo);
+                        *reinterpret_cast<double2*>(Xr + (size_t)qs * T * LD + 2 * qo) = v;
+                    }
                 }
             }
         }
@@ -204,63 +396,94 @@ __global__ void __launch_bounds__(32) k_filter_chain(const double* __restrict__ 
     }
     cp_async_wait<0>();
     // ---- final state and NLL of each sequence ---------------------------------------------------------
-    if (xT && seq_ok) {
+    if (xT && active && seq_ok) {
 #pragma unroll
         for (int a = 0; a < D; ++a) xT[((size_t)n * L + j) * D + a] = x[a];
     }
+    if (saw_nan) *nan_flag = 1;
     if (nll) {
         // sum_t 1/2 rho_t / sigma  +  sum_l 1/2 sum_t v^2 / S_l          moihgp.h:653, ihgp.h:207
-        double part = 0.5 * rho_acc / sigma + 0.5 * vsq_acc / __ldg(&lc->S);
+        xch[lane] = rho_acc;                                                      // owner lane -> sequence own_s
+        __syncwarp();
+        double part = active ? 0.5 * vsq_acc / __ldg(&lc->S) : 0.0;
 #pragma unroll
         for (int o = 1; o < L; o <<= 1) part += __shfl_xor_sync(FULL, part, o);
-        if (j == 0 && seq_ok) nll[n] = part + nll_const;
+        if (j == 0 && active && seq_ok) {
+            double rho = 0.0;
+            for (int q = 0; q < 32; ++q)
+                if ((q & 3) < RB && (8 * (q & 3) + (q >> 2)) / L == s) rho += xch[q];
+            nll[n] = 0.5 * rho / sigma + part + nll_const;
+        }
     }
 }
 
-template <int L, int D>
-struct SmoothSmem {
-    static constexpr int NS = 32 / L;
-    static constexpr int RUN = L * L * D;              // doubles per sequence-round
-    static constexpr int OSEQ = RUN + 4;
+template <int L, int D, int NS_>
+struct SmoothCfg {
+    static constexpr int NS = NS_;
+    static constexpr int LD = L * D;
+    static constexpr int RUN = L * LD;                 // doubles per sequence-round
+    static constexpr int PS = RUN / 2;                 // 16-byte pieces per sequence-round
+    static constexpr int OSEQ = staging_pitch(L, D);
     static constexpr int BYTES = STAGES * NS * OSEQ * 8;
 };
 
 // Backward sweep over the stored filtered states.  MODE 0: reference_literal (ihgp.h:108-113, Q3)
-//   Xs[T-1] = X[T-1];  Xs[j] = X[j+1] + G Xs[j+1] - A X[j+1]
-// MODE 1: rts_correct   Xs[j] = X[j] + G (Xs[j+1] - A X[j]).
+//   Xs[T-1] = X[T-1];  Xs[j] = (I - A) X[j+1] + G Xs[j+1]
+// MODE 1: rts_correct   Xs[j] = X[j] + G (Xs[j+1] - A X[j]) = (I - G A) X[j] + G Xs[j+1].
 // grid: ceil(N / NS) CTAs of one warp; rounds of L steps from the end of the sequence.
-template <int L, int D, int MODE>
-__global__ void __launch_bounds__(32) k_smooth_chain(const double* __restrict__ X, const LatentConsts* __restrict__ consts,
+template <int L, int D, int MODE, int NS_>
+__global__ void __launch_bounds__(32, 14) k_smooth_chain(const double* __restrict__ X, const LatentConsts* __restrict__ consts,
                                                     long long N, long long T, double* __restrict__ Xs) {
-    using SM = SmoothSmem<L, D>;
-    constexpr int NS = SM::NS, RUN = SM::RUN, RUN16 = RUN / 2;
+    using C = SmoothCfg<L, D, NS_>;
+    constexpr int NS = C::NS, LD = C::LD, PS = C::PS;
+    constexpr int NPASS = (NS * PS + 31) / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* tiles = reinterpret_cast<double*>(smem_raw);                       // [STAGES][NS][OSEQ]
     const int lane = threadIdx.x;
     const int s = lane / L, j = lane % L;
+    const bool active = lane < NS * L;
     const long long n0 = (long long)blockIdx.x * NS;
-    const bool seq_ok = n0 + s < N;
+    const int nvalid = (int)(N - n0 < NS ? N - n0 : NS);
     const long long rounds = (T + L - 1) / L;
     const LatentConsts* lc = consts + j;
-    double G[D * D], A[D * D];
+    double G[D * D], B[D * D];                     // B: I - A (literal, applied to X[j+1]) or I - G A (rts, applied to X[j])
 #pragma unroll
     for (int a = 0; a < D; ++a)
 #pragma unroll
-        for (int b = 0; b < D; ++b) { G[a * D + b] = __ldg(&lc->G[MODE][a * 3 + b]); A[a * D + b] = __ldg(&lc->A[a * 3 + b]); }
+        for (int b = 0; b < D; ++b) {
+            G[a * D + b] = __ldg(&lc->G[MODE][a * 3 + b]);
+            B[a * D + b] = MODE == 0 ? __ldg(&lc->ImA[a * 3 + b]) : __ldg(&lc->Bs[a * 3 + b]);
+        }
+    const double* const Xcta = X + (size_t)n0 * T * LD;
+    double* const Xscta = Xs + (size_t)n0 * T * LD;
 
+    // per-pass (sequence, piece) of the warp-wide copies
+    auto piece = [&](int k, int& qs, int& qo) {
+        if (PS % 32 == 0) { qs = k / (PS / 32); qo = lane + 32 * (k % (PS / 32)); }
+        else { const int q = lane + 32 * k; qs = q / PS; qo = q % PS; }
+    };
     // round index k counts from the END: it covers steps t0 = (rounds - 1 - k) * L ...
     auto issue = [&](long long k) {
         if (k < rounds) {
-            double* st = tiles + (size_t)(k % STAGES) * NS * SM::OSEQ;
+            double* st = tiles + (size_t)(k % STAGES) * NS * C::OSEQ;
             const long long t0 = (rounds - 1 - k) * L;
-            const long long rows_left = T - t0;
-            const int valid16 = (int)(rows_left >= L ? RUN16 : rows_left * (L * D / 2));
+            const double* Xr = Xcta + (size_t)t0 * LD;
+            if (nvalid == NS && t0 + L <= T) {
 #pragma unroll
-            for (int m = 0; m < (NS * RUN16 + 31) / 32; ++m) {
-                const int q = lane + 32 * m;
-                const int qs = q / RUN16, qo = q % RUN16;
-                if (q < NS * RUN16 && n0 + qs < N && qo < valid16)
-                    cp_async16(st + qs * SM::OSEQ + 2 * qo, X + ((size_t)(n0 + qs) * T + t0) * (L * D) + 2 * qo);
+                for (int m = 0; m < NPASS; ++m) {
+                    int qs, qo;
+                    piece(m, qs, qo);
+                    if ((NS * PS) % 32 == 0 || qs < NS) cp_async16(st + qs * C::OSEQ + 2 * qo, Xr + (size_t)qs * T * LD + 2 * qo);
+                }
+            } else {
+                const long long rows_left = T - t0;
+                const int valid16 = (int)(rows_left >= L ? PS : rows_left * (LD / 2));
+#pragma unroll
+                for (int m = 0; m < NPASS; ++m) {
+                    const int q = lane + 32 * m;
+                    const int qs = q / PS, qo = q % PS;
+                    if (qs < nvalid && qo < valid16) cp_async16(st + qs * C::OSEQ + 2 * qo, Xr + (size_t)qs * T * LD + 2 * qo);
+                }
             }
         }
         cp_async_commit();
@@ -275,91 +498,135 @@ __global__ void __launch_bounds__(32) k_smooth_chain(const double* __restrict__ 
         issue(k + STAGES - 1);
         cp_async_wait<STAGES - 1>();
         __syncwarp();
-        double* st = tiles + (size_t)(k % STAGES) * NS * SM::OSEQ + s * SM::OSEQ + j * D;
+        double* stw = tiles + (size_t)(k % STAGES) * NS * C::OSEQ;
+        double* st = stw + s * C::OSEQ + j * D;
         const long long t0 = (rounds - 1 - k) * L;
+        const bool fast = nvalid == NS && t0 + L <= T;
+        if (!active) {
+        } else if (fast && t0 + L < T) {
+            // interior round: no boundary, no predicates
+            double xin[L][D];
 #pragma unroll
-        for (int i = L - 1; i >= 0; --i) {
-            const long long t = t0 + i;
-            if (t < T) {
+            for (int i = 0; i < L; ++i) load_state<D>(st + i * LD, xin[i]);
+#pragma unroll
+            for (int i = L - 1; i >= 0; --i) {
                 double xx[D], out[D];
 #pragma unroll
-                for (int a = 0; a < D; ++a) xx[a] = st[i * (L * D) + a];
-                if (t == T - 1) {
+                for (int a = 0; a < D; ++a) xx[a] = xin[i][a];
 #pragma unroll
-                    for (int a = 0; a < D; ++a) out[a] = xx[a];                    // ihgp.h:108
-                } else if (MODE == 0) {
+                for (int a = 0; a < D; ++a) {
+                    double acc = G[a * D] * xs[0];
 #pragma unroll
-                    for (int a = 0; a < D; ++a) {                                  // ihgp.h:111
-                        double g = 0.0, aa = 0.0;
+                    for (int b = 1; b < D; ++b) acc = fma(G[a * D + b], xs[b], acc);
 #pragma unroll
-                        for (int b = 0; b < D; ++b) { g = fma(G[a * D + b], xs[b], g); aa = fma(A[a * D + b], xnext[b], aa); }
-                        out[a] = xnext[a] + g - aa;
-                    }
-                } else {
-                    double rr[D];
-#pragma unroll
-                    for (int a = 0; a < D; ++a) {
-                        double aa = 0.0;
-#pragma unroll
-                        for (int b = 0; b < D; ++b) aa = fma(A[a * D + b], xx[b], aa);
-                        rr[a] = xs[a] - aa;
-                    }
-#pragma unroll
-                    for (int a = 0; a < D; ++a) {
-                        double g = 0.0;
-#pragma unroll
-                        for (int b = 0; b < D; ++b) g = fma(G[a * D + b], rr[b], g);
-                        out[a] = xx[a] + g;
-                    }
+                    for (int b = 0; b < D; ++b) acc = fma(B[a * D + b], MODE == 0 ? xnext[b] : xx[b], acc);
+                    out[a] = acc;
                 }
 #pragma unroll
-                for (int a = 0; a < D; ++a) { xs[a] = out[a]; xnext[a] = xx[a]; st[i * (L * D) + a] = out[a]; }
+                for (int a = 0; a < D; ++a) { xs[a] = out[a]; xnext[a] = xx[a]; }
+                store_state<D>(st + i * LD, out);
+            }
+        } else {
+#pragma unroll
+            for (int i = L - 1; i >= 0; --i) {
+                const long long t = t0 + i;
+                if (t < T) {
+                    double xx[D], out[D];
+                    load_state<D>(st + i * LD, xx);
+                    if (t == T - 1) {
+#pragma unroll
+                        for (int a = 0; a < D; ++a) out[a] = xx[a];                // ihgp.h:108
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < D; ++a) {                              // ihgp.h:111 / RTS
+                            double acc = G[a * D] * xs[0];
+#pragma unroll
+                            for (int b = 1; b < D; ++b) acc = fma(G[a * D + b], xs[b], acc);
+#pragma unroll
+                            for (int b = 0; b < D; ++b) acc = fma(B[a * D + b], MODE == 0 ? xnext[b] : xx[b], acc);
+                            out[a] = acc;
+                        }
+                    }
+#pragma unroll
+                    for (int a = 0; a < D; ++a) { xs[a] = out[a]; xnext[a] = xx[a]; }
+                    store_state<D>(st + i * LD, out);
+                }
             }
         }
         __syncwarp();
         {
-            double* stw = tiles + (size_t)(k % STAGES) * NS * SM::OSEQ;
-            const long long rows_left = T - t0;
-            const int valid16 = (int)(rows_left >= L ? RUN16 : rows_left * (L * D / 2));
+            double* Xr = Xscta + (size_t)t0 * LD;
+            if (fast) {
+                double2 v[NPASS];
 #pragma unroll
-            for (int m = 0; m < (NS * RUN16 + 31) / 32; ++m) {
-                const int q = lane + 32 * m;
-                const int qs = q / RUN16, qo = q % RUN16;
-                if (q < NS * RUN16 && n0 + qs < N && qo < valid16) {
-                    const double2 v = *reinterpret_cast<const double2*>(stw + qs * SM::OSEQ + 2 * qo);
-                    *reinterpret_cast<double2*>(Xs + ((size_t)(n0 + qs) * T + t0) * (L * D) + 2 * qo) = v;
+                for (int m = 0; m < NPASS; ++m) {
+                    int qs, qo;
+                    piece(m, qs, qo);
+                    if ((NS * PS) % 32 == 0 || qs < NS) v[m] = *reinterpret_cast<const double2*>(stw + qs * C::OSEQ + 2 * qo);
+                }
+#pragma unroll
+                for (int m = 0; m < NPASS; ++m) {
+                    int qs, qo;
+                    piece(m, qs, qo);
+                    if ((NS * PS) % 32 == 0 || qs < NS) *reinterpret_cast<double2*>(Xr + (size_t)qs * T * LD + 2 * qo) = v[m];
+                }
+            } else {
+                const long long rows_left = T - t0;
+                const int valid16 = (int)(rows_left >= L ? PS : rows_left * (LD / 2));
+#pragma unroll
+                for (int m = 0; m < NPASS; ++m) {
+                    const int q = lane + 32 * m;
+                    const int qs = q / PS, qo = q % PS;
+                    if (qs < nvalid && qo < valid16) {
+                        const double2 v = *reinterpret_cast<const double2*>(stw + qs * C::OSEQ + 2 * qo);
+                        *reinterpret_cast<double2*>(Xr + (size_t)qs * T * LD + 2 * qo) = v;
+                    }
                 }
             }
         }
         __syncwarp();
     }
     cp_async_wait<0>();
-    (void)seq_ok;
 }
 
-template <int P, int L, int D>
-cudaError_t run_chain(const ChainArgs& a, cudaStream_t st) {
-    using FS = FilterSmem<P, L, D>;
-    using SS = SmoothSmem<L, D>;
+template <int P, int L, int D, int NS>
+cudaError_t run_chain_ns(const ChainArgs& a, cudaStream_t st) {
+    using FS = FilterCfg<P, L, D, NS>;
+    using SS = SmoothCfg<L, D, NS>;
     ProjConsts<P, L> pc;
     for (int r = 0; r < P; ++r) for (int l = 0; l < L; ++l) pc.U[r][l] = a.U_host[(size_t)r * L + l];
     for (int l = 0; l < L; ++l) pc.rs[l] = 1.0 / std::sqrt(a.S_host[l]);
-    const unsigned grid = (unsigned)((a.N + FS::NS - 1) / FS::NS);
+    const unsigned grid = (unsigned)((a.N + NS - 1) / NS);
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(k_filter_chain<P, L, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS::BYTES);
-        cudaFuncSetAttribute(k_smooth_chain<L, D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS::BYTES);
-        cudaFuncSetAttribute(k_smooth_chain<L, D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS::BYTES);
+        cudaFuncSetAttribute(k_filter_chain<P, L, D, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS::BYTES);
+        cudaFuncSetAttribute(k_smooth_chain<L, D, 0, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS::BYTES);
+        cudaFuncSetAttribute(k_smooth_chain<L, D, 1, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS::BYTES);
         attr_done = true;
     }
-    k_filter_chain<P, L, D><<<grid, 32, FS::BYTES, st>>>(a.Y, pc, a.consts, a.sigma, a.nll_const, a.N, a.T, a.x0, a.X, a.nll, a.xT);
+    k_filter_chain<P, L, D, NS><<<grid, 32, FS::BYTES, st>>>(a.Y, pc, a.consts, a.sigma, a.nll_const, a.N, a.T, a.x0, a.X, a.nll, a.xT, a.nan_flag);
     mark(a.mk, "k_filter_chain");
     if (a.Xs) {
-        if (a.mode == 0) k_smooth_chain<L, D, 0><<<grid, 32, SS::BYTES, st>>>(a.X, a.consts, a.N, a.T, a.Xs);
-        else k_smooth_chain<L, D, 1><<<grid, 32, SS::BYTES, st>>>(a.X, a.consts, a.N, a.T, a.Xs);
+        if (a.mode == 0) k_smooth_chain<L, D, 0, NS><<<grid, 32, SS::BYTES, st>>>(a.X, a.consts, a.N, a.T, a.Xs);
+        else k_smooth_chain<L, D, 1, NS><<<grid, 32, SS::BYTES, st>>>(a.X, a.consts, a.N, a.T, a.Xs);
         mark(a.mk, "k_smooth_chain");
     }
     return cudaGetLastError();
+}
+
+// sequences per warp: the full warp (32 / L) when that already gives every SM sub-partition several warps,
+// otherwise fewer sequences per warp (idle lanes in the recurrence phase, but more warps to hide its latency)
+template <int P, int L, int D>
+cudaError_t run_chain(const ChainArgs& a, cudaStream_t st) {
+    constexpr int NSMAX = 32 / L, NSMIN = L >= 8 ? 1 : 8 / L;
+    int ns = a.seqs_per_warp;
+    if (ns <= 0) {
+        ns = NSMAX;
+        while (ns > NSMIN && (a.N + ns - 1) / ns < 148LL * 16) ns /= 2;
+    }
+    if (ns >= NSMAX) return run_chain_ns<P, L, D, NSMAX>(a, st);
+    if (NSMAX / 2 >= NSMIN && ns >= NSMAX / 2) return run_chain_ns<P, L, D, (NSMAX / 2 >= NSMIN ? NSMAX / 2 : NSMAX)>(a, st);
+    return run_chain_ns<P, L, D, (NSMAX / 4 >= NSMIN ? NSMAX / 4 : NSMIN)>(a, st);
 }
 
 }  // namespace

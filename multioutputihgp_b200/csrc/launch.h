@@ -62,6 +62,8 @@ struct ChainArgs {
     int mode;                     // smoother mode 0 / 1 (used when Xs != null)
     const double* x0;
     double *X, *Xs, *nll, *xT;    // X must be non-null when Xs is requested
+    int* nan_flag;                // set to 1 if a NaN observation was seen
+    int seqs_per_warp = 0;        // 0 = automatic
     Marker* mk = nullptr;
 };
 bool chain_supported(int p, int L, int dim);
