@@ -614,16 +614,13 @@ cudaError_t run_chain_ns(const ChainArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-// sequences per warp: the full warp (32 / L) when that already gives every SM sub-partition several warps,
-// otherwise fewer sequences per warp (idle lanes in the recurrence phase, but more warps to hide its latency)
+// Sequences per warp.  Measured on B200 (BASELINE config 3, profiles/r01): a full warp (32 / L sequences) is fastest
+// even when that leaves < 2 warps per SM sub-partition - the pass is bound by HBM, not by latency - so that is the
+// automatic choice; fewer sequences per warp (idle lanes in the recurrence phase, more warps) stay selectable.
 template <int P, int L, int D>
 cudaError_t run_chain(const ChainArgs& a, cudaStream_t st) {
     constexpr int NSMAX = 32 / L, NSMIN = L >= 8 ? 1 : 8 / L;
-    int ns = a.seqs_per_warp;
-    if (ns <= 0) {
-        ns = NSMAX;
-        while (ns > NSMIN && (a.N + ns - 1) / ns < 148LL * 16) ns /= 2;
-    }
+    const int ns = a.seqs_per_warp <= 0 ? NSMAX : a.seqs_per_warp;
     if (ns >= NSMAX) return run_chain_ns<P, L, D, NSMAX>(a, st);
     if (NSMAX / 2 >= NSMIN && ns >= NSMAX / 2) return run_chain_ns<P, L, D, (NSMAX / 2 >= NSMIN ? NSMAX / 2 : NSMAX)>(a, st);
     return run_chain_ns<P, L, D, (NSMAX / 4 >= NSMIN ? NSMAX / 4 : NSMIN)>(a, st);

@@ -1,0 +1,164 @@
+// GPU test of the C++ host mirror (include/moihgp_b200/moihgp.hpp) against the CPU oracle (oracle/_build/liboracle.so,
+// test infrastructure).  Reads like the reference's own usage (cpp_examples/example_regression.cpp:11-41,
+// example_online_learning.cpp): build a MOIHGP, fill the objective's Y, evaluate the functor the optimiser would call.
+// Prints "OK" and exits 0 when every comparison is within 1e-9 (norm-wise relative).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <vector>
+#include <moihgp_b200/moihgp.hpp>
+
+extern "C" {
+void* oracle_new(int kernel, double dt, size_t p, size_t L, int threading);
+void oracle_del(void* h);
+size_t oracle_num_param(void* h);
+void oracle_update(void* h, const double* params);
+void oracle_step1(void* h, const double* x, const double* y, const double* dx, double* xn, double* yh, double* dxn);
+void oracle_step2(void* h, const double* x, const double* y, const double* dx, double* xn, double* dxn);
+double oracle_lik1(void* h, const double* x, const double* y, const double* dx, double* grad, int literal);
+double oracle_lik2(void* h, const double* x, const double* y, int literal);
+double oracle_objective(void* h, const double* Y, size_t N, size_t T, double* x, double* dx, double* grad, int literal);
+void oracle_filter_smoother_nll(void* h, const double* Y, size_t N, size_t T, double* x, double* X, double* Xs, double* Yhat, double* nll,
+                                int smoother_mode, int nthreads);
+}
+
+typedef std::vector<double> Vec;
+static int failures = 0;
+
+static double rel_err(const double* a, const double* b, size_t n) {
+    double num = 0.0, den = 0.0;
+    for (size_t i = 0; i < n; ++i) { num = std::fmax(num, std::fabs(a[i] - b[i])); den = std::fmax(den, std::fabs(b[i])); }
+    return num / std::fmax(den, 1e-300);
+}
+static void expect(const char* what, double err, double tol = 1e-9) {
+    std::printf("%-58s rel.err %.3e %s\n", what, err, err <= tol ? "ok" : "FAIL");
+    if (!(err <= tol)) ++failures;
+}
+
+template <typename SS>
+static void run(int kernel, size_t p, size_t L, size_t T, bool threading, unsigned seed) {
+    using namespace moihgp_b200;
+    std::mt19937 gen(seed);
+    std::normal_distribution<> nrm(0.0, 1.0);
+    const double dt = 0.1;
+    MOIHGP<SS> gp(dt, p, L, threading);
+    void* o = oracle_new(kernel, dt, p, L, threading ? 1 : 0);
+    const size_t np = gp.getNumParam(), d = gp.getIGPDim();
+    if (np != oracle_num_param(o)) { std::printf("num_param mismatch\n"); ++failures; }
+    // hyper-parameters: U block near identity (update() takes its polar factor), S, sigma, (magnitude, lengthscale, noise) x L
+    Vec params(np);
+    for (size_t r = 0; r < p; ++r) for (size_t c = 0; c < L; ++c) params[r * L + c] = (r == c ? 1.0 : 0.0) + 0.3 * nrm(gen);
+    for (size_t l = 0; l < L; ++l) params[p * L + l] = 0.5 + 0.25 * l;
+    params[p * L + L] = 0.05;
+    const double table[4][3] = {{1, 1, .1}, {.5, .5, .1}, {2, .3, .05}, {.5, .3, .5}};
+    for (size_t l = 0; l < L; ++l) for (int k = 0; k < 3; ++k) params[p * L + L + 1 + 3 * l + k] = table[l % 4][k];
+    gp.update(params);
+    oracle_update(o, params.data());
+
+    // data: mixed sinusoids + noise (cpp_examples/example_regression.cpp:18-28)
+    std::vector<Vec> Y(T, Vec(p));
+    std::vector<double> Yflat(T * p);
+    for (size_t t = 0; t < T; ++t) for (size_t r = 0; r < p; ++r) {
+        Y[t][r] = std::sin((1.0 + r % 3) * dt * t) + 0.1 * nrm(gen);
+        Yflat[t * p + r] = Y[t][r];
+    }
+
+    // (1) RegressionObjective::operator() == the oracle's loop of step + negLogLikelihood
+    RegressionObjective<SS> f(T, &gp, /*update_params=*/true);
+    f.Y = Y;
+    Vec grad(np), go(np), x0(L * d, 0.0), dx0(L * 3 * d, 0.0);
+    const double loss = f(params, grad);
+    const double lo = oracle_objective(o, Yflat.data(), 1, T, x0.data(), dx0.data(), go.data(), 0);
+    expect("RegressionObjective loss", std::fabs(loss - lo) / std::fabs(lo));
+    expect("RegressionObjective grad", rel_err(grad.data(), go.data(), np));
+
+    // (2) per-observation methods: a few steps of step(x,y,dx,xnew,yhat,dxnew) + both negLogLikelihood overloads
+    typename MOIHGP<SS>::State x(L, Vec(d, 0.0)), xn;
+    typename MOIHGP<SS>::DState dx(L, std::vector<Vec>(3, Vec(d, 0.0))), dxn;
+    Vec xo(L * d, 0.0), dxo(L * 3 * d, 0.0), xno(L * d), dxno(L * 3 * d), yh, yho(p), g1, g1o(np);
+    double e_x = 0, e_y = 0, e_l1 = 0, e_l2 = 0, e_g = 0;
+    for (size_t t = 0; t < 5 && t < T; ++t) {
+        const double l1 = gp.negLogLikelihood(x, Y[t], dx, g1), l1o = oracle_lik1(o, xo.data(), Yflat.data() + t * p, dxo.data(), g1o.data(), 0);
+        const double l2 = gp.negLogLikelihood(x, Y[t]), l2o = oracle_lik2(o, xo.data(), Yflat.data() + t * p, 0);
+        gp.step(x, Y[t], dx, xn, yh, dxn);
+        oracle_step1(o, xo.data(), Yflat.data() + t * p, dxo.data(), xno.data(), yho.data(), dxno.data());
+        Vec flat(L * d);
+        for (size_t l = 0; l < L; ++l) for (size_t i = 0; i < d; ++i) flat[l * d + i] = xn[l][i];
+        e_x = std::fmax(e_x, rel_err(flat.data(), xno.data(), L * d));
+        e_y = std::fmax(e_y, rel_err(yh.data(), yho.data(), p));
+        e_l1 = std::fmax(e_l1, std::fabs(l1 - l1o) / std::fabs(l1o));
+        e_l2 = std::fmax(e_l2, std::fabs(l2 - l2o) / std::fabs(l2o));
+        e_g = std::fmax(e_g, rel_err(g1.data(), g1o.data(), np));
+        x = xn; dx = dxn; xo = xno; dxo = dxno;
+    }
+    expect("MOIHGP::step xnew", e_x);
+    expect("MOIHGP::step yhat", e_y);
+    expect("MOIHGP::negLogLikelihood(x,y,dx,grad) loss", e_l1);
+    expect("MOIHGP::negLogLikelihood(x,y,dx,grad) grad", e_g);
+    expect("MOIHGP::negLogLikelihood(x,y)", e_l2);
+
+    // (3) OnlineObjective: window maintenance + objective == the same loop on the oracle (no BFGS corrections yet: identity proximal term)
+    {
+        const size_t W = 4;
+        OnlineObjective<SS> fo(&gp, 0.9, W);
+        // oracle twin of the window logic (moihgp_online.h:75-93)
+        std::vector<Vec> win;
+        Vec ma(p, 0.0), sx(L * d, 0.0), sdx(L * 3 * d, 0.0), tx(L * d), tdx(L * 3 * d);
+        for (size_t t = 0; t < 9 && t < T; ++t) {
+            fo.push_back(Y[t]);
+            win.push_back(Y[t]);
+            for (size_t r = 0; r < p; ++r) { ma[r] = 0.0; for (size_t k = 0; k < win.size(); ++k) ma[r] += win[k][r]; ma[r] /= double(win.size()); }
+            while (win.size() > W) {
+                win.erase(win.begin());
+                Vec yc(p);
+                for (size_t r = 0; r < p; ++r) yc[r] = win.front()[r] - ma[r];
+                oracle_step2(o, sx.data(), yc.data(), sdx.data(), tx.data(), tdx.data());
+                sx = tx; sdx = tdx;
+            }
+        }
+        Vec p2 = params;
+        for (size_t i = 0; i < np; ++i) p2[i] *= 1.0 + 0.01 * std::sin(double(i));          // a trial point of the line search
+        // keep the U block orthonormal-ish is not needed: update() re-takes the polar factor
+        Vec g2(np), g2o(np);
+        const double l2 = fo(p2, g2);
+        oracle_update(o, p2.data());
+        std::vector<double> wflat(win.size() * p);
+        for (size_t k = 0; k < win.size(); ++k) for (size_t r = 0; r < p; ++r) wflat[k * p + r] = win[k][r] - ma[r];
+        Vec cx = sx, cdx = sdx;
+        double l2o = oracle_objective(o, wflat.data(), 1, win.size(), cx.data(), cdx.data(), g2o.data(), 0);
+        double prox = 0.0;
+        for (size_t i = 0; i < np; ++i) { const double dp = p2[i] - params[i]; prox += 0.5 * dp * dp; g2o[i] += dp; }
+        l2o += prox;
+        expect("OnlineObjective loss (window 4, proximal identity)", std::fabs(l2 - l2o) / std::fabs(l2o));
+        expect("OnlineObjective grad", rel_err(g2.data(), g2o.data(), np));
+        gp.update(params);
+        oracle_update(o, params.data());
+    }
+
+    // (4) predict(): loop of step(x, y, xnew, yhat) + smoother, one device pass
+    {
+        typename MOIHGP<SS>::State xs(L, Vec(d, 0.0));
+        std::vector<double> Yh(T * p), X(T * L * d), Xs(T * L * d), Yho(T * p), Xo(T * L * d), Xso(T * L * d), xz(L * d, 0.0);
+        double nll = 0.0, nllo = 0.0;
+        gp.predict(Yflat.data(), T, xs, Yh.data(), X.data(), Xs.data(), MOIHGP_SMOOTH_RTS, &nll);
+        oracle_filter_smoother_nll(o, Yflat.data(), 1, T, xz.data(), Xo.data(), Xso.data(), Yho.data(), &nllo, 1, 1);
+        expect("predict Yhat", rel_err(Yh.data(), Yho.data(), T * p));
+        expect("predict filtered states", rel_err(X.data(), Xo.data(), T * L * d));
+        expect("predict smoothed states (RTS)", rel_err(Xs.data(), Xso.data(), T * L * d));
+        expect("predict NLL", std::fabs(nll - nllo) / std::fabs(nllo));
+    }
+    oracle_del(o);
+}
+
+int main() {
+    std::printf("-- Matern32, p=2, L=1, T=63 (example_regression shape)\n");
+    run<moihgp_b200::Matern32StateSpace>(32, 2, 1, 63, false, 1);
+    std::printf("-- Matern32, p=8, L=4, T=300, threading\n");
+    run<moihgp_b200::Matern32StateSpace>(32, 8, 4, 300, true, 2);
+    std::printf("-- Matern52, p=16, L=8, T=700, threading\n");
+    run<moihgp_b200::Matern52StateSpace>(52, 16, 8, 700, true, 3);
+    if (failures) { std::printf("FAILED: %d comparison(s)\n", failures); return 1; }
+    std::printf("OK\n");
+    return 0;
+}
