@@ -82,10 +82,18 @@ class ClockSampler:
     def __init__(self, index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+
+    def mark_timed_region_start(self):
+        """Samples taken before this point (start-up, warm-up) are dropped."""
+        self.f.flush()
+        try:
+            self.skip = sum(1 for _ in open(self.f.name))
+        except Exception:
+            self.skip = 0
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -97,7 +105,7 @@ class ClockSampler:
         except Exception:
             self.p.kill()
         self.f.flush()
-        rows = [r.strip().split(", ") for r in open(self.f.name).read().splitlines() if r.strip()]
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().splitlines() if r.strip()][getattr(self, "skip", 0):]
         os.unlink(self.f.name)
         sm, mx, reasons = [], [], set()
         for r in rows:
@@ -183,7 +191,7 @@ def cpu_reference_rate(kind, kernel, p, L, N, T, seed, budget_s, nthreads):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
@@ -289,10 +297,12 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None     # started before the warm-up: nvidia-smi needs ~0.3 s to produce its first line
     for _ in range(warmup):
         step()
     sync_all()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.mark_timed_region_start()
     l0 = model.launch_count
     model.profile(True)    # one CUDA event after every kernel of the library, on the launching stream, inside the timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

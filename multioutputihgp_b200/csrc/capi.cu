@@ -454,9 +454,10 @@ int moihgp_cuda_filter_smoother_nll_dev(moihgp_handle* h, const double* Y, size_
     } else {
         // time-parallel chunked scan: project.cu + scan.cu
         const size_t nC = scan_chunks((long long)T);
-        double *u, *rho, *fsum, *bsum, *xin, *bin, *Bx, *vsq;
+        double *u, *rho, *fsum, *bsum, *xin, *bin, *Bx, *vsq, *npart;
         int* nanf;
-        if (ws_get(h, "u", N * L * T, &u) || ws_get(h, "rho", N * T, &rho) || ws_get(h, "fsum", nC * N * L * D, &fsum) ||
+        if (ws_get(h, "u", N * L * T, &u) || ws_get(h, "rho", N * project_tiles((long long)T), &rho) || ws_get(h, "npart", nll_partials((long long)N), &npart) ||
+            ws_get(h, "fsum", nC * N * L * D, &fsum) ||
             ws_get(h, "bsum", nC * N * L * D, &bsum) || ws_get(h, "xin", nC * N * L * D, &xin) || ws_get(h, "bin", nC * N * L * D, &bin) ||
             ws_get(h, "Bx", (size_t)L * 2 * 9, &Bx) || ws_get(h, "vsq", nC * N * L, &vsq) || ws_get(h, "nanf", 4, &nanf))
             return -1;
@@ -469,7 +470,7 @@ int moihgp_cuda_filter_smoother_nll_dev(moihgp_handle* h, const double* Y, size_
         a.fsum = fsum; a.bsum = bsum; a.xin = xin; a.bin = bin; a.Bx = Bx; a.X = X; a.Xs = Xs; a.vsq = vsq; a.xT = xT;
         CK(launch_scan(D, mode < 0 ? 1 : mode, a, h->stream));
         h->launches += 1 + scan_launch_count((long long)T);
-        if (nll) { CK(launch_nll_reduce(rho, vsq, h->d_consts, h->d_S, h->sigma, h->p, L, (long long)N, (long long)T, nll, h->stream)); h->launches += 1; mark(mk, "k_nll_reduce"); }
+        if (nll) { CK(launch_nll_reduce(rho, vsq, h->d_consts, h->d_S, h->sigma, h->p, L, (long long)N, (long long)T, npart, nll, h->stream)); h->launches += 2; mark(mk, "k_nll_reduce"); }
     }
     if (Yhat) { CK(launch_backproject(X, h->d_U, h->d_S, h->p, L, D, (long long)N, (long long)T, Yhat, h->stream)); h->launches += 1; mark(mk, "k_backproject"); }
     return 0;
@@ -516,9 +517,9 @@ int moihgp_cuda_objective_dev(moihgp_handle* h, const double* Y, size_t N, size_
     const size_t nC = obj_chunks((long long)T), nsplit = obj_gu_splits((long long)N, (long long)T);
     double *u, *w, *yl, *rho, *zsum, *zin, *part, *gU, *Ek, *lat;
     int* nanf;
-    if (ws_get(h, "u", N * L * T, &u) || ws_get(h, "w", N * L * T, &w) || ws_get(h, "yl", N * L * T, &yl) || ws_get(h, "rho", N * T, &rho) ||
+    if (ws_get(h, "u", N * L * T, &u) || ws_get(h, "w", N * L * T, &w) || ws_get(h, "yl", N * L * T, &yl) || ws_get(h, "rho", N * project_tiles((long long)T), &rho) ||
         ws_get(h, "zsum", nC * N * L * 4 * D, &zsum) || ws_get(h, "zin", nC * N * L * 4 * D, &zin) || ws_get(h, "part", nC * N * L * 8, &part) ||
-        ws_get(h, "gU", nsplit * p * L, &gU) || ws_get(h, "Ek", (size_t)L * 27, &Ek) || ws_get(h, "lat", ((size_t)L + 1) * 8, &lat) ||
+        ws_get(h, "gU", nsplit * p * L, &gU) || ws_get(h, "Ek", (size_t)L * 27 * 16, &Ek) || ws_get(h, "lat", ((size_t)L + 1) * 8, &lat) ||
         ws_get(h, "nanf", 4, &nanf))
         return -1;
     CK(cudaMemsetAsync(nanf, 0, sizeof(int), h->stream));

@@ -27,8 +27,9 @@ inline void mark(Marker* m, const char* name) { if (m) m->mark(name); }
 cudaError_t launch_setup(int dim, const double* d_igp_params, double dt, int L, LatentConsts* d_out, cudaStream_t stream);
 
 // project.cu
+size_t project_tiles(long long T);     // tiles of 128 time steps per sequence: rho_part is [N][project_tiles(T)]
 cudaError_t launch_project(const double* Y, const double* U, const double* S, int p, int L, long long N, long long T,
-                           double* u, double* w, double* yl, double* rho, int* nan_flag, cudaStream_t stream);
+                           double* u, double* w, double* yl, double* rho_part, int* nan_flag, cudaStream_t stream);
 cudaError_t launch_backproject(const double* X, const double* U, const double* S, int p, int L, int d, long long N,
                                long long T, double* Yhat, cudaStream_t stream);
 
@@ -49,8 +50,9 @@ struct ScanArgs {
 size_t scan_chunks(long long T);
 int scan_launch_count(long long T);
 cudaError_t launch_scan(int dim, int mode, const ScanArgs& a, cudaStream_t st);
-cudaError_t launch_nll_reduce(const double* rho, const double* vsq, const LatentConsts* consts, const double* S, double sigma,
-                              int p, int L, long long N, long long T, double* nll, cudaStream_t st);
+size_t nll_partials(long long N);
+cudaError_t launch_nll_reduce(const double* rho_part, const double* vsq, const LatentConsts* consts, const double* S, double sigma,
+                              int p, int L, long long N, long long T, double* part, double* nll, cudaStream_t st);
 
 // chain.cu  (many-chains path: thread per (sequence, latent), sequential in time)
 struct ChainArgs {
@@ -72,7 +74,7 @@ cudaError_t launch_chain(int p, int L, int dim, const ChainArgs& a, cudaStream_t
 // objective.cu
 struct ObjArgs {
     const double* Y;              // [N][T][p]
-    const double *u, *w, *yl, *rho;   // [N][L][T] x3, [N][T]   (from k_project)
+    const double *u, *w, *yl, *rho;   // [N][L][T] x3, rho_part [N][project_tiles(T)]   (from k_project)
     double* wgt;                  // [N][L][T] workspace: per-step weights of the dU contraction
     const LatentConsts* consts;
     const double *U, *S;

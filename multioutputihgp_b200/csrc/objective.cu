@@ -128,9 +128,25 @@ __global__ void __launch_bounds__(128) k_obj_scan(const double* __restrict__ u, 
     load_mat<D>(lc->AKHA, M);
     load_vec<D>(lc->K, K);
     load_vec<D>(lc->HA, HA);
-    double uu[SUB];
+    // this lane's 8 consecutive steps: 16-byte loads when the run is whole and aligned (T even or an aligned row start)
+    const bool vec = tf + SUB <= T && (((so + tf) & 1) == 0) && ((reinterpret_cast<size_t>(u) & 15) == 0) &&
+                     ((reinterpret_cast<size_t>(w) & 15) == 0) && ((reinterpret_cast<size_t>(yl) & 15) == 0) &&
+                     (wgt == nullptr || (reinterpret_cast<size_t>(wgt) & 15) == 0);
+    auto load8 = [&](const double* src, double (&dst)[SUB]) {
+        if (vec) {
 #pragma unroll
-    for (int i = 0; i < SUB; ++i) uu[i] = tf + i < T ? __ldg(u + so + tf + i) : 0.0;
+            for (int i = 0; i < SUB; i += 2) {
+                const double2 t2 = __ldg(reinterpret_cast<const double2*>(src + so + tf + i));
+                dst[i] = t2.x;
+                dst[i + 1] = t2.y;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < SUB; ++i) dst[i] = tf + i < T ? __ldg(src + so + tf + i) : 0.0;
+        }
+    };
+    double uu[SUB];
+    load8(u, uu);
 
     const size_t ci = (((size_t)c * N + n) * L + l) * 4 * D;
     double zi[4][D];
@@ -170,20 +186,29 @@ __global__ void __launch_bounds__(128) k_obj_scan(const double* __restrict__ u, 
     if (FINAL) {
         const double Sl = __ldg(S + l);
         const double rsS = 1.0 / sqrt(Sl);
+        double ww[SUB], yy[SUB], wg[SUB];
+        load8(w, ww);
+        load8(yl, yy);
 #pragma unroll
         for (int i = 0; i < SUB; ++i) {
             double hax = HA[0] * xpre[i][0];
 #pragma unroll
             for (int q = 1; q < D; ++q) hax = fma(HA[q], xpre[i][q], hax);
             v[i] = uu[i] - hax;                                                     // ihgp.h:214
+            const double pv = (yy[i] - hax) * (1 - hak) / Si;                       // moihgp.h:510-511 (raw y(l), Q8)
+            wg[i] = -ww[i] / sigma + pv * rsS;                                      // moihgp.h:546-550 (rank-1 form)
             if (tf + i < T) {
-                const double wt = __ldg(w + so + tf + i);
-                const double yr = __ldg(yl + so + tf + i);
-                const double pv = (yr - hax) * (1 - hak) / Si;                      // moihgp.h:510-511 (raw y(l), Q8)
                 acc_loss += 0.5 * (v[i] * v[i] / Si + logSi);                       // ihgp.h:215
-                acc_pvw = fma(pv, wt, acc_pvw);                                     // moihgp.h:558-560
-                wgt[so + tf + i] = -wt / sigma + pv * rsS;                          // moihgp.h:546-550 (rank-1 form)
+                acc_pvw = fma(pv, ww[i], acc_pvw);                                  // moihgp.h:558-560
             }
+        }
+        if (vec) {
+#pragma unroll
+            for (int i = 0; i < SUB; i += 2) *reinterpret_cast<double2*>(wgt + so + tf + i) = make_double2(wg[i], wg[i + 1]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < SUB; ++i)
+                if (tf + i < T) wgt[so + tf + i] = wg[i];
         }
     }
 
@@ -244,8 +269,12 @@ __global__ void __launch_bounds__(128) k_obj_scan(const double* __restrict__ u, 
     }
 }
 
-// Cross-chunk coupling matrices E_k = sum_i M^(CH-1-i) dM_k M^i by doubling: E(2n) = E(n) M^n + M^n E(n).
-// One thread per (latent, k).  Ek layout [l][3][D*D].
+// Cross-chunk coupling matrices by doubling: for a span of n steps  E_k(n) = sum_i M^(n-1-i) dM_k M^i,  and
+// E(2n) = E(n) M^n + M^n E(n).  Levels stored for spans of 2^j CHUNKS, j = 0..NLEV-1 (j = 0: one chunk), which is what
+// the carry scan over chunks needs.  One thread per (latent, k).  Ek layout [level][l][3][D*D].
+constexpr int CG = 8;              // chunks per lane in the carry scan
+constexpr int LOG2_CG = 3;
+constexpr int NLEV = LOG2_CG + 5 + 1;
 template <int D>
 __global__ void k_obj_coupling(const LatentConsts* __restrict__ consts, int L, double* __restrict__ Ek) {
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
@@ -254,7 +283,9 @@ __global__ void k_obj_coupling(const LatentConsts* __restrict__ consts, int L, d
     const LatentConsts* lc = consts + l;
     double E[D * D], Mn[D * D];
     load_mat<D>(lc->dAKHA[k], E);
-    for (int lev = 0; lev < LOG2_CH; ++lev) {
+    for (int lev = 0; lev < LOG2_CH + NLEV - 1; ++lev) {
+        if (lev >= LOG2_CH)
+            for (int i = 0; i < D * D; ++i) Ek[(((size_t)(lev - LOG2_CH) * L + l) * 3 + k) * D * D + i] = E[i];
         load_mat<D>(lc->powM[lev], Mn);
         double a[D * D];
         for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) {
@@ -264,34 +295,98 @@ __global__ void k_obj_coupling(const LatentConsts* __restrict__ consts, int L, d
         }
         for (int i = 0; i < D * D; ++i) E[i] = a[i];
     }
-    for (int i = 0; i < D * D; ++i) Ek[((size_t)l * 3 + k) * D * D + i] = E[i];
+    for (int i = 0; i < D * D; ++i) Ek[(((size_t)(NLEV - 1) * L + l) * 3 + k) * D * D + i] = E[i];
 }
 
-// zin[c+1] = Z^CH zin[c] + zsum[c], one thread per (sequence, latent)
+// zin[c+1] = Z^CH zin[c] + zsum[c] on the augmented state z = [x; dx_0; dx_1; dx_2]:
+//   x' = M^CH x + f_x,   dx_k' = M^CH dx_k + E_k x + f_k.
+// One WARP per (sequence, latent): groups of 256 chunks (lane = 8 consecutive chunks, Kogge-Stone over lanes with the
+// span-(8 * 2^j) transition), groups in sequence.
 template <int D>
 __global__ void __launch_bounds__(128) k_obj_carry(const LatentConsts* __restrict__ consts, const double* __restrict__ Ek, int L,
                                                   long long N, long long nC, const double* __restrict__ x0,
                                                   const double* __restrict__ dx0, const double* __restrict__ zsum,
                                                   double* __restrict__ zin) {
-    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const long long id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (id >= N * L) return;
     const int l = (int)(id % L);
     double MC[D * D], E[3][D * D];
     load_mat<D>(consts[l].powM[LOG2_CH], MC);
-    for (int k = 0; k < 3; ++k) for (int i = 0; i < D * D; ++i) E[k][i] = Ek[((size_t)l * 3 + k) * D * D + i];
-    double z[4][D];
-    for (int q = 0; q < D; ++q) {
-        z[0][q] = x0 ? x0[(size_t)id * D + q] : 0.0;
-        for (int k = 0; k < 3; ++k) z[1 + k][q] = dx0 ? dx0[((size_t)id * 3 + k) * D + q] : 0.0;
-    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) E[k][i] = Ek[((size_t)l * 3 + k) * D * D + i];
     const size_t stride = (size_t)N * L * 4 * D, base = (size_t)id * 4 * D;
-    for (long long c = 0; c < nC; ++c) {
-        for (int a = 0; a < 4; ++a) for (int q = 0; q < D; ++q) zin[c * stride + base + a * D + q] = z[a][q];
-        if (c + 1 < nC) {
-            double zn[4][D];
-            mv<D>(MC, z[0], zn[0]);
-            for (int k = 0; k < 3; ++k) { mv<D>(MC, z[1 + k], zn[1 + k]); mv_acc<D>(E[k], z[0], zn[1 + k]); }
-            for (int a = 0; a < 4; ++a) for (int q = 0; q < D; ++q) z[a][q] = zn[a][q] + zsum[c * stride + base + a * D + q];
+    const long long nG = (nC + 32 * CG - 1) / (32 * CG);
+    double carry[4][D];
+#pragma unroll
+    for (int q = 0; q < D; ++q) {
+        carry[0][q] = x0 ? x0[(size_t)id * D + q] : 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) carry[1 + k][q] = dx0 ? dx0[((size_t)id * 3 + k) * D + q] : 0.0;
+    }
+    // one chunk: z <- Z^CH z + zsum[c]   (zsum of the last chunk is never used)
+    auto advance = [&](double (&z)[4][D], long long c) {
+        double zn[4][D];
+        mv<D>(MC, z[0], zn[0]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { mv<D>(MC, z[1 + k], zn[1 + k]); mv_acc<D>(E[k], z[0], zn[1 + k]); }
+        const bool have = c < nC - 1;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int q = 0; q < D; ++q) z[a][q] = zn[a][q] + (have ? zsum[c * stride + base + a * D + q] : 0.0);
+    };
+    for (long long g = 0; g < nG; ++g) {
+        const long long c0 = (g * 32 + lane) * CG;
+        double z[4][D];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int q = 0; q < D; ++q) z[a][q] = lane == 0 ? carry[a][q] : 0.0;
+#pragma unroll 1
+        for (int i = 0; i < CG; ++i) advance(z, c0 + i);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const int o = 1 << j;
+            double zo[4][D], P[D * D];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int q = 0; q < D; ++q) zo[a][q] = __shfl_up_sync(FULL, z[a][q], o);
+            load_mat<D>(consts[l].powM[LOG2_CH + LOG2_CG + j], P);
+            if (lane >= o) {
+#pragma unroll
+                for (int a = 0; a < 4; ++a) mv_acc<D>(P, zo[a], z[a]);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    double Ej[D * D];
+#pragma unroll
+                    for (int i = 0; i < D * D; ++i) Ej[i] = Ek[(((size_t)(LOG2_CG + j) * L + l) * 3 + k) * D * D + i];
+                    mv_acc<D>(Ej, zo[0], z[1 + k]);
+                }
+            }
+        }
+        double x[4][D];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int q = 0; q < D; ++q) {
+                const double up = __shfl_up_sync(FULL, z[a][q], 1);
+                x[a][q] = lane == 0 ? carry[a][q] : up;
+                carry[a][q] = __shfl_sync(FULL, z[a][q], 31);
+            }
+#pragma unroll 1
+        for (int i = 0; i < CG; ++i) {
+            const long long c = c0 + i;
+            if (c < nC) {
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int q = 0; q < D; ++q) zin[c * stride + base + a * D + q] = x[a][q];
+            }
+            advance(x, c);
         }
     }
 }
@@ -353,7 +448,7 @@ __global__ void __launch_bounds__(256) k_gradU(const double* __restrict__ Y, con
 
 // Per-latent reduction of the chunk partials (blocks 0..L-1) and of rho (block L): fixed order.
 __global__ void __launch_bounds__(256) k_obj_reduce(const double* __restrict__ part, const double* __restrict__ rho, int L,
-                                                   long long N, long long T, long long nC, double* __restrict__ lat_sums /*[L+1][8]*/) {
+                                                   long long N, long long tiles, long long nC, double* __restrict__ lat_sums /*[L+1][8]*/) {
     __shared__ double red[256][5];
     const int tid = threadIdx.x;
     const int l = blockIdx.x;
@@ -365,7 +460,7 @@ __global__ void __launch_bounds__(256) k_obj_reduce(const double* __restrict__ p
             for (int j = 0; j < 5; ++j) s[j] += pp[j];
         }
     } else {
-        for (long long i = tid; i < N * T; i += 256) s[0] += rho[i];
+        for (long long i = tid; i < N * tiles; i += 256) s[0] += rho[i];
     }
 #pragma unroll
     for (int j = 0; j < 5; ++j) red[tid][j] = s[j];
@@ -381,18 +476,23 @@ __global__ void __launch_bounds__(256) k_obj_reduce(const double* __restrict__ p
 }
 
 // Assemble loss and gradient [U (p*L row-major) | S (L) | sigma | (mag, len, noise) x L]  (moihgp.h:553-609)
+// grid: enough CTAs of 256 threads to cover the p*L entries of dU (fixed-order sum over the split-K partials);
+// thread 0 of CTA 0 assembles the scalar / per-latent entries.
 __global__ void __launch_bounds__(256) k_obj_finish(const double* __restrict__ lat_sums, const double* __restrict__ gU_part,
                                                    int nsplit, const double* __restrict__ S, double sigma, int p, int L,
                                                    long long N, long long T, int threading, double* __restrict__ loss,
                                                    double* __restrict__ grad) {
     const int tid = threadIdx.x;
     const int sizeU = p * L;
-    for (int i = tid; i < sizeU; i += 256) {
-        double s = 0.0;
-        for (int k = 0; k < nsplit; ++k) s += gU_part[(size_t)k * sizeU + i];
-        grad[i] = s;
+    {
+        const int i = blockIdx.x * 256 + tid;
+        if (i < sizeU) {
+            double s = 0.0;
+            for (int k = 0; k < nsplit; ++k) s += gU_part[(size_t)k * sizeU + i];
+            grad[i] = s;
+        }
     }
-    if (tid == 0) {
+    if (tid == 0 && blockIdx.x == 0) {
         const double steps = (double)N * (double)T;
         const double rho_sum = lat_sums[(size_t)L * 8];
         const double m_n = fmax((double)(p - L), 0.0);                                     // moihgp.h:502
@@ -424,9 +524,9 @@ cudaError_t run_objective(const ObjArgs& a, cudaStream_t st) {
         k_obj_scan<D, false><<<grid, 128, 0, st>>>(a.u, a.w, a.yl, a.consts, a.S, a.sigma, a.L, a.N, a.T, nC, nullptr, a.zsum,
                                                    nullptr, nullptr, nullptr, nullptr);
         mark(a.mk, "k_obj_scan_summaries");
-        k_obj_coupling<D><<<(3 * a.L + 63) / 64, 64, 0, st>>>(a.consts, a.L, Ek);
     }
-    k_obj_carry<D><<<(unsigned)((a.N * a.L + 127) / 128), 128, 0, st>>>(a.consts, Ek, a.L, a.N, nC, a.x0, a.dx0, a.zsum, a.zin);
+    k_obj_coupling<D><<<(3 * a.L + 63) / 64, 64, 0, st>>>(a.consts, a.L, Ek);
+    k_obj_carry<D><<<(unsigned)((a.N * a.L * 32 + 127) / 128), 128, 0, st>>>(a.consts, Ek, a.L, a.N, nC, a.x0, a.dx0, a.zsum, a.zin);
     mark(a.mk, "k_obj_carry");
     k_obj_scan<D, true><<<grid, 128, 0, st>>>(a.u, a.w, a.yl, a.consts, a.S, a.sigma, a.L, a.N, a.T, nC, a.zin, nullptr, a.wgt,
                                               a.part, a.xT, a.dxT);
@@ -438,8 +538,8 @@ cudaError_t run_objective(const ObjArgs& a, cudaStream_t st) {
     k_gradU<<<gg, 256, 0, st>>>(a.Y, a.wgt, a.p, a.L, a.N, a.T, per, a.gU_part);
     mark(a.mk, "k_gradU");
     double* lat_sums = a.lat_sums;
-    k_obj_reduce<<<a.L + 1, 256, 0, st>>>(a.part, a.rho, a.L, a.N, a.T, nC, lat_sums);
-    k_obj_finish<<<1, 256, 0, st>>>(lat_sums, a.gU_part, (int)nsplit, a.S, a.sigma, a.p, a.L, a.N, a.T, a.threading, a.loss, a.grad);
+    k_obj_reduce<<<a.L + 1, 256, 0, st>>>(a.part, a.rho, a.L, a.N, (long long)project_tiles(a.T), nC, lat_sums);
+    k_obj_finish<<<(a.p * a.L + 255) / 256, 256, 0, st>>>(lat_sums, a.gU_part, (int)nsplit, a.S, a.sigma, a.p, a.L, a.N, a.T, a.threading, a.loss, a.grad);
     mark(a.mk, "k_obj_reduce");
     return cudaGetLastError();
 }
@@ -457,7 +557,7 @@ size_t obj_gu_splits(long long N, long long T) {
     return (size_t)s;
 }
 
-int obj_launch_count(long long T) { return (T + CH - 1) / CH > 1 ? 7 : 5; }
+int obj_launch_count(long long T) { return (T + CH - 1) / CH > 1 ? 7 : 6; }
 
 cudaError_t launch_objective(int dim, const ObjArgs& a, cudaStream_t st) {
     return dim == 2 ? run_objective<2>(a, st) : run_objective<3>(a, st);

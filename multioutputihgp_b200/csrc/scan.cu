@@ -225,7 +225,7 @@ __device__ __forceinline__ void chunk_pass(const LC<D>& c, const LatentConsts* l
         for (int q = 0; q < D; ++q) b[q] = bn[q] + g[q];
         if (tf + i < T) {
 #pragma unroll
-            for (int q = 0; q < D; ++q) tXs[i * RS + q] = MODE == 1 ? X[i][q] + b[q] : b[q];
+            for (int q = 0; q < D; ++q) tXs[i * RS + q] = MODE == 1 ? tX[i * RS + q] + b[q] : b[q];
         }
     }
 }
@@ -233,7 +233,7 @@ __device__ __forceinline__ void chunk_pass(const LC<D>& c, const LatentConsts* l
 // grid: N * nC * nLG CTAs (latent-group minor), block: 32 * lg threads (lg = latents in the group, <= LGMAX).
 // Per-chunk arrays are laid out [c][n][l][D].
 template <int D, int MODE, bool FINAL>
-__global__ void __launch_bounds__(32 * LGMAX) k_scan(const double* __restrict__ u, const LatentConsts* __restrict__ consts,
+__global__ void __launch_bounds__(32 * LGMAX, 2) k_scan(const double* __restrict__ u, const LatentConsts* __restrict__ consts,
                                                     int L, long long N, long long T, long long nC, int nLG,
                                                     const double* __restrict__ xin, const double* __restrict__ bin,
                                                     double* __restrict__ fsum, double* __restrict__ bsum,
@@ -262,8 +262,17 @@ __global__ void __launch_bounds__(32 * LGMAX) k_scan(const double* __restrict__ 
         const long long tf = t0 + (long long)lane * SUB;
         const double* up = u + ((size_t)n * L + l) * T;
         double uu[SUB];
+        if (tf + SUB <= T && ((reinterpret_cast<size_t>(up + tf) & 15) == 0)) {
 #pragma unroll
-        for (int i = 0; i < SUB; ++i) uu[i] = tf + i < T ? __ldg(up + tf + i) : 0.0;
+            for (int i = 0; i < SUB; i += 2) {
+                const double2 t2 = __ldg(reinterpret_cast<const double2*>(up + tf + i));
+                uu[i] = t2.x;
+                uu[i + 1] = t2.y;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < SUB; ++i) uu[i] = tf + i < T ? __ldg(up + tf + i) : 0.0;
+        }
         const double u_next = t0 + CH < T ? __ldg(up + t0 + CH) : 0.0;
         double x_in[D], b_in[D], f_end[D], beta[D], x_last[D], vsq;
         const size_t ci = (((size_t)c * N + n) * L + l) * D;
@@ -338,15 +347,20 @@ __global__ void __launch_bounds__(32) k_response(const LatentConsts* __restrict_
     }
 }
 
-// Chain the chunk summaries: one thread per (sequence, latent).
+// Chain the chunk summaries: one WARP per (sequence, latent); the nC chunks are themselves scanned in groups of
+// 256 (lane = 8 consecutive chunks, Kogge-Stone over lanes with the powers M^(CH * 8 * 2^k)), groups in sequence.
 //   forward : xin[c+1] = M^CH xin[c] + f[c]
 //   backward: bin[c-1] = beta0[c] + Bx(kind c) xin[c] + G^CH bin[c]
+// (A single long sequence has tens of thousands of chunks: BASELINE config 4, T = 1e7.)
+constexpr int CG = 8;              // chunks per lane
+constexpr int LOG2_CG = 3;
 template <int D, int MODE>
 __global__ void __launch_bounds__(128) k_carry(const LatentConsts* __restrict__ consts, const double* __restrict__ Bx, int L,
                                               long long N, long long nC, const double* __restrict__ x0,
                                               const double* __restrict__ fsum, const double* __restrict__ bsum,
                                               double* __restrict__ xin, double* __restrict__ bin) {
-    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const long long id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // (sequence, latent)
     if (id >= N * L) return;
     const int l = (int)(id % L);
     const LatentConsts* lc = consts + l;
@@ -357,51 +371,139 @@ __global__ void __launch_bounds__(128) k_carry(const LatentConsts* __restrict__ 
     for (int i = 0; i < D * D; ++i) { Bf[i] = Bx[((size_t)l * 2 + 0) * D * D + i]; Bl[i] = Bx[((size_t)l * 2 + 1) * D * D + i]; }
     const size_t stride = (size_t)N * L * D;   // between consecutive chunks
     const size_t base = (size_t)id * D;
-    double x[D];
+    const long long nG = (nC + 32 * CG - 1) / (32 * CG);
+
+    // ---- forward ---------------------------------------------------------------------------------
+    double carry[D];
 #pragma unroll
-    for (int q = 0; q < D; ++q) x[q] = x0 ? x0[base + q] : 0.0;
-    for (long long c = 0; c < nC; ++c) {
+    for (int q = 0; q < D; ++q) carry[q] = x0 ? x0[base + q] : 0.0;
+    for (long long g = 0; g < nG; ++g) {
+        const long long c0 = (g * 32 + lane) * CG;
+        double f[CG][D];
 #pragma unroll
-        for (int q = 0; q < D; ++q) xin[c * stride + base + q] = x[q];
-        if (c + 1 < nC) {
+        for (int i = 0; i < CG; ++i)
+#pragma unroll
+            for (int q = 0; q < D; ++q) f[i][q] = (c0 + i < nC - 1) ? fsum[(c0 + i) * stride + base + q] : 0.0;   // f of the last chunk is never used
+        double z[D];
+#pragma unroll
+        for (int q = 0; q < D; ++q) z[q] = lane == 0 ? carry[q] : 0.0;
+#pragma unroll
+        for (int i = 0; i < CG; ++i) {
+            double zn[D];
+            mv<D>(MC, z, zn);
+#pragma unroll
+            for (int q = 0; q < D; ++q) z[q] = zn[q] + f[i][q];
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const int o = 1 << k;
+            double zo[D], P[D * D];
+#pragma unroll
+            for (int q = 0; q < D; ++q) zo[q] = __shfl_up_sync(FULL, z[q], o);
+            load_mat<D>(lc->powM[LOG2_CH + LOG2_CG + k], P);
+            if (lane >= o) mv_acc<D>(P, zo, z);
+        }
+        double x[D];
+#pragma unroll
+        for (int q = 0; q < D; ++q) {
+            const double up = __shfl_up_sync(FULL, z[q], 1);
+            x[q] = lane == 0 ? carry[q] : up;
+            carry[q] = __shfl_sync(FULL, z[q], 31);
+        }
+#pragma unroll
+        for (int i = 0; i < CG; ++i) {
+            if (c0 + i < nC) {
+#pragma unroll
+                for (int q = 0; q < D; ++q) xin[(c0 + i) * stride + base + q] = x[q];
+            }
             double xn[D];
             mv<D>(MC, x, xn);
 #pragma unroll
-            for (int q = 0; q < D; ++q) x[q] = xn[q] + fsum[c * stride + base + q];
+            for (int q = 0; q < D; ++q) x[q] = xn[q] + f[i][q];
         }
     }
-    double b[D];
+    __syncwarp();
+    // ---- backward: b[c] := bin[c], the carry entering chunk c from the future -----------------------
+    //   b[nC-1] = 0;  b[c-1] = G^CH b[c] + d[c],  d[c] = beta0[c] + B(kind c) xin[c]
 #pragma unroll
-    for (int q = 0; q < D; ++q) b[q] = 0.0;
-    for (long long c = nC - 1; c >= 0; --c) {
+    for (int q = 0; q < D; ++q) carry[q] = 0.0;
+    for (long long g = nG - 1; g >= 0; --g) {
+        const long long c0 = (g * 32 + lane) * CG;       // this lane produces b[c0-1 .. c0+CG-2] from b[c0+CG-1]
+        double dv[CG][D];
 #pragma unroll
-        for (int q = 0; q < D; ++q) bin[c * stride + base + q] = b[q];
-        if (c > 0) {
-            double xi[D], bn[D];
+        for (int i = 0; i < CG; ++i) {
+            const long long c = c0 + i;
+            if (c >= 1 && c < nC) {
+                double xi[D], bn[D];
 #pragma unroll
-            for (int q = 0; q < D; ++q) { xi[q] = xin[c * stride + base + q]; bn[q] = bsum[c * stride + base + q]; }
-            mv_acc<D>(c == nC - 1 ? Bl : Bf, xi, bn);
-            if (c < nC - 1) mv_acc<D>(GC, b, bn);
+                for (int q = 0; q < D; ++q) { xi[q] = xin[c * stride + base + q]; bn[q] = bsum[c * stride + base + q]; }
+                mv_acc<D>(c == nC - 1 ? Bl : Bf, xi, bn);
 #pragma unroll
-            for (int q = 0; q < D; ++q) b[q] = bn[q];
+                for (int q = 0; q < D; ++q) dv[i][q] = bn[q];
+            } else {
+#pragma unroll
+                for (int q = 0; q < D; ++q) dv[i][q] = 0.0;
+            }
+        }
+        // local: from zero (lane 31: from the carry of the later groups)
+        double z[D];
+#pragma unroll
+        for (int q = 0; q < D; ++q) z[q] = lane == 31 ? carry[q] : 0.0;
+#pragma unroll
+        for (int i = CG - 1; i >= 0; --i) {
+            double zn[D];
+            mv<D>(GC, z, zn);
+#pragma unroll
+            for (int q = 0; q < D; ++q) z[q] = zn[q] + dv[i][q];
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const int o = 1 << k;
+            double zo[D], P[D * D];
+#pragma unroll
+            for (int q = 0; q < D; ++q) zo[q] = __shfl_down_sync(FULL, z[q], o);
+            load_mat<D>(lc->powG[MODE][LOG2_CH + LOG2_CG + k], P);
+            if (lane + o < 32) mv_acc<D>(P, zo, z);
+        }
+        double b[D];                                     // b[c0 + CG - 1]
+#pragma unroll
+        for (int q = 0; q < D; ++q) {
+            const double dn = __shfl_down_sync(FULL, z[q], 1);
+            b[q] = lane == 31 ? carry[q] : dn;
+            carry[q] = __shfl_sync(FULL, z[q], 0);       // b[c0(lane 0) - 1]: enters the previous group
+        }
+#pragma unroll
+        for (int i = CG - 1; i >= 0; --i) {
+            const long long c = c0 + i;
+            if (c < nC) {
+#pragma unroll
+                for (int q = 0; q < D; ++q) bin[c * stride + base + q] = c == nC - 1 ? 0.0 : b[q];
+            }
+            double bn[D];
+            mv<D>(GC, b, bn);
+#pragma unroll
+            for (int q = 0; q < D; ++q) b[q] = bn[q] + dv[i][q];
         }
     }
 }
 
 // nll[n] = sum_t [ 1/2 log(sum S) + 1/2 m_n log(sigma) + 1/2 rho_t / sigma ]            moihgp.h:653
 //        + sum_l sum_t 1/2 ( v^2 / S_l + log S_l )                                       ihgp.h:207, moihgp.h:675,684
-// One CTA per sequence; fixed-order (deterministic) reduction.
-__global__ void __launch_bounds__(256) k_nll_reduce(const double* __restrict__ rho, const double* __restrict__ vsq,
-                                                   const LatentConsts* __restrict__ consts, const double* __restrict__ S,
-                                                   double sigma, int p, int L, long long N, long long T, long long nC,
-                                                   double* __restrict__ nll) {
+// Two stages, fixed order (deterministic): NSPLIT CTAs per sequence, then one thread per sequence.
+constexpr int NSPLIT = 64;
+__global__ void __launch_bounds__(256) k_nll_partial(const double* __restrict__ rho_part, const double* __restrict__ vsq,
+                                                    const LatentConsts* __restrict__ consts, double sigma, int L, long long N,
+                                                    long long tiles, long long nC, double* __restrict__ part) {
     __shared__ double red[256];
-    const long long n = blockIdx.x;
+    const long long n = blockIdx.x / NSPLIT;
+    const int sp = blockIdx.x % NSPLIT;
     const int tid = threadIdx.x;
     double acc = 0.0;
-    for (long long t = tid; t < T; t += 256) acc += rho[(size_t)n * T + t];
+    const long long tb = (tiles + NSPLIT - 1) / NSPLIT;
+    for (long long i = sp * tb + tid; i < min(tiles, (sp + 1) * tb); i += 256) acc += rho_part[n * tiles + i];
     acc *= 0.5 / sigma;
-    for (long long i = tid; i < nC * L; i += 256) {
+    const long long cb = (nC + NSPLIT - 1) / NSPLIT;
+    for (long long i = sp * cb * L + tid; i < min(nC, (sp + 1) * cb) * L; i += 256) {
         const long long c = i / L;
         const int l = (int)(i - c * L);
         acc += 0.5 * vsq[((size_t)c * N + n) * L + l] / consts[l].S;
@@ -412,12 +514,19 @@ __global__ void __launch_bounds__(256) k_nll_reduce(const double* __restrict__ r
         if (tid < o) red[tid] += red[tid + o];
         __syncthreads();
     }
-    if (tid == 0) {
-        double Ssum = 0.0, logs = 0.0;
-        for (int l = 0; l < L; ++l) { Ssum += S[l]; logs += consts[l].logS; }
-        const double m_n = fmax((double)(p - L), 0.0);                       // moihgp.h:652
-        nll[n] = red[0] + (double)T * (0.5 * log(Ssum) + 0.5 * m_n * log(sigma) + 0.5 * logs);
-    }
+    if (tid == 0) part[n * NSPLIT + sp] = red[0];
+}
+__global__ void __launch_bounds__(128) k_nll_reduce(const double* __restrict__ part, const LatentConsts* __restrict__ consts,
+                                                   const double* __restrict__ S, double sigma, int p, int L, long long N,
+                                                   long long T, double* __restrict__ nll) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    double acc = 0.0;
+    for (int i = 0; i < NSPLIT; ++i) acc += part[n * NSPLIT + i];
+    double Ssum = 0.0, logs = 0.0;
+    for (int l = 0; l < L; ++l) { Ssum += S[l]; logs += consts[l].logS; }
+    const double m_n = fmax((double)(p - L), 0.0);                       // moihgp.h:652
+    nll[n] = acc + (double)T * (0.5 * log(Ssum) + 0.5 * m_n * log(sigma) + 0.5 * logs);
 }
 
 template <int D, int MODE>
@@ -439,7 +548,7 @@ cudaError_t run_scan(const ScanArgs& a, cudaStream_t st) {
         k_response<D, MODE><<<a.L * 2 * D, 32, 0, st>>>(a.consts, r_last, a.Bx);
         mark(a.mk, "k_response");
     }
-    k_carry<D, MODE><<<(unsigned)((a.N * a.L + 127) / 128), 128, 0, st>>>(a.consts, a.Bx, a.L, a.N, nC, a.x0, a.fsum, a.bsum, a.xin, a.bin);
+    k_carry<D, MODE><<<(unsigned)((a.N * a.L * 32 + 127) / 128), 128, 0, st>>>(a.consts, a.Bx, a.L, a.N, nC, a.x0, a.fsum, a.bsum, a.xin, a.bin);
     mark(a.mk, "k_carry");
     k_scan<D, MODE, true><<<grid, 32 * lg, smem, st>>>(a.u, a.consts, a.L, a.N, a.T, nC, nLG, a.xin, a.bin, nullptr, nullptr, a.X, a.Xs,
                                                        a.vsq, a.xT);
@@ -458,11 +567,15 @@ cudaError_t launch_scan(int dim, int mode, const ScanArgs& a, cudaStream_t st) {
     return mode == 0 ? run_scan<3, 0>(a, st) : run_scan<3, 1>(a, st);
 }
 
-cudaError_t launch_nll_reduce(const double* rho, const double* vsq, const LatentConsts* consts, const double* S, double sigma,
-                              int p, int L, long long N, long long T, double* nll, cudaStream_t st) {
+cudaError_t launch_nll_reduce(const double* rho_part, const double* vsq, const LatentConsts* consts, const double* S, double sigma,
+                              int p, int L, long long N, long long T, double* part, double* nll, cudaStream_t st) {
     const long long nC = (T + CH - 1) / CH;
-    k_nll_reduce<<<(unsigned)N, 256, 0, st>>>(rho, vsq, consts, S, sigma, p, L, N, T, nC, nll);
+    const long long tiles = (long long)project_tiles(T);
+    k_nll_partial<<<(unsigned)(N * NSPLIT), 256, 0, st>>>(rho_part, vsq, consts, sigma, L, N, tiles, nC, part);
+    k_nll_reduce<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(part, consts, S, sigma, p, L, N, T, nll);
     return cudaGetLastError();
 }
+
+size_t nll_partials(long long N) { return (size_t)N * NSPLIT; }
 
 }  // namespace moihgp

@@ -128,7 +128,8 @@ static void run(int kernel, size_t p, size_t L, size_t T, bool threading, unsign
         Vec cx = sx, cdx = sdx;
         double l2o = oracle_objective(o, wflat.data(), 1, win.size(), cx.data(), cdx.data(), g2o.data(), 0);
         double prox = 0.0;
-        for (size_t i = 0; i < np; ++i) { const double dp = p2[i] - params[i]; prox += 0.5 * dp * dp; g2o[i] += dp; }
+        // oldparams = getParams() at construction: holds the POLAR FACTOR in its U block, not the raw block (moihgp_online.h:31, Q22)
+        for (size_t i = 0; i < np; ++i) { const double dp = p2[i] - fo.oldparams[i]; prox += 0.5 * dp * dp; g2o[i] += dp; }
         l2o += prox;
         expect("OnlineObjective loss (window 4, proximal identity)", std::fabs(l2 - l2o) / std::fabs(l2o));
         expect("OnlineObjective grad", rel_err(g2.data(), g2o.data(), np));
