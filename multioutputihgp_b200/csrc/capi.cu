@@ -441,7 +441,7 @@ int moihgp_cuda_filter_smoother_nll_dev(moihgp_handle* h, const double* Y, size_
         // one thread per (sequence, latent) chain, sequential in time: chain.cu
         int* nanf;
         if (ws_get(h, "nanf", 4, &nanf)) return -1;
-        CK(cudaMemsetAsync(nanf, 0, sizeof(int), h->stream));
+        CK(cudaMemsetAsync(nanf, 0, 2 * sizeof(int), h->stream));
         double Ssum = 0.0, logs = 0.0;
         for (int l = 0; l < L; ++l) { Ssum += h->S[l]; logs += h->consts[l].logS; }
         const double m_n = std::max((double)(h->p - L), 0.0);
@@ -456,20 +456,24 @@ int moihgp_cuda_filter_smoother_nll_dev(moihgp_handle* h, const double* Y, size_
         const size_t nC = scan_chunks((long long)T);
         double *u, *rho, *fsum, *bsum, *xin, *bin, *Bx, *vsq, *npart;
         int* nanf;
+        long long* nanrows;
+        const size_t nan_cap = std::min<size_t>(N * T, (size_t)1 << 22);
+        if (ws_get(h, "nanrows", nan_cap, &nanrows)) return -1;
         if (ws_get(h, "u", N * L * T, &u) || ws_get(h, "rho", N * project_tiles((long long)T), &rho) || ws_get(h, "npart", nll_partials((long long)N), &npart) ||
             ws_get(h, "fsum", nC * N * L * D, &fsum) ||
             ws_get(h, "bsum", nC * N * L * D, &bsum) || ws_get(h, "xin", nC * N * L * D, &xin) || ws_get(h, "bin", nC * N * L * D, &bin) ||
             ws_get(h, "Bx", (size_t)L * 2 * 9, &Bx) || ws_get(h, "vsq", nC * N * L, &vsq) || ws_get(h, "nanf", 4, &nanf))
             return -1;
-        CK(cudaMemsetAsync(nanf, 0, sizeof(int), h->stream));
-        CK(launch_project(Y, h->d_U, h->d_S, h->p, L, (long long)N, (long long)T, u, nullptr, nullptr, nll ? rho : nullptr, nanf, h->stream));
+        CK(cudaMemsetAsync(nanf, 0, 2 * sizeof(int), h->stream));
+        CK(launch_project(Y, h->d_U, h->d_S, h->p, L, (long long)N, (long long)T, u, nullptr, nullptr, nll ? rho : nullptr, nanf, nanrows,
+                          (long long)nan_cap, h->stream));
         mark(mk, "k_project");
         ScanArgs a;
         a.mk = mk;
         a.u = u; a.consts = h->d_consts; a.L = L; a.N = (long long)N; a.T = (long long)T; a.x0 = x0;
         a.fsum = fsum; a.bsum = bsum; a.xin = xin; a.bin = bin; a.Bx = Bx; a.X = X; a.Xs = Xs; a.vsq = vsq; a.xT = xT;
         CK(launch_scan(D, mode < 0 ? 1 : mode, a, h->stream));
-        h->launches += 1 + scan_launch_count((long long)T);
+        h->launches += 2 + scan_launch_count((long long)T);
         if (nll) { CK(launch_nll_reduce(rho, vsq, h->d_consts, h->d_S, h->sigma, h->p, L, (long long)N, (long long)T, npart, nll, h->stream)); h->launches += 2; mark(mk, "k_nll_reduce"); }
     }
     if (Yhat) { CK(launch_backproject(X, h->d_U, h->d_S, h->p, L, D, (long long)N, (long long)T, Yhat, h->stream)); h->launches += 1; mark(mk, "k_backproject"); }
@@ -504,7 +508,7 @@ int moihgp_cuda_filter_smoother_nll(moihgp_handle* h, const double* Y, size_t N,
     if (ws_get(h, "nanf", 4, &nanf)) return -1;
     CK(cudaMemcpyAsync(&flag, nanf, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    if (flag) return fail(h, "Y contains NaN (missing observations): not supported by the whole-sequence pass yet; use gpXX_step*");
+    if (flag == 2) return fail(h, "more than 2^22 observations with missing (NaN) outputs in one call: split the batch");
     return 0;
 }
 
@@ -517,15 +521,18 @@ int moihgp_cuda_objective_dev(moihgp_handle* h, const double* Y, size_t N, size_
     const size_t nC = obj_chunks((long long)T), nsplit = obj_gu_splits((long long)N, (long long)T);
     double *u, *w, *yl, *rho, *zsum, *zin, *part, *gU, *Ek, *lat;
     int* nanf;
+    long long* nanrows;
+    const size_t nan_cap = std::min<size_t>(N * T, (size_t)1 << 22);
+    if (ws_get(h, "nanrows", nan_cap, &nanrows)) return -1;
     if (ws_get(h, "u", N * L * T, &u) || ws_get(h, "w", N * L * T, &w) || ws_get(h, "yl", N * L * T, &yl) || ws_get(h, "rho", N * project_tiles((long long)T), &rho) ||
         ws_get(h, "zsum", nC * N * L * 4 * D, &zsum) || ws_get(h, "zin", nC * N * L * 4 * D, &zin) || ws_get(h, "part", nC * N * L * 8, &part) ||
         ws_get(h, "gU", nsplit * p * L, &gU) || ws_get(h, "Ek", (size_t)L * 27 * 16, &Ek) || ws_get(h, "lat", ((size_t)L + 1) * 8, &lat) ||
         ws_get(h, "nanf", 4, &nanf))
         return -1;
-    CK(cudaMemsetAsync(nanf, 0, sizeof(int), h->stream));
+    CK(cudaMemsetAsync(nanf, 0, 2 * sizeof(int), h->stream));
     Marker* mk = h->profiling ? &h->marker : nullptr;
     if (mk) { mk->st = h->stream; mk->mark("begin"); }
-    CK(launch_project(Y, h->d_U, h->d_S, p, L, (long long)N, (long long)T, u, w, yl, rho, nanf, h->stream));
+    CK(launch_project(Y, h->d_U, h->d_S, p, L, (long long)N, (long long)T, u, w, yl, rho, nanf, nanrows, (long long)nan_cap, h->stream));
     mark(mk, "k_project");
     ObjArgs a;
     a.mk = mk;
@@ -534,7 +541,7 @@ int moihgp_cuda_objective_dev(moihgp_handle* h, const double* Y, size_t N, size_
     a.N = (long long)N; a.T = (long long)T; a.x0 = x0; a.dx0 = dx0; a.zsum = zsum; a.zin = zin; a.part = part; a.gU_part = gU;
     a.Ek = Ek; a.lat_sums = lat; a.loss = loss; a.grad = grad; a.xT = xT; a.dxT = dxT;
     CK(launch_objective(D, a, h->stream));
-    h->launches += 1 + obj_launch_count((long long)T);
+    h->launches += 2 + obj_launch_count((long long)T);
     return 0;
 }
 
@@ -566,8 +573,8 @@ int moihgp_cuda_objective(moihgp_handle* h, const double* Y, size_t N, size_t T,
     CK(cudaStreamSynchronize(h->stream));
     *loss = host[0];
     std::copy(host.begin() + 2, host.end(), grad);
-    if (flag) return fail(h, "Y contains NaN (missing observations): not supported by the whole-sequence pass yet; use gpXX_lik*");
-    return 0;
+    if (flag == 2) return fail(h, "more than 2^22 observations with missing (NaN) outputs in one call: split the batch");
+    return 0;   // with NaN observations the loss is NaN, exactly as the reference's (moihgp.h:501 uses the full y)
 }
 
 // ---------------------------------------------------------------------------------------------

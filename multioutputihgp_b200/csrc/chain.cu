@@ -31,6 +31,7 @@
 #include <cmath>
 #include "moihgp_device.cuh"
 #include "launch.h"
+#include "ls_project.cuh"
 
 namespace moihgp {
 
@@ -124,7 +125,9 @@ struct FilterCfg {
     static constexpr int RPP = 32 / CH > 0 ? 32 / CH : 1;   // rows of Y covered by one warp-wide cp.async pass
     static constexpr int PASSES = R / RPP;             // cp.async passes per round
     static constexpr int XCH = NS * XSEQ < 32 ? 32 : NS * XSEQ;   // exchange tile (doubles); also holds 32 partial sums at the end
-    static constexpr int BYTES = STAGES * TILE + XCH * 8 + NS * OSEQ * 8;
+    static constexpr int OSTD = NS * OSEQ > ls_scratch_doubles(L) ? NS * OSEQ : ls_scratch_doubles(L);   // staging tile; also the NaN-row scratch
+    static constexpr int PSD = PS / 32 > 0 ? PS / 32 : 1;
+    static constexpr int BYTES = STAGES * TILE + XCH * 8 + OSTD * 8;
     // XOR swizzle of the 16-byte chunk index within a row.  A tensor-core A-fragment load is an 8-byte access of
     // lanes (row g, columns 4 kb + q): a half-warp covers 4 consecutive rows x 2 adjacent chunks, which this
     // swizzle spreads over 8 distinct 16-byte bank groups.
@@ -301,7 +304,25 @@ __global__ void __launch_bounds__(32, 14) k_filter_chain(const double* __restric
             const bool own_ok = owner && (fast || (own_s < nvalid && t0 + own_i < T));
             if (own_ok) {
                 saw_nan = saw_nan || (q != q);
-                rho_acc += sqrt(q);                                               // norm, not squared (Q9)
+                rho_acc += sqrt(q);                                               // norm, not squared (Q9); NaN row => NaN NLL, as the reference
+            }
+            // missing observations (NaN): least-squares projection on the observed outputs, moihgp.h:167-178.  Rare: the
+            // whole warp solves one such row at a time, scratch in the (idle) staging tile.
+            unsigned nanrows = __ballot_sync(FULL, own_ok && (ysq != ysq));
+            while (nanrows) {
+                const int ol = __ffs(nanrows) - 1;
+                nanrows &= nanrows - 1;
+                const int row = 8 * (ol & 3) + (ol >> 2);
+                const unsigned char* yrow = tile + row * C::ROWB;
+                const int sw_ = C::swz(row);
+                double* sc = ost;
+                ls_solve_coop(P, L,
+                              [&](int r) { return *reinterpret_cast<const double*>(yrow + (((r >> 1) ^ sw_) << 4) + ((r & 1) << 3)); },
+                              [&](int r, int l) { return pc.U[r][l]; },
+                              sc, sc + L * L, sc + 2 * L * L, sc + 2 * L * L + L, reinterpret_cast<int*>(sc + 2 * L * L + 2 * L),
+                              lane, 32, [] { __syncwarp(); });
+                if (lane < L) xch[(row / L) * C::XSEQ + (row % L) * C::XROW + lane] = sc[2 * L * L + L + lane];   // z; phase 2 applies S^-1/2
+                __syncwarp();
             }
         }
         __syncwarp();
@@ -367,14 +388,14 @@ __global__ void __launch_bounds__(32, 14) k_filter_chain(const double* __restric
 #pragma unroll
                 for (int k = 0; k < NPASS; ++k) {
                     int qs, qo;
-                    if (C::PS % 32 == 0) { qs = k / (C::PS / 32); qo = lane + 32 * (k % (C::PS / 32)); }
+                    if (C::PS % 32 == 0) { qs = k / C::PSD; qo = lane + 32 * (k % C::PSD); }
                     else { const int q = lane + 32 * k; qs = q / C::PS; qo = q % C::PS; }
                     if ((NS * C::PS) % 32 == 0 || qs < NS) v[k] = *reinterpret_cast<const double2*>(ost + qs * C::OSEQ + 2 * qo);
                 }
 #pragma unroll
                 for (int k = 0; k < NPASS; ++k) {
                     int qs, qo;
-                    if (C::PS % 32 == 0) { qs = k / (C::PS / 32); qo = lane + 32 * (k % (C::PS / 32)); }
+                    if (C::PS % 32 == 0) { qs = k / C::PSD; qo = lane + 32 * (k % C::PSD); }
                     else { const int q = lane + 32 * k; qs = q / C::PS; qo = q % C::PS; }
                     if ((NS * C::PS) % 32 == 0 || qs < NS) *reinterpret_cast<double2*>(Xr + (size_t)qs * T * LD + 2 * qo) = v[k];
                 }
@@ -424,6 +445,7 @@ struct SmoothCfg {
     static constexpr int RUN = L * LD;                 // doubles per sequence-round
     static constexpr int PS = RUN / 2;                 // 16-byte pieces per sequence-round
     static constexpr int OSEQ = staging_pitch(L, D);
+    static constexpr int PSD = PS / 32 > 0 ? PS / 32 : 1;
     static constexpr int BYTES = STAGES * NS * OSEQ * 8;
 };
 
@@ -459,7 +481,7 @@ __global__ void __launch_bounds__(32, 14) k_smooth_chain(const double* __restric
 
     // per-pass (sequence, piece) of the warp-wide copies
     auto piece = [&](int k, int& qs, int& qo) {
-        if (PS % 32 == 0) { qs = k / (PS / 32); qo = lane + 32 * (k % (PS / 32)); }
+        if (PS % 32 == 0) { qs = k / C::PSD; qo = lane + 32 * (k % C::PSD); }
         else { const int q = lane + 32 * k; qs = q / PS; qo = q % PS; }
     };
     // round index k counts from the END: it covers steps t0 = (rounds - 1 - k) * L ...

@@ -29,7 +29,8 @@ cudaError_t launch_setup(int dim, const double* d_igp_params, double dt, int L, 
 // project.cu
 size_t project_tiles(long long T);     // tiles of 128 time steps per sequence: rho_part is [N][project_tiles(T)]
 cudaError_t launch_project(const double* Y, const double* U, const double* S, int p, int L, long long N, long long T,
-                           double* u, double* w, double* yl, double* rho_part, int* nan_flag, cudaStream_t stream);
+                           double* u, double* w, double* yl, double* rho_part, int* nan_info /*{flag, count}*/, long long* nan_rows,
+                           long long nan_cap, cudaStream_t stream);
 cudaError_t launch_backproject(const double* X, const double* U, const double* S, int p, int L, int d, long long N,
                                long long T, double* Yhat, cudaStream_t stream);
 

@@ -20,6 +20,7 @@
 #include <math.h>
 #include "moihgp_device.cuh"
 #include "launch.h"
+#include "ls_project.cuh"
 
 namespace moihgp {
 
@@ -49,11 +50,20 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 //   w[n][l][t]    = sum_r U[r][l] y[r]                      (optional, objective path)
 //   yl[n][l][t]   = y[l]  (raw output l, for pv: moihgp.h:510, Q8)   (optional, objective path)
 //   rho_part[n][tile] = sum over the tile of || y - U U' y ||_2      (optional)
-//   nan_flag      = set to 1 if any y is NaN (missing-data rows need the LS projection path)
+//   nan_info      = {flag, count}: flag set to 1 if any y is NaN; rows with a NaN are appended to nan_rows (global row
+//                   index n*T + t, at most nan_cap entries) and re-projected by k_nan_fix (missing-data LS projection)
+__device__ __forceinline__ void note_nan_row(int* nan_info, long long* nan_rows, long long nan_cap, long long row) {
+    nan_info[0] = 1;
+    const int idx = atomicAdd(nan_info + 1, 1);
+    if (idx < nan_cap) nan_rows[idx] = row;
+    else nan_info[0] = 2;                    // overflow: reported by the host entry points
+}
+
 __global__ void __launch_bounds__(PT) k_project(const double* __restrict__ Y, const double* __restrict__ U,
                                                const double* __restrict__ S, int p, int L, long long T,
                                                double* __restrict__ u, double* __restrict__ w, double* __restrict__ yl,
-                                               double* __restrict__ rho_part, int* __restrict__ nan_flag) {
+                                               double* __restrict__ rho_part, int* __restrict__ nan_info,
+                                               long long* __restrict__ nan_rows, long long nan_cap) {
     extern __shared__ double sm[];
     __shared__ double red[PT / 32];
     double* ys = sm;                       // [PT][PC + 1]
@@ -106,7 +116,7 @@ __global__ void __launch_bounds__(PT) k_project(const double* __restrict__ Y, co
                 }
         }
     }
-    if (saw_nan) *nan_flag = 1;
+    if (saw_nan) note_nan_row(nan_info, nan_rows, nan_cap, n * T + t);
 
     // ---- pass 2: residual norm and raw y(l) ---------------------------------------------------
     if (rho_part || yl) {
@@ -168,7 +178,8 @@ template <int NB>
 __global__ void __launch_bounds__(MT) k_project_mma(const double* __restrict__ Y, const double* __restrict__ U,
                                                    const double* __restrict__ S, int p, int L, long long T,
                                                    double* __restrict__ u, double* __restrict__ w, double* __restrict__ yl,
-                                                   double* __restrict__ rho_part, int* __restrict__ nan_flag) {
+                                                   double* __restrict__ rho_part, int* __restrict__ nan_info,
+                                                   long long* __restrict__ nan_rows, long long nan_cap) {
     using SMC = MmaSmem<NB>;
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ double red[MW];
@@ -288,7 +299,7 @@ __global__ void __launch_bounds__(MT) k_project_mma(const double* __restrict__ Y
     }
     if (bad_row[0] || bad_row[1]) any_bad = 1;
     __syncthreads();
-    if (any_bad && (rho_part || nan_flag)) {
+    if (any_bad) {
         // explicit || y - U (U' y) ||_2 (moihgp.h:651) for the rows whose norm difference cancelled (or is NaN): one
         // lane of the quad per row, straight from global memory.  Rare.
 #pragma unroll
@@ -309,7 +320,7 @@ __global__ void __launch_bounds__(MT) k_project_mma(const double* __restrict__ Y
                     for (int l = 0; l < L; ++l) e = fma(-__ldg(U + (size_t)r * L + l), wl[l], e);
                     q = fma(e, e, q);
                 }
-                if (isn) *nan_flag = 1;
+                if (isn) note_nan_row(nan_info, nan_rows, nan_cap, n * T + t0 + row0 + 8 * rb);
                 rho_sum += sqrt(q);
             }
         }
@@ -317,6 +328,32 @@ __global__ void __launch_bounds__(MT) k_project_mma(const double* __restrict__ Y
     if (rho_part) {
         const double s = block_sum<MT>(rho_sum, red);
         if (tid == 0) rho_part[n * tiles + tile] = s;
+    }
+}
+
+// Missing observations (moihgp.h:167-178): every listed row gets  u = S^-1/2 (U0'U0)^-1 U0' y_obs  (and w unscaled).
+// grid-stride over the list, one CTA per row, scratch in dynamic shared memory.
+__global__ void __launch_bounds__(128) k_nan_fix(const double* __restrict__ Y, const double* __restrict__ U, const double* __restrict__ S,
+                                                int p, int L, long long T, const int* __restrict__ nan_info,
+                                                const long long* __restrict__ nan_rows, long long nan_cap,
+                                                double* __restrict__ u, double* __restrict__ w) {
+    extern __shared__ double sc[];
+    long long count = nan_info[1];
+    if (count > nan_cap) count = nan_cap;
+    for (long long i = blockIdx.x; i < count; i += gridDim.x) {
+        const long long row = nan_rows[i];
+        const long long n = row / T, t = row - n * T;
+        const double* yr = Y + (size_t)row * p;
+        ls_solve_coop(p, L, [&](int r) { return yr[r]; }, [&](int r, int l) { return __ldg(U + (size_t)r * L + l); },
+                      sc, sc + L * L, sc + 2 * L * L, sc + 2 * L * L + L, reinterpret_cast<int*>(sc + 2 * L * L + 2 * L),
+                      (int)threadIdx.x, (int)blockDim.x, [] { __syncthreads(); });
+        for (int l = threadIdx.x; l < L; l += blockDim.x) {
+            const double z = sc[2 * L * L + L + l];
+            const size_t o = ((size_t)n * L + l) * T + t;
+            u[o] = z * (1.0 / sqrt(S[l]));
+            if (w) w[o] = z;
+        }
+        __syncthreads();
     }
 }
 
@@ -348,7 +385,8 @@ __global__ void __launch_bounds__(PT) k_backproject(const double* __restrict__ X
 
 template <int NB>
 cudaError_t run_project_mma(const double* Y, const double* U, const double* S, int p, int L, long long N, long long T, double* u,
-                            double* w, double* yl, double* rho_part, int* nan_flag, cudaStream_t stream) {
+                            double* w, double* yl, double* rho_part, int* nan_info, long long* nan_rows, long long nan_cap,
+                            cudaStream_t stream) {
     using SMC = MmaSmem<NB>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -356,7 +394,7 @@ cudaError_t run_project_mma(const double* Y, const double* U, const double* S, i
         attr_done = true;
     }
     const unsigned grid = (unsigned)(((T + PT - 1) / PT) * N);
-    k_project_mma<NB><<<grid, MT, SMC::BYTES, stream>>>(Y, U, S, p, L, T, u, w, yl, rho_part, nan_flag);
+    k_project_mma<NB><<<grid, MT, SMC::BYTES, stream>>>(Y, U, S, p, L, T, u, w, yl, rho_part, nan_info, nan_rows, nan_cap);
     return cudaGetLastError();
 }
 
@@ -365,18 +403,27 @@ cudaError_t run_project_mma(const double* Y, const double* U, const double* S, i
 size_t project_tiles(long long T) { return (size_t)((T + PT - 1) / PT); }
 
 cudaError_t launch_project(const double* Y, const double* U, const double* S, int p, int L, long long N, long long T,
-                           double* u, double* w, double* yl, double* rho_part, int* nan_flag, cudaStream_t stream) {
+                           double* u, double* w, double* yl, double* rho_part, int* nan_info, long long* nan_rows, long long nan_cap,
+                           cudaStream_t stream) {
     const bool aligned = (reinterpret_cast<size_t>(Y) & 15) == 0;
+    cudaError_t e;
     if (p % 2 == 0 && aligned && L <= 64 && p >= 8) {
-        if (L <= 8) return run_project_mma<1>(Y, U, S, p, L, N, T, u, w, yl, rho_part, nan_flag, stream);
-        if (L <= 16) return run_project_mma<2>(Y, U, S, p, L, N, T, u, w, yl, rho_part, nan_flag, stream);
-        if (L <= 32) return run_project_mma<4>(Y, U, S, p, L, N, T, u, w, yl, rho_part, nan_flag, stream);
-        return run_project_mma<8>(Y, U, S, p, L, N, T, u, w, yl, rho_part, nan_flag, stream);
+        if (L <= 8) e = run_project_mma<1>(Y, U, S, p, L, N, T, u, w, yl, rho_part, nan_info, nan_rows, nan_cap, stream);
+        else if (L <= 16) e = run_project_mma<2>(Y, U, S, p, L, N, T, u, w, yl, rho_part, nan_info, nan_rows, nan_cap, stream);
+        else if (L <= 32) e = run_project_mma<4>(Y, U, S, p, L, N, T, u, w, yl, rho_part, nan_info, nan_rows, nan_cap, stream);
+        else e = run_project_mma<8>(Y, U, S, p, L, N, T, u, w, yl, rho_part, nan_info, nan_rows, nan_cap, stream);
+    } else {
+        const size_t smem = sizeof(double) * ((size_t)PT * (PC + 1) + (size_t)PC * L + (size_t)PT * (L + 1));
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const unsigned grid = (unsigned)(((T + PT - 1) / PT) * N);
+        k_project<<<grid, PT, smem, stream>>>(Y, U, S, p, L, T, u, w, yl, rho_part, nan_info, nan_rows, nan_cap);
+        e = cudaGetLastError();
     }
-    const size_t smem = sizeof(double) * ((size_t)PT * (PC + 1) + (size_t)PC * L + (size_t)PT * (L + 1));
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const unsigned grid = (unsigned)(((T + PT - 1) / PT) * N);
-    k_project<<<grid, PT, smem, stream>>>(Y, U, S, p, L, T, u, w, yl, rho_part, nan_flag);
+    if (e != cudaSuccess) return e;
+    // missing-data rows (usually none: the kernel then exits at once)
+    const size_t sc = sizeof(double) * (size_t)ls_scratch_doubles(L);
+    if (sc > 48 * 1024) cudaFuncSetAttribute(k_nan_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc);
+    k_nan_fix<<<592, 128, sc, stream>>>(Y, U, S, p, L, T, nan_info, nan_rows, nan_cap, u, w);
     return cudaGetLastError();
 }
 

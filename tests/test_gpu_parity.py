@@ -278,3 +278,52 @@ def test_online_learner_runs_like_the_reference_example(cuda_lib):
         yhat = gp.step(y)
         assert yhat.shape == (8,) and np.all(np.isfinite(yhat))
     assert np.all(np.isfinite(gp.params)) and gp.covariance.shape == (8, 8)
+
+
+NAN_CONFIGS = [
+    # kernel, p, L, N, T, path
+    ("Matern52", 16, 8, 6, 300, "chain"),
+    ("Matern52", 16, 8, 6, 300, "scan"),
+    ("Matern32", 8, 4, 9, 120, "chain"),
+    ("Matern32", 5, 3, 3, 280, "scan"),       # odd p: scalar projection kernel
+    ("Matern32", 64, 32, 1, 600, "scan"),     # tensor-pipe projection kernel, large L
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel,p,L,N,T,path", NAN_CONFIGS)
+def test_missing_observations_whole_sequence(cuda_lib, kernel, p, L, N, T, path):
+    """NaN = missing output (moihgp.h:150-178): least-squares projection on the observed outputs, per observation.
+    Filtered / smoothed states and Yhat match the oracle; the NLL of a sequence with missing data is NaN, as the
+    reference's is (moihgp.h:651 uses the full y), and untouched sequences keep their NLL."""
+    from multioutputihgp_b200 import MOIHGPSequences
+    from oracle.binding import OracleMOIHGP
+    from oracle.gen_golden import make_data, make_params
+    rng = np.random.default_rng(1000 + p + T)
+    params = make_params(rng, p, L, kernel)
+    Y = np.stack([make_data(rng, p, L, T) for _ in range(N)])
+    Y[0, 3, 1] = np.nan                       # a single missing output
+    Y[0, 10, :] = np.nan                      # everything missing: Ty = 0 (LDLT of the zero matrix)
+    Y[0, 11, : max(0, p - L - 2)] = np.nan    # L + 2 outputs left (with fewer than L observed outputs U0'U0 is singular and the
+                                              # reference's LDLT result is rounding noise: no defined answer to compare with)
+    Y[0, T - 1, 0] = np.nan                   # last step
+    miss = rng.random((T, p)) < 0.15          # scattered, but never fewer than L + 2 observed outputs in a row
+    miss[(~miss).sum(axis=1) < L + 2] = False
+    miss[:20] = False                         # (N = 1: keep the hand-placed rows of sequence 0 as they are)
+    miss[T - 1] = False
+    Y[N - 1][miss] = np.nan
+    m = MOIHGPSequences(0.1, p, L, kernel, True)
+    o = OracleMOIHGP(0.1, p, L, kernel, True)
+    m.update(params)
+    o.update(params)
+    m.set_path(path)
+    r = m.filter_smoother_nll(Y, smoother_mode=1, want_yhat=True)
+    ro = o.filter_smoother_nll(Y, smoother_mode=1, want_yhat=True)
+    for k in ("X", "Xs", "Yhat", "xT"):
+        assert np.all(np.isfinite(r[k])), k
+        assert rel_err(r[k], ro[k]) < TOL, k
+    assert np.array_equal(np.isnan(r["nll"]), np.isnan(ro["nll"]))
+    ok = ~np.isnan(ro["nll"])
+    assert np.isnan(r["nll"][0]) and (N == 1 or ok.any() or N == 2)
+    if ok.any():
+        assert rel_err(r["nll"][ok], ro["nll"][ok]) < TOL
