@@ -153,39 +153,73 @@ def check_stability(model, L):
     return worst
 
 
-def cpu_reference_rate(kind, kernel, p, L, N, T, seed, budget_s, nthreads):
-    """Time the CPU implementation of the same pass (the oracle port, -O3, std::thread over sequences) on a
-    bounded sample of the workload: as many sequences (full length when the workload has many, a T-prefix when it is
-    one long sequence) as fit in ~budget_s seconds.  Returns (latent-steps/s, description, seconds)."""
-    from oracle.binding import OracleMOIHGP
+def cpu_reference_rate(kind, kernel, p, L, N, T, seed, budget_s, nthreads, repeats=1):
+    """Time the CPU implementation of the same pass on the host cores, on a bounded sample of the workload: as many
+    sequences (full length when the workload has many, a T-prefix when it is one long sequence) as fit in ~budget_s
+    seconds.  Filter + smoother + NLL: the reference's OWN classes (MOIHGP::step / negLogLikelihood / IHGP::
+    backwardSmoother, compiled -O3 from /root/reference against the Eigen-API shim into oracle/_ref, one model object per
+    host thread, threads over sequences) when that build exists, else the oracle port.  Objective: the oracle port (the
+    reference's O(p^3 L^2)-per-step gradient loop cannot finish at these sizes).
+    `repeats` > 1: the sample is sized once (budget_s seconds each) and timed `repeats` times; the rate and seconds
+    returned are then lists.  Returns (latent-steps/s, sample description, seconds, threads used, kind)."""
+    from oracle import binding
     from oracle.gen_golden import make_data
     params, Hmix = model_params(p, L, kernel, seed)
-    o = OracleMOIHGP(DT, p, L, kernel, threading=True)
-    o.update(params)
     rng = np.random.default_rng(seed)
     many = N >= nthreads
-    Ts = T if many else min(T, 20000 if kind == "fsn" else 2000)
+    use_ref = kind == "fsn" and binding.ref_pass_available()
+    if use_ref:
+        Ts = T if many else min(T, 4000)
+    else:
+        Ts = T if many else min(T, 20000 if kind == "fsn" else 2000)
     base = make_data(rng, p, L, Ts, DT)
 
-    def run(nseq):
-        Y = np.ascontiguousarray(np.broadcast_to(base, (nseq, Ts, p))) + 0.01 * rng.standard_normal((nseq, 1, p))
-        t0 = time.perf_counter()
-        if kind == "fsn":
-            o.filter_smoother_nll(Y, smoother_mode=1, nthreads=nthreads)
-        else:
-            o.objective(Y)       # single thread: the reference's objective loop is sequential (moihgp_regression.h:42-50)
-        return time.perf_counter() - t0
+    if use_ref:
+        import threading
+        workers = [binding.RefPass(DT, p, L, kernel, params) for _ in range(nthreads)]
 
-    n0 = max(nthreads, 1) if kind == "fsn" else 1
+        def run(nseq):
+            Y = np.ascontiguousarray(np.broadcast_to(base, (nseq, Ts, p))) + 0.01 * rng.standard_normal((nseq, 1, p))
+            d = 3 if kernel == "Matern52" else 2
+            outs = [(np.empty((Ts, L, d)), np.empty((Ts, L, d))) for _ in range(nthreads)]
+
+            def work(k):
+                for n in range(k, nseq, nthreads):
+                    workers[k].run(Y[n], outs[k][0], outs[k][1], smooth=True)
+            th = [threading.Thread(target=work, args=(k,)) for k in range(nthreads)]
+            t0 = time.perf_counter()
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            return time.perf_counter() - t0
+        n0, used, what_impl = nthreads, nthreads, "reference classes (-O3, Eigen-API shim), one model per thread, threads over sequences"
+    else:
+        o = binding.OracleMOIHGP(DT, p, L, kernel, threading=True)
+        o.update(params)
+
+        def run(nseq):
+            Y = np.ascontiguousarray(np.broadcast_to(base, (nseq, Ts, p))) + 0.01 * rng.standard_normal((nseq, 1, p))
+            t0 = time.perf_counter()
+            if kind == "fsn":
+                o.filter_smoother_nll(Y, smoother_mode=1, nthreads=nthreads)
+            else:
+                o.objective(Y)       # single thread: the reference's objective loop is sequential (moihgp_regression.h:42-50)
+            return time.perf_counter() - t0
+        n0 = max(nthreads, 1) if kind == "fsn" else 1
+        used = nthreads if kind == "fsn" else 1
+        what_impl = "oracle/moihgp_oracle.cpp -O3" + (", std::thread over sequences" if used > 1 else ", one thread")
+
     t_cal = run(n0)
     cap = 4096 if many else 64 * n0
     nseq = int(max(n0, min(cap, n0 * budget_s / max(t_cal, 1e-3))))
     nseq = (nseq // n0) * n0
-    dt_ = run(nseq)
+    times = [run(nseq) for _ in range(repeats)]
+    dt_ = times[0] if repeats == 1 else times
     what = ("%d full-length sequences of the workload (T=%d)" % (nseq, Ts)) if many else \
            ("%d copies of a T=%d prefix of the workload's single sequence (T=%d)" % (nseq, Ts, T))
-    used = nthreads if kind == "fsn" else 1
-    return nseq * Ts * L / dt_, what, dt_, used
+    rate = nseq * Ts * L / dt_ if repeats == 1 else [nseq * Ts * L / t for t in times]
+    return rate, what + ", " + what_impl, dt_, used, ("reference" if use_ref else "port")
 
 
 def main():
@@ -229,22 +263,21 @@ def main():
         if rank != 0:
             return
         t0 = time.perf_counter()
-        rates, samples = [], []
-        for i in range(warmup + steps):
-            r, what, dt_, used = cpu_reference_rate(kind, kernel, p, L, N, T, seed, budget_s=max(2.0, 60.0 / (warmup + steps)), nthreads=cores)
-            if i >= warmup:
-                rates.append(r)
-                samples.append((what, dt_))
+        # every step is the same bounded sample, sized so that warmup + steps of them take about two minutes
+        per = max(1.0, min(10.0, 120.0 / (warmup + steps)))
+        r, what, dts, used, ckind = cpu_reference_rate(kind, kernel, p, L, N, T, seed, budget_s=per, nthreads=cores, repeats=warmup + steps)
+        rates = r[warmup:]
+        samples = [(what, t) for t in dts[warmup:]]
         value = float(np.mean(rates))
         sample = samples[-1][0] + " per step"
         line = {"impl": "reference", "metric": metric, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": warmup,
                 "ms_per_step": 1e3 * float(np.mean([s[1] for s in samples])), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-                "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": ckind, "sample": sample},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "note": "CPU oracle port of the reference path (oracle/moihgp_oracle.cpp, -O3, std::thread over sequences); the reference's "
-                        "own classes have no whole-sequence filter+smoother entry point (backwardSmoother has no caller) and need Eigen, "
-                        "absent from the image; wall %.0f s" % (time.perf_counter() - t0)}
+                "note": "kind=reference: the reference's own classes (MOIHGP::step v3 + negLogLikelihood(x,y) per observation, then "
+                        "IHGP::backwardSmoother per latent) compiled from /root/reference against the Eigen-API shim (Eigen itself is "
+                        "absent from the image), literal smoother; kind=port: oracle/moihgp_oracle.cpp; wall %.0f s" % (time.perf_counter() - t0)}
         print(json.dumps(line))
         return
 
@@ -411,9 +444,8 @@ def main():
     # ------------------------------------------------------------------ CPU baseline beside it (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
-        r, what, dt_, used = cpu_reference_rate(kind, kernel, p, L, N, T, seed, budget_s=a.cpu_seconds, nthreads=cores)
-        cpu = {"value": r, "unit": UNIT, "cores": used, "kind": "port",
-               "sample": "%s, %.1f s, oracle/moihgp_oracle.cpp -O3%s" % (what, dt_, ", std::thread over sequences" if used > 1 else ", one thread")}
+        r, what, dt_, used, ckind = cpu_reference_rate(kind, kernel, p, L, N, T, seed, budget_s=a.cpu_seconds, nthreads=cores)
+        cpu = {"value": r, "unit": UNIT, "cores": used, "kind": ckind, "sample": "%s, %.1f s" % (what, dt_)}
 
     if rank == 0:
         line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,

@@ -31,7 +31,8 @@ def build(force=False):
     src = os.path.join(_HERE, "moihgp_oracle.cpp")
     if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
         subprocess.check_call(["make", "-C", _HERE, "_build/liboracle.so"], stdout=subprocess.DEVNULL)
-    if os.path.isdir("/root/reference/moihgp/include") and (force or not os.path.exists(os.path.join(_HERE, "_ref", "libmoihgp_ref_probe.so"))):
+    if os.path.isdir("/root/reference/moihgp/include") and (force or not os.path.exists(os.path.join(_HERE, "_ref", "libmoihgp_ref_probe_O3.so"))
+                                                            or os.path.getmtime(os.path.join(_HERE, "_ref", "libmoihgp_ref_probe_O3.so")) < os.path.getmtime(os.path.join(_HERE, "ref_probe.cpp"))):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
     return so
 
@@ -329,3 +330,33 @@ class RefMOIHGP:
         G = np.zeros((self.d, self.d))
         fn(self.dt, _P(np.ascontiguousarray(igp_params, dtype=np.float64)), _P(X), X.shape[0], _P(Xs), _P(P), _P(G))
         return Xs, P, G
+
+
+class RefPass:
+    """The reference's own classes running the fused pass (oracle/ref_probe.cpp: run_pass), -O3 build, threading=false.
+    One instance per host thread (the reference's objects are not thread-safe).  CPU arm of bench.py only."""
+
+    def __init__(self, dt, num_output, num_latent, kernel, params):
+        self.lib = ctypes.CDLL(os.path.join(_HERE, "_ref", "libmoihgp_ref_probe_O3.so"))
+        self.pre = "probe32_" if kernel == "Matern32" else "probe52_"
+        f = lambda n: getattr(self.lib, self.pre + n)
+        f("new").restype = _vp
+        f("new").argtypes = [ctypes.c_double, _sz, _sz, ctypes.c_bool]
+        f("update").argtypes = [_vp, _dp]
+        f("run_pass").restype = ctypes.c_double
+        f("run_pass").argtypes = [_vp, ctypes.c_double, _dp, _dp, _sz, _dp, _dp, ctypes.c_int]
+        self.dt, self.p, self.L = dt, num_output, num_latent
+        self.h = f("new")(dt, num_output, num_latent, False)
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        f("update")(self.h, _P(params))
+        self.igp = np.ascontiguousarray(params[num_output * num_latent + num_latent + 1:])
+        self._run = f("run_pass")
+
+    def run(self, Y, X=None, Xs=None, smooth=True):
+        """Y [T][p] -> summed NLL (and, if given, the filtered / smoothed states [T][L][d])."""
+        Y = np.ascontiguousarray(Y, dtype=np.float64)
+        return float(self._run(self.h, self.dt, _P(self.igp), _P(Y), Y.shape[0], _P(X), _P(Xs), int(smooth)))
+
+
+def ref_pass_available():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libmoihgp_ref_probe_O3.so"))

@@ -6,7 +6,8 @@
 //   * IHGP's public steady-state members A,Q,K,S,PF,HA,AKHA,dS,dA,dK,dAKHA,HdA (ihgp.h:243-254),
 //   * IHGP::backwardSmoother (ihgp.h:103-114), which has no caller in the reference.
 // It is used only to pin the CPU restatement (moihgp_oracle.cpp) and to generate the golden
-// fixtures under tests/golden/ (oracle/gen_golden.py).  It is never timed and never shipped.
+// fixtures under tests/golden/ (oracle/gen_golden.py), and - probeXX_run_pass, the -O2 flavour - as the CPU arm of
+// bench.py (`--impl reference`, cpu_baseline kind "reference").  It is never shipped.
 #include <cstddef>
 #include <vector>
 #include <Eigen/Core>
@@ -136,6 +137,41 @@ struct Probe {
         for (size_t t = 0; t < n; ++t) for (size_t i = 0; i < d; ++i) Xs[t * d + i] = Xout[t](i);
         for (size_t i = 0; i < d; ++i) for (size_t j = 0; j < d; ++j) { P[i * d + j] = Pm(i, j); G[i * d + j] = Gm(i, j); }
     }
+
+    // The fused pass as the reference's own classes run it: the loop of MOIHGPRegression::predict
+    // (moihgp_regression.h:127-139: step(x, y, xnew, yhat)) with negLogLikelihood(x, y) on the pre-step state
+    // (moihgp.h:614-688), then IHGP::backwardSmoother (ihgp.h:103-114) per latent on the stored filtered states.
+    // Y[T][p]; igp_params[L][3]; X, Xs [T][L][d] (may be null).  Returns the summed NLL.
+    static double run_pass(GP* gp, double dt, const double* igp_params, const double* Y, size_t T, double* Xo, double* Xso, int smooth) {
+        const size_t L = gp->getNumLatent(), d = gp->getIGPDim(), p = gp->getNumOutput();
+        VecList X(L, Eigen::VectorXd(d)), Xn(L, Eigen::VectorXd(d));
+        for (size_t l = 0; l < L; ++l) for (size_t i = 0; i < d; ++i) X[l](i) = 0.0;
+        Xn = X;
+        std::vector<VecList> series(L, VecList(T, Eigen::VectorXd(d)));
+        Eigen::VectorXd y(p), yh(p);
+        double nll = 0.0;
+        for (size_t t = 0; t < T; ++t) {
+            for (size_t i = 0; i < p; ++i) y(i) = Y[t * p + i];
+            nll += gp->negLogLikelihood(X, y);
+            gp->step(X, y, Xn, yh);
+            X = Xn;
+            for (size_t l = 0; l < L; ++l) series[l][t] = X[l];
+            if (Xo) for (size_t l = 0; l < L; ++l) for (size_t i = 0; i < d; ++i) Xo[(t * L + l) * d + i] = X[l](i);
+        }
+        if (smooth) {
+            for (size_t l = 0; l < L; ++l) {
+                moihgp::IHGP<SS> ig(dt);
+                Eigen::VectorXd q(3);
+                q(0) = igp_params[3 * l]; q(1) = igp_params[3 * l + 1]; q(2) = igp_params[3 * l + 2];
+                ig.update(q);
+                VecList out;
+                Eigen::MatrixXd Pm, Gm;
+                ig.backwardSmoother(series[l], out, Pm, Gm);
+                if (Xso) for (size_t t = 0; t < T; ++t) for (size_t i = 0; i < d; ++i) Xso[(t * L + l) * d + i] = out[t](i);
+            }
+        }
+        return nll;
+    }
 };
 
 typedef Probe<moihgp::Matern32StateSpace> P32;
@@ -171,7 +207,8 @@ typedef Probe<moihgp::Matern52StateSpace> P52;
     double probe##XX##_lik1(void* gp, const double* x, const double* y, const double* dx, double* grad) { return PXX::lik1(static_cast<PXX::GP*>(gp), x, y, dx, grad); } \
     double probe##XX##_lik2(void* gp, const double* x, const double* y) { return PXX::lik2(static_cast<PXX::GP*>(gp), x, y); } \
     size_t probe##XX##_ihgp_consts(double dt, const double* params, double* out) { return PXX::ihgp_consts(dt, params, out); } \
-    void probe##XX##_ihgp_smoother(double dt, const double* params, const double* X, size_t n, double* Xs, double* P, double* G) { PXX::ihgp_smoother(dt, params, X, n, Xs, P, G); }
+    void probe##XX##_ihgp_smoother(double dt, const double* params, const double* X, size_t n, double* Xs, double* P, double* G) { PXX::ihgp_smoother(dt, params, X, n, Xs, P, G); } \
+    double probe##XX##_run_pass(void* gp, double dt, const double* igp_params, const double* Y, size_t T, double* X, double* Xs, int smooth) { return PXX::run_pass(static_cast<PXX::GP*>(gp), dt, igp_params, Y, T, X, Xs, smooth); }
 
 extern "C" {
 PROBE_API(32, P32)
