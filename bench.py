@@ -222,7 +222,20 @@ def cpu_reference_rate(kind, kernel, p, L, N, T, seed, budget_s, nthreads, repea
     return rate, what + ", " + what_impl, dt_, used, ("reference" if use_ref else "port")
 
 
+def emit(line):
+    """The ONE JSON line goes to the process's real stdout; everything else printed while running (NCCL's version
+    banner, library chatter) was redirected to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
@@ -278,7 +291,7 @@ def main():
                 "note": "kind=reference: the reference's own classes (MOIHGP::step v3 + negLogLikelihood(x,y) per observation, then "
                         "IHGP::backwardSmoother per latent) compiled from /root/reference against the Eigen-API shim (Eigen itself is "
                         "absent from the image), literal smoother; kind=port: oracle/moihgp_oracle.cpp; wall %.0f s" % (time.perf_counter() - t0)}
-        print(json.dumps(line))
+        emit(line)
         return
 
     # ------------------------------------------------------------------ our arm (B200)
@@ -453,7 +466,7 @@ def main():
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "hbm_GBps_alg": balg * units / world / (ms_per_step * 1e-3) / 1e9,
                 ("nll_total" if kind == "fsn" else "loss_total"): result_scalar, "stability": stab}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -438,29 +438,63 @@ __global__ void __launch_bounds__(32, 14) k_filter_chain(const double* __restric
     }
 }
 
+// ---- TMA bulk copies (cp.async.bulk, 1-D) and their mbarrier ------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+constexpr int SSTAGES = 5;        // smoother ring: 3 loads in flight, 1 tile being processed, 1 tile being stored
+
 template <int L, int D, int NS_>
 struct SmoothCfg {
     static constexpr int NS = NS_;
     static constexpr int LD = L * D;
     static constexpr int RUN = L * LD;                 // doubles per sequence-round
-    static constexpr int PS = RUN / 2;                 // 16-byte pieces per sequence-round
     static constexpr int OSEQ = staging_pitch(L, D);
-    static constexpr int PSD = PS / 32 > 0 ? PS / 32 : 1;
-    static constexpr int BYTES = STAGES * NS * OSEQ * 8;
+    static constexpr int BYTES = SSTAGES * NS * OSEQ * 8 + SSTAGES * 8;
 };
 
 // Backward sweep over the stored filtered states.  MODE 0: reference_literal (ihgp.h:108-113, Q3)
 //   Xs[T-1] = X[T-1];  Xs[j] = (I - A) X[j+1] + G Xs[j+1]
 // MODE 1: rts_correct   Xs[j] = X[j] + G (Xs[j+1] - A X[j]) = (I - G A) X[j] + G Xs[j+1].
-// grid: ceil(N / NS) CTAs of one warp; rounds of L steps from the end of the sequence.
+// grid: ceil(N / NS) CTAs of one warp; rounds of L steps from the end of the sequence.  Each sequence-round of X is one
+// contiguous run of L*L*D doubles: it is brought in by ONE TMA bulk copy (mbarrier-tracked), smoothed in place in
+// shared memory, and written out by ONE bulk store - no per-lane load/store instructions touch HBM.
 template <int L, int D, int MODE, int NS_>
 __global__ void __launch_bounds__(32, 14) k_smooth_chain(const double* __restrict__ X, const LatentConsts* __restrict__ consts,
-                                                    long long N, long long T, double* __restrict__ Xs) {
+                                                        long long N, long long T, double* __restrict__ Xs) {
     using C = SmoothCfg<L, D, NS_>;
-    constexpr int NS = C::NS, LD = C::LD, PS = C::PS;
-    constexpr int NPASS = (NS * PS + 31) / 32;
+    constexpr int NS = C::NS, LD = C::LD;
+    constexpr int LOOK = SSTAGES - 2;                  // loads in flight ahead of the round being processed
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* tiles = reinterpret_cast<double*>(smem_raw);                       // [STAGES][NS][OSEQ]
+    double* tiles = reinterpret_cast<double*>(smem_raw);                                   // [SSTAGES][NS][OSEQ]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(tiles + SSTAGES * NS * C::OSEQ);
     const int lane = threadIdx.x;
     const int s = lane / L, j = lane % L;
     const bool active = lane < NS * L;
@@ -478,49 +512,39 @@ __global__ void __launch_bounds__(32, 14) k_smooth_chain(const double* __restric
         }
     const double* const Xcta = X + (size_t)n0 * T * LD;
     double* const Xscta = Xs + (size_t)n0 * T * LD;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < SSTAGES; ++i) mbar_init(bars + i, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
 
-    // per-pass (sequence, piece) of the warp-wide copies
-    auto piece = [&](int k, int& qs, int& qo) {
-        if (PS % 32 == 0) { qs = k / C::PSD; qo = lane + 32 * (k % C::PSD); }
-        else { const int q = lane + 32 * k; qs = q / PS; qo = q % PS; }
-    };
-    // round index k counts from the END: it covers steps t0 = (rounds - 1 - k) * L ...
-    auto issue = [&](long long k) {
+    // round index k counts from the END: it covers steps t0 = (rounds - 1 - k) * L ...; bytes of one sequence's run
+    auto run_bytes = [&](long long t0) { return (unsigned)((T - t0 >= L ? (long long)L : T - t0) * LD * 8); };
+    auto issue = [&](long long k) {               // lane 0 only
         if (k < rounds) {
-            double* st = tiles + (size_t)(k % STAGES) * NS * C::OSEQ;
+            const int st = (int)(k % SSTAGES);
+            double* tile = tiles + (size_t)st * NS * C::OSEQ;
             const long long t0 = (rounds - 1 - k) * L;
-            const double* Xr = Xcta + (size_t)t0 * LD;
-            if (nvalid == NS && t0 + L <= T) {
-#pragma unroll
-                for (int m = 0; m < NPASS; ++m) {
-                    int qs, qo;
-                    piece(m, qs, qo);
-                    if ((NS * PS) % 32 == 0 || qs < NS) cp_async16(st + qs * C::OSEQ + 2 * qo, Xr + (size_t)qs * T * LD + 2 * qo);
-                }
-            } else {
-                const long long rows_left = T - t0;
-                const int valid16 = (int)(rows_left >= L ? PS : rows_left * (LD / 2));
-#pragma unroll
-                for (int m = 0; m < NPASS; ++m) {
-                    const int q = lane + 32 * m;
-                    const int qs = q / PS, qo = q % PS;
-                    if (qs < nvalid && qo < valid16) cp_async16(st + qs * C::OSEQ + 2 * qo, Xr + (size_t)qs * T * LD + 2 * qo);
-                }
-            }
+            const unsigned bytes = run_bytes(t0);
+            bulk_wait_read<1>();                   // the store that last read this stage (two rounds ago) is done with it
+            mbar_expect_tx(bars + st, bytes * (unsigned)nvalid);
+            for (int qs = 0; qs < nvalid; ++qs) bulk_g2s(tile + qs * C::OSEQ, Xcta + ((size_t)qs * T + t0) * LD, bytes, bars + st);
         }
-        cp_async_commit();
     };
+    if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < STAGES - 1; ++k) issue(k);
+        for (int k = 0; k < LOOK; ++k) issue(k);
+    }
 
     double xs[D], xnext[D];                       // Xs[j+1] and X[j+1]
 #pragma unroll
     for (int a = 0; a < D; ++a) { xs[a] = 0.0; xnext[a] = 0.0; }
     for (long long k = 0; k < rounds; ++k) {
-        issue(k + STAGES - 1);
-        cp_async_wait<STAGES - 1>();
-        __syncwarp();
-        double* stw = tiles + (size_t)(k % STAGES) * NS * C::OSEQ;
+        if (lane == 0) issue(k + LOOK);
+        const int stg = (int)(k % SSTAGES);
+        mbar_wait(bars + stg, (unsigned)((k / SSTAGES) & 1));
+        double* stw = tiles + (size_t)stg * NS * C::OSEQ;
         double* st = stw + s * C::OSEQ + j * D;
         const long long t0 = (rounds - 1 - k) * L;
         const bool fast = nvalid == NS && t0 + L <= T;
@@ -548,7 +572,7 @@ __global__ void __launch_bounds__(32, 14) k_smooth_chain(const double* __restric
                 for (int a = 0; a < D; ++a) { xs[a] = out[a]; xnext[a] = xx[a]; }
                 store_state<D>(st + i * LD, out);
             }
-        } else {
+        } else if (s < nvalid) {
 #pragma unroll
             for (int i = L - 1; i >= 0; --i) {
                 const long long t = t0 + i;
@@ -575,40 +599,15 @@ __global__ void __launch_bounds__(32, 14) k_smooth_chain(const double* __restric
                 }
             }
         }
+        fence_async_smem();                        // this lane's shared-memory writes -> visible to the bulk-copy engine
         __syncwarp();
-        {
-            double* Xr = Xscta + (size_t)t0 * LD;
-            if (fast) {
-                double2 v[NPASS];
-#pragma unroll
-                for (int m = 0; m < NPASS; ++m) {
-                    int qs, qo;
-                    piece(m, qs, qo);
-                    if ((NS * PS) % 32 == 0 || qs < NS) v[m] = *reinterpret_cast<const double2*>(stw + qs * C::OSEQ + 2 * qo);
-                }
-#pragma unroll
-                for (int m = 0; m < NPASS; ++m) {
-                    int qs, qo;
-                    piece(m, qs, qo);
-                    if ((NS * PS) % 32 == 0 || qs < NS) *reinterpret_cast<double2*>(Xr + (size_t)qs * T * LD + 2 * qo) = v[m];
-                }
-            } else {
-                const long long rows_left = T - t0;
-                const int valid16 = (int)(rows_left >= L ? PS : rows_left * (LD / 2));
-#pragma unroll
-                for (int m = 0; m < NPASS; ++m) {
-                    const int q = lane + 32 * m;
-                    const int qs = q / PS, qo = q % PS;
-                    if (qs < nvalid && qo < valid16) {
-                        const double2 v = *reinterpret_cast<const double2*>(stw + qs * C::OSEQ + 2 * qo);
-                        *reinterpret_cast<double2*>(Xr + (size_t)qs * T * LD + 2 * qo) = v;
-                    }
-                }
-            }
+        if (lane == 0) {
+            const unsigned bytes = run_bytes(t0);
+            for (int qs = 0; qs < nvalid; ++qs) bulk_s2g(Xscta + ((size_t)qs * T + t0) * LD, stw + qs * C::OSEQ, bytes);
+            bulk_commit();
         }
-        __syncwarp();
     }
-    cp_async_wait<0>();
+    if (lane == 0) bulk_wait_read<0>();            // shared memory must outlive the last bulk store's reads
 }
 
 template <int P, int L, int D, int NS>
