@@ -7,7 +7,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmoihgp.so")
+LIB_PATH = os.environ.get("MOIHGP_B200_LIB") or os.path.join(_HERE, "lib", "libmoihgp.so")   # override: A/B experiments only
 CSRC = os.path.join(_HERE, "csrc")
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
