@@ -87,45 +87,41 @@ int ws_get(moihgp_handle* h, const char* name, size_t count, T** out) {
 // Polar factor U = W V' of a (p x L, row-major, p >= L) via one-sided Jacobi: a V = W diag(s).
 // (MOIHGP::update forms svd.matrixU() * svd.matrixV().transpose(), moihgp.h:439,446.)
 void polar_factor(const double* a, int p, int L, double* out) {
-    std::vector<double> W(a, a + (size_t)p * L), V((size_t)L * L, 0.0);
-    for (int i = 0; i < L; ++i) V[(size_t)i * L + i] = 1.0;
+    // columns stored contiguously (Wt[j][r], Vt[j][r]): the pair sweeps are unit-stride and vectorise
+    std::vector<double> Wt((size_t)L * p), Vt((size_t)L * L, 0.0);
+    for (int r = 0; r < p; ++r) for (int c = 0; c < L; ++c) Wt[(size_t)c * p + r] = a[(size_t)r * L + c];
+    for (int i = 0; i < L; ++i) Vt[(size_t)i * L + i] = 1.0;
     for (int sweep = 0; sweep < 60; ++sweep) {
         double off = 0.0;
         for (int i = 0; i < L - 1; ++i)
             for (int j = i + 1; j < L; ++j) {
+                double* wi = &Wt[(size_t)i * p];
+                double* wj = &Wt[(size_t)j * p];
                 double al = 0.0, be = 0.0, ga = 0.0;
-                for (int r = 0; r < p; ++r) {
-                    const double wi = W[(size_t)r * L + i], wj = W[(size_t)r * L + j];
-                    al += wi * wi; be += wj * wj; ga += wi * wj;
-                }
+                for (int r = 0; r < p; ++r) { al += wi[r] * wi[r]; be += wj[r] * wj[r]; ga += wi[r] * wj[r]; }
                 if (ga == 0.0) continue;
                 off = std::max(off, std::fabs(ga) / std::sqrt(al * be));
                 const double zeta = (be - al) / (2.0 * ga);
                 const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
                 const double c = 1.0 / std::sqrt(1.0 + t * t), s = c * t;
-                for (int r = 0; r < p; ++r) {
-                    const double wi = W[(size_t)r * L + i], wj = W[(size_t)r * L + j];
-                    W[(size_t)r * L + i] = c * wi - s * wj;
-                    W[(size_t)r * L + j] = s * wi + c * wj;
-                }
-                for (int r = 0; r < L; ++r) {
-                    const double vi = V[(size_t)r * L + i], vj = V[(size_t)r * L + j];
-                    V[(size_t)r * L + i] = c * vi - s * vj;
-                    V[(size_t)r * L + j] = s * vi + c * vj;
-                }
+                for (int r = 0; r < p; ++r) { const double x = wi[r], y = wj[r]; wi[r] = c * x - s * y; wj[r] = s * x + c * y; }
+                double* vi = &Vt[(size_t)i * L];
+                double* vj = &Vt[(size_t)j * L];
+                for (int r = 0; r < L; ++r) { const double x = vi[r], y = vj[r]; vi[r] = c * x - s * y; vj[r] = s * x + c * y; }
             }
         if (off < 1e-15) break;
     }
     for (int j = 0; j < L; ++j) {
+        double* wj = &Wt[(size_t)j * p];
         double q = 0.0;
-        for (int r = 0; r < p; ++r) q += W[(size_t)r * L + j] * W[(size_t)r * L + j];
+        for (int r = 0; r < p; ++r) q += wj[r] * wj[r];
         const double s = std::sqrt(q);
-        for (int r = 0; r < p; ++r) W[(size_t)r * L + j] = s > 0.0 ? W[(size_t)r * L + j] / s : 0.0;
+        for (int r = 0; r < p; ++r) wj[r] = s > 0.0 ? wj[r] / s : 0.0;
     }
     for (int r = 0; r < p; ++r)
         for (int c = 0; c < L; ++c) {
             double s = 0.0;
-            for (int k = 0; k < L; ++k) s += W[(size_t)r * L + k] * V[(size_t)c * L + k];
+            for (int k = 0; k < L; ++k) s += Wt[(size_t)k * p + r] * Vt[(size_t)k * L + c];
             out[(size_t)r * L + c] = s;
         }
 }

@@ -108,7 +108,7 @@ __device__ __forceinline__ void lti_scan(const double (&M)[D * D], const LatentC
 
 // grid: N * nC * L warps, 4 warps per CTA (one warp = one (sequence, chunk, latent)); arrays [c][n][l][...]
 template <int D, bool FINAL>
-__global__ void __launch_bounds__(128) k_obj_scan(const double* __restrict__ u, const double* __restrict__ w,
+__global__ void __launch_bounds__(128, 3) k_obj_scan(const double* __restrict__ u, const double* __restrict__ w,
                                                  const double* __restrict__ yl, const LatentConsts* __restrict__ consts,
                                                  const double* __restrict__ S, double sigma, int L, long long N, long long T,
                                                  long long nC, const double* __restrict__ zin, double* __restrict__ zsum,
@@ -446,6 +446,85 @@ __global__ void __launch_bounds__(256) k_gradU(const double* __restrict__ Y, con
         }
 }
 
+// The same contraction on the FP64 tensor pipe (DMMA m8n8k4): CTA tile 64 (outputs r) x 64 (latents c), K panels of 16
+// time steps double-buffered by cp.async; 8 warps, warp w owns rows 8w..8w+7 and all 8 column blocks.
+// A[m = r][k = t] = Y[t][r] comes from the staged panel ys[t][r] (pitch 68), B[k = t][n = c] = wgt[c][t] from ws[c][t]
+// (pitch 20): both fragment loads are bank-conflict free.  Needs p even, T even and 16-byte aligned bases.
+__device__ __forceinline__ void gu_dmma(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void gu_cp16(void* smem, const void* gmem, int bytes) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(bytes) : "memory");
+}
+constexpr int GYP = GT + 4;       // pitch of ys rows (doubles)
+constexpr int GWP = GK + 4;       // pitch of ws rows (doubles)
+__global__ void __launch_bounds__(256) k_gradU_mma(const double* __restrict__ Y, const double* __restrict__ wgt, int p, int L,
+                                                  long long N, long long T, long long slabs_per_split, double* __restrict__ gU_part) {
+    __shared__ __align__(16) double ys[2][GK][GYP];
+    __shared__ __align__(16) double ws[2][GT][GWP];
+    const int tid = threadIdx.x, lane = tid & 31, wi = tid >> 5;
+    const int g4 = lane >> 2, q4 = lane & 3;
+    const int r0 = blockIdx.x * GT, c0 = blockIdx.y * GT, split = blockIdx.z;
+    const long long slabs_per_seq = (T + GK - 1) / GK;
+    const long long total = N * slabs_per_seq;
+    const long long s_begin = (long long)split * slabs_per_split;
+    const long long s_end = min(total, s_begin + slabs_per_split);
+    double acc[8][2];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) { acc[nb][0] = 0.0; acc[nb][1] = 0.0; }
+
+    auto stage = [&](long long sl, int buf) {
+        const long long n = sl / slabs_per_seq;
+        const long long t0 = (sl - n * slabs_per_seq) * GK;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {                       // Y panel: 16 steps x 32 chunks of 2 outputs
+            const int q = tid + 256 * i;
+            const int kk = q >> 5, ch = q & 31;
+            const long long t = t0 + kk;
+            const int col = r0 + 2 * ch;
+            const int bytes = (t < T && col < p) ? 16 : 0;
+            gu_cp16(&ys[buf][kk][2 * ch], Y + ((size_t)n * T + (t < T ? t : 0)) * p + (col < p ? col : 0), bytes);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {                       // weights panel: 64 latents x 8 chunks of 2 steps
+            const int q = tid + 256 * i;
+            const int cc = q >> 3, ch = q & 7;
+            const long long t = t0 + 2 * ch;
+            const int bytes = (c0 + cc < L && t < T) ? 16 : 0;
+            gu_cp16(&ws[buf][cc][2 * ch], wgt + ((size_t)n * L + (c0 + cc < L ? c0 + cc : 0)) * T + (t < T ? t : 0), bytes);
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+
+    if (s_begin < s_end) stage(s_begin, 0);
+    for (long long sl = s_begin; sl < s_end; ++sl) {
+        const int buf = (int)((sl - s_begin) & 1);
+        if (sl + 1 < s_end) { stage(sl + 1, buf ^ 1); asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();
+#pragma unroll
+        for (int kb = 0; kb < GK / 4; ++kb) {
+            const double a = ys[buf][4 * kb + q4][8 * wi + g4];
+            double b[8];
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) b[nb] = ws[buf][8 * nb + g4][4 * kb + q4];
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) gu_dmma(acc[nb][0], acc[nb][1], a, b[nb]);
+        }
+        __syncthreads();
+    }
+    double* out = gU_part + (size_t)split * p * L;
+    const int r = r0 + 8 * wi + g4;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int c = c0 + 8 * nb + 2 * q4 + e;
+            if (r < p && c < L) out[(size_t)r * L + c] = acc[nb][e];
+        }
+}
+
 // Per-latent reduction of the chunk partials (blocks 0..L-1) and of rho (block L): fixed order.
 __global__ void __launch_bounds__(256) k_obj_reduce(const double* __restrict__ part, const double* __restrict__ rho, int L,
                                                    long long N, long long tiles, long long nC, double* __restrict__ lat_sums /*[L+1][8]*/) {
@@ -535,7 +614,9 @@ cudaError_t run_objective(const ObjArgs& a, cudaStream_t st) {
     const long long slabs = a.N * ((a.T + GK - 1) / GK);
     const long long per = (slabs + (long long)nsplit - 1) / (long long)nsplit;
     dim3 gg((a.p + GT - 1) / GT, (a.L + GT - 1) / GT, (unsigned)nsplit);
-    k_gradU<<<gg, 256, 0, st>>>(a.Y, a.wgt, a.p, a.L, a.N, a.T, per, a.gU_part);
+    const bool mma_ok = a.p % 2 == 0 && a.T % 2 == 0 && (reinterpret_cast<size_t>(a.Y) & 15) == 0 && (reinterpret_cast<size_t>(a.wgt) & 15) == 0;
+    if (mma_ok) k_gradU_mma<<<gg, 256, 0, st>>>(a.Y, a.wgt, a.p, a.L, a.N, a.T, per, a.gU_part);
+    else k_gradU<<<gg, 256, 0, st>>>(a.Y, a.wgt, a.p, a.L, a.N, a.T, per, a.gU_part);
     mark(a.mk, "k_gradU");
     double* lat_sums = a.lat_sums;
     k_obj_reduce<<<a.L + 1, 256, 0, st>>>(a.part, a.rho, a.L, a.N, (long long)project_tiles(a.T), nC, lat_sums);

@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(MT) k_project_mma(const double* __restrict__ Y
     const double* Yn = Y + ((size_t)n * T + t0) * p;
     const int npanels = (p + KP - 1) / KP;
     if (tid == 0) any_bad = 0;
+    const bool u_vec = L % 2 == 0 && (reinterpret_cast<size_t>(U) & 15) == 0;
 
     // stage panel kp: Y rows [0, PT) x columns [kp*KP, kp*KP + KP) and U rows [kp*KP, +KP) x [0, LP)
     auto stage = [&](int kp, int buf) {
@@ -211,9 +212,18 @@ __global__ void __launch_bounds__(MT) k_project_mma(const double* __restrict__ Y
             cp_async16_zfill(yb + row * YROWB + ((ch ^ (2 * (row & 3))) << 4), src, bytes);
         }
         double* ub = usm + buf * (SMC::UBYTES / 8);
-        for (int i = tid; i < KP * SMC::LP; i += MT) {
-            const int k = i / SMC::LP, l = i - k * SMC::LP;
-            ub[k * SMC::UPITCH + l] = (c0 + k < p && l < L) ? __ldg(U + (size_t)(c0 + k) * L + l) : 0.0;
+        if (u_vec) {
+            // U rows are 16-byte aligned (L even): asynchronous 16-byte copies, zero fill beyond p / L
+            for (int i = tid; i < KP * (SMC::LP / 2); i += MT) {
+                const int k = i / (SMC::LP / 2), l = 2 * (i - k * (SMC::LP / 2));
+                const int bytes = (c0 + k < p && l < L) ? 16 : 0;
+                cp_async16_zfill(ub + k * SMC::UPITCH + l, U + (size_t)(c0 + k < p ? c0 + k : 0) * L + (l < L ? l : 0), bytes);
+            }
+        } else {
+            for (int i = tid; i < KP * SMC::LP; i += MT) {
+                const int k = i / SMC::LP, l = i - k * SMC::LP;
+                ub[k * SMC::UPITCH + l] = (c0 + k < p && l < L) ? __ldg(U + (size_t)(c0 + k) * L + l) : 0.0;
+            }
         }
         cp_async_commit();
     };
