@@ -40,6 +40,10 @@ struct moihgp_handle {
     double *d_U = nullptr, *d_S = nullptr, *d_igp = nullptr;
     LatentConsts* d_consts = nullptr;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the pipelined host-buffer pass (created on first use)
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_c[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    int* h_flags = nullptr;                   // pinned per-slice status words
+    size_t h_flags_cap = 0;
     std::map<std::string, Buf> ws;            // grow-only device workspace
     double* h_stage = nullptr;                // pinned host staging for the per-observation calls
     double* d_stage = nullptr;
@@ -286,6 +290,10 @@ void moihgp_cuda_destroy(moihgp_handle* h) {
     cudaFree(h->d_U); cudaFree(h->d_S); cudaFree(h->d_igp); cudaFree(h->d_consts); cudaFree(h->d_stage);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
+    if (h->h_flags) cudaFreeHost(h->h_flags);
+    for (int i = 0; i < 2; ++i) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_c[i]) cudaEventDestroy(h->ev_c[i]); if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]); }
     delete h;
 }
 
@@ -476,35 +484,81 @@ int moihgp_cuda_filter_smoother_nll_dev(moihgp_handle* h, const double* Y, size_
     return 0;
 }
 
+// Host buffers.  Independent sequences are processed in slices, software-pipelined over three streams: the H2D copy of
+// slice i+1 and the D2H copy of slice i-1 overlap the kernels of slice i (PCIe is full duplex), with two sets of
+// device buffers.  (Pinned host memory is needed for the copies to be asynchronous; pageable memory still works.)
 int moihgp_cuda_filter_smoother_nll(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0, int mode, double* X,
                                     double* Xs, double* Yhat, double* nll, double* xT) {
     if (!h || !Y) return -2;
     if (N == 0 || T == 0) return fail(h, "N and T must be positive");
+    if (mode < -1 || mode > 1) return fail(h, "smoother_mode must be -1, 0 or 1");
+    if (mode < 0 && Xs) return fail(h, "Xs requested with smoother_mode = none");
     cudaSetDevice(h->device);
     const size_t L = h->L, D = h->dim, p = h->p;
-    double *dY, *dx0 = nullptr, *dX = nullptr, *dXs = nullptr, *dYh = nullptr, *dnll = nullptr, *dxT = nullptr;
-    if (ws_get(h, "hY", N * T * p, &dY)) return -1;
-    if (x0 && ws_get(h, "hx0", N * L * D, &dx0)) return -1;
-    if ((X || Yhat) && ws_get(h, "hX", N * T * L * D, &dX)) return -1;
-    if (Xs && ws_get(h, "hXs", N * T * L * D, &dXs)) return -1;
-    if (Yhat && ws_get(h, "hYh", N * T * p, &dYh)) return -1;
-    if (nll && ws_get(h, "hnll", N, &dnll)) return -1;
-    if (xT && ws_get(h, "hxT", N * L * D, &dxT)) return -1;
-    CK(cudaMemcpyAsync(dY, Y, sizeof(double) * N * T * p, cudaMemcpyHostToDevice, h->stream));
-    if (x0) CK(cudaMemcpyAsync(dx0, x0, sizeof(double) * N * L * D, cudaMemcpyHostToDevice, h->stream));
-    const int rc = moihgp_cuda_filter_smoother_nll_dev(h, dY, N, T, dx0, mode, dX, dXs, dYh, dnll, dxT);
-    if (rc) return rc;
-    if (X) CK(cudaMemcpyAsync(X, dX, sizeof(double) * N * T * L * D, cudaMemcpyDeviceToHost, h->stream));
-    if (Xs) CK(cudaMemcpyAsync(Xs, dXs, sizeof(double) * N * T * L * D, cudaMemcpyDeviceToHost, h->stream));
-    if (Yhat) CK(cudaMemcpyAsync(Yhat, dYh, sizeof(double) * N * T * p, cudaMemcpyDeviceToHost, h->stream));
-    if (nll) CK(cudaMemcpyAsync(nll, dnll, sizeof(double) * N, cudaMemcpyDeviceToHost, h->stream));
-    if (xT) CK(cudaMemcpyAsync(xT, dxT, sizeof(double) * N * L * D, cudaMemcpyDeviceToHost, h->stream));
-    int flag = 0;
+    // slices: enough chains per slice to keep every SM busy (the many-chains kernels want >= 2 warps per SM), about
+    // eight slices when the batch is large; a multiple of 32 sequences
+    size_t Ns = std::max<size_t>((2 * 148 * 32 + L - 1) / L, (N + 7) / 8);
+    Ns = ((Ns + 31) / 32) * 32;
+    if (Ns > N) Ns = N;
+    const size_t nsl = (N + Ns - 1) / Ns;
+    if (!h->s_in) {
+        CK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->ev_c[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+        }
+    }
+    const int nbuf = nsl > 1 ? 2 : 1;
+    double *dY[2] = {}, *dx0[2] = {}, *dX[2] = {}, *dXs[2] = {}, *dYh[2] = {}, *dnll[2] = {}, *dxT[2] = {};
+    static const char* names[2][7] = {{"hY0", "hx00", "hX0", "hXs0", "hYh0", "hnll0", "hxT0"}, {"hY1", "hx01", "hX1", "hXs1", "hYh1", "hnll1", "hxT1"}};
+    for (int b = 0; b < nbuf; ++b) {
+        if (ws_get(h, names[b][0], Ns * T * p, &dY[b])) return -1;
+        if (x0 && ws_get(h, names[b][1], Ns * L * D, &dx0[b])) return -1;
+        if ((X || Yhat || Xs) && ws_get(h, names[b][2], Ns * T * L * D, &dX[b])) return -1;
+        if (Xs && ws_get(h, names[b][3], Ns * T * L * D, &dXs[b])) return -1;
+        if (Yhat && ws_get(h, names[b][4], Ns * T * p, &dYh[b])) return -1;
+        if (nll && ws_get(h, names[b][5], Ns, &dnll[b])) return -1;
+        if (xT && ws_get(h, names[b][6], Ns * L * D, &dxT[b])) return -1;
+    }
     int* nanf;
     if (ws_get(h, "nanf", 4, &nanf)) return -1;
-    CK(cudaMemcpyAsync(&flag, nanf, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (h->h_flags_cap < nsl) {
+        if (h->h_flags) cudaFreeHost(h->h_flags);
+        h->h_flags = nullptr;
+        h->h_flags_cap = 0;
+        CK(cudaMallocHost(&h->h_flags, sizeof(int) * nsl));
+        h->h_flags_cap = nsl;
+    }
+    int* flags = h->h_flags;
+    for (size_t i = 0; i < nsl; ++i) flags[i] = 0;
+    CK(cudaStreamSynchronize(h->stream));            // earlier work on the compute stream may still use the buffers
+    for (size_t i = 0; i < nsl; ++i) {
+        const int b = (int)(i & 1) % nbuf;
+        const size_t n0 = i * Ns, ns = std::min(Ns, N - n0);
+        if (i >= 2) CK(cudaStreamWaitEvent(h->s_in, h->ev_c[b], 0));                   // input buffer b is free again
+        CK(cudaMemcpyAsync(dY[b], Y + n0 * T * p, sizeof(double) * ns * T * p, cudaMemcpyHostToDevice, h->s_in));
+        if (x0) CK(cudaMemcpyAsync(dx0[b], x0 + n0 * L * D, sizeof(double) * ns * L * D, cudaMemcpyHostToDevice, h->s_in));
+        CK(cudaEventRecord(h->ev_in[b], h->s_in));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_in[b], 0));
+        if (i >= 2) CK(cudaStreamWaitEvent(h->stream, h->ev_out[b], 0));               // output buffers b have been copied out
+        const int rc = moihgp_cuda_filter_smoother_nll_dev(h, dY[b], ns, T, x0 ? dx0[b] : nullptr, mode, dX[b], dXs[b], dYh[b], dnll[b], dxT[b]);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(&flags[i], nanf, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaEventRecord(h->ev_c[b], h->stream));
+        CK(cudaStreamWaitEvent(h->s_out, h->ev_c[b], 0));
+        if (X) CK(cudaMemcpyAsync(X + n0 * T * L * D, dX[b], sizeof(double) * ns * T * L * D, cudaMemcpyDeviceToHost, h->s_out));
+        if (Xs) CK(cudaMemcpyAsync(Xs + n0 * T * L * D, dXs[b], sizeof(double) * ns * T * L * D, cudaMemcpyDeviceToHost, h->s_out));
+        if (Yhat) CK(cudaMemcpyAsync(Yhat + n0 * T * p, dYh[b], sizeof(double) * ns * T * p, cudaMemcpyDeviceToHost, h->s_out));
+        if (nll) CK(cudaMemcpyAsync(nll + n0, dnll[b], sizeof(double) * ns, cudaMemcpyDeviceToHost, h->s_out));
+        if (xT) CK(cudaMemcpyAsync(xT + n0 * L * D, dxT[b], sizeof(double) * ns * L * D, cudaMemcpyDeviceToHost, h->s_out));
+        CK(cudaEventRecord(h->ev_out[b], h->s_out));
+    }
+    CK(cudaStreamSynchronize(h->s_out));
     CK(cudaStreamSynchronize(h->stream));
-    if (flag == 2) return fail(h, "more than 2^22 observations with missing (NaN) outputs in one call: split the batch");
+    for (size_t i = 0; i < nsl; ++i)
+        if (flags[i] == 2) return fail(h, "more than 2^22 observations with missing (NaN) outputs in one call: split the batch");
     return 0;
 }
 
