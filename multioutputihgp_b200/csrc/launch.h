@@ -41,7 +41,7 @@ struct ScanArgs {
     int L;
     long long N, T;
     const double* x0;             // [N][L][D] carried-in filter state or null (zeros)
-    double *fsum, *bsum, *xin, *bin;   // [nC][N][L][D] chunk summaries / carries (workspace)
+    double *fsum, *bsum, *xin, *bin;   // [N][L][nC][D] chunk summaries / carries (workspace)
     double* Bx;                   // [L][2][D*D] chunk responses (workspace)
     double *X, *Xs;               // [N][T][L][D] outputs (either may be null)
     double* vsq;                  // [nC][N][L] sum of squared innovations (workspace)

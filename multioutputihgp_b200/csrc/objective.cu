@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(128, 3) k_obj_scan(const double* __restrict__ 
     double uu[SUB];
     load8(u, uu);
 
-    const size_t ci = (((size_t)c * N + n) * L + l) * 4 * D;
+    const size_t ci = (((size_t)n * L + l) * nC + c) * 4 * D;     // carries are chunk-minor: [n][l][chunk][4*D]
     double zi[4][D];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(128) k_obj_carry(const LatentConsts* __restric
     for (int k = 0; k < 3; ++k)
 #pragma unroll
         for (int i = 0; i < D * D; ++i) E[k][i] = Ek[((size_t)l * 3 + k) * D * D + i];
-    const size_t stride = (size_t)N * L * 4 * D, base = (size_t)id * 4 * D;
+    const size_t stride = 4 * D, base = (size_t)id * nC * 4 * D;   // [n][l][chunk][4*D]
     const long long nG = (nC + 32 * CG - 1) / (32 * CG);
     double carry[4][D];
 #pragma unroll

@@ -91,8 +91,10 @@ __host__ __device__ __forceinline__ int tile_group_stride(int RS) { return SUB *
 // step of the next chunk (0 if none), tf = global index of this lane's first step.
 //   FINAL = false: x_in / b_in are zero (or a unit vector for k_response); returns f_end (lane 31) and beta (lane 0).
 //   FINAL = true : additionally stores X / Xs rows into the shared tiles and returns sum v^2 (per lane).
-template <int D, int MODE, bool FINAL>
-__device__ __forceinline__ void chunk_pass(const LC<D>& c, const LatentConsts* lc, const double (&uu)[SUB], double u_next,
+//   INTERIOR     : every step of the chunk is < T - 1 (no end-of-sequence predicates).
+//   pw           : the latent's scan powers, [2][5][D*D] doubles: M^(SUB 2^k) then G^(SUB 2^k), k = 0..4.
+template <int D, int MODE, bool FINAL, bool INTERIOR>
+__device__ __forceinline__ void chunk_pass(const LC<D>& c, const double* __restrict__ pw, const double (&uu)[SUB], double u_next,
                                            long long tf, long long T, const double (&x_in)[D], const double (&b_in)[D],
                                            int lane, double (&f_end)[D], double (&beta)[D], double& vsq,
                                            double* tX, double* tXs, int RS, double (&x_last_out)[D]) {
@@ -113,9 +115,10 @@ __device__ __forceinline__ void chunk_pass(const LC<D>& c, const LatentConsts* l
         const int o = 1 << k;
         double zo[D], P[D * D];
 #pragma unroll
-        for (int q = 0; q < D; ++q) zo[q] = __shfl_up_sync(FULL, z[q], o);
-        load_mat<D>(lc->powM[LOG2_SUB + k], P);
-        if (lane >= o) mv_acc<D>(P, zo, z);
+        for (int q = 0; q < D; ++q) { const double t = __shfl_up_sync(FULL, z[q], o); zo[q] = lane >= o ? t : 0.0; }
+#pragma unroll
+        for (int q = 0; q < D * D; ++q) P[q] = pw[k * D * D + q];
+        mv_acc<D>(P, zo, z);
     }
 #pragma unroll
     for (int q = 0; q < D; ++q) f_end[q] = z[q];
@@ -138,7 +141,7 @@ __device__ __forceinline__ void chunk_pass(const LC<D>& c, const LatentConsts* l
         mv<D>(c.M, x, xn);
 #pragma unroll
         for (int q = 0; q < D; ++q) { x[q] = fma(c.K[q], uu[i], xn[q]); X[i][q] = x[q]; }   // ihgp.h:90
-        if (FINAL && tf + i < T) {
+        if (FINAL && (INTERIOR || tf + i < T)) {
             vsq = fma(v[i], v[i], vsq);
 #pragma unroll
             for (int q = 0; q < D; ++q) tX[i * RS + q] = x[q];
@@ -172,7 +175,7 @@ __device__ __forceinline__ void chunk_pass(const LC<D>& c, const LatentConsts* l
         const long long t = tf + i;
         if (MODE == 1) {
             const double vn = (i + 1 < SUB) ? v[(i + 1) % SUB] : v_next;
-            const double s = t < T - 1 ? vn : 0.0;
+            const double s = (INTERIOR || t < T - 1) ? vn : 0.0;
 #pragma unroll
             for (int q = 0; q < D; ++q) g[q] = c.drv[q] * s;
         } else {
@@ -182,7 +185,7 @@ __device__ __forceinline__ void chunk_pass(const LC<D>& c, const LatentConsts* l
             double im[D];
             mv<D>(c.drv, xn, im);
 #pragma unroll
-            for (int q = 0; q < D; ++q) g[q] = t < T - 1 ? im[q] : (t == T - 1 ? X[i][q] : 0.0);
+            for (int q = 0; q < D; ++q) g[q] = (INTERIOR || t < T - 1) ? im[q] : (t == T - 1 ? X[i][q] : 0.0);
         }
     };
     // ---- backward, local --------------------------------------------------------------------
@@ -203,9 +206,10 @@ __device__ __forceinline__ void chunk_pass(const LC<D>& c, const LatentConsts* l
         const int o = 1 << k;
         double bo[D], P[D * D];
 #pragma unroll
-        for (int q = 0; q < D; ++q) bo[q] = __shfl_down_sync(FULL, b[q], o);
-        load_mat<D>(lc->powG[MODE][LOG2_SUB + k], P);
-        if (lane + o < 32) mv_acc<D>(P, bo, b);
+        for (int q = 0; q < D; ++q) { const double t = __shfl_down_sync(FULL, b[q], o); bo[q] = lane + o < 32 ? t : 0.0; }
+#pragma unroll
+        for (int q = 0; q < D * D; ++q) P[q] = pw[(5 + k) * D * D + q];
+        mv_acc<D>(P, bo, b);
     }
 #pragma unroll
     for (int q = 0; q < D; ++q) beta[q] = b[q];
@@ -223,7 +227,7 @@ __device__ __forceinline__ void chunk_pass(const LC<D>& c, const LatentConsts* l
         mv<D>(c.G, b, bn);
 #pragma unroll
         for (int q = 0; q < D; ++q) b[q] = bn[q] + g[q];
-        if (tf + i < T) {
+        if (INTERIOR || tf + i < T) {
 #pragma unroll
             for (int q = 0; q < D; ++q) tXs[i * RS + q] = MODE == 1 ? tX[i * RS + q] + b[q] : b[q];
         }
@@ -231,7 +235,7 @@ __device__ __forceinline__ void chunk_pass(const LC<D>& c, const LatentConsts* l
 }
 
 // grid: N * nC * nLG CTAs (latent-group minor), block: 32 * lg threads (lg = latents in the group, <= LGMAX).
-// Per-chunk arrays are laid out [c][n][l][D].
+// Per-chunk carries are laid out [n][l][c][D] (chunk-minor: the carry kernel reads them with unit stride); vsq is [c][n][l].
 template <int D, int MODE, bool FINAL>
 __global__ void __launch_bounds__(32 * LGMAX, 2) k_scan(const double* __restrict__ u, const LatentConsts* __restrict__ consts,
                                                     int L, long long N, long long T, long long nC, int nLG,
@@ -240,6 +244,7 @@ __global__ void __launch_bounds__(32 * LGMAX, 2) k_scan(const double* __restrict
                                                     double* __restrict__ X, double* __restrict__ Xs,
                                                     double* __restrict__ vsq_out, double* __restrict__ xT) {
     extern __shared__ double tile[];
+    __shared__ double pws[LGMAX][10 * D * D];       // per latent of the CTA: M^(SUB 2^k), then G^(SUB 2^k), k = 0..4
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
     const long long bid = blockIdx.x;
     const int lgi = (int)(bid % nLG);
@@ -254,6 +259,14 @@ __global__ void __launch_bounds__(32 * LGMAX, 2) k_scan(const double* __restrict
     const int GS = tile_group_stride(RS);
     double* tileX = tile;
     double* tileXs = tile + 32 * GS;
+    for (int i = threadIdx.x; i < lg * 10 * D * D; i += blockDim.x) {
+        const int w = i / (10 * D * D), r = i - w * (10 * D * D);
+        const int m = r / (D * D), e = r - m * (D * D);
+        const LatentConsts* lcw = consts + l0 + w;
+        const double* src = m < 5 ? lcw->powM[LOG2_SUB + m] : lcw->powG[MODE][LOG2_SUB + m - 5];
+        pws[w][r] = src[(e / D) * 3 + (e % D)];
+    }
+    __syncthreads();
 
     if (active) {
         const LatentConsts* lc = consts + l;
@@ -275,7 +288,7 @@ __global__ void __launch_bounds__(32 * LGMAX, 2) k_scan(const double* __restrict
         }
         const double u_next = t0 + CH < T ? __ldg(up + t0 + CH) : 0.0;
         double x_in[D], b_in[D], f_end[D], beta[D], x_last[D], vsq;
-        const size_t ci = (((size_t)c * N + n) * L + l) * D;
+        const size_t ci = (((size_t)n * L + l) * nC + c) * D;      // carries are chunk-minor: [n][l][chunk][D]
 #pragma unroll
         for (int q = 0; q < D; ++q) {
             x_in[q] = FINAL ? xin[ci + q] : 0.0;
@@ -283,7 +296,8 @@ __global__ void __launch_bounds__(32 * LGMAX, 2) k_scan(const double* __restrict
         }
         double* tX = tileX + lane * GS + wi * D;
         double* tXs = tileXs + lane * GS + wi * D;
-        chunk_pass<D, MODE, FINAL>(cst, lc, uu, u_next, tf, T, x_in, b_in, lane, f_end, beta, vsq, tX, tXs, RS, x_last);
+        if (t0 + CH < T) chunk_pass<D, MODE, FINAL, true>(cst, pws[wi], uu, u_next, tf, T, x_in, b_in, lane, f_end, beta, vsq, tX, tXs, RS, x_last);
+        else chunk_pass<D, MODE, FINAL, false>(cst, pws[wi], uu, u_next, tf, T, x_in, b_in, lane, f_end, beta, vsq, tX, tXs, RS, x_last);
         if (!FINAL) {
             if (lane == 31) {
 #pragma unroll
@@ -333,6 +347,13 @@ __global__ void __launch_bounds__(32) k_response(const LatentConsts* __restrict_
     const LatentConsts* lc = consts + l;
     LC<D> cst;
     load_lc<D, MODE>(lc, cst);
+    __shared__ double pw[10 * D * D];
+    for (int i = lane; i < 10 * D * D; i += 32) {
+        const int m = i / (D * D), e = i - m * (D * D);
+        const double* src = m < 5 ? lc->powM[LOG2_SUB + m] : lc->powG[MODE][LOG2_SUB + m - 5];
+        pw[i] = src[(e / D) * 3 + (e % D)];
+    }
+    __syncwarp();
     double uu[SUB];
 #pragma unroll
     for (int i = 0; i < SUB; ++i) uu[i] = 0.0;
@@ -340,7 +361,7 @@ __global__ void __launch_bounds__(32) k_response(const LatentConsts* __restrict_
 #pragma unroll
     for (int q = 0; q < D; ++q) { x_in[q] = q == k ? 1.0 : 0.0; b_in[q] = 0.0; }
     const long long T = kind == 0 ? (1LL << 60) : r_last;
-    chunk_pass<D, MODE, false>(cst, lc, uu, 0.0, (long long)lane * SUB, T, x_in, b_in, lane, f_end, beta, vsq, nullptr, nullptr, 0, x_last);
+    chunk_pass<D, MODE, false, false>(cst, pw, uu, 0.0, (long long)lane * SUB, T, x_in, b_in, lane, f_end, beta, vsq, nullptr, nullptr, 0, x_last);
     if (lane == 0) {
 #pragma unroll
         for (int q = 0; q < D; ++q) Bx[((size_t)l * 2 + kind) * D * D + q * D + k] = beta[q];
@@ -369,21 +390,32 @@ __global__ void __launch_bounds__(128) k_carry(const LatentConsts* __restrict__ 
     load_mat<D>(lc->powG[MODE][LOG2_CH], GC);
 #pragma unroll
     for (int i = 0; i < D * D; ++i) { Bf[i] = Bx[((size_t)l * 2 + 0) * D * D + i]; Bl[i] = Bx[((size_t)l * 2 + 1) * D * D + i]; }
-    const size_t stride = (size_t)N * L * D;   // between consecutive chunks
-    const size_t base = (size_t)id * D;
+    const size_t stride = D;                   // between consecutive chunks of one (sequence, latent): [n][l][chunk][D]
+    const size_t base = (size_t)id * nC * D;
     const long long nG = (nC + 32 * CG - 1) / (32 * CG);
 
     // ---- forward ---------------------------------------------------------------------------------
     double carry[D];
 #pragma unroll
-    for (int q = 0; q < D; ++q) carry[q] = x0 ? x0[base + q] : 0.0;
+    for (int q = 0; q < D; ++q) carry[q] = x0 ? x0[(size_t)id * D + q] : 0.0;
+    // the summaries of the next group are fetched while the current one is scanned (the groups run in sequence)
+    auto load_f = [&](long long g, double (&f)[CG][D]) {
+        const long long c0 = (g * 32 + lane) * CG;
+#pragma unroll
+        for (int i = 0; i < CG; ++i)
+#pragma unroll
+            for (int q = 0; q < D; ++q) f[i][q] = (c0 + i < nC - 1) ? fsum[(c0 + i) * stride + base + q] : 0.0;   // f of the last chunk is never used
+    };
+    double fnext[CG][D];
+    load_f(0, fnext);
     for (long long g = 0; g < nG; ++g) {
         const long long c0 = (g * 32 + lane) * CG;
         double f[CG][D];
 #pragma unroll
         for (int i = 0; i < CG; ++i)
 #pragma unroll
-            for (int q = 0; q < D; ++q) f[i][q] = (c0 + i < nC - 1) ? fsum[(c0 + i) * stride + base + q] : 0.0;   // f of the last chunk is never used
+            for (int q = 0; q < D; ++q) f[i][q] = fnext[i][q];
+        if (g + 1 < nG) load_f(g + 1, fnext);
         double z[D];
 #pragma unroll
         for (int q = 0; q < D; ++q) z[q] = lane == 0 ? carry[q] : 0.0;
@@ -427,9 +459,8 @@ __global__ void __launch_bounds__(128) k_carry(const LatentConsts* __restrict__ 
     //   b[nC-1] = 0;  b[c-1] = G^CH b[c] + d[c],  d[c] = beta0[c] + B(kind c) xin[c]
 #pragma unroll
     for (int q = 0; q < D; ++q) carry[q] = 0.0;
-    for (long long g = nG - 1; g >= 0; --g) {
-        const long long c0 = (g * 32 + lane) * CG;       // this lane produces b[c0-1 .. c0+CG-2] from b[c0+CG-1]
-        double dv[CG][D];
+    auto load_d = [&](long long g, double (&dv)[CG][D]) {
+        const long long c0 = (g * 32 + lane) * CG;
 #pragma unroll
         for (int i = 0; i < CG; ++i) {
             const long long c = c0 + i;
@@ -445,6 +476,17 @@ __global__ void __launch_bounds__(128) k_carry(const LatentConsts* __restrict__ 
                 for (int q = 0; q < D; ++q) dv[i][q] = 0.0;
             }
         }
+    };
+    double dnext[CG][D];
+    load_d(nG - 1, dnext);
+    for (long long g = nG - 1; g >= 0; --g) {
+        const long long c0 = (g * 32 + lane) * CG;       // this lane produces b[c0-1 .. c0+CG-2] from b[c0+CG-1]
+        double dv[CG][D];
+#pragma unroll
+        for (int i = 0; i < CG; ++i)
+#pragma unroll
+            for (int q = 0; q < D; ++q) dv[i][q] = dnext[i][q];
+        if (g > 0) load_d(g - 1, dnext);
         // local: from zero (lane 31: from the carry of the later groups)
         double z[D];
 #pragma unroll

@@ -327,3 +327,25 @@ def test_missing_observations_whole_sequence(cuda_lib, kernel, p, L, N, T, path)
     assert np.isnan(r["nll"][0]) and (N == 1 or ok.any() or N == 2)
     if ok.any():
         assert rel_err(r["nll"][ok], ro["nll"][ok]) < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["online_py_p8L4_w2", "online_py_p4L2_w1"])
+def test_online_learner_follows_the_reference_python_driver(cuda_lib, name):
+    """BASELINE config 2 protocol (streaming update, online_learning.py:53-105): the golden trajectory was produced by the
+    reference's OWN pywrapper.py + online_learning.py on the reference's C ABI (oracle/gen_golden_online.py); here the same
+    stream goes through this package's mirror on the GPU.  L-BFGS-B (5 iterations, 3 line-search steps per sample) feeds
+    rounding differences back into the parameters, hence the looser tolerance on the trajectory."""
+    import os
+    from conftest import ROOT
+    from multioutputihgp_b200 import MOIHGPOnlineLearning
+    z = np.load(os.path.join(ROOT, "tests", "golden_online", name + ".npz"))
+    gp = MOIHGPOnlineLearning(float(z["dt"]), int(z["p"]), int(z["L"]), gamma=float(z["gamma"]), windowsize=int(z["window"]), threading=False)
+    gp._update(z["params0"])
+    worst_y = worst_p = 0.0
+    for y, yh_ref, p_ref in zip(z["data"], z["yhat"], z["params"]):
+        yh = gp.step(y.copy())
+        worst_y = max(worst_y, rel_err(yh, yh_ref))
+        worst_p = max(worst_p, rel_err(gp.params, p_ref))
+    print(name, "worst rel. err yhat %.2e params %.2e" % (worst_y, worst_p))
+    assert worst_y < 1e-9 and worst_p < 1e-9
