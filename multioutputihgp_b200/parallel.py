@@ -87,3 +87,112 @@ def sharded_nll(local_nll, group=None, device=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return float(t.item())
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# One LONG sequence sharded over ranks in TIME (BASELINE configs 4 and 5).
+#
+# The recursion is LTI-affine (ihgp.h:50,54): over a block of n steps the augmented state z = [x; dx_0; dx_1; dx_2] of a
+# latent maps as  z_out = T(n) z_in + z_out(z_in = 0),  with  T(n): x -> M^n x,  dx_k -> M^n dx_k + E_k(n) x,
+# M = AKHA, E_k(n) = sum_i M^(n-1-i) dAKHA_k M^i.  So every rank (1) runs its block from a ZERO carry-in, (2) all-gathers
+# the L*d*(1+K) end-state doubles, (3) forms its true carry-in from the blocks before it, (4) runs its block again from
+# the true carry-in - the loss / gradient are quadratic in the state, so they need the true states - and (5) all-reduces
+# [loss, grad].  Two passes per rank, no other exchange: a G-rank job runs G/2 times faster than one GPU.
+
+def block_transition(AKHA, dAKHA, n):
+    """(M^n, E_k(n)) by binary powering: doubling (P, E) -> (P P, P E + E P), increment (P, E) -> (M P, M E + dM P).
+    Batched over leading axes: AKHA [..., d, d], dAKHA [..., K, d, d] (or a list of K [d, d] matrices for one latent)."""
+    AKHA = np.asarray(AKHA, dtype=np.float64)
+    as_list = isinstance(dAKHA, (list, tuple))
+    dM = np.stack([np.asarray(m_, dtype=np.float64) for m_ in dAKHA], axis=-3) if as_list else np.asarray(dAKHA, dtype=np.float64)
+    d = AKHA.shape[-1]
+    M = AKHA[..., None, :, :]                                   # broadcast over K
+    P = np.broadcast_to(np.eye(d), AKHA.shape).copy()
+    E = np.zeros(dM.shape)
+    for bit in bin(int(n))[2:]:
+        Pk = P[..., None, :, :]
+        E = Pk @ E + E @ Pk
+        P = P @ P
+        if bit == "1":
+            E = M @ E + dM @ P[..., None, :, :]
+            P = AKHA @ P
+    return (P, [E[..., k, :, :] for k in range(E.shape[-3])]) if as_list else (P, E)
+
+
+def stack_consts(consts):
+    """Per-latent constant dicts (latent_consts / ihgp_consts) -> (AKHA [L,d,d], dAKHA [L,3,d,d])."""
+    return (np.stack([c["AKHA"] for c in consts]), np.stack([np.stack([c["dAKHA%d" % k] for k in range(3)]) for c in consts]))
+
+
+def carry_in_from_block_ends(consts, block_lengths, ends_x, ends_dx, x0, dx0, rank):
+    """True carry-in (x [L,d], dx [L,3,d]) of block `rank`, given every block's end state from a zero carry-in.
+    consts: list of per-latent dicts or the stacked pair of stack_consts(); ends_x [G,L,d], ends_dx [G,L,3,d]."""
+    AK, dAK = consts if isinstance(consts, tuple) else stack_consts(consts)
+    x = np.array(x0, dtype=np.float64).copy()
+    dx = np.array(dx0, dtype=np.float64).copy()
+    cache = {}
+    for g in range(rank):
+        n = int(block_lengths[g])
+        if n not in cache:
+            cache[n] = block_transition(AK, dAK, n)
+        P, E = cache[n]                                          # [L,d,d], [L,3,d,d]
+        xo = x
+        x = np.einsum("lij,lj->li", P, xo) + ends_x[g]
+        dx = np.einsum("lij,lkj->lki", P, dx) + np.einsum("lkij,lj->lki", E, xo) + ends_dx[g]
+    return x, dx
+
+
+class TimeShardedObjective(object):
+    """loss, grad of ONE long sequence whose contiguous time blocks live on different ranks.
+
+    ``evaluate(Y_block, x0, dx0) -> (loss, grad, xT, dxT)`` is the local evaluator (``MOIHGPSequences.objective`` with
+    ``want_state=True`` on a GPU box); ``consts`` the per-latent constants of the CURRENT hyper-parameters
+    (``[model.latent_consts(l) for l in range(L)]``); ``block_lengths[g]`` the number of time steps of rank g's block."""
+
+    def __init__(self, evaluate, consts, block_lengths, num_param, group=None, device=None):
+        self.evaluate, self.block_lengths = evaluate, [int(b) for b in block_lengths]
+        self.consts = consts if isinstance(consts, tuple) else stack_consts(consts)
+        self.num_param, self.group, self.device = int(num_param), group, device
+
+    def _gather(self, vec, world):
+        import torch
+        dist = _dist()
+        t = torch.from_numpy(np.ascontiguousarray(vec))
+        if self.device is not None:
+            t = t.to(self.device)
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t, group=self.group)
+        return [o.cpu().numpy() for o in out]
+
+    def __call__(self, Y_block, x0=None, dx0=None):
+        import torch
+        dist = _dist()
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        world = dist.get_world_size(self.group) if multi else 1
+        rank = dist.get_rank(self.group) if multi else 0
+        L, d = self.consts[0].shape[0], self.consts[0].shape[-1]
+        x0 = np.zeros((L, d)) if x0 is None else np.asarray(x0, dtype=np.float64).reshape(L, d)
+        dx0 = np.zeros((L, 3, d)) if dx0 is None else np.asarray(dx0, dtype=np.float64).reshape(L, 3, d)
+        if not multi:
+            loss, grad, xT, dxT = self.evaluate(Y_block, x0, dx0)
+            return loss, grad
+        # (1) block from a zero carry-in -> its end state; (2) all-gather
+        _, _, xT, dxT = self.evaluate(Y_block, np.zeros((L, d)), np.zeros((L, 3, d)))
+        flat = np.concatenate([np.asarray(xT).ravel(), np.asarray(dxT).ravel()])
+        ends = self._gather(flat, world)
+        ends_x = [e[:L * d].reshape(L, d) for e in ends]
+        ends_dx = [e[L * d:].reshape(L, 3, d) for e in ends]
+        # (3) true carry-in, (4) the block again, (5) all-reduce
+        xin, dxin = carry_in_from_block_ends(self.consts, self.block_lengths, ends_x, ends_dx, x0, dx0, rank)
+        loss, grad, _, _ = self.evaluate(Y_block, xin, dxin)
+        buf = torch.from_numpy(np.concatenate([[loss], np.asarray(grad, dtype=np.float64)]))
+        if self.device is not None:
+            buf = buf.to(self.device)
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+        buf = buf.cpu().numpy()
+        return float(buf[0]), buf[1:].copy()
+
+
+def time_block_bounds(T, world_size, rank):
+    """Contiguous time block [t0, t1) of rank `rank` (same balancing rule as shard_bounds)."""
+    return shard_bounds(T, world_size, rank)

@@ -3,6 +3,8 @@
   * the CPU oracle on the same seeded inputs at sizes it finishes in seconds,
   * size-independent properties at larger sizes (chunk invariance, carried state, linearity).
 Tolerance: 1e-9 norm-wise relative in fp64 (BASELINE.json north_star), written as conftest.TOL."""
+import os
+
 import numpy as np
 import pytest
 
@@ -349,3 +351,20 @@ def test_online_learner_follows_the_reference_python_driver(cuda_lib, name):
         worst_p = max(worst_p, rel_err(gp.params, p_ref))
     print(name, "worst rel. err yhat %.2e params %.2e" % (worst_y, worst_p))
     assert worst_y < 1e-9 and worst_p < 1e-9
+
+
+@pytest.mark.gpu
+def test_time_sharded_objective_two_gpus(cuda_lib):
+    """one long sequence split in time over two GPUs (carry all-gather + NCCL all-reduce) equals the
+    single-GPU evaluation.  Needs two devices; skipped on a one-GPU box (the gloo twin runs in the CPU suite)."""
+    import subprocess
+    import sys
+    import torch
+    from conftest import ROOT
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, TS_T="60000", TS_P="16", TS_L="8")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", os.path.join(ROOT, "scripts", "gpu_time_shard.py")], capture_output=True, text=True, env=env, timeout=600)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "time-sharded objective" in r.stdout
