@@ -324,7 +324,7 @@ def main():
         def step():
             device_pass()
             torch.sum(nll, dim=0, keepdim=True, out=out)
-            if world > 1:
+            if world > 1 and not os.environ.get("BENCH_SKIP_ALLREDUCE"):      # (diagnosis only: isolates the collective's cost)
                 dist.all_reduce(out)
     else:
         out = torch.zeros(2 + model.num_param, dtype=torch.float64, device=dev)   # [loss, pad, grad...] (all-reduced)
