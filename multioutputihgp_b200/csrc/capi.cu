@@ -130,8 +130,10 @@ void polar_factor(const double* a, int p, int L, double* out) {
         }
 }
 
-int push_model(moihgp_handle* h) {
-    CK(cudaMemcpyAsync(h->d_U, h->U.data(), sizeof(double) * h->U.size(), cudaMemcpyHostToDevice, h->stream));
+// device_polar: d_U already holds the polar factor (k_polar); bring it to the host copy instead of uploading it
+int push_model(moihgp_handle* h, bool device_polar = false) {
+    if (device_polar) CK(cudaMemcpyAsync(h->U.data(), h->d_U, sizeof(double) * h->U.size(), cudaMemcpyDeviceToHost, h->stream));
+    else CK(cudaMemcpyAsync(h->d_U, h->U.data(), sizeof(double) * h->U.size(), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_S, h->S.data(), sizeof(double) * h->S.size(), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_igp, h->igp.data(), sizeof(double) * h->igp.size(), cudaMemcpyHostToDevice, h->stream));
     CK(launch_setup(h->dim, h->d_igp, h->dt, h->L, h->d_consts, h->stream));
@@ -367,11 +369,21 @@ int moihgp_cuda_update(moihgp_handle* h, const double* params) {
     if (!h || !params) return -2;
     cudaSetDevice(h->device);
     const int p = h->p, L = h->L;
-    polar_factor(params, p, L, h->U.data());                               // moihgp.h:436-446
+    // moihgp.h:436-446: polar factor of the U block - on the device when the block is large (k_polar), else host Jacobi
+    const bool dev_polar = (size_t)p * L >= 2048 && polar_smem_bytes(p, L) <= 200 * 1024;
+    if (dev_polar) {
+        double* d_raw;
+        if (ws_get(h, "Uraw", (size_t)p * L, &d_raw)) return -1;
+        CK(cudaMemcpyAsync(d_raw, params, sizeof(double) * p * L, cudaMemcpyHostToDevice, h->stream));
+        CK(launch_polar(d_raw, p, L, h->d_U, h->stream));
+        h->launches += 1;
+    } else {
+        polar_factor(params, p, L, h->U.data());
+    }
     for (int l = 0; l < L; ++l) h->S[l] = params[p * L + l];               // moihgp.h:448
     h->sigma = params[p * L + L];                                          // moihgp.h:449
     for (int i = 0; i < 3 * L; ++i) h->igp[i] = params[p * L + L + 1 + i]; // moihgp.h:450-456
-    return push_model(h);
+    return push_model(h, dev_polar);
 }
 
 int moihgp_cuda_get_params(moihgp_handle* h, double* params) {

@@ -26,6 +26,10 @@ inline void mark(Marker* m, const char* name) { if (m) m->mark(name); }
 // setup.cu
 cudaError_t launch_setup(int dim, const double* d_igp_params, double dt, int L, LatentConsts* d_out, cudaStream_t stream);
 
+// polar.cu  (MOIHGP::update's polar factor on the device, for large p * L)
+size_t polar_smem_bytes(int p, int L);
+cudaError_t launch_polar(const double* A /*[p][L]*/, int p, int L, double* U, cudaStream_t st);
+
 // project.cu
 size_t project_tiles(long long T);     // tiles of 128 time steps per sequence: rho_part is [N][project_tiles(T)]
 cudaError_t launch_project(const double* Y, const double* U, const double* S, int p, int L, long long N, long long T,

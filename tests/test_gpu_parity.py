@@ -118,6 +118,7 @@ def test_cuda_matches_oracle(cuda_lib, kernel, threading, p, L, N, T, seed):
     o = OracleMOIHGP(0.1, p, L, kernel, threading)
     m.update(params)
     o.update(params)
+    assert rel_err(m.U, o.U) < TOL and rel_err(m.params, o.params) < TOL      # polar factor (host Jacobi, or k_polar when p * L >= 2048)
     d = m.igp_dim
     x0 = 0.2 * rng.standard_normal((N, L, d))
     dx0 = 0.1 * rng.standard_normal((N, L, 3, d))
@@ -368,3 +369,22 @@ def test_time_sharded_objective_two_gpus(cuda_lib):
                         "--master-port", "29541", os.path.join(ROOT, "scripts", "gpu_time_shard.py")], capture_output=True, text=True, env=env, timeout=600)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0 and "time-sharded objective" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("p,L", [(256, 64), (64, 32), (96, 33), (200, 11)])
+def test_update_polar_factor_on_device(cuda_lib, p, L):
+    """MOIHGP::update (moihgp.h:431-447): U = polar factor of the raw block; large blocks go through k_polar.  Checked against
+    the SVD-based polar factor; update(getParams()) leaves U unchanged (the polar factor of an orthonormal matrix is itself)."""
+    from multioutputihgp_b200 import MOIHGPSequences
+    rng = np.random.default_rng(p + L)
+    m = MOIHGPSequences(0.1, p, L, "Matern32", True)
+    raw = rng.standard_normal((p, L)) / np.sqrt(L) + np.eye(p, L)
+    params = np.concatenate([raw.ravel(), np.ones(L), [1e-2], np.tile([1.0, 1.0, 0.1], L)])
+    m.update(params)
+    u, _, vt = np.linalg.svd(raw, full_matrices=False)
+    assert rel_err(m.U, u @ vt) < 1e-12
+    assert np.max(np.abs(m.U.T @ m.U - np.eye(L))) < 1e-13
+    U1 = m.U.copy()
+    m.update(m.params)
+    assert rel_err(m.U, U1) < 1e-13
