@@ -1,0 +1,3 @@
+// many-chains kernels for p = 16 outputs, L = 8 latents (see chain_kernels.cuh)
+#include "chain_kernels.cuh"
+MOIHGP_CHAIN_INSTANCE(16, 8, true)

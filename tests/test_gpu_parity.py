@@ -145,6 +145,14 @@ CHAIN_CONFIGS = [
     ("Matern32", 8, 4, 11, 333, 23),
     ("Matern52", 8, 4, 1, 7, 24),
     ("Matern52", 16, 8, 6, 1, 25),
+    ("Matern32", 32, 16, 3, 150, 26),            # further instantiated shapes (full warp only)
+    ("Matern52", 32, 8, 5, 97, 27),
+    ("Matern52", 32, 4, 9, 65, 28),
+    ("Matern32", 16, 16, 2, 200, 29),
+    ("Matern52", 16, 4, 10, 130, 30),
+    ("Matern32", 16, 2, 17, 60, 31),
+    ("Matern52", 8, 8, 5, 120, 32),
+    ("Matern32", 8, 2, 33, 50, 33),
 ]
 
 
