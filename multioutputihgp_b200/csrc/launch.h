@@ -47,12 +47,14 @@ struct ScanArgs {
     const double* x0;             // [N][L][D] carried-in filter state or null (zeros)
     double *fsum, *bsum, *xin, *bin;   // [N][L][nC][D] chunk summaries / carries (workspace)
     double* Bx;                   // [L][2][D*D] chunk responses (workspace)
+    double* Wsum;                 // [L][scan_weights_doubles / L] weights of the interior-chunk summaries (workspace)
     double *X, *Xs;               // [N][T][L][D] outputs (either may be null)
     double* vsq;                  // [nC][N][L] sum of squared innovations (workspace)
     double* xT;                   // [N][L][D] final filtered state or null
     Marker* mk = nullptr;
 };
 size_t scan_chunks(long long T);
+size_t scan_weights_doubles(int L);
 int scan_launch_count(long long T);
 cudaError_t launch_scan(int dim, int mode, const ScanArgs& a, cudaStream_t st);
 size_t nll_partials(long long N);

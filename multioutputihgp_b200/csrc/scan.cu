@@ -234,11 +234,14 @@ __device__ __forceinline__ void chunk_pass(const LC<D>& c, const double* __restr
     }
 }
 
-// grid: N * nC * nLG CTAs (latent-group minor), block: 32 * lg threads (lg = latents in the group, <= LGMAX).
+// grid: N * nG * nLG CTAs (latent-group minor), block: 32 * lg threads (lg = latents in the group, <= LGMAX); CTA
+// (n, g, latent group) walks the chunks c_base + g * cpc ... (cpc chunks, fewer for the last group) so that the latent
+// constants and power tables are loaded once per CTA, not once per chunk.
 // Per-chunk carries are laid out [n][l][c][D] (chunk-minor: the carry kernel reads them with unit stride); vsq is [c][n][l].
 template <int D, int MODE, bool FINAL>
 __global__ void __launch_bounds__(32 * LGMAX, 2) k_scan(const double* __restrict__ u, const LatentConsts* __restrict__ consts,
                                                     int L, long long N, long long T, long long nC, int nLG,
+                                                    long long c_base, long long c_cnt, long long cpc,
                                                     const double* __restrict__ xin, const double* __restrict__ bin,
                                                     double* __restrict__ fsum, double* __restrict__ bsum,
                                                     double* __restrict__ X, double* __restrict__ Xs,
@@ -246,15 +249,15 @@ __global__ void __launch_bounds__(32 * LGMAX, 2) k_scan(const double* __restrict
     extern __shared__ double tile[];
     __shared__ double pws[LGMAX][10 * D * D];       // per latent of the CTA: M^(SUB 2^k), then G^(SUB 2^k), k = 0..4
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const long long nG = (c_cnt + cpc - 1) / cpc;
     const long long bid = blockIdx.x;
     const int lgi = (int)(bid % nLG);
-    const long long c = (bid / nLG) % nC;
-    const long long n = bid / ((long long)nLG * nC);
+    const long long gi = (bid / nLG) % nG;
+    const long long n = bid / ((long long)nLG * nG);
     const int l0 = lgi * LGMAX;
     const int lg = min(LGMAX, L - l0);          // == blockDim.x / 32 for all but a ragged last group
     const int l = l0 + wi;
     const bool active = wi < lg;
-    const long long t0 = c * CH;
     const int RS = lg * D;
     const int GS = tile_group_stride(RS);
     double* tileX = tile;
@@ -267,15 +270,116 @@ __global__ void __launch_bounds__(32 * LGMAX, 2) k_scan(const double* __restrict
         pws[w][r] = src[(e / D) * 3 + (e % D)];
     }
     __syncthreads();
+    const LatentConsts* lc = consts + (active ? l : l0);
+    LC<D> cst;
+    load_lc<D, MODE>(lc, cst);
+    const double* up = u + ((size_t)n * L + (active ? l : l0)) * T;
+    const long long c_lo = c_base + gi * cpc, c_hi = min(c_base + c_cnt, c_lo + cpc);
 
-    if (active) {
-        const LatentConsts* lc = consts + l;
-        LC<D> cst;
-        load_lc<D, MODE>(lc, cst);
-        const long long tf = t0 + (long long)lane * SUB;
-        const double* up = u + ((size_t)n * L + l) * T;
+    for (long long c = c_lo; c < c_hi; ++c) {
+        const long long t0 = c * CH;
+        if (active) {
+            const long long tf = t0 + (long long)lane * SUB;
+            double uu[SUB];
+            if (tf + SUB <= T && ((reinterpret_cast<size_t>(up + tf) & 15) == 0)) {
+#pragma unroll
+                for (int i = 0; i < SUB; i += 2) {
+                    const double2 t2 = __ldg(reinterpret_cast<const double2*>(up + tf + i));
+                    uu[i] = t2.x;
+                    uu[i + 1] = t2.y;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < SUB; ++i) uu[i] = tf + i < T ? __ldg(up + tf + i) : 0.0;
+            }
+            const double u_next = t0 + CH < T ? __ldg(up + t0 + CH) : 0.0;
+            double x_in[D], b_in[D], f_end[D], beta[D], x_last[D], vsq;
+            const size_t ci = (((size_t)n * L + l) * nC + c) * D;      // carries are chunk-minor: [n][l][chunk][D]
+#pragma unroll
+            for (int q = 0; q < D; ++q) {
+                x_in[q] = FINAL ? xin[ci + q] : 0.0;
+                b_in[q] = FINAL ? bin[ci + q] : 0.0;
+            }
+            double* tX = tileX + lane * GS + wi * D;
+            double* tXs = tileXs + lane * GS + wi * D;
+            if (t0 + CH < T) chunk_pass<D, MODE, FINAL, true>(cst, pws[wi], uu, u_next, tf, T, x_in, b_in, lane, f_end, beta, vsq, tX, tXs, RS, x_last);
+            else chunk_pass<D, MODE, FINAL, false>(cst, pws[wi], uu, u_next, tf, T, x_in, b_in, lane, f_end, beta, vsq, tX, tXs, RS, x_last);
+            if (!FINAL) {
+                if (lane == 31) {
+#pragma unroll
+                    for (int q = 0; q < D; ++q) fsum[ci + q] = f_end[q];
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int q = 0; q < D; ++q) bsum[ci + q] = beta[q];
+                }
+            } else {
+                // deterministic warp reduction of sum v^2
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) vsq += __shfl_xor_sync(FULL, vsq, o);
+                if (lane == 0) vsq_out[((size_t)c * N + n) * L + l] = vsq;
+                // final filtered state of the sequence: X[T-1]
+                if (xT && T - 1 >= tf && T - 1 < tf + SUB) {
+                    const int i = (int)(T - 1 - tf);
+#pragma unroll
+                    for (int q = 0; q < D; ++q) xT[((size_t)n * L + l) * D + q] = tX[i * RS + q];
+                }
+            }
+        }
+        if (FINAL) {
+            __syncthreads();
+            // ---- coalesced copy-out of the staged rows ------------------------------------------------
+            const int rows = (int)min((long long)CH, T - t0);
+            const size_t grow = (size_t)L * D;                       // global row pitch (doubles)
+            const size_t gbase = ((size_t)n * T + t0) * grow + (size_t)l0 * D;
+            for (int i = threadIdx.x; i < rows * RS; i += blockDim.x) {
+                const int row = i / RS, col = i - row * RS;
+                const int so = (row / SUB) * GS + (row % SUB) * RS + col;
+                const size_t go = gbase + (size_t)row * grow + col;
+                if (X) X[go] = tileX[so];
+                if (Xs) Xs[go] = tileXs[so];
+            }
+            __syncthreads();                                        // the tiles are reused by the next chunk
+        }
+    }
+}
+
+// Summaries of the INTERIOR chunks (every chunk but the last of a sequence) from zero carries.  Both summaries are
+// linear in the chunk's inputs, so they are dot products with the weights k_scan_weights tabulated (f_end and beta per
+// unit input) plus beta's response to u_next.  One warp per (sequence, latent, group of chunks): the lane's 2 D x SUB
+// weights stay in registers while it walks its chunks - the pass is a pure stream over u.
+constexpr int WS_STRIDE = 2 * DMAX * CH + 4;       // doubles per latent in Wsum (even: 16-byte loads)
+template <int D>
+__global__ void __launch_bounds__(128) k_scan_summaries_dot(const double* __restrict__ u, const double* __restrict__ Wsum, int L,
+                                                           long long N, long long T, long long nC, long long cpw,
+                                                           double* __restrict__ fsum, double* __restrict__ bsum) {
+    const int lane = threadIdx.x & 31;
+    const long long nI = nC - 1;                                    // interior chunks
+    const long long nG = (nI + cpw - 1) / cpw;
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= N * L * nG) return;
+    const long long g = wid % nG;
+    const int l = (int)((wid / nG) % L);
+    const long long n = wid / (nG * L);
+    const double* wl = Wsum + (size_t)l * WS_STRIDE;
+    double w[2 * D][SUB], wn[D];
+#pragma unroll
+    for (int k = 0; k < 2 * D; ++k)
+#pragma unroll
+        for (int i = 0; i < SUB; i += 2) {
+            const double2 t2 = __ldg(reinterpret_cast<const double2*>(wl + k * CH + lane * SUB + i));
+            w[k][i] = t2.x;
+            w[k][i + 1] = t2.y;
+        }
+#pragma unroll
+    for (int q = 0; q < D; ++q) wn[q] = __ldg(wl + 2 * D * CH + q);
+    const double* up = u + ((size_t)n * L + l) * T;
+    const bool vec = (reinterpret_cast<size_t>(up) & 15) == 0;      // chunk starts are multiples of 256 steps
+    const long long c_hi = min(nI, (g + 1) * cpw);
+    for (long long c = g * cpw; c < c_hi; ++c) {
+        const long long tf = c * CH + (long long)lane * SUB;
         double uu[SUB];
-        if (tf + SUB <= T && ((reinterpret_cast<size_t>(up + tf) & 15) == 0)) {
+        if (vec) {
 #pragma unroll
             for (int i = 0; i < SUB; i += 2) {
                 const double2 t2 = __ldg(reinterpret_cast<const double2*>(up + tf + i));
@@ -284,54 +388,67 @@ __global__ void __launch_bounds__(32 * LGMAX, 2) k_scan(const double* __restrict
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < SUB; ++i) uu[i] = tf + i < T ? __ldg(up + tf + i) : 0.0;
+            for (int i = 0; i < SUB; ++i) uu[i] = __ldg(up + tf + i);
         }
-        const double u_next = t0 + CH < T ? __ldg(up + t0 + CH) : 0.0;
-        double x_in[D], b_in[D], f_end[D], beta[D], x_last[D], vsq;
-        const size_t ci = (((size_t)n * L + l) * nC + c) * D;      // carries are chunk-minor: [n][l][chunk][D]
+        const double u_next = __ldg(up + (c + 1) * CH);
+        double acc[2 * D];
 #pragma unroll
-        for (int q = 0; q < D; ++q) {
-            x_in[q] = FINAL ? xin[ci + q] : 0.0;
-            b_in[q] = FINAL ? bin[ci + q] : 0.0;
+        for (int k = 0; k < 2 * D; ++k) {
+            double a = w[k][0] * uu[0];
+#pragma unroll
+            for (int i = 1; i < SUB; ++i) a = fma(w[k][i], uu[i], a);
+            acc[k] = a;
         }
-        double* tX = tileX + lane * GS + wi * D;
-        double* tXs = tileXs + lane * GS + wi * D;
-        if (t0 + CH < T) chunk_pass<D, MODE, FINAL, true>(cst, pws[wi], uu, u_next, tf, T, x_in, b_in, lane, f_end, beta, vsq, tX, tXs, RS, x_last);
-        else chunk_pass<D, MODE, FINAL, false>(cst, pws[wi], uu, u_next, tf, T, x_in, b_in, lane, f_end, beta, vsq, tX, tXs, RS, x_last);
-        if (!FINAL) {
-            if (lane == 31) {
 #pragma unroll
-                for (int q = 0; q < D; ++q) fsum[ci + q] = f_end[q];
-            }
-            if (lane == 0) {
+        for (int k = 0; k < 2 * D; ++k)
 #pragma unroll
-                for (int q = 0; q < D; ++q) bsum[ci + q] = beta[q];
-            }
-        } else {
-            // deterministic warp reduction of sum v^2
+            for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(FULL, acc[k], o);
+        if (lane == 0) {
+            const size_t ci = (((size_t)n * L + l) * nC + c) * D;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) vsq += __shfl_xor_sync(FULL, vsq, o);
-            if (lane == 0) vsq_out[((size_t)c * N + n) * L + l] = vsq;
-            // final filtered state of the sequence: X[T-1]
-            if (xT && T - 1 >= tf && T - 1 < tf + SUB) {
-                const int i = (int)(T - 1 - tf);
-#pragma unroll
-                for (int q = 0; q < D; ++q) xT[((size_t)n * L + l) * D + q] = tX[i * RS + q];
-            }
+            for (int q = 0; q < D; ++q) { fsum[ci + q] = acc[q]; bsum[ci + q] = fma(wn[q], u_next, acc[D + q]); }
         }
     }
-    if (!FINAL) return;
-    __syncthreads();
-    // ---- coalesced copy-out of the staged rows ----------------------------------------------------
-    const int rows = (int)min((long long)CH, T - t0);
-    const size_t grow = (size_t)L * D;                       // global row pitch (doubles)
-    const size_t gbase = ((size_t)n * T + t0) * grow + (size_t)l0 * D;
-    for (int i = threadIdx.x; i < rows * RS; i += blockDim.x) {
-        const int row = i / RS, col = i - row * RS;
-        const int so = (row / SUB) * GS + (row % SUB) * RS + col;
-        const size_t go = gbase + (size_t)row * grow + col;
-        if (X) X[go] = tileX[so];
-        if (Xs) Xs[go] = tileXs[so];
+}
+
+// Weights of the summaries of an INTERIOR chunk run from zero carries: with unit input at step i (or at u_next) the chunk
+// returns f_end (lane 31) and beta (lane 0).  Layout per latent (stride WS_STRIDE): [2 D][CH] (f_end rows, then beta
+// rows), then beta's response to u_next [D].  grid: L * (CH + 1) blocks of one warp.
+template <int D, int MODE>
+__global__ void __launch_bounds__(32) k_scan_weights(const LatentConsts* __restrict__ consts, double* __restrict__ Wsum) {
+    const int lane = threadIdx.x;
+    const int i = blockIdx.x % (CH + 1);
+    const int l = blockIdx.x / (CH + 1);
+    const LatentConsts* lc = consts + l;
+    LC<D> cst;
+    load_lc<D, MODE>(lc, cst);
+    __shared__ double pw[10 * D * D];
+    for (int k = lane; k < 10 * D * D; k += 32) {
+        const int m = k / (D * D), e = k - m * (D * D);
+        const double* src = m < 5 ? lc->powM[LOG2_SUB + m] : lc->powG[MODE][LOG2_SUB + m - 5];
+        pw[k] = src[(e / D) * 3 + (e % D)];
+    }
+    __syncwarp();
+    double uu[SUB];
+#pragma unroll
+    for (int k = 0; k < SUB; ++k) uu[k] = (i < CH && lane * SUB + k == i) ? 1.0 : 0.0;
+    double x_in[D], b_in[D], f_end[D], beta[D], x_last[D], vsq;
+#pragma unroll
+    for (int q = 0; q < D; ++q) { x_in[q] = 0.0; b_in[q] = 0.0; }
+    chunk_pass<D, MODE, false, true>(cst, pw, uu, i == CH ? 1.0 : 0.0, (long long)lane * SUB, 1LL << 60, x_in, b_in, lane, f_end, beta, vsq, nullptr, nullptr, 0, x_last);
+    double* wl = Wsum + (size_t)l * WS_STRIDE;
+    if (i < CH) {
+        if (lane == 31) {
+#pragma unroll
+            for (int q = 0; q < D; ++q) wl[q * CH + i] = f_end[q];
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < D; ++q) wl[(D + q) * CH + i] = beta[q];
+        }
+    } else if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < D; ++q) wl[2 * D * CH + q] = beta[q];
     }
 }
 
@@ -577,23 +694,38 @@ cudaError_t run_scan(const ScanArgs& a, cudaStream_t st) {
     const int nLG = (a.L + LGMAX - 1) / LGMAX;
     const int lg = a.L < LGMAX ? a.L : LGMAX;
     const long long r_last = a.T - (nC - 1) * CH;
-    const unsigned grid = (unsigned)(a.N * nC * nLG);
     const int RS = lg * D;
     const size_t smem = sizeof(double) * 2 * 32 * (size_t)tile_group_stride(RS);
     if (smem > 48 * 1024) {
         cudaFuncSetAttribute(k_scan<D, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
+    // chunks per CTA / warp: enough CTAs to fill the machine several times over, as few prologues as that allows
+    const long long target = 148LL * 16;
+    auto per_unit = [&](long long units, long long chunks) {
+        long long groups = (target + units - 1) / units;
+        if (groups < 1) groups = 1;
+        if (groups > chunks) groups = chunks;
+        return (chunks + groups - 1) / groups;
+    };
     if (nC > 1) {
-        k_scan<D, MODE, false><<<grid, 32 * lg, 0, st>>>(a.u, a.consts, a.L, a.N, a.T, nC, nLG, nullptr, nullptr, a.fsum, a.bsum,
-                                                         nullptr, nullptr, nullptr, nullptr);
+        // summaries: interior chunks as dot products with tabulated weights, the last chunk by the recurrence itself
+        k_scan_weights<D, MODE><<<a.L * (CH + 1), 32, 0, st>>>(a.consts, a.Wsum);
+        const long long nI = nC - 1;
+        const long long cpw = per_unit(a.N * a.L, nI);
+        const long long warps = a.N * a.L * ((nI + cpw - 1) / cpw);
+        k_scan_summaries_dot<D><<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(a.u, a.Wsum, a.L, a.N, a.T, nC, cpw, a.fsum, a.bsum);
+        k_scan<D, MODE, false><<<(unsigned)(a.N * nLG), 32 * lg, 0, st>>>(a.u, a.consts, a.L, a.N, a.T, nC, nLG, nC - 1, 1, 1, nullptr, nullptr,
+                                                                         a.fsum, a.bsum, nullptr, nullptr, nullptr, nullptr);
         mark(a.mk, "k_scan_summaries");
         k_response<D, MODE><<<a.L * 2 * D, 32, 0, st>>>(a.consts, r_last, a.Bx);
         mark(a.mk, "k_response");
     }
     k_carry<D, MODE><<<(unsigned)((a.N * a.L * 32 + 127) / 128), 128, 0, st>>>(a.consts, a.Bx, a.L, a.N, nC, a.x0, a.fsum, a.bsum, a.xin, a.bin);
     mark(a.mk, "k_carry");
-    k_scan<D, MODE, true><<<grid, 32 * lg, smem, st>>>(a.u, a.consts, a.L, a.N, a.T, nC, nLG, a.xin, a.bin, nullptr, nullptr, a.X, a.Xs,
-                                                       a.vsq, a.xT);
+    const long long cpc = per_unit(a.N * nLG, nC);
+    const long long nG = (nC + cpc - 1) / cpc;
+    k_scan<D, MODE, true><<<(unsigned)(a.N * nG * nLG), 32 * lg, smem, st>>>(a.u, a.consts, a.L, a.N, a.T, nC, nLG, 0, nC, cpc, a.xin, a.bin,
+                                                                            nullptr, nullptr, a.X, a.Xs, a.vsq, a.xT);
     mark(a.mk, "k_scan_final");
     return cudaGetLastError();
 }
@@ -602,7 +734,9 @@ cudaError_t run_scan(const ScanArgs& a, cudaStream_t st) {
 
 size_t scan_chunks(long long T) { return (size_t)((T + CH - 1) / CH); }
 
-int scan_launch_count(long long T) { return (T + CH - 1) / CH > 1 ? 4 : 2; }
+int scan_launch_count(long long T) { return (T + CH - 1) / CH > 1 ? 6 : 2; }
+
+size_t scan_weights_doubles(int L) { return (size_t)L * WS_STRIDE; }
 
 cudaError_t launch_scan(int dim, int mode, const ScanArgs& a, cudaStream_t st) {
     if (dim == 2) return mode == 0 ? run_scan<2, 0>(a, st) : run_scan<2, 1>(a, st);
