@@ -470,7 +470,7 @@ int moihgp_cuda_filter_smoother_nll_dev(moihgp_handle* h, const double* Y, size_
     } else {
         // time-parallel chunked scan: project.cu + scan.cu
         const size_t nC = scan_chunks((long long)T);
-        double *u, *rho, *fsum, *bsum, *xin, *bin, *Bx, *vsq, *npart, *Wsum;
+        double *u, *rho, *fsum, *bsum, *xin, *bin, *Bx, *vsq, *npart, *Wsum, *sbe, *sbi;
         int* nanf;
         long long* nanrows;
         const size_t nan_cap = std::min<size_t>(N * T, (size_t)1 << 22);
@@ -478,7 +478,8 @@ int moihgp_cuda_filter_smoother_nll_dev(moihgp_handle* h, const double* Y, size_
         if (ws_get(h, "u", N * L * T, &u) || ws_get(h, "rho", N * project_tiles((long long)T), &rho) || ws_get(h, "npart", nll_partials((long long)N), &npart) ||
             ws_get(h, "fsum", nC * N * L * D, &fsum) ||
             ws_get(h, "bsum", nC * N * L * D, &bsum) || ws_get(h, "xin", nC * N * L * D, &xin) || ws_get(h, "bin", nC * N * L * D, &bin) ||
-            ws_get(h, "Bx", (size_t)L * 2 * 9, &Bx) || ws_get(h, "Wsum", scan_weights_doubles(L), &Wsum) || ws_get(h, "vsq", nC * N * L, &vsq) || ws_get(h, "nanf", 4, &nanf))
+            ws_get(h, "Bx", (size_t)L * 2 * 9, &Bx) || ws_get(h, "Wsum", scan_weights_doubles(L), &Wsum) ||
+            ws_get(h, "sbe", N * L * scan_superblocks((long long)T) * D, &sbe) || ws_get(h, "sbi", N * L * scan_superblocks((long long)T) * D, &sbi) || ws_get(h, "vsq", nC * N * L, &vsq) || ws_get(h, "nanf", 4, &nanf))
             return -1;
         CK(cudaMemsetAsync(nanf, 0, 2 * sizeof(int), h->stream));
         CK(launch_project(Y, h->d_U, h->d_S, h->p, L, (long long)N, (long long)T, u, nullptr, nullptr, nll ? rho : nullptr, nanf, nanrows,
@@ -487,7 +488,7 @@ int moihgp_cuda_filter_smoother_nll_dev(moihgp_handle* h, const double* Y, size_
         ScanArgs a;
         a.mk = mk;
         a.u = u; a.consts = h->d_consts; a.L = L; a.N = (long long)N; a.T = (long long)T; a.x0 = x0;
-        a.fsum = fsum; a.bsum = bsum; a.xin = xin; a.bin = bin; a.Bx = Bx; a.Wsum = Wsum; a.X = X; a.Xs = Xs; a.vsq = vsq; a.xT = xT;
+        a.fsum = fsum; a.bsum = bsum; a.xin = xin; a.bin = bin; a.Bx = Bx; a.Wsum = Wsum; a.sb_end = sbe; a.sb_in = sbi; a.X = X; a.Xs = Xs; a.vsq = vsq; a.xT = xT;
         CK(launch_scan(D, mode < 0 ? 1 : mode, a, h->stream));
         h->launches += 2 + scan_launch_count((long long)T);
         if (nll) { CK(launch_nll_reduce(rho, vsq, h->d_consts, h->d_S, h->sigma, h->p, L, (long long)N, (long long)T, npart, nll, h->stream)); h->launches += 2; mark(mk, "k_nll_reduce"); }

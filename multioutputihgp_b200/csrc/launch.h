@@ -48,6 +48,7 @@ struct ScanArgs {
     double *fsum, *bsum, *xin, *bin;   // [N][L][nC][D] chunk summaries / carries (workspace)
     double* Bx;                   // [L][2][D*D] chunk responses (workspace)
     double* Wsum;                 // [L][scan_weights_doubles / L] weights of the interior-chunk summaries (workspace)
+    double *sb_end, *sb_in;       // [N][L][scan_superblocks(T)][D] carries of the super-blocks (workspace)
     double *X, *Xs;               // [N][T][L][D] outputs (either may be null)
     double* vsq;                  // [nC][N][L] sum of squared innovations (workspace)
     double* xT;                   // [N][L][D] final filtered state or null
@@ -55,6 +56,7 @@ struct ScanArgs {
 };
 size_t scan_chunks(long long T);
 size_t scan_weights_doubles(int L);
+size_t scan_superblocks(long long T);
 int scan_launch_count(long long T);
 cudaError_t launch_scan(int dim, int mode, const ScanArgs& a, cudaStream_t st);
 size_t nll_partials(long long N);

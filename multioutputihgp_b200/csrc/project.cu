@@ -175,7 +175,7 @@ struct MmaSmem {
 
 // grid: ceil(T / PT) * N CTAs (tile-minor), MT threads.  Same outputs as k_project.
 template <int NB>
-__global__ void __launch_bounds__(MT) k_project_mma(const double* __restrict__ Y, const double* __restrict__ U,
+__global__ void __launch_bounds__(MT, NB <= 4 ? 3 : 2) k_project_mma(const double* __restrict__ Y, const double* __restrict__ U,
                                                    const double* __restrict__ S, int p, int L, long long T,
                                                    double* __restrict__ u, double* __restrict__ w, double* __restrict__ yl,
                                                    double* __restrict__ rho_part, int* __restrict__ nan_info,
@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(MT) k_project_mma(const double* __restrict__ Y
     using SMC = MmaSmem<NB>;
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ double red[MW];
+    __shared__ double rs_s[8 * NB];                 // S^-1/2 per latent (moihgp.h:181)
     __shared__ int any_bad;
     unsigned char* ysm = smraw;                                                   // [2][PT][KP] swizzled 16-byte chunks
     double* usm = reinterpret_cast<double*>(smraw + 2 * SMC::YBYTES);             // [2][KP][UPITCH]
@@ -196,6 +197,7 @@ __global__ void __launch_bounds__(MT) k_project_mma(const double* __restrict__ Y
     const double* Yn = Y + ((size_t)n * T + t0) * p;
     const int npanels = (p + KP - 1) / KP;
     if (tid == 0) any_bad = 0;
+    if (tid < 8 * NB) rs_s[tid] = tid < L ? 1.0 / sqrt(__ldg(S + tid)) : 0.0;
     const bool u_vec = L % 2 == 0 && (reinterpret_cast<size_t>(U) & 15) == 0;
 
     // stage panel kp: Y rows [0, PT) x columns [kp*KP, kp*KP + KP) and U rows [kp*KP, +KP) x [0, LP)
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(MT) k_project_mma(const double* __restrict__ Y
         for (int e = 0; e < 2; ++e) {
             const int l = 8 * nb + 2 * q4 + e;
             if (l < L) {
-                const double rs = 1.0 / sqrt(__ldg(S + l));
+                const double rs = rs_s[l];
 #pragma unroll
                 for (int rb = 0; rb < 2; ++rb) {
                     const long long t = rb == 0 ? tA : tB;

@@ -363,11 +363,13 @@ __global__ void __launch_bounds__(128) k_scan_summaries_dot(const double* __rest
     const long long n = wid / (nG * L);
     const double* wl = Wsum + (size_t)l * WS_STRIDE;
     double w[2 * D][SUB], wn[D];
+    // a dot product does not care which lane owns which step: lane takes steps 64 i + 2 lane + {0, 1}, i = 0..3, so that
+    // every warp-wide 16-byte load of u is one contiguous 512-byte run
 #pragma unroll
     for (int k = 0; k < 2 * D; ++k)
 #pragma unroll
         for (int i = 0; i < SUB; i += 2) {
-            const double2 t2 = __ldg(reinterpret_cast<const double2*>(wl + k * CH + lane * SUB + i));
+            const double2 t2 = __ldg(reinterpret_cast<const double2*>(wl + k * CH + 32 * i + 2 * lane));
             w[k][i] = t2.x;
             w[k][i + 1] = t2.y;
         }
@@ -377,18 +379,18 @@ __global__ void __launch_bounds__(128) k_scan_summaries_dot(const double* __rest
     const bool vec = (reinterpret_cast<size_t>(up) & 15) == 0;      // chunk starts are multiples of 256 steps
     const long long c_hi = min(nI, (g + 1) * cpw);
     for (long long c = g * cpw; c < c_hi; ++c) {
-        const long long tf = c * CH + (long long)lane * SUB;
+        const long long tb = c * CH + 2 * lane;
         double uu[SUB];
         if (vec) {
 #pragma unroll
             for (int i = 0; i < SUB; i += 2) {
-                const double2 t2 = __ldg(reinterpret_cast<const double2*>(up + tf + i));
+                const double2 t2 = __ldg(reinterpret_cast<const double2*>(up + tb + 32 * i));
                 uu[i] = t2.x;
                 uu[i + 1] = t2.y;
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < SUB; ++i) uu[i] = __ldg(up + tf + i);
+            for (int i = 0; i < SUB; i += 2) { uu[i] = __ldg(up + tb + 32 * i); uu[i + 1] = __ldg(up + tb + 32 * i + 1); }
         }
         const double u_next = __ldg(up + (c + 1) * CH);
         double acc[2 * D];
@@ -485,103 +487,73 @@ __global__ void __launch_bounds__(32) k_response(const LatentConsts* __restrict_
     }
 }
 
-// Chain the chunk summaries: one WARP per (sequence, latent); the nC chunks are themselves scanned in groups of
-// 256 (lane = 8 consecutive chunks, Kogge-Stone over lanes with the powers M^(CH * 8 * 2^k)), groups in sequence.
+// Chain the chunk summaries.
 //   forward : xin[c+1] = M^CH xin[c] + f[c]
 //   backward: bin[c-1] = beta0[c] + Bx(kind c) xin[c] + G^CH bin[c]
-// (A single long sequence has tens of thousands of chunks: BASELINE config 4, T = 1e7.)
+// Three levels (a single long sequence has tens of thousands of chunks: BASELINE config 4, T = 1e7, 39 063 chunks):
+//   group       = 256 chunks scanned by one warp (lane = CG = 8 consecutive chunks, Kogge-Stone over lanes with the
+//                 powers M^(CH CG 2^k));
+//   super-block = SB = 8 consecutive groups walked in sequence by that warp;
+//   k_carry_super chains the super-blocks (one thread per (sequence, latent), power M^(CH CG 32 SB)).
+// k_carry<DIR, PHASE>: PHASE 0 runs every super-block from a zero carry and only reports its end value; PHASE 1 runs it
+// from the true carry and writes xin / bin.  When there is one super-block PHASE 1 alone is launched.
 constexpr int CG = 8;              // chunks per lane
 constexpr int LOG2_CG = 3;
-template <int D, int MODE>
+constexpr int SB = 8;              // groups per super-block
+constexpr int LOG2_SB = 3;
+template <int D, int MODE, int DIR, int PHASE>
 __global__ void __launch_bounds__(128) k_carry(const LatentConsts* __restrict__ consts, const double* __restrict__ Bx, int L,
-                                              long long N, long long nC, const double* __restrict__ x0,
+                                              long long N, long long nC, long long nS, const double* __restrict__ x0,
                                               const double* __restrict__ fsum, const double* __restrict__ bsum,
-                                              double* __restrict__ xin, double* __restrict__ bin) {
+                                              double* __restrict__ xin, double* __restrict__ bin,
+                                              const double* __restrict__ sb_in, double* __restrict__ sb_end) {
     const int lane = threadIdx.x & 31;
-    const long long id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // (sequence, latent)
-    if (id >= N * L) return;
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= N * L * nS) return;
+    const long long sbi = wid % nS;                                  // super-block
+    const long long id = wid / nS;                                   // (sequence, latent)
     const int l = (int)(id % L);
     const LatentConsts* lc = consts + l;
-    double MC[D * D], GC[D * D], Bf[D * D], Bl[D * D];
-    load_mat<D>(lc->powM[LOG2_CH], MC);
-    load_mat<D>(lc->powG[MODE][LOG2_CH], GC);
+    double TC[D * D];                                                // one-chunk transition: M^CH (forward) / G^CH (backward)
+    load_mat<D>(DIR == 0 ? lc->powM[LOG2_CH] : lc->powG[MODE][LOG2_CH], TC);
+    double Bf[D * D], Bl[D * D];
+    if (DIR == 1) {
 #pragma unroll
-    for (int i = 0; i < D * D; ++i) { Bf[i] = Bx[((size_t)l * 2 + 0) * D * D + i]; Bl[i] = Bx[((size_t)l * 2 + 1) * D * D + i]; }
+        for (int i = 0; i < D * D; ++i) { Bf[i] = Bx[((size_t)l * 2 + 0) * D * D + i]; Bl[i] = Bx[((size_t)l * 2 + 1) * D * D + i]; }
+    }
+    __shared__ double pcs[4][5 * D * D];       // per warp: the scan powers T^(CG 2^k), k = 0..4
+    {
+        double* pc = pcs[threadIdx.x >> 5];
+        for (int i = lane; i < 5 * D * D; i += 32) {
+            const int m = i / (D * D), e = i - m * (D * D);
+            const double* src = DIR == 0 ? lc->powM[LOG2_CH + LOG2_CG + m] : lc->powG[MODE][LOG2_CH + LOG2_CG + m];
+            pc[i] = src[(e / D) * 3 + (e % D)];
+        }
+        __syncwarp();
+    }
+    const double* pcw = pcs[threadIdx.x >> 5];
     const size_t stride = D;                   // between consecutive chunks of one (sequence, latent): [n][l][chunk][D]
     const size_t base = (size_t)id * nC * D;
     const long long nG = (nC + 32 * CG - 1) / (32 * CG);
+    const long long g_lo = sbi * SB, g_hi = min(nG, g_lo + SB);
 
-    // ---- forward ---------------------------------------------------------------------------------
     double carry[D];
 #pragma unroll
-    for (int q = 0; q < D; ++q) carry[q] = x0 ? x0[(size_t)id * D + q] : 0.0;
-    // the summaries of the next group are fetched while the current one is scanned (the groups run in sequence)
-    auto load_f = [&](long long g, double (&f)[CG][D]) {
-        const long long c0 = (g * 32 + lane) * CG;
-#pragma unroll
-        for (int i = 0; i < CG; ++i)
-#pragma unroll
-            for (int q = 0; q < D; ++q) f[i][q] = (c0 + i < nC - 1) ? fsum[(c0 + i) * stride + base + q] : 0.0;   // f of the last chunk is never used
-    };
-    double fnext[CG][D];
-    load_f(0, fnext);
-    for (long long g = 0; g < nG; ++g) {
-        const long long c0 = (g * 32 + lane) * CG;
-        double f[CG][D];
-#pragma unroll
-        for (int i = 0; i < CG; ++i)
-#pragma unroll
-            for (int q = 0; q < D; ++q) f[i][q] = fnext[i][q];
-        if (g + 1 < nG) load_f(g + 1, fnext);
-        double z[D];
-#pragma unroll
-        for (int q = 0; q < D; ++q) z[q] = lane == 0 ? carry[q] : 0.0;
-#pragma unroll
-        for (int i = 0; i < CG; ++i) {
-            double zn[D];
-            mv<D>(MC, z, zn);
-#pragma unroll
-            for (int q = 0; q < D; ++q) z[q] = zn[q] + f[i][q];
-        }
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const int o = 1 << k;
-            double zo[D], P[D * D];
-#pragma unroll
-            for (int q = 0; q < D; ++q) zo[q] = __shfl_up_sync(FULL, z[q], o);
-            load_mat<D>(lc->powM[LOG2_CH + LOG2_CG + k], P);
-            if (lane >= o) mv_acc<D>(P, zo, z);
-        }
-        double x[D];
-#pragma unroll
-        for (int q = 0; q < D; ++q) {
-            const double up = __shfl_up_sync(FULL, z[q], 1);
-            x[q] = lane == 0 ? carry[q] : up;
-            carry[q] = __shfl_sync(FULL, z[q], 31);
-        }
-#pragma unroll
-        for (int i = 0; i < CG; ++i) {
-            if (c0 + i < nC) {
-#pragma unroll
-                for (int q = 0; q < D; ++q) xin[(c0 + i) * stride + base + q] = x[q];
-            }
-            double xn[D];
-            mv<D>(MC, x, xn);
-#pragma unroll
-            for (int q = 0; q < D; ++q) x[q] = xn[q] + f[i][q];
-        }
+    for (int q = 0; q < D; ++q) {
+        if (PHASE == 0) carry[q] = 0.0;
+        else if (sb_in) carry[q] = sb_in[(size_t)wid * D + q];
+        else carry[q] = (DIR == 0 && x0) ? x0[(size_t)id * D + q] : 0.0;
     }
-    __syncwarp();
-    // ---- backward: b[c] := bin[c], the carry entering chunk c from the future -----------------------
-    //   b[nC-1] = 0;  b[c-1] = G^CH b[c] + d[c],  d[c] = beta0[c] + B(kind c) xin[c]
-#pragma unroll
-    for (int q = 0; q < D; ++q) carry[q] = 0.0;
-    auto load_d = [&](long long g, double (&dv)[CG][D]) {
+    // drive of chunk c:  forward f[c] (f of the last chunk is never used);  backward d[c] = beta0[c] + B(kind c) xin[c]
+    auto load_drive = [&](long long g, double (&dv)[CG][D]) {
         const long long c0 = (g * 32 + lane) * CG;
 #pragma unroll
         for (int i = 0; i < CG; ++i) {
             const long long c = c0 + i;
-            if (c >= 1 && c < nC) {
+            if (DIR == 0) {
+#pragma unroll
+                for (int q = 0; q < D; ++q) dv[i][q] = (c < nC - 1) ? fsum[c * stride + base + q] : 0.0;
+            } else if (c >= 1 && c < nC) {
                 double xi[D], bn[D];
 #pragma unroll
                 for (int q = 0; q < D; ++q) { xi[q] = xin[c * stride + base + q]; bn[q] = bsum[c * stride + base + q]; }
@@ -594,24 +566,21 @@ __global__ void __launch_bounds__(128) k_carry(const LatentConsts* __restrict__ 
             }
         }
     };
-    double dnext[CG][D];
-    load_d(nG - 1, dnext);
-    for (long long g = nG - 1; g >= 0; --g) {
-        const long long c0 = (g * 32 + lane) * CG;       // this lane produces b[c0-1 .. c0+CG-2] from b[c0+CG-1]
+    const int lane_in = DIR == 0 ? 0 : 31;       // the lane that receives the carry
+    for (long long gg = 0; gg < g_hi - g_lo; ++gg) {
+        const long long g = DIR == 0 ? g_lo + gg : g_hi - 1 - gg;
+        const long long c0 = (g * 32 + lane) * CG;
         double dv[CG][D];
-#pragma unroll
-        for (int i = 0; i < CG; ++i)
-#pragma unroll
-            for (int q = 0; q < D; ++q) dv[i][q] = dnext[i][q];
-        if (g > 0) load_d(g - 1, dnext);
-        // local: from zero (lane 31: from the carry of the later groups)
+        load_drive(g, dv);
+        // local run of this lane's CG chunks (ascending for the forward chain, descending for the backward one)
         double z[D];
 #pragma unroll
-        for (int q = 0; q < D; ++q) z[q] = lane == 31 ? carry[q] : 0.0;
+        for (int q = 0; q < D; ++q) z[q] = lane == lane_in ? carry[q] : 0.0;
 #pragma unroll
-        for (int i = CG - 1; i >= 0; --i) {
+        for (int ii = 0; ii < CG; ++ii) {
+            const int i = DIR == 0 ? ii : CG - 1 - ii;
             double zn[D];
-            mv<D>(GC, z, zn);
+            mv<D>(TC, z, zn);
 #pragma unroll
             for (int q = 0; q < D; ++q) z[q] = zn[q] + dv[i][q];
         }
@@ -620,29 +589,68 @@ __global__ void __launch_bounds__(128) k_carry(const LatentConsts* __restrict__ 
             const int o = 1 << k;
             double zo[D], P[D * D];
 #pragma unroll
-            for (int q = 0; q < D; ++q) zo[q] = __shfl_down_sync(FULL, z[q], o);
-            load_mat<D>(lc->powG[MODE][LOG2_CH + LOG2_CG + k], P);
-            if (lane + o < 32) mv_acc<D>(P, zo, z);
+            for (int q = 0; q < D; ++q) {
+                const double t = DIR == 0 ? __shfl_up_sync(FULL, z[q], o) : __shfl_down_sync(FULL, z[q], o);
+                zo[q] = (DIR == 0 ? lane >= o : lane + o < 32) ? t : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < D * D; ++q) P[q] = pcw[k * D * D + q];
+            mv_acc<D>(P, zo, z);
         }
-        double b[D];                                     // b[c0 + CG - 1]
+        double x[D];                                 // the value entering this lane's first chunk (forward) / last chunk (backward)
 #pragma unroll
         for (int q = 0; q < D; ++q) {
-            const double dn = __shfl_down_sync(FULL, z[q], 1);
-            b[q] = lane == 31 ? carry[q] : dn;
-            carry[q] = __shfl_sync(FULL, z[q], 0);       // b[c0(lane 0) - 1]: enters the previous group
+            const double nb = DIR == 0 ? __shfl_up_sync(FULL, z[q], 1) : __shfl_down_sync(FULL, z[q], 1);
+            x[q] = lane == lane_in ? carry[q] : nb;
+            carry[q] = __shfl_sync(FULL, z[q], DIR == 0 ? 31 : 0);
         }
+        if (PHASE == 1) {
 #pragma unroll
-        for (int i = CG - 1; i >= 0; --i) {
-            const long long c = c0 + i;
-            if (c < nC) {
+            for (int ii = 0; ii < CG; ++ii) {
+                const int i = DIR == 0 ? ii : CG - 1 - ii;
+                const long long c = c0 + i;
+                if (c < nC) {
 #pragma unroll
-                for (int q = 0; q < D; ++q) bin[c * stride + base + q] = c == nC - 1 ? 0.0 : b[q];
+                    for (int q = 0; q < D; ++q) {
+                        if (DIR == 0) xin[c * stride + base + q] = x[q];
+                        else bin[c * stride + base + q] = c == nC - 1 ? 0.0 : x[q];
+                    }
+                }
+                double xn[D];
+                mv<D>(TC, x, xn);
+#pragma unroll
+                for (int q = 0; q < D; ++q) x[q] = xn[q] + dv[i][q];
             }
-            double bn[D];
-            mv<D>(GC, b, bn);
-#pragma unroll
-            for (int q = 0; q < D; ++q) b[q] = bn[q] + dv[i][q];
         }
+    }
+    if (PHASE == 0 && lane == 0) {
+#pragma unroll
+        for (int q = 0; q < D; ++q) sb_end[(size_t)wid * D + q] = carry[q];
+    }
+}
+
+// Chain the super-blocks: one thread per (sequence, latent).  forward: in[S+1] = M^span in[S] + end[S], in[0] = x0;
+// backward: in[S-1] = G^span in[S] + end[S], in[nS-1] = 0.  span = CH * CG * 32 * SB steps.
+template <int D, int MODE, int DIR>
+__global__ void __launch_bounds__(128) k_carry_super(const LatentConsts* __restrict__ consts, int L, long long N, long long nS,
+                                                    const double* __restrict__ x0, const double* __restrict__ sb_end,
+                                                    double* __restrict__ sb_in) {
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= N * L) return;
+    const LatentConsts* lc = consts + (int)(id % L);
+    double P[D * D], v[D];
+    load_mat<D>(DIR == 0 ? lc->powM[LOG2_CH + LOG2_CG + 5 + LOG2_SB] : lc->powG[MODE][LOG2_CH + LOG2_CG + 5 + LOG2_SB], P);
+#pragma unroll
+    for (int q = 0; q < D; ++q) v[q] = (DIR == 0 && x0) ? x0[(size_t)id * D + q] : 0.0;
+    for (long long k = 0; k < nS; ++k) {
+        const long long sb = DIR == 0 ? k : nS - 1 - k;
+        const size_t o = ((size_t)id * nS + sb) * D;
+        double vn[D];
+#pragma unroll
+        for (int q = 0; q < D; ++q) sb_in[o + q] = v[q];
+        mv<D>(P, v, vn);
+#pragma unroll
+        for (int q = 0; q < D; ++q) v[q] = vn[q] + sb_end[o + q];
     }
 }
 
@@ -720,7 +728,22 @@ cudaError_t run_scan(const ScanArgs& a, cudaStream_t st) {
         k_response<D, MODE><<<a.L * 2 * D, 32, 0, st>>>(a.consts, r_last, a.Bx);
         mark(a.mk, "k_response");
     }
-    k_carry<D, MODE><<<(unsigned)((a.N * a.L * 32 + 127) / 128), 128, 0, st>>>(a.consts, a.Bx, a.L, a.N, nC, a.x0, a.fsum, a.bsum, a.xin, a.bin);
+    {
+        const long long nGr = (nC + 32 * CG - 1) / (32 * CG), nS = (nGr + SB - 1) / SB;
+        const unsigned gw = (unsigned)((a.N * a.L * nS * 32 + 127) / 128), gt = (unsigned)((a.N * a.L + 127) / 128);
+        const double* in = nullptr;
+        if (nS > 1) {
+            k_carry<D, MODE, 0, 0><<<gw, 128, 0, st>>>(a.consts, a.Bx, a.L, a.N, nC, nS, a.x0, a.fsum, a.bsum, a.xin, a.bin, nullptr, a.sb_end);
+            k_carry_super<D, MODE, 0><<<gt, 128, 0, st>>>(a.consts, a.L, a.N, nS, a.x0, a.sb_end, a.sb_in);
+            in = a.sb_in;
+        }
+        k_carry<D, MODE, 0, 1><<<gw, 128, 0, st>>>(a.consts, a.Bx, a.L, a.N, nC, nS, a.x0, a.fsum, a.bsum, a.xin, a.bin, in, nullptr);
+        if (nS > 1) {
+            k_carry<D, MODE, 1, 0><<<gw, 128, 0, st>>>(a.consts, a.Bx, a.L, a.N, nC, nS, a.x0, a.fsum, a.bsum, a.xin, a.bin, nullptr, a.sb_end);
+            k_carry_super<D, MODE, 1><<<gt, 128, 0, st>>>(a.consts, a.L, a.N, nS, a.x0, a.sb_end, a.sb_in);
+        }
+        k_carry<D, MODE, 1, 1><<<gw, 128, 0, st>>>(a.consts, a.Bx, a.L, a.N, nC, nS, a.x0, a.fsum, a.bsum, a.xin, a.bin, in, nullptr);
+    }
     mark(a.mk, "k_carry");
     const long long cpc = per_unit(a.N * nLG, nC);
     const long long nG = (nC + cpc - 1) / cpc;
@@ -734,7 +757,12 @@ cudaError_t run_scan(const ScanArgs& a, cudaStream_t st) {
 
 size_t scan_chunks(long long T) { return (size_t)((T + CH - 1) / CH); }
 
-int scan_launch_count(long long T) { return (T + CH - 1) / CH > 1 ? 6 : 2; }
+int scan_launch_count(long long T) {
+    const long long nC = (T + CH - 1) / CH, nS = ((nC + 32 * CG - 1) / (32 * CG) + SB - 1) / SB;
+    return (nC > 1 ? 5 : 1) + (nS > 1 ? 6 : 2);
+}
+
+size_t scan_superblocks(long long T) { const long long nC = (T + CH - 1) / CH; return (size_t)(((nC + 32 * CG - 1) / (32 * CG) + SB - 1) / SB); }
 
 size_t scan_weights_doubles(int L) { return (size_t)L * WS_STRIDE; }
 
