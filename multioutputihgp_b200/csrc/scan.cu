@@ -262,6 +262,9 @@ __global__ void __launch_bounds__(32 * LGMAX, 2) k_scan(const double* __restrict
     const int GS = tile_group_stride(RS);
     double* tileX = tile;
     double* tileXs = tile + 32 * GS;
+    // 16-byte copy-out needs even row widths / offsets and aligned output bases (GS = SUB RS + 2 is then even too)
+    const bool vec_out = FINAL && (RS & 1) == 0 && (((size_t)L * D) & 1) == 0 && ((l0 * D) & 1) == 0 &&
+                         (reinterpret_cast<size_t>(X) & 15) == 0 && (reinterpret_cast<size_t>(Xs) & 15) == 0;
     for (int i = threadIdx.x; i < lg * 10 * D * D; i += blockDim.x) {
         const int w = i / (10 * D * D), r = i - w * (10 * D * D);
         const int m = r / (D * D), e = r - m * (D * D);
@@ -332,12 +335,31 @@ __global__ void __launch_bounds__(32 * LGMAX, 2) k_scan(const double* __restrict
             const int rows = (int)min((long long)CH, T - t0);
             const size_t grow = (size_t)L * D;                       // global row pitch (doubles)
             const size_t gbase = ((size_t)n * T + t0) * grow + (size_t)l0 * D;
-            for (int i = threadIdx.x; i < rows * RS; i += blockDim.x) {
-                const int row = i / RS, col = i - row * RS;
-                const int so = (row / SUB) * GS + (row % SUB) * RS + col;
-                const size_t go = gbase + (size_t)row * grow + col;
-                if (X) X[go] = tileX[so];
-                if (Xs) Xs[go] = tileXs[so];
+            // element (row, col) of the staged tile, walked without integer divisions: this thread starts at
+            // (tid / W, tid % W) and advances by blockDim.x elements per iteration (W = row width in copy units)
+            if (vec_out) {
+                const int W = RS >> 1;                               // 16-byte units per row
+                int row = threadIdx.x / W, col = threadIdx.x - row * W;
+                const int drow = blockDim.x / W, dcol = blockDim.x - drow * W;
+                while (row < rows) {
+                    const int so = (row / SUB) * GS + (row % SUB) * RS + 2 * col;
+                    const size_t go = gbase + (size_t)row * grow + 2 * col;
+                    if (X) *reinterpret_cast<double2*>(X + go) = *reinterpret_cast<const double2*>(tileX + so);
+                    if (Xs) *reinterpret_cast<double2*>(Xs + go) = *reinterpret_cast<const double2*>(tileXs + so);
+                    row += drow; col += dcol;
+                    if (col >= W) { col -= W; ++row; }
+                }
+            } else {
+                int row = threadIdx.x / RS, col = threadIdx.x - row * RS;
+                const int drow = blockDim.x / RS, dcol = blockDim.x - drow * RS;
+                while (row < rows) {
+                    const int so = (row / SUB) * GS + (row % SUB) * RS + col;
+                    const size_t go = gbase + (size_t)row * grow + col;
+                    if (X) X[go] = tileX[so];
+                    if (Xs) Xs[go] = tileXs[so];
+                    row += drow; col += dcol;
+                    if (col >= RS) { col -= RS; ++row; }
+                }
             }
             __syncthreads();                                        // the tiles are reused by the next chunk
         }
