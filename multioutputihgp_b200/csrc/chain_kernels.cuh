@@ -30,6 +30,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <cmath>
+#include <cstdlib>
 #include "moihgp_device.cuh"
 #include "launch.h"
 #include "ls_project.cuh"
@@ -472,12 +473,14 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 constexpr int SSTAGES = 5;        // smoother ring: 3 loads in flight, 1 tile being processed, 1 tile being stored
 
-template <int L, int D, int NS_>
+template <int L, int D, int NS_, int RM_>
 struct SmoothCfg {
     static constexpr int NS = NS_;
+    static constexpr int RM = RM_;                     // a round covers RM * L steps of each sequence
+    static constexpr int RL = RM * L;
     static constexpr int LD = L * D;
-    static constexpr int RUN = L * LD;                 // doubles per sequence-round
-    static constexpr int OSEQ = staging_pitch(L, D);
+    static constexpr int RUN = RL * LD;                // doubles per sequence-round
+    static constexpr int OSEQ = RUN + (staging_pitch(L, D) - L * LD);
     static constexpr int BYTES = SSTAGES * NS * OSEQ * 8 + SSTAGES * 8;
 };
 
@@ -487,11 +490,11 @@ struct SmoothCfg {
 // grid: ceil(N / NS) CTAs of one warp; rounds of L steps from the end of the sequence.  Each sequence-round of X is one
 // contiguous run of L*L*D doubles: it is brought in by ONE TMA bulk copy (mbarrier-tracked), smoothed in place in
 // shared memory, and written out by ONE bulk store - no per-lane load/store instructions touch HBM.
-template <int L, int D, int MODE, int NS_>
+template <int L, int D, int MODE, int NS_, int RM_>
 __global__ void __launch_bounds__(32, 14) k_smooth_chain(const double* __restrict__ X, const LatentConsts* __restrict__ consts,
                                                         long long N, long long T, double* __restrict__ Xs) {
-    using C = SmoothCfg<L, D, NS_>;
-    constexpr int NS = C::NS, LD = C::LD;
+    using C = SmoothCfg<L, D, NS_, RM_>;
+    constexpr int NS = C::NS, LD = C::LD, RL = C::RL, RM = C::RM;
     constexpr int LOOK = SSTAGES - 2;                  // loads in flight ahead of the round being processed
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* tiles = reinterpret_cast<double*>(smem_raw);                                   // [SSTAGES][NS][OSEQ]
@@ -501,7 +504,7 @@ __global__ void __launch_bounds__(32, 14) k_smooth_chain(const double* __restric
     const bool active = lane < NS * L;
     const long long n0 = (long long)blockIdx.x * NS;
     const int nvalid = (int)(N - n0 < NS ? N - n0 : NS);
-    const long long rounds = (T + L - 1) / L;
+    const long long rounds = (T + RL - 1) / RL;
     const LatentConsts* lc = consts + j;
     double G[D * D], B[D * D];                     // B: I - A (literal, applied to X[j+1]) or I - G A (rts, applied to X[j])
 #pragma unroll
@@ -521,12 +524,12 @@ __global__ void __launch_bounds__(32, 14) k_smooth_chain(const double* __restric
     __syncwarp();
 
     // round index k counts from the END: it covers steps t0 = (rounds - 1 - k) * L ...; bytes of one sequence's run
-    auto run_bytes = [&](long long t0) { return (unsigned)((T - t0 >= L ? (long long)L : T - t0) * LD * 8); };
+    auto run_bytes = [&](long long t0) { return (unsigned)((T - t0 >= RL ? (long long)RL : T - t0) * LD * 8); };
     auto issue = [&](long long k) {               // lane 0 only
         if (k < rounds) {
             const int st = (int)(k % SSTAGES);
             double* tile = tiles + (size_t)st * NS * C::OSEQ;
-            const long long t0 = (rounds - 1 - k) * L;
+            const long long t0 = (rounds - 1 - k) * RL;
             const unsigned bytes = run_bytes(t0);
             bulk_wait_read<1>();                   // the store that last read this stage (two rounds ago) is done with it
             mbar_expect_tx(bars + st, bytes * (unsigned)nvalid);
@@ -547,35 +550,39 @@ __global__ void __launch_bounds__(32, 14) k_smooth_chain(const double* __restric
         mbar_wait(bars + stg, (unsigned)((k / SSTAGES) & 1));
         double* stw = tiles + (size_t)stg * NS * C::OSEQ;
         double* st = stw + s * C::OSEQ + j * D;
-        const long long t0 = (rounds - 1 - k) * L;
-        const bool fast = nvalid == NS && t0 + L <= T;
+        const long long t0 = (rounds - 1 - k) * RL;
+        const bool fast = nvalid == NS && t0 + RL <= T;
         if (!active) {
-        } else if (fast && t0 + L < T) {
-            // interior round: no boundary, no predicates
-            double xin[L][D];
+        } else if (fast && t0 + RL < T) {
+            // interior round: no boundary, no predicates; L steps at a time (registers)
 #pragma unroll
-            for (int i = 0; i < L; ++i) load_state<D>(st + i * LD, xin[i]);
+            for (int h = RM - 1; h >= 0; --h) {
+                double* sth = st + h * L * LD;
+                double xin[L][D];
 #pragma unroll
-            for (int i = L - 1; i >= 0; --i) {
-                double xx[D], out[D];
+                for (int i = 0; i < L; ++i) load_state<D>(sth + i * LD, xin[i]);
 #pragma unroll
-                for (int a = 0; a < D; ++a) xx[a] = xin[i][a];
+                for (int i = L - 1; i >= 0; --i) {
+                    double xx[D], out[D];
 #pragma unroll
-                for (int a = 0; a < D; ++a) {
-                    double acc = G[a * D] * xs[0];
+                    for (int a = 0; a < D; ++a) xx[a] = xin[i][a];
 #pragma unroll
-                    for (int b = 1; b < D; ++b) acc = fma(G[a * D + b], xs[b], acc);
+                    for (int a = 0; a < D; ++a) {
+                        double acc = G[a * D] * xs[0];
 #pragma unroll
-                    for (int b = 0; b < D; ++b) acc = fma(B[a * D + b], MODE == 0 ? xnext[b] : xx[b], acc);
-                    out[a] = acc;
+                        for (int b = 1; b < D; ++b) acc = fma(G[a * D + b], xs[b], acc);
+#pragma unroll
+                        for (int b = 0; b < D; ++b) acc = fma(B[a * D + b], MODE == 0 ? xnext[b] : xx[b], acc);
+                        out[a] = acc;
+                    }
+#pragma unroll
+                    for (int a = 0; a < D; ++a) { xs[a] = out[a]; xnext[a] = xx[a]; }
+                    store_state<D>(sth + i * LD, out);
                 }
-#pragma unroll
-                for (int a = 0; a < D; ++a) { xs[a] = out[a]; xnext[a] = xx[a]; }
-                store_state<D>(st + i * LD, out);
             }
         } else if (s < nvalid) {
-#pragma unroll
-            for (int i = L - 1; i >= 0; --i) {
+#pragma unroll 1
+            for (int i = RL - 1; i >= 0; --i) {
                 const long long t = t0 + i;
                 if (t < T) {
                     double xx[D], out[D];
@@ -614,7 +621,9 @@ __global__ void __launch_bounds__(32, 14) k_smooth_chain(const double* __restric
 template <int P, int L, int D, int NS>
 cudaError_t run_chain_ns(const ChainArgs& a, cudaStream_t st) {
     using FS = FilterCfg<P, L, D, NS>;
-    using SS = SmoothCfg<L, D, NS>;
+    constexpr int SNS = (NS >= 2 && NS == 32 / L) ? NS / 2 : NS;     // smoother: half the sequences per warp ...
+    constexpr int SRM = (NS >= 2 && NS == 32 / L) ? 2 : 1;           // ... rounds twice as long: 2x longer contiguous runs per bulk copy
+    using SS = SmoothCfg<L, D, SNS, SRM>;
     ProjConsts<P, L> pc;
     for (int r = 0; r < P; ++r) for (int l = 0; l < L; ++l) pc.U[r][l] = a.U_host[(size_t)r * L + l];
     for (int l = 0; l < L; ++l) pc.rs[l] = 1.0 / std::sqrt(a.S_host[l]);
@@ -622,15 +631,24 @@ cudaError_t run_chain_ns(const ChainArgs& a, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(k_filter_chain<P, L, D, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS::BYTES);
-        cudaFuncSetAttribute(k_smooth_chain<L, D, 0, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS::BYTES);
-        cudaFuncSetAttribute(k_smooth_chain<L, D, 1, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS::BYTES);
+        cudaFuncSetAttribute(k_smooth_chain<L, D, 0, SNS, SRM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS::BYTES);
+        cudaFuncSetAttribute(k_smooth_chain<L, D, 1, SNS, SRM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS::BYTES);
+        cudaFuncSetAttribute(k_smooth_chain<L, D, 0, NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmoothCfg<L, D, NS, 1>::BYTES);
+        cudaFuncSetAttribute(k_smooth_chain<L, D, 1, NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmoothCfg<L, D, NS, 1>::BYTES);
         attr_done = true;
     }
     k_filter_chain<P, L, D, NS><<<grid, 32, FS::BYTES, st>>>(a.Y, pc, a.consts, a.sigma, a.nll_const, a.N, a.T, a.x0, a.X, a.nll, a.xT, a.nan_flag);
     mark(a.mk, "k_filter_chain");
     if (a.Xs) {
-        if (a.mode == 0) k_smooth_chain<L, D, 0, NS><<<grid, 32, SS::BYTES, st>>>(a.X, a.consts, a.N, a.T, a.Xs);
-        else k_smooth_chain<L, D, 1, NS><<<grid, 32, SS::BYTES, st>>>(a.X, a.consts, a.N, a.T, a.Xs);
+        static const bool long_rounds = []() { const char* e = std::getenv("MOIHGP_SMOOTH_LONG_ROUNDS"); return !(e && e[0] == '0'); }();
+        if (long_rounds) {
+            const unsigned sgrid = (unsigned)((a.N + SNS - 1) / SNS);
+            if (a.mode == 0) k_smooth_chain<L, D, 0, SNS, SRM><<<sgrid, 32, SS::BYTES, st>>>(a.X, a.consts, a.N, a.T, a.Xs);
+            else k_smooth_chain<L, D, 1, SNS, SRM><<<sgrid, 32, SS::BYTES, st>>>(a.X, a.consts, a.N, a.T, a.Xs);
+        } else {
+            if (a.mode == 0) k_smooth_chain<L, D, 0, NS, 1><<<grid, 32, SmoothCfg<L, D, NS, 1>::BYTES, st>>>(a.X, a.consts, a.N, a.T, a.Xs);
+            else k_smooth_chain<L, D, 1, NS, 1><<<grid, 32, SmoothCfg<L, D, NS, 1>::BYTES, st>>>(a.X, a.consts, a.N, a.T, a.Xs);
+        }
         mark(a.mk, "k_smooth_chain");
     }
     return cudaGetLastError();
