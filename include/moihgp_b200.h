@@ -133,6 +133,12 @@ int moihgp_cuda_filter_smoother_nll_dev(moihgp_handle* h, const double* Y, size_
  * HOST buffers. */
 int moihgp_cuda_objective(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0, const double* dx0,
                           double* loss, double* grad, double* xT, double* dxT);
+/* The optimiser evaluates the objective many times on the SAME observations (LBFGSB.h:137, LineSearchMoreThuente.h:212,
+ * :295): bind_data copies Y[N][T][p] to the device once (Y = NULL unbinds), objective_bound evaluates on the bound data
+ * at the handle's current parameters.  The caller must re-bind after changing the observations. */
+int moihgp_cuda_bind_data(moihgp_handle* h, const double* Y, size_t N, size_t T);
+int moihgp_cuda_objective_bound(moihgp_handle* h, const double* x0, const double* dx0, double* loss, double* grad,
+                                double* xT, double* dxT);
 /* same, DEVICE buffers (loss[1], grad[num_param] on the device); asynchronous on the handle's stream */
 int moihgp_cuda_objective_dev(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0, const double* dx0,
                               double* loss, double* grad, double* xT, double* dxT);

@@ -156,6 +156,19 @@ public:
         unpack_x(&_xb[nx()], x);
     }
 
+    // Keep the data set resident on the device across objective evaluations (the optimiser calls the functor tens of times
+    // on the same observations); the caller re-binds after changing them.  Y = NULL releases it.
+    void bindData(const double* Y, size_t T) { detail::check(_h, moihgp_cuda_bind_data(_h, Y, Y ? 1 : 0, T), "MOIHGP::bindData"); }
+    double objectiveBound(State& x, DState& dx, Vec& grad) {
+        pack_x(x, &_xb[0]); pack_dx(dx, &_dxb[0]);
+        double loss = 0.0;
+        detail::check(_h, moihgp_cuda_objective_bound(_h, &_xb[0], &_dxb[0], &loss, &_pb[0], &_xb[nx()], &_dxb[ndx()]), "MOIHGP::objectiveBound");
+        unpack_x(&_xb[nx()], x); unpack_dx(&_dxb[ndx()], dx);
+        grad.resize(_num_param);
+        for (size_t i = 0; i < _num_param; ++i) grad[i] = _pb[i];
+        return loss;
+    }
+
     moihgp_handle* handle() { return _h; }
 
 private:
@@ -195,10 +208,26 @@ template <typename StateSpace, typename Vec = std::vector<double> >
 class RegressionObjective {
 public:
     typedef MOIHGP<StateSpace, Vec> GP;
-    RegressionObjective(const size_t& num_data, GP* gp, bool update_params = false) : _gp(gp), _update(update_params) { Y.reserve(num_data); }
+    RegressionObjective(const size_t& num_data, GP* gp, bool update_params = false) : _gp(gp), _update(update_params), _bound(0) { Y.reserve(num_data); }
+
+    // Copy Y to the device once: every later operator() evaluates on that resident copy until rebind() / unbind().
+    // (The optimiser calls the functor tens of times on the same data; call rebind() after changing Y.)
+    void rebind() {
+        const size_t p = _gp->getNumOutput(), T = Y.size();
+        _buf.resize(T * p);
+        for (size_t t = 0; t < T; ++t) for (size_t r = 0; r < p; ++r) _buf[t * p + r] = Y[t][r];
+        _gp->bindData(T ? &_buf[0] : NULL, T);
+        _bound = T;
+    }
+    void unbind() { _gp->bindData(NULL, 0); _bound = 0; }
 
     double operator()(const Vec& params, Vec& grad) {
         if (_update) _gp->update(params);
+        if (_bound) {
+            typename GP::State xb(_gp->getNumLatent(), detail::make_vec<Vec>(_gp->getIGPDim()));
+            typename GP::DState dxb(_gp->getNumLatent(), std::vector<Vec>(_gp->getNumIGPParam(), detail::make_vec<Vec>(_gp->getIGPDim())));
+            return _gp->objectiveBound(xb, dxb, grad);
+        }
         const size_t p = _gp->getNumOutput(), T = Y.size();
         _buf.resize(T * p);
         for (size_t t = 0; t < T; ++t) for (size_t r = 0; r < p; ++r) _buf[t * p + r] = Y[t][r];
@@ -213,6 +242,7 @@ public:
 private:
     GP* _gp;
     bool _update;
+    size_t _bound;
     std::vector<double> _buf;
 };
 

@@ -177,6 +177,33 @@ class MOIHGPSequences(object):
             return float(loss[0]), grad, xT, dxT
         return float(loss[0]), grad
 
+    def bind(self, Y):
+        """Copy the observations to the device once; ``objective_bound`` then evaluates on them at the current parameters
+        (the L-BFGS loop calls the objective tens of times on the same data).  ``bind(None)`` releases them."""
+        if Y is None:
+            self._check(self._lib.moihgp_cuda_bind_data(self._h, None, 0, 0))
+            self._bound = None
+            return
+        Y = _np(Y)
+        if Y.ndim == 2:
+            Y = Y[None]
+        N, T, p = Y.shape
+        assert p == self.num_output
+        self._check(self._lib.moihgp_cuda_bind_data(self._h, _ptr(Y), N, T))
+        self._bound = (N, T)
+
+    def objective_bound(self, x0=None, dx0=None):
+        if getattr(self, "_bound", None) is None:
+            raise RuntimeError("no data bound: call bind(Y) first")
+        N, T = self._bound
+        L, d = self.num_latent, self.igp_dim
+        x0 = None if x0 is None else _np(x0).reshape(N, L, d)
+        dx0 = None if dx0 is None else _np(dx0).reshape(N, L, 3, d)
+        loss = np.zeros(1)
+        grad = np.zeros(self.num_param)
+        self._check(self._lib.moihgp_cuda_objective_bound(self._h, _ptr(x0), _ptr(dx0), _ptr(loss), _ptr(grad), None, None))
+        return float(loss[0]), grad
+
     def objective_device(self, Y, loss, grad, x0=None, dx0=None, xT=None, dxT=None):
         import torch
         assert Y.is_cuda and Y.dtype == torch.float64 and Y.is_contiguous() and Y.dim() == 3

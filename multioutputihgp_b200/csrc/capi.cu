@@ -43,6 +43,8 @@ struct moihgp_handle {
     cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the pipelined host-buffer pass (created on first use)
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_c[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     int* h_flags = nullptr;                   // pinned per-slice status words
+    double* d_bound = nullptr;                // data set bound by moihgp_cuda_bind_data (resident in HBM across evaluations)
+    size_t bound_N = 0, bound_T = 0;
     size_t h_flags_cap = 0;
     std::map<std::string, Buf> ws;            // grow-only device workspace
     double* h_stage = nullptr;                // pinned host staging for the per-observation calls
@@ -295,6 +297,7 @@ void moihgp_cuda_destroy(moihgp_handle* h) {
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
     if (h->h_flags) cudaFreeHost(h->h_flags);
+    if (h->d_bound) cudaFree(h->d_bound);
     for (int i = 0; i < 2; ++i) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_c[i]) cudaEventDestroy(h->ev_c[i]); if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]); }
     delete h;
 }
@@ -539,6 +542,7 @@ int moihgp_cuda_filter_smoother_nll(moihgp_handle* h, const double* Y, size_t N,
     if (ws_get(h, "nanf", 4, &nanf)) return -1;
     if (h->h_flags_cap < nsl) {
         if (h->h_flags) cudaFreeHost(h->h_flags);
+    if (h->d_bound) cudaFree(h->d_bound);
         h->h_flags = nullptr;
         h->h_flags_cap = 0;
         CK(cudaMallocHost(&h->h_flags, sizeof(int) * nsl));
@@ -638,6 +642,48 @@ int moihgp_cuda_objective(moihgp_handle* h, const double* Y, size_t N, size_t T,
     std::copy(host.begin() + 2, host.end(), grad);
     if (flag == 2) return fail(h, "more than 2^22 observations with missing (NaN) outputs in one call: split the batch");
     return 0;   // with NaN observations the loss is NaN, exactly as the reference's (moihgp.h:501 uses the full y)
+}
+
+// Resident data set: the L-BFGS loop evaluates the objective tens of times on the SAME observations (LBFGSB.h:137,
+// LineSearchMoreThuente.h:212,295), so the H2D copy of Y is paid once.
+int moihgp_cuda_bind_data(moihgp_handle* h, const double* Y, size_t N, size_t T) {
+    if (!h) return -2;
+    cudaSetDevice(h->device);
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->d_bound) { cudaFree(h->d_bound); h->d_bound = nullptr; }
+    h->bound_N = h->bound_T = 0;
+    if (!Y || N == 0 || T == 0) return 0;                    // unbind
+    CK(cudaMalloc(&h->d_bound, sizeof(double) * N * T * h->p));
+    CK(cudaMemcpyAsync(h->d_bound, Y, sizeof(double) * N * T * h->p, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->bound_N = N;
+    h->bound_T = T;
+    return 0;
+}
+
+int moihgp_cuda_objective_bound(moihgp_handle* h, const double* x0, const double* dx0, double* loss, double* grad, double* xT, double* dxT) {
+    if (!h || !loss || !grad) return -2;
+    if (!h->d_bound) return fail(h, "no data bound: call moihgp_cuda_bind_data first");
+    cudaSetDevice(h->device);
+    const size_t N = h->bound_N, T = h->bound_T, L = h->L, D = h->dim, np = h->num_param;
+    double *dx = nullptr, *ddx = nullptr, *dout, *dxT_ = nullptr, *ddxT = nullptr;
+    if (ws_get(h, "hout", np + 2, &dout)) return -1;
+    if (x0 && ws_get(h, "hx0", N * L * D, &dx)) return -1;
+    if (dx0 && ws_get(h, "hdx0", N * L * 3 * D, &ddx)) return -1;
+    if (xT && ws_get(h, "hxT", N * L * D, &dxT_)) return -1;
+    if (dxT && ws_get(h, "hdxT", N * L * 3 * D, &ddxT)) return -1;
+    if (x0) CK(cudaMemcpyAsync(dx, x0, sizeof(double) * N * L * D, cudaMemcpyHostToDevice, h->stream));
+    if (dx0) CK(cudaMemcpyAsync(ddx, dx0, sizeof(double) * N * L * 3 * D, cudaMemcpyHostToDevice, h->stream));
+    const int rc = moihgp_cuda_objective_dev(h, h->d_bound, N, T, dx, ddx, dout, dout + 2, dxT_, ddxT);
+    if (rc) return rc;
+    std::vector<double> host(np + 2);
+    CK(cudaMemcpyAsync(host.data(), dout, sizeof(double) * (np + 2), cudaMemcpyDeviceToHost, h->stream));
+    if (xT) CK(cudaMemcpyAsync(xT, dxT_, sizeof(double) * N * L * D, cudaMemcpyDeviceToHost, h->stream));
+    if (dxT) CK(cudaMemcpyAsync(dxT, ddxT, sizeof(double) * N * L * 3 * D, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *loss = host[0];
+    std::copy(host.begin() + 2, host.end(), grad);
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------

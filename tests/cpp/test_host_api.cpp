@@ -72,6 +72,15 @@ static void run(int kernel, size_t p, size_t L, size_t T, bool threading, unsign
     const double lo = oracle_objective(o, Yflat.data(), 1, T, x0.data(), dx0.data(), go.data(), 0);
     expect("RegressionObjective loss", std::fabs(loss - lo) / std::fabs(lo));
     expect("RegressionObjective grad", rel_err(grad.data(), go.data(), np));
+    // the data set resident on the device (what the optimiser loop uses): identical results
+    {
+        f.rebind();
+        Vec gb(np);
+        const double lb = f(params, gb);
+        expect("RegressionObjective (bound data) loss", std::fabs(lb - loss) / std::fabs(loss), 0.0);
+        expect("RegressionObjective (bound data) grad", rel_err(gb.data(), grad.data(), np), 0.0);
+        f.unbind();
+    }
 
     // (2) per-observation methods: a few steps of step(x,y,dx,xnew,yhat,dxnew) + both negLogLikelihood overloads
     typename MOIHGP<SS>::State x(L, Vec(d, 0.0)), xn;

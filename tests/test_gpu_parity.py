@@ -396,3 +396,24 @@ def test_update_polar_factor_on_device(cuda_lib, p, L):
     U1 = m.U.copy()
     m.update(m.params)
     assert rel_err(m.U, U1) < 1e-13
+
+
+@pytest.mark.gpu
+def test_bound_data_objective_equals_host_buffer_objective(cuda_lib):
+    """moihgp_cuda_bind_data + moihgp_cuda_objective_bound (data resident across the optimiser's evaluations) give the
+    same numbers as passing the observations with every call, also after update(params)."""
+    from multioutputihgp_b200 import MOIHGPSequences
+    from oracle.gen_golden import make_data, make_params
+    rng = np.random.default_rng(41)
+    p, L, N, T = 16, 8, 3, 900
+    m = MOIHGPSequences(0.1, p, L, "Matern52", True)
+    Y = np.stack([make_data(rng, p, L, T) for _ in range(N)])
+    m.bind(Y)
+    for k in range(2):
+        m.update(make_params(rng, p, L, "Matern52"))
+        la, ga = m.objective(Y)
+        lb, gb = m.objective_bound()
+        assert la == lb and np.array_equal(ga, gb)
+    m.bind(None)
+    with pytest.raises(RuntimeError):
+        m.objective_bound()
