@@ -561,7 +561,12 @@ int moihgp_cuda_filter_smoother_nll(moihgp_handle* h, const double* Y, size_t N,
         CK(cudaStreamWaitEvent(h->stream, h->ev_in[b], 0));
         if (i >= 2) CK(cudaStreamWaitEvent(h->stream, h->ev_out[b], 0));               // output buffers b have been copied out
         const int rc = moihgp_cuda_filter_smoother_nll_dev(h, dY[b], ns, T, x0 ? dx0[b] : nullptr, mode, dX[b], dXs[b], dYh[b], dnll[b], dxT[b]);
-        if (rc) return rc;
+        if (rc) {                                    // drain the copies already in flight into the caller's buffers
+            cudaStreamSynchronize(h->s_in);
+            cudaStreamSynchronize(h->stream);
+            cudaStreamSynchronize(h->s_out);
+            return rc;
+        }
         CK(cudaMemcpyAsync(&flags[i], nanf, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaEventRecord(h->ev_c[b], h->stream));
         CK(cudaStreamWaitEvent(h->s_out, h->ev_c[b], 0));

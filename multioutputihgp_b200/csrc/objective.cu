@@ -66,8 +66,9 @@ template <int D> __device__ __forceinline__ void mv_acc(const double* M, const d
 // Warp-level LTI scan  z+ = M z + r_i  over this lane's SUB steps: returns, per step, the state BEFORE
 // the step (pre[i]) and the lane's end state after the inclusive scan (z_end; lane 31 = chunk end).
 template <int D>
-__device__ __forceinline__ void lti_scan(const double (&M)[D * D], const LatentConsts* lc, const double (&r)[SUB][D],
-                                         const double (&z_in)[D], int lane, double (&pre)[SUB][D], double (&z_end)[D]) {
+__device__ __forceinline__ void lti_scan(const double (&M)[D * D], const double* __restrict__ pw /*[5][D*D]: M^(SUB 2^k)*/,
+                                         const double (&r)[SUB][D], const double (&z_in)[D], int lane, double (&pre)[SUB][D],
+                                         double (&z_end)[D]) {
     double z[D];
 #pragma unroll
     for (int q = 0; q < D; ++q) z[q] = lane == 0 ? z_in[q] : 0.0;
@@ -83,9 +84,10 @@ __device__ __forceinline__ void lti_scan(const double (&M)[D * D], const LatentC
         const int o = 1 << k;
         double zo[D], P[D * D];
 #pragma unroll
-        for (int q = 0; q < D; ++q) zo[q] = __shfl_up_sync(FULL, z[q], o);
-        load_mat<D>(lc->powM[LOG2_SUB + k], P);
-        if (lane >= o) mv_acc<D>(P, zo, z);
+        for (int q = 0; q < D; ++q) { const double t = __shfl_up_sync(FULL, z[q], o); zo[q] = lane >= o ? t : 0.0; }
+#pragma unroll
+        for (int q = 0; q < D * D; ++q) P[q] = pw[k * D * D + q];
+        mv_acc<D>(P, zo, z);
     }
 #pragma unroll
     for (int q = 0; q < D; ++q) z_end[q] = z[q];
@@ -106,28 +108,44 @@ __device__ __forceinline__ void lti_scan(const double (&M)[D * D], const LatentC
     }
 }
 
-// grid: N * nC * L warps, 4 warps per CTA (one warp = one (sequence, chunk, latent)); arrays [c][n][l][...]
+// grid: N * L * nG warps, 4 warps per CTA; warp (n, l, g) walks the chunks g * cpw ... (cpw chunks, fewer for the last
+// group): the latent's constants and scan powers are loaded once per warp, not once per chunk.
 template <int D, bool FINAL>
 __global__ void __launch_bounds__(128, 3) k_obj_scan(const double* __restrict__ u, const double* __restrict__ w,
                                                  const double* __restrict__ yl, const LatentConsts* __restrict__ consts,
                                                  const double* __restrict__ S, double sigma, int L, long long N, long long T,
-                                                 long long nC, const double* __restrict__ zin, double* __restrict__ zsum,
+                                                 long long nC, long long c_base, long long c_cnt, long long cpw,
+                                                 const double* __restrict__ zin, double* __restrict__ zsum,
                                                  double* __restrict__ wgt, double* __restrict__ part,
                                                  double* __restrict__ xT, double* __restrict__ dxT) {
     const int lane = threadIdx.x & 31;
-    const long long wid = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (wid >= N * nC * L) return;
-    const int l = (int)(wid % L);
-    const long long c = (wid / L) % nC;
-    const long long n = wid / ((long long)L * nC);
+    __shared__ double pws[4][5 * D * D];
+    const long long nG = (c_cnt + cpw - 1) / cpw;
+    const long long wid0 = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const bool live = wid0 < N * L * nG;
+    const long long wid = live ? wid0 : 0;
+    const long long g = wid % nG;
+    const int l = (int)((wid / nG) % L);
+    const long long n = wid / (nG * L);
     const LatentConsts* lc = consts + l;
-    const long long tf = c * CH + (long long)lane * SUB;
+    {
+        double* pwm = pws[threadIdx.x >> 5];
+        for (int i = lane; i < 5 * D * D; i += 32) {
+            const int m = i / (D * D), e = i - m * (D * D);
+            pwm[i] = lc->powM[LOG2_SUB + m][(e / D) * 3 + (e % D)];
+        }
+        __syncwarp();
+    }
+    if (!live) return;
+    const double* pw = pws[threadIdx.x >> 5];
     const size_t so = ((size_t)n * L + l) * T;
-
     double M[D * D], K[D], HA[D];
     load_mat<D>(lc->AKHA, M);
     load_vec<D>(lc->K, K);
     load_vec<D>(lc->HA, HA);
+    const long long c_lo = c_base + g * cpw, c_hi = min(c_base + c_cnt, c_lo + cpw);
+  for (long long c = c_lo; c < c_hi; ++c) {
+    const long long tf = c * CH + (long long)lane * SUB;
     // this lane's 8 consecutive steps: 16-byte loads when the run is whole and aligned (T even or an aligned row start)
     const bool vec = tf + SUB <= T && (((so + tf) & 1) == 0) && ((reinterpret_cast<size_t>(u) & 15) == 0) &&
                      ((reinterpret_cast<size_t>(w) & 15) == 0) && ((reinterpret_cast<size_t>(yl) & 15) == 0) &&
@@ -161,7 +179,7 @@ __global__ void __launch_bounds__(128, 3) k_obj_scan(const double* __restrict__ 
     for (int i = 0; i < SUB; ++i)
 #pragma unroll
         for (int q = 0; q < D; ++q) r[i][q] = K[q] * uu[i];
-    lti_scan<D>(M, lc, r, zi[0], lane, xpre, zend);
+    lti_scan<D>(M, pw, r, zi[0], lane, xpre, zend);
     if (!FINAL && lane == 31) {
 #pragma unroll
         for (int q = 0; q < D; ++q) zsum[ci + q] = zend[q];
@@ -225,7 +243,7 @@ __global__ void __launch_bounds__(128, 3) k_obj_scan(const double* __restrict__ 
 #pragma unroll
             for (int q = 0; q < D; ++q) r[i][q] = fma(dK[q], uu[i], t1[q]);         // ihgp.h:75
         }
-        lti_scan<D>(M, lc, r, zi[1 + k], lane, pre, zend);
+        lti_scan<D>(M, pw, r, zi[1 + k], lane, pre, zend);
         if (!FINAL) {
             if (lane == 31) {
 #pragma unroll
@@ -267,6 +285,7 @@ __global__ void __launch_bounds__(128, 3) k_obj_scan(const double* __restrict__ 
             for (int j = 0; j < 5; ++j) pp[j] = s[j];
         }
     }
+  }
 }
 
 // Cross-chunk coupling matrices by doubling: for a span of n steps  E_k(n) = sum_i M^(n-1-i) dM_k M^i,  and
@@ -596,18 +615,26 @@ __global__ void __launch_bounds__(256) k_obj_finish(const double* __restrict__ l
 template <int D>
 cudaError_t run_objective(const ObjArgs& a, cudaStream_t st) {
     const long long nC = (a.T + CH - 1) / CH;
-    const long long warps = a.N * nC * a.L;
+    // chunks per warp: enough warps to fill the machine several times over, as few prologues as that allows
+    auto per_unit = [&](long long units, long long chunks) {
+        long long groups = (148LL * 48 + units - 1) / units;
+        if (groups < 1) groups = 1;
+        if (groups > chunks) groups = chunks;
+        return (chunks + groups - 1) / groups;
+    };
+    const long long cpw = per_unit(a.N * a.L, nC);
+    const long long warps = a.N * a.L * ((nC + cpw - 1) / cpw);
     const unsigned grid = (unsigned)((warps + 3) / 4);
     double* Ek = a.Ek;
     if (nC > 1) {
-        k_obj_scan<D, false><<<grid, 128, 0, st>>>(a.u, a.w, a.yl, a.consts, a.S, a.sigma, a.L, a.N, a.T, nC, nullptr, a.zsum,
+        k_obj_scan<D, false><<<grid, 128, 0, st>>>(a.u, a.w, a.yl, a.consts, a.S, a.sigma, a.L, a.N, a.T, nC, 0, nC, cpw, nullptr, a.zsum,
                                                    nullptr, nullptr, nullptr, nullptr);
         mark(a.mk, "k_obj_scan_summaries");
     }
     k_obj_coupling<D><<<(3 * a.L + 63) / 64, 64, 0, st>>>(a.consts, a.L, Ek);
     k_obj_carry<D><<<(unsigned)((a.N * a.L * 32 + 127) / 128), 128, 0, st>>>(a.consts, Ek, a.L, a.N, nC, a.x0, a.dx0, a.zsum, a.zin);
     mark(a.mk, "k_obj_carry");
-    k_obj_scan<D, true><<<grid, 128, 0, st>>>(a.u, a.w, a.yl, a.consts, a.S, a.sigma, a.L, a.N, a.T, nC, a.zin, nullptr, a.wgt,
+    k_obj_scan<D, true><<<grid, 128, 0, st>>>(a.u, a.w, a.yl, a.consts, a.S, a.sigma, a.L, a.N, a.T, nC, 0, nC, cpw, a.zin, nullptr, a.wgt,
                                               a.part, a.xT, a.dxT);
     mark(a.mk, "k_obj_scan_final");
     const size_t nsplit = obj_gu_splits(a.N, a.T);

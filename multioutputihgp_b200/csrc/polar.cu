@@ -100,8 +100,13 @@ size_t polar_smem_bytes(int p, int L) {
 cudaError_t launch_polar(const double* A, int p, int L, double* U, cudaStream_t st) {
     const size_t smem = polar_smem_bytes(p, L);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
-    static bool attr_done = false;
-    if (!attr_done) { cudaFuncSetAttribute(k_polar, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_done = true; }
+    static bool attr_done[64] = {};          // per device: function attributes belong to the device's context
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+        cudaFuncSetAttribute(k_polar, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
     const int Lp = (L + 1) & ~1;
     int warps = Lp / 2;
     if (warps > 32) warps = 32;

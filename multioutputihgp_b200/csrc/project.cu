@@ -400,10 +400,12 @@ cudaError_t run_project_mma(const double* Y, const double* U, const double* S, i
                             double* w, double* yl, double* rho_part, int* nan_info, long long* nan_rows, long long nan_cap,
                             cudaStream_t stream) {
     using SMC = MmaSmem<NB>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {};          // per device: function attributes belong to the device's context
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
         cudaFuncSetAttribute(k_project_mma<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMC::BYTES);
-        attr_done = true;
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     const unsigned grid = (unsigned)(((T + PT - 1) / PT) * N);
     k_project_mma<NB><<<grid, MT, SMC::BYTES, stream>>>(Y, U, S, p, L, T, u, w, yl, rho_part, nan_info, nan_rows, nan_cap);
