@@ -417,3 +417,42 @@ def test_bound_data_objective_equals_host_buffer_objective(cuda_lib):
     m.bind(None)
     with pytest.raises(RuntimeError):
         m.objective_bound()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path,kernel,p,L,N,T", [("chain", "Matern52", 16, 8, 5, 203), ("chain", "Matern32", 8, 4, 9, 37),
+                                                 ("scan", "Matern52", 16, 8, 3, 515), ("scan", "Matern32", 5, 3, 2, 257)])
+def test_outputs_stay_inside_their_buffers(cuda_lib, path, kernel, p, L, N, T):
+    """Ragged N / T through the device entry points with every output placed between guard zones: the guards are intact
+    afterwards (no out-of-bounds store) and the payload equals the host-buffer result."""
+    import torch
+    from multioutputihgp_b200 import MOIHGPSequences
+    from oracle.gen_golden import make_data, make_params
+    rng = np.random.default_rng(3 * N + T)
+    m = MOIHGPSequences(0.1, p, L, kernel, True)
+    m.update(make_params(rng, p, L, kernel))
+    m.set_path(path)
+    Y = np.stack([make_data(rng, p, L, T) for _ in range(N)])
+    host = m.filter_smoother_nll(Y, smoother_mode=1, want_yhat=True)
+    dev = torch.device("cuda:0")
+    d, G, SENT = m.igp_dim, 512, 1234.5
+
+    def guarded(n):
+        n_al = (n + 1) & ~1                     # keep the payload 16-byte aligned (the many-chains kernels require it)
+        buf = torch.full((G + n_al + G,), SENT, dtype=torch.float64, device=dev)
+        return buf, buf[G:G + n]
+    bX, X = guarded(N * T * L * d)
+    bXs, Xs = guarded(N * T * L * d)
+    bYh, Yh = guarded(N * T * p)
+    bn, nll = guarded(N)
+    bx, xT = guarded(N * L * d)
+    Yd = torch.from_numpy(Y).to(dev)
+    m.filter_smoother_nll_device(Yd, smoother_mode=1, X=X.view(N, T, L, d), Xs=Xs.view(N, T, L, d), Yhat=Yh.view(N, T, p), nll=nll, xT=xT.view(N, L, d))
+    torch.cuda.synchronize()
+    for name, buf, n in (("X", bX, N * T * L * d), ("Xs", bXs, N * T * L * d), ("Yhat", bYh, N * T * p), ("nll", bn, N), ("xT", bx, N * L * d)):
+        h = buf.cpu().numpy()
+        assert np.all(h[:G] == SENT) and np.all(h[G + ((n + 1) & ~1):] == SENT), name
+    assert rel_err(X.cpu().numpy().reshape(N, T, L, d), host["X"]) < 1e-13
+    assert rel_err(Xs.cpu().numpy().reshape(N, T, L, d), host["Xs"]) < 1e-13
+    assert rel_err(Yh.cpu().numpy().reshape(N, T, p), host["Yhat"]) < 1e-13
+    assert rel_err(nll.cpu().numpy(), host["nll"]) < 1e-13
