@@ -75,7 +75,8 @@ enum { MOIHGP_SMOOTH_NONE = -1, MOIHGP_SMOOTH_REFERENCE_LITERAL = 0, MOIHGP_SMOO
 int moihgp_cuda_create(moihgp_handle** out, int kernel, double dt, size_t num_output, size_t num_latent,
                        int threading, int device);
 void moihgp_cuda_destroy(moihgp_handle* h);
-/* run every kernel of this handle on `cuda_stream` (a cudaStream_t); NULL = the handle's own stream */
+/* run every kernel of this handle on `cuda_stream` (a cudaStream_t); NULL = the handle's own (non-blocking) stream.
+ * To share the legacy default stream pass cudaStreamLegacy ((cudaStream_t)0x1), not 0. */
 int moihgp_cuda_set_stream(moihgp_handle* h, void* cuda_stream);
 int moihgp_cuda_sync(moihgp_handle* h);
 const char* moihgp_cuda_last_error(moihgp_handle* h);
@@ -142,6 +143,16 @@ int moihgp_cuda_objective_bound(moihgp_handle* h, const double* x0, const double
 /* same, DEVICE buffers (loss[1], grad[num_param] on the device); asynchronous on the handle's stream */
 int moihgp_cuda_objective_dev(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0, const double* dx0,
                               double* loss, double* grad, double* xT, double* dxT);
+
+/* ONE long sequence sharded over several devices in TIME (one process per GPU): every device holds a contiguous block of
+ * T steps, DEVICE buffers.  begin projects the block and returns (HOST, zend[N][L][4][d] = [x; dx_0; dx_1; dx_2]) its end
+ * state from a ZERO carry-in - needs T % 256 == 0; pass NULL on the last block, whose end state nobody needs.  The caller
+ * exchanges the end states, forms this block's true carry-in (z_in(g+1) = T(n_g) z_in(g) + zend_g, see
+ * multioutputihgp_b200/parallel.py) and calls finish, which evaluates loss / grad of the block from that carry-in reusing
+ * the projection of begin; the blocks' [loss, grad] are then summed (all-reduce). */
+int moihgp_cuda_objective_begin_dev(moihgp_handle* h, const double* Y, size_t N, size_t T, double* zend_host);
+int moihgp_cuda_objective_finish_dev(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0, const double* dx0,
+                                     double* loss, double* grad, double* xT, double* dxT);
 
 #ifdef __cplusplus
 }

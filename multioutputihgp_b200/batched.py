@@ -31,6 +31,14 @@ def _ptr(a):
     return a.data_ptr()  # torch tensor
 
 
+def _torch_stream(device):
+    """cudaStream_t of torch's current stream on `device`.  torch reports its default stream as handle 0, which the C ABI
+    reads as "the handle's own stream": pass CUDA's explicit alias of the legacy default stream (cudaStreamLegacy = 0x1)
+    instead, so that the library's kernels are ordered with torch's own work on that stream."""
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream or 1
+
+
 class MOIHGPSequences(object):
 
     def __init__(self, dt, num_output, num_latent, kernel="Matern32", threading=False, device=-1):
@@ -152,7 +160,7 @@ class MOIHGPSequences(object):
         import torch
         assert Y.is_cuda and Y.dtype == torch.float64 and Y.is_contiguous() and Y.dim() == 3
         N, T, _ = Y.shape
-        self.set_stream(torch.cuda.current_stream(Y.device).cuda_stream)
+        self.set_stream(_torch_stream(Y.device))
         self._check(self._lib.moihgp_cuda_filter_smoother_nll_dev(self._h, _ptr(Y), N, T, _ptr(x0), smoother_mode, _ptr(X), _ptr(Xs),
                                                                   _ptr(Yhat), _ptr(nll), _ptr(xT)))
 
@@ -176,6 +184,23 @@ class MOIHGPSequences(object):
         if want_state:
             return float(loss[0]), grad, xT, dxT
         return float(loss[0]), grad
+
+    def objective_begin_device(self, Y, want_end=True):
+        """Time-sharded evaluation, step 1 (torch CUDA tensor Y [N,T,p] = this rank's block of time): projection + summaries;
+        returns the block's end state from a zero carry-in as (x [N,L,d], dx [N,L,3,d]) NumPy arrays (needs T % 256 == 0)."""
+        import torch
+        assert Y.is_cuda and Y.dtype == torch.float64 and Y.is_contiguous() and Y.dim() == 3
+        N, T, _ = Y.shape
+        L, d = self.num_latent, self.igp_dim
+        self.set_stream(_torch_stream(Y.device))
+        z = np.zeros((N, L, 4, d)) if want_end else None
+        self._check(self._lib.moihgp_cuda_objective_begin_dev(self._h, _ptr(Y), N, T, _ptr(z)))
+        return (z[:, :, 0].copy(), z[:, :, 1:].copy()) if want_end else None
+
+    def objective_finish_device(self, Y, loss, grad, x0=None, dx0=None):
+        """Step 2: loss / grad of the block from its true carry-in (torch CUDA tensors), reusing step 1's projection."""
+        N, T, _ = Y.shape
+        self._check(self._lib.moihgp_cuda_objective_finish_dev(self._h, _ptr(Y), N, T, _ptr(x0), _ptr(dx0), _ptr(loss), _ptr(grad), None, None))
 
     def bind(self, Y):
         """Copy the observations to the device once; ``objective_bound`` then evaluates on them at the current parameters
@@ -208,5 +233,5 @@ class MOIHGPSequences(object):
         import torch
         assert Y.is_cuda and Y.dtype == torch.float64 and Y.is_contiguous() and Y.dim() == 3
         N, T, _ = Y.shape
-        self.set_stream(torch.cuda.current_stream(Y.device).cuda_stream)
+        self.set_stream(_torch_stream(Y.device))
         self._check(self._lib.moihgp_cuda_objective_dev(self._h, _ptr(Y), N, T, _ptr(x0), _ptr(dx0), _ptr(loss), _ptr(grad), _ptr(xT), _ptr(dxT)))

@@ -304,8 +304,11 @@ void moihgp_cuda_destroy(moihgp_handle* h) {
 
 int moihgp_cuda_set_stream(moihgp_handle* h, void* s) {
     if (!h) return -2;
-    cudaStreamSynchronize(h->stream);
-    h->stream = s ? static_cast<cudaStream_t>(s) : h->own_stream;
+    cudaStream_t ns = s ? static_cast<cudaStream_t>(s) : h->own_stream;
+    if (ns != h->stream) {
+        cudaStreamSynchronize(h->stream);      // work queued on the old stream finishes before the handle moves
+        h->stream = ns;
+    }
     return 0;
 }
 
@@ -584,9 +587,11 @@ int moihgp_cuda_filter_smoother_nll(moihgp_handle* h, const double* Y, size_t N,
     return 0;
 }
 
-int moihgp_cuda_objective_dev(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0, const double* dx0,
-                              double* loss, double* grad, double* xT, double* dxT) {
-    if (!h || !Y || !loss || !grad) return -2;
+// phase 0: whole evaluation; 1: begin (projection, summaries, block end from a zero carry-in -> zend, device);
+// 2: finish (from the true carry-in; reuses the workspace phase 1 filled)
+static int objective_phase(moihgp_handle* h, int phase, const double* Y, size_t N, size_t T, const double* x0, const double* dx0,
+                           double* loss, double* grad, double* xT, double* dxT, double* zend) {
+    if (!h || !Y) return -2;
     if (N == 0 || T == 0) return fail(h, "N and T must be positive");
     cudaSetDevice(h->device);
     const int L = h->L, D = h->dim, p = h->p;
@@ -601,20 +606,53 @@ int moihgp_cuda_objective_dev(moihgp_handle* h, const double* Y, size_t N, size_
         ws_get(h, "gU", nsplit * p * L, &gU) || ws_get(h, "Ek", (size_t)L * 27 * 16, &Ek) || ws_get(h, "lat", ((size_t)L + 1) * 8, &lat) ||
         ws_get(h, "nanf", 4, &nanf))
         return -1;
-    CK(cudaMemsetAsync(nanf, 0, 2 * sizeof(int), h->stream));
     Marker* mk = h->profiling ? &h->marker : nullptr;
     if (mk) { mk->st = h->stream; mk->mark("begin"); }
-    CK(launch_project(Y, h->d_U, h->d_S, p, L, (long long)N, (long long)T, u, w, yl, rho, nanf, nanrows, (long long)nan_cap, h->stream));
-    mark(mk, "k_project");
+    if (phase != 2) {
+        CK(cudaMemsetAsync(nanf, 0, 2 * sizeof(int), h->stream));
+        CK(launch_project(Y, h->d_U, h->d_S, p, L, (long long)N, (long long)T, u, w, yl, rho, nanf, nanrows, (long long)nan_cap, h->stream));
+        mark(mk, "k_project");
+        h->launches += 2;
+    }
     ObjArgs a;
     a.mk = mk;
+    a.phase = phase;
+    a.zend = zend;
     a.Y = Y; a.u = u; a.w = w; a.yl = yl; a.rho = rho; a.wgt = w;   // the weights overwrite w in place (same thread, same index)
     a.consts = h->d_consts; a.U = h->d_U; a.S = h->d_S; a.sigma = h->sigma; a.p = p; a.L = L; a.threading = h->threading;
     a.N = (long long)N; a.T = (long long)T; a.x0 = x0; a.dx0 = dx0; a.zsum = zsum; a.zin = zin; a.part = part; a.gU_part = gU;
     a.Ek = Ek; a.lat_sums = lat; a.loss = loss; a.grad = grad; a.xT = xT; a.dxT = dxT;
     CK(launch_objective(D, a, h->stream));
-    h->launches += 2 + obj_launch_count((long long)T);
+    h->launches += obj_launch_count((long long)T);
     return 0;
+}
+
+int moihgp_cuda_objective_dev(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0, const double* dx0,
+                              double* loss, double* grad, double* xT, double* dxT) {
+    if (!loss || !grad) return -2;
+    return objective_phase(h, 0, Y, N, T, x0, dx0, loss, grad, xT, dxT, nullptr);
+}
+
+// Time-sharded evaluation: this device holds a contiguous block of T time steps of each sequence.
+int moihgp_cuda_objective_begin_dev(moihgp_handle* h, const double* Y, size_t N, size_t T, double* zend_host) {
+    if (!h) return -2;
+    if (zend_host && T % 256 != 0) return fail(h, "objective_begin: the block end state needs a block length that is a multiple of 256 steps");
+    double* dz = nullptr;
+    const size_t nz = N * (size_t)h->L * 4 * h->dim;
+    if (zend_host && ws_get(h, "zend", nz, &dz)) return -1;
+    const int rc = objective_phase(h, 1, Y, N, T, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, dz);
+    if (rc) return rc;
+    if (zend_host) {
+        CK(cudaMemcpyAsync(zend_host, dz, sizeof(double) * nz, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+int moihgp_cuda_objective_finish_dev(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0, const double* dx0,
+                                     double* loss, double* grad, double* xT, double* dxT) {
+    if (!loss || !grad) return -2;
+    return objective_phase(h, 2, Y, N, T, x0, dx0, loss, grad, xT, dxT, nullptr);
 }
 
 int moihgp_cuda_objective(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0, const double* dx0, double* loss,

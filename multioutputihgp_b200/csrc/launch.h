@@ -98,6 +98,8 @@ struct ObjArgs {
     double* lat_sums;             // [L+1][8] per-latent reduced sums (workspace)
     double *loss, *grad;          // [1], [num_param] outputs (device)
     double *xT, *dxT;             // final state or null
+    int phase = 0;                // 0: whole evaluation, 1: begin (summaries + block end from zero carry), 2: finish
+    double* zend = nullptr;       // phase 1: [N][L][4][D] end state of the block from a zero carry-in (device)
     Marker* mk = nullptr;
 };
 size_t obj_chunks(long long T);

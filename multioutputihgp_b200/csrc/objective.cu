@@ -410,6 +410,37 @@ __global__ void __launch_bounds__(128) k_obj_carry(const LatentConsts* __restric
     }
 }
 
+// End state of the block from its carry-in: z_end = Z^CH zin[nC-1] + zsum[nC-1] (exact when the last chunk is full, i.e.
+// T is a multiple of CH).  One thread per (sequence, latent).  zend layout [N][L][4][D].
+template <int D>
+__global__ void __launch_bounds__(128) k_obj_block_end(const LatentConsts* __restrict__ consts, const double* __restrict__ Ek, int L,
+                                                      long long N, long long nC, const double* __restrict__ zsum,
+                                                      const double* __restrict__ zin, double* __restrict__ zend) {
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= N * L) return;
+    const int l = (int)(id % L);
+    double MC[D * D];
+    load_mat<D>(consts[l].powM[LOG2_CH], MC);
+    const size_t o = ((size_t)id * nC + (nC - 1)) * 4 * D;
+    double x[D], out[D];
+#pragma unroll
+    for (int q = 0; q < D; ++q) x[q] = zin[o + q];
+    mv<D>(MC, x, out);
+#pragma unroll
+    for (int q = 0; q < D; ++q) zend[(size_t)id * 4 * D + q] = out[q] + zsum[o + q];
+    for (int k = 0; k < 3; ++k) {
+        double dz[D], E[D * D];
+#pragma unroll
+        for (int q = 0; q < D; ++q) dz[q] = zin[o + (1 + k) * D + q];
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) E[i] = Ek[((size_t)l * 3 + k) * D * D + i];
+        mv<D>(MC, dz, out);
+        mv_acc<D>(E, x, out);
+#pragma unroll
+        for (int q = 0; q < D; ++q) zend[(size_t)id * 4 * D + (1 + k) * D + q] = out[q] + zsum[o + (1 + k) * D + q];
+    }
+}
+
 // dU partials: gU_part[split][r][c] = sum over the split's (n, t) range of Y[n][t][r] * wgt[n][c][t].
 // CTA tile: 64 x 64 outputs, 16 x 16 threads, 4 x 4 outputs per thread, K panels of 16 steps.
 constexpr int GT = 64, GK = 16;
@@ -626,7 +657,9 @@ cudaError_t run_objective(const ObjArgs& a, cudaStream_t st) {
     const long long warps = a.N * a.L * ((nC + cpw - 1) / cpw);
     const unsigned grid = (unsigned)((warps + 3) / 4);
     double* Ek = a.Ek;
-    if (nC > 1) {
+    // phase 0: the whole evaluation; phase 1 ("begin"): summaries + the block's end state from a zero carry-in;
+    // phase 2 ("finish"): from the true carry-in, reusing the projected series and the summaries of phase 1
+    if (a.phase != 2 && (nC > 1 || a.phase == 1)) {
         k_obj_scan<D, false><<<grid, 128, 0, st>>>(a.u, a.w, a.yl, a.consts, a.S, a.sigma, a.L, a.N, a.T, nC, 0, nC, cpw, nullptr, a.zsum,
                                                    nullptr, nullptr, nullptr, nullptr);
         mark(a.mk, "k_obj_scan_summaries");
@@ -634,6 +667,10 @@ cudaError_t run_objective(const ObjArgs& a, cudaStream_t st) {
     k_obj_coupling<D><<<(3 * a.L + 63) / 64, 64, 0, st>>>(a.consts, a.L, Ek);
     k_obj_carry<D><<<(unsigned)((a.N * a.L * 32 + 127) / 128), 128, 0, st>>>(a.consts, Ek, a.L, a.N, nC, a.x0, a.dx0, a.zsum, a.zin);
     mark(a.mk, "k_obj_carry");
+    if (a.phase == 1) {
+        if (a.zend) k_obj_block_end<D><<<(unsigned)((a.N * a.L + 127) / 128), 128, 0, st>>>(a.consts, Ek, a.L, a.N, nC, a.zsum, a.zin, a.zend);
+        return cudaGetLastError();
+    }
     k_obj_scan<D, true><<<grid, 128, 0, st>>>(a.u, a.w, a.yl, a.consts, a.S, a.sigma, a.L, a.N, a.T, nC, 0, nC, cpw, a.zin, nullptr, a.wgt,
                                               a.part, a.xT, a.dxT);
     mark(a.mk, "k_obj_scan_final");

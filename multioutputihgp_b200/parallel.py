@@ -196,3 +196,57 @@ class TimeShardedObjective(object):
 def time_block_bounds(T, world_size, rank):
     """Contiguous time block [t0, t1) of rank `rank` (same balancing rule as shard_bounds)."""
     return shard_bounds(T, world_size, rank)
+
+
+def time_block_bounds_aligned(T, world_size, rank, align=256):
+    """Like time_block_bounds, but every block except the last is a whole number of `align`-step chunks (the scan's chunk
+    length): what the one-pass time-sharded evaluation needs."""
+    chunks = int(T) // align
+    lo_c, hi_c = shard_bounds(chunks, world_size, rank)
+    lo, hi = lo_c * align, hi_c * align
+    if rank == world_size - 1:
+        hi = int(T)
+    return lo, hi
+
+
+class TimeShardedDeviceObjective(object):
+    """One-pass variant on the GPU library: ``objective_begin_device`` projects the block and returns its end state from
+    a zero carry-in, the end states are all-gathered, ``objective_finish_device`` evaluates from the true carry-in reusing
+    the projection, and [loss, grad] is all-reduced in place on the device (NCCL).  One pass over the data per rank."""
+
+    def __init__(self, model, block_lengths, group=None):
+        import torch
+        self.model, self.group = model, group
+        self.block_lengths = [int(b) for b in block_lengths]
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.buf = torch.zeros(2 + model.num_param, dtype=torch.float64, device=self.dev)
+
+    def __call__(self, Y_block_dev, x0=None, dx0=None):
+        import torch
+        dist = _dist()
+        m = self.model
+        L, d = m.num_latent, m.igp_dim
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        world = dist.get_world_size(self.group) if multi else 1
+        rank = dist.get_rank(self.group) if multi else 0
+        x0 = np.zeros((L, d)) if x0 is None else np.asarray(x0, dtype=np.float64).reshape(L, d)
+        dx0 = np.zeros((L, 3, d)) if dx0 is None else np.asarray(dx0, dtype=np.float64).reshape(L, 3, d)
+        last = rank == world - 1
+        end = m.objective_begin_device(Y_block_dev, want_end=not last)
+        xin, dxin = x0, dx0
+        if multi:
+            flat = np.zeros(L * d * 4) if last else np.concatenate([end[0][0].ravel(), end[1][0].ravel()])
+            t = torch.from_numpy(flat).to(self.dev)
+            out = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(out, t, group=self.group)
+            ends = [o.cpu().numpy() for o in out]
+            consts = stack_consts([m.latent_consts(l) for l in range(L)])
+            xin, dxin = carry_in_from_block_ends(consts, self.block_lengths, [e[:L * d].reshape(L, d) for e in ends],
+                                                 [e[L * d:].reshape(L, 3, d) for e in ends], x0, dx0, rank)
+        x0d = torch.from_numpy(np.ascontiguousarray(xin[None])).to(self.dev)
+        dx0d = torch.from_numpy(np.ascontiguousarray(dxin[None])).to(self.dev)
+        m.objective_finish_device(Y_block_dev, self.buf[0:1], self.buf[2:], x0=x0d, dx0=dx0d)
+        if multi:
+            dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, group=self.group)
+        host = self.buf.cpu().numpy()
+        return float(host[0]), host[2:].copy()

@@ -456,3 +456,37 @@ def test_outputs_stay_inside_their_buffers(cuda_lib, path, kernel, p, L, N, T):
     assert rel_err(Xs.cpu().numpy().reshape(N, T, L, d), host["Xs"]) < 1e-13
     assert rel_err(Yh.cpu().numpy().reshape(N, T, p), host["Yhat"]) < 1e-13
     assert rel_err(nll.cpu().numpy(), host["nll"]) < 1e-13
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel,p,L,T,cut", [("Matern32", 16, 8, 60000, 29952), ("Matern52", 8, 4, 3000, 1024), ("Matern32", 64, 32, 5000, 2560)])
+def test_objective_begin_finish_blocks_equal_the_whole_sequence(cuda_lib, kernel, p, L, T, cut):
+    """The one-pass time-sharded protocol on ONE device: block 0 = steps [0, cut), block 1 = [cut, T).  begin returns block
+    0's end state from a zero carry-in, finish evaluates each block from its true carry-in; the two [loss, grad] add up to
+    the evaluation of the whole sequence."""
+    import torch
+    from multioutputihgp_b200 import MOIHGPSequences
+    from multioutputihgp_b200.parallel import carry_in_from_block_ends, stack_consts
+    from oracle.gen_golden import make_data, make_params
+    rng = np.random.default_rng(T + p)
+    m = MOIHGPSequences(0.1, p, L, kernel, True)
+    m.update(make_params(rng, p, L, kernel))
+    Y = make_data(rng, p, L, T)
+    lw, gw = m.objective(Y[None])
+    dev = torch.device("cuda:0")
+    d = m.igp_dim
+    Yd = [torch.from_numpy(np.ascontiguousarray(Y[:cut]))[None].to(dev).contiguous(), torch.from_numpy(np.ascontiguousarray(Y[cut:]))[None].to(dev).contiguous()]
+    out = [torch.zeros(2 + m.num_param, dtype=torch.float64, device=dev) for _ in range(2)]
+    ex, edx = m.objective_begin_device(Yd[0])
+    m.objective_finish_device(Yd[0], out[0][0:1], out[0][2:])
+    consts = stack_consts([m.latent_consts(l) for l in range(L)])
+    xin, dxin = carry_in_from_block_ends(consts, [cut, T - cut], [ex[0], np.zeros((L, d))], [edx[0], np.zeros((L, 3, d))], np.zeros((L, d)), np.zeros((L, 3, d)), 1)
+    # the carried state equals the state the whole-block evaluation ends in
+    _, _, xT, dxT = m.objective(Y[None, :cut], want_state=True)
+    assert rel_err(xin, xT[0]) < 1e-11 and rel_err(dxin, dxT[0]) < 1e-10
+    m.objective_begin_device(Yd[1], want_end=False)
+    m.objective_finish_device(Yd[1], out[1][0:1], out[1][2:], x0=torch.from_numpy(xin[None]).to(dev), dx0=torch.from_numpy(dxin[None]).to(dev))
+    torch.cuda.synchronize()
+    h0, h1 = out[0].cpu().numpy(), out[1].cpu().numpy()
+    assert abs(h0[0] + h1[0] - lw) <= 1e-10 * abs(lw)
+    assert rel_err(h0[2:] + h1[2:], gw) < TOL
