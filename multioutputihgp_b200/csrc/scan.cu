@@ -25,7 +25,9 @@
 // outputs X/Xs [n][t][l][d] are staged in shared memory and written as contiguous rows.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include "moihgp_device.cuh"
+#include "tma.cuh"
 #include "launch.h"
 
 namespace moihgp {
@@ -718,6 +720,301 @@ __global__ void __launch_bounds__(128) k_nll_reduce(const double* __restrict__ p
     nll[n] = acc + (double)T * (0.5 * log(Ssum) + 0.5 * m_n * log(sigma) + 0.5 * logs);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// k_scan_lanes: the FINAL pass with one THREAD per (latent, sub-chunk of SL = 32 steps) instead of one warp per
+// (latent, chunk).  A CTA owns (sequence, group of LG latents, chunk of CH = 256 steps): thread (s, l) runs sub-chunk s
+// of latent l sequentially, exactly as the reference's loop does (ihgp.h:81-93, :108-113), four times:
+//   A  forward from zero                          -> sub-chunk summary f_s
+//      carries: x_in(s+1) = M^32 x_in(s) + f_s, x_in(0) = the chunk's carry-in (k_carry)
+//   B  forward from the true carry: X (registers -> HBM, 16 bytes per lane, LG*D*8 contiguous bytes per step) and a
+//      private copy in shared memory for the way back; sum v^2
+//   C  backward from zero over the stored X       -> beta_s;  b_in(s-1) = G^32 b_in(s) + beta_s
+//   D  backward from the true carry: Xs -> HBM.
+// No warp shuffles, no staging tile, ~45 instructions per latent-step and lane (the warp-per-chunk kernel above executes
+// ~215): the pass becomes a stream over u (read) and X, Xs (written).  The per-step arithmetic is the literal recurrence;
+// as in k_scan only the carries differ from the sequential loop, by rounding.
+constexpr int SL = 32;                 // steps per thread
+constexpr int NSUBC = CH / SL;         // sub-chunks per chunk
+constexpr int LOG2_SL = 5;
+
+template <int D, int MODE, int LG, bool INTERIOR>
+__device__ __forceinline__ void lanes_chunk(const LC<D>& c, const double (&PM)[D * D], const double (&PG)[D * D],
+                                            const double* __restrict__ up, long long ts, long long T, int s, int li, int tid,
+                                            const double* x_chunk, const double* b_chunk, double* tile,
+                                            unsigned long long* ubar, unsigned uphase,
+                                            double (*exch)[LG][D], double (*vred)[LG], double* __restrict__ Xg,
+                                            double* __restrict__ Xsg, size_t gstride, bool vec_x, double* __restrict__ vsq_dst,
+                                            double* __restrict__ xT_dst) {
+    constexpr int NT = NSUBC * LG;
+    const int len = INTERIOR ? SL : (int)max(0LL, min((long long)SL, T - ts));
+    // ---- inputs: this thread's 32 steps of u (contiguous) and the step after them --------------------------------
+    // A lane-private 256-byte run per thread would cost 32 LSU wavefronts per warp-wide load; instead every thread has
+    // the copy engine (cp.async.bulk) drop its run into a slot of the (currently idle) X tile and reads it back with
+    // conflict-free 16-byte shared-memory loads (slot pitch 34 doubles).
+    constexpr int UP = SL + 2;
+    double* slot = tile + tid * UP;
+    const bool bulk = (INTERIOR || len == SL) && ((reinterpret_cast<size_t>(up + ts) & 15) == 0);
+    fence_async_smem();                               // the tile was last read through the generic proxy (previous chunk)
+    if (bulk) {
+        mbar_expect_tx(ubar, SL * (unsigned)sizeof(double));
+        bulk_g2s(slot, up + ts, SL * (unsigned)sizeof(double), ubar);
+    } else mbar_arrive(ubar);
+    const double u_nx = (INTERIOR || ts + SL < T) ? __ldg(up + ts + SL) : 0.0;
+    if (!bulk) {                                      // ragged end of the sequence / odd alignment: fill the slot by hand
+        for (int j = 0; j < SL; ++j) slot[j] = (INTERIOR || j < len) ? __ldg(up + ts + j) : 0.0;
+    }
+    mbar_wait(ubar, uphase);
+    double uu[SL];
+#pragma unroll
+    for (int j = 0; j < SL; j += 2) {
+        const double2 t2 = reinterpret_cast<const double2*>(slot)[j >> 1];
+        uu[j] = t2.x;
+        uu[j + 1] = t2.y;
+    }
+    // ---- A: forward from zero ---------------------------------------------------------------------------------------
+    double z[D];
+#pragma unroll
+    for (int q = 0; q < D; ++q) z[q] = 0.0;
+#pragma unroll
+    for (int j = 0; j < SL; ++j) {
+        if (INTERIOR || j < len) {
+            double zn[D];
+            mv<D>(c.M, z, zn);
+#pragma unroll
+            for (int q = 0; q < D; ++q) z[q] = fma(c.K[q], uu[j], zn[q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < D; ++q) exch[s][li][q] = z[q];
+    __syncthreads();
+    double x[D];
+#pragma unroll
+    for (int q = 0; q < D; ++q) x[q] = x_chunk[q];
+    for (int k = 0; k < s; ++k) {                    // sub-chunks before s are complete (32 steps) whenever s has any step
+        double xn[D];
+        mv<D>(PM, x, xn);
+#pragma unroll
+        for (int q = 0; q < D; ++q) x[q] = xn[q] + exch[k][li][q];
+    }
+    // ---- B: forward from the true carry ---------------------------------------------------------------------------
+    double vsq = 0.0;
+#pragma unroll
+    for (int j = 0; j < SL; ++j) {
+        if (INTERIOR || j < len) {
+            double hax = c.HA[0] * x[0];
+#pragma unroll
+            for (int q = 1; q < D; ++q) hax = fma(c.HA[q], x[q], hax);
+            const double v = uu[j] - hax;                                   // ihgp.h:206 (pre-step state)
+            vsq = fma(v, v, vsq);
+            double xn[D];
+            mv<D>(c.M, x, xn);
+#pragma unroll
+            for (int q = 0; q < D; ++q) x[q] = fma(c.K[q], uu[j], xn[q]);   // ihgp.h:90
+            if (D == 2) {
+                reinterpret_cast<double2*>(tile)[j * NT + tid] = make_double2(x[0], x[1]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < D; ++q) tile[(q * SL + j) * NT + tid] = x[q];
+            }
+            if (Xg) {
+                double* dst = Xg + (size_t)j * gstride;
+                if (D == 2 && vec_x) *reinterpret_cast<double2*>(dst) = make_double2(x[0], x[1]);
+                else {
+#pragma unroll
+                    for (int q = 0; q < D; ++q) dst[q] = x[q];
+                }
+            }
+        }
+    }
+    if (xT_dst && !INTERIOR && len > 0 && ts + len == T) {
+#pragma unroll
+        for (int q = 0; q < D; ++q) xT_dst[q] = x[q];
+    }
+    // fixed-order reduction of sum v^2 over the chunk's sub-chunks
+    vred[s][li] = vsq;
+    asm volatile("" ::: "memory");                    // X comes back from shared memory, not from 64 live registers
+    // ---- the step after this thread's last one (drive of the backward recursion at j = SL - 1) --------------------
+    double v_next = 0.0, X_next[D];
+    if (MODE == 1) {
+        double hax = c.HA[0] * x[0];
+#pragma unroll
+        for (int q = 1; q < D; ++q) hax = fma(c.HA[q], x[q], hax);
+        v_next = u_nx - hax;
+    } else {
+        double xn[D];
+        mv<D>(c.M, x, xn);
+#pragma unroll
+        for (int q = 0; q < D; ++q) X_next[q] = fma(c.K[q], u_nx, xn[q]);
+    }
+    auto tile_load = [&](int j, double (&o)[D]) {
+        if (D == 2) {
+            const double2 t2 = reinterpret_cast<const double2*>(tile)[j * NT + tid];
+            o[0] = t2.x;
+            o[1] = t2.y;
+        } else {
+#pragma unroll
+            for (int q = 0; q < D; ++q) o[q] = tile[(q * SL + j) * NT + tid];
+        }
+    };
+    // one step of b[j] = G b[j+1] + g[j]  (drives as in chunk_pass above); Xj = X[j], Xn = X[j+1] (literal mode)
+    auto back_step = [&](int j, const double (&Xj)[D], const double (&Xn)[D], double (&b)[D]) {
+        const long long t = ts + j;
+        double g[D];
+        if (MODE == 1) {
+            double vn;
+            if (j + 1 < SL) {
+                double hax = c.HA[0] * Xj[0];
+#pragma unroll
+                for (int q = 1; q < D; ++q) hax = fma(c.HA[q], Xj[q], hax);
+                vn = uu[(j + 1) % SL] - hax;
+            } else vn = v_next;
+            const double sgn = (INTERIOR || t < T - 1) ? vn : 0.0;
+#pragma unroll
+            for (int q = 0; q < D; ++q) g[q] = c.drv[q] * sgn;
+        } else {
+            double im[D];
+            mv<D>(c.drv, Xn, im);
+#pragma unroll
+            for (int q = 0; q < D; ++q) g[q] = (INTERIOR || t < T - 1) ? im[q] : Xj[q];
+        }
+        double bn[D];
+        mv<D>(c.G, b, bn);
+#pragma unroll
+        for (int q = 0; q < D; ++q) b[q] = bn[q] + g[q];
+    };
+    // ---- C: backward from zero ----------------------------------------------------------------------------------------
+    double b[D], Xn[D];
+#pragma unroll
+    for (int q = 0; q < D; ++q) { b[q] = 0.0; Xn[q] = X_next[q]; }
+#pragma unroll
+    for (int j = SL - 1; j >= 0; --j) {
+        if (INTERIOR || j < len) {
+            double Xj[D];
+            tile_load(j, Xj);
+            back_step(j, Xj, Xn, b);
+#pragma unroll
+            for (int q = 0; q < D; ++q) Xn[q] = Xj[q];
+        }
+    }
+    __syncthreads();                                  // everyone is done reading the forward summaries
+#pragma unroll
+    for (int q = 0; q < D; ++q) exch[s][li][q] = b[q];
+    __syncthreads();
+    if (vsq_dst && s == 0) {
+        double a = vred[0][li];
+#pragma unroll
+        for (int k = 1; k < NSUBC; ++k) a += vred[k][li];
+        *vsq_dst = a;
+    }
+#pragma unroll
+    for (int q = 0; q < D; ++q) b[q] = b_chunk[q];
+    for (int k = NSUBC - 1; k > s; --k) {
+        double bn[D];
+        mv<D>(PG, b, bn);
+#pragma unroll
+        for (int q = 0; q < D; ++q) b[q] = bn[q] + exch[k][li][q];
+    }
+    // ---- D: backward from the true carry ------------------------------------------------------------------------------
+#pragma unroll
+    for (int q = 0; q < D; ++q) Xn[q] = X_next[q];
+#pragma unroll
+    for (int j = SL - 1; j >= 0; --j) {
+        if (INTERIOR || j < len) {
+            double Xj[D];
+            tile_load(j, Xj);
+            back_step(j, Xj, Xn, b);
+#pragma unroll
+            for (int q = 0; q < D; ++q) Xn[q] = Xj[q];
+            if (Xsg) {
+                double o[D];
+#pragma unroll
+                for (int q = 0; q < D; ++q) o[q] = MODE == 1 ? Xj[q] + b[q] : b[q];
+                double* dst = Xsg + (size_t)j * gstride;
+                if (D == 2 && vec_x) *reinterpret_cast<double2*>(dst) = make_double2(o[0], o[1]);
+                else {
+#pragma unroll
+                    for (int q = 0; q < D; ++q) dst[q] = o[q];
+                }
+            }
+        }
+    }
+    __syncthreads();                                  // exch / vred are reused by the next chunk
+}
+
+// grid: N * nG * (L / LG) CTAs (latent-group minor), block: NSUBC * LG threads; CTA (n, g, latent group) walks cpc chunks.
+template <int D, int MODE, int LG>
+__global__ void __launch_bounds__(NSUBC * LG, (D == 2 ? 384 : 256) / (NSUBC * LG)) k_scan_lanes(const double* __restrict__ u, const LatentConsts* __restrict__ consts,
+                                                          int L, long long N, long long T, long long nC, long long cpc,
+                                                          const double* __restrict__ xin, const double* __restrict__ bin,
+                                                          double* __restrict__ X, double* __restrict__ Xs,
+                                                          double* __restrict__ vsq_out, double* __restrict__ xT) {
+    extern __shared__ double tile[];                  // the CTA's filtered states: [SL][NT] double2 (D = 2) or [D][SL][NT]
+    __shared__ double exch[NSUBC][LG][D];
+    __shared__ double vred[NSUBC][LG];
+    __shared__ unsigned long long ubar;               // completion of the chunk's u copies (one phase per chunk)
+    const int tid = threadIdx.x, s = tid / LG, li = tid % LG;
+    if (tid == 0) {
+        mbar_init(&ubar, NSUBC * LG);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int nLG = L / LG;
+    const long long nG = (nC + cpc - 1) / cpc;
+    const long long bid = blockIdx.x;
+    const int lgi = (int)(bid % nLG);
+    const long long gi = (bid / nLG) % nG;
+    const long long n = bid / ((long long)nLG * nG);
+    const int l = lgi * LG + li;
+    const LatentConsts* lc = consts + l;
+    LC<D> cst;
+    load_lc<D, MODE>(lc, cst);
+    double PM[D * D], PG[D * D];
+    load_mat<D>(lc->powM[LOG2_SL], PM);
+    load_mat<D>(lc->powG[MODE][LOG2_SL], PG);
+    const double* up = u + ((size_t)n * L + l) * T;
+    const size_t gstride = (size_t)L * D;
+    const bool vec_x = D == 2 && (reinterpret_cast<size_t>(X) & 15) == 0 && (reinterpret_cast<size_t>(Xs) & 15) == 0;
+    const long long c_lo = gi * cpc, c_hi = min(nC, c_lo + cpc);
+    for (long long c = c_lo; c < c_hi; ++c) {
+        const long long ts = c * CH + (long long)s * SL;
+        const size_t ci = (((size_t)n * L + l) * nC + c) * D;
+        double x_chunk[D], b_chunk[D];
+#pragma unroll
+        for (int q = 0; q < D; ++q) { x_chunk[q] = xin[ci + q]; b_chunk[q] = bin[ci + q]; }
+        const size_t go = ((size_t)n * T + ts) * gstride + (size_t)l * D;
+        double* Xg = X ? X + go : nullptr;
+        double* Xsg = Xs ? Xs + go : nullptr;
+        double* vdst = vsq_out + ((size_t)c * N + n) * L + l;
+        double* xTd = xT ? xT + ((size_t)n * L + l) * D : nullptr;
+        if (c * CH + CH < T)
+            lanes_chunk<D, MODE, LG, true>(cst, PM, PG, up, ts, T, s, li, tid, x_chunk, b_chunk, tile, &ubar, (unsigned)((c - c_lo) & 1), exch, vred, Xg, Xsg, gstride, vec_x, vdst, xTd);
+        else
+            lanes_chunk<D, MODE, LG, false>(cst, PM, PG, up, ts, T, s, li, tid, x_chunk, b_chunk, tile, &ubar, (unsigned)((c - c_lo) & 1), exch, vred, Xg, Xsg, gstride, vec_x, vdst, xTd);
+    }
+}
+
+template <int D, int MODE, int LG>
+cudaError_t launch_scan_lanes(const ScanArgs& a, long long nC, cudaStream_t st) {
+    constexpr int NT = NSUBC * LG;
+    const size_t smem = sizeof(double) * D * SL * NT;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_scan_lanes<D, MODE, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const int nLG = a.L / LG;
+    const long long target = 148LL * 24;
+    long long groups = (target + a.N * nLG - 1) / (a.N * nLG);
+    if (groups < 1) groups = 1;
+    if (groups > nC) groups = nC;
+    const long long cpc = (nC + groups - 1) / groups;
+    const long long nG = (nC + cpc - 1) / cpc;
+    k_scan_lanes<D, MODE, LG><<<(unsigned)(a.N * nG * nLG), NT, smem, st>>>(a.u, a.consts, a.L, a.N, a.T, nC, cpc, a.xin, a.bin, a.X, a.Xs,
+                                                                            a.vsq, a.xT);
+    return cudaGetLastError();
+}
+
 template <int D, int MODE>
 cudaError_t run_scan(const ScanArgs& a, cudaStream_t st) {
     const long long nC = (a.T + CH - 1) / CH;
@@ -767,6 +1064,13 @@ cudaError_t run_scan(const ScanArgs& a, cudaStream_t st) {
         k_carry<D, MODE, 1, 1><<<gw, 128, 0, st>>>(a.consts, a.Bx, a.L, a.N, nC, nS, a.x0, a.fsum, a.bsum, a.xin, a.bin, in, nullptr);
     }
     mark(a.mk, "k_carry");
+    // final pass: thread-per-sub-chunk kernel when the latents come in whole groups of 16 or 8, else the warp-per-chunk one
+    const bool force_warp = getenv("MOIHGP_SCAN_FINAL_WARP") != nullptr;   // A/B switch, read per call
+    if (!force_warp && a.L % 8 == 0) {
+        const cudaError_t e = a.L % 16 == 0 ? launch_scan_lanes<D, MODE, 16>(a, nC, st) : launch_scan_lanes<D, MODE, 8>(a, nC, st);
+        mark(a.mk, "k_scan_final");
+        return e;
+    }
     const long long cpc = per_unit(a.N * nLG, nC);
     const long long nG = (nC + cpc - 1) / cpc;
     k_scan<D, MODE, true><<<(unsigned)(a.N * nG * nLG), 32 * lg, smem, st>>>(a.u, a.consts, a.L, a.N, a.T, nC, nLG, 0, nC, cpc, a.xin, a.bin,

@@ -490,3 +490,29 @@ def test_objective_begin_finish_blocks_equal_the_whole_sequence(cuda_lib, kernel
     h0, h1 = out[0].cpu().numpy(), out[1].cpu().numpy()
     assert abs(h0[0] + h1[0] - lw) <= 1e-10 * abs(lw)
     assert rel_err(h0[2:] + h1[2:], gw) < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel,p,L,N,T", [("Matern32", 64, 32, 1, 5000), ("Matern52", 16, 8, 2, 1300), ("Matern32", 32, 16, 2, 256),
+                                            ("Matern52", 24, 24, 1, 777)])
+def test_scan_final_kernels_agree(cuda_lib, kernel, p, L, N, T, monkeypatch):
+    """The two final-pass kernels of the chunked-scan path (thread per sub-chunk, warp per chunk) evaluate the same
+    recurrence from the same carries: outputs agree to rounding, in both smoother modes."""
+    from multioutputihgp_b200 import MOIHGPSequences
+    from oracle.gen_golden import make_data, make_params
+    rng = np.random.default_rng(T)
+    m = MOIHGPSequences(0.1, p, L, kernel, True)
+    m.update(make_params(rng, p, L, kernel))
+    m.set_path("scan")
+    Y = np.stack([make_data(rng, p, L, T) for _ in range(N)])
+    x0 = 0.3 * rng.standard_normal((N, L, m.igp_dim))
+    for mode in (1, 0):
+        monkeypatch.delenv("MOIHGP_SCAN_FINAL_WARP", raising=False)
+        a = m.filter_smoother_nll(Y, x0=x0, smoother_mode=mode)
+        monkeypatch.setenv("MOIHGP_SCAN_FINAL_WARP", "1")
+        b = m.filter_smoother_nll(Y, x0=x0, smoother_mode=mode)
+        monkeypatch.delenv("MOIHGP_SCAN_FINAL_WARP", raising=False)
+        for k in ("X", "nll", "xT"):
+            assert rel_err(a[k], b[k]) < 1e-12, (k, mode)
+        if mode == 1 or np.max(np.abs(b["Xs"])) < 1e100:
+            assert rel_err(a["Xs"], b["Xs"]) < (1e-12 if mode == 1 else 1e-7), mode
