@@ -623,7 +623,7 @@ static int objective_phase(moihgp_handle* h, int phase, const double* Y, size_t 
     a.N = (long long)N; a.T = (long long)T; a.x0 = x0; a.dx0 = dx0; a.zsum = zsum; a.zin = zin; a.part = part; a.gU_part = gU;
     a.Ek = Ek; a.lat_sums = lat; a.loss = loss; a.grad = grad; a.xT = xT; a.dxT = dxT;
     CK(launch_objective(D, a, h->stream));
-    h->launches += obj_launch_count((long long)T);
+    h->launches += obj_launch_count((long long)T, L);
     return 0;
 }
 

@@ -104,7 +104,7 @@ struct ObjArgs {
 };
 size_t obj_chunks(long long T);
 size_t obj_gu_splits(long long N, long long T);
-int obj_launch_count(long long T);
+int obj_launch_count(long long T, int L);
 cudaError_t launch_objective(int dim, const ObjArgs& a, cudaStream_t st);
 
 // step.cu  (one observation per call: the legacy gpXX_* entry points)

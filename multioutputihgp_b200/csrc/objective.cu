@@ -20,7 +20,9 @@
 // Q8 (pv uses the RAW y(l)), Q9 (norm not squared; 1/2 log(sum S)), Q20 (dv_k uses HdA_k(0) x(0)).
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include "moihgp_device.cuh"
+#include "tma.cuh"
 #include "launch.h"
 
 namespace moihgp {
@@ -286,6 +288,298 @@ __global__ void __launch_bounds__(128, 3) k_obj_scan(const double* __restrict__ 
         }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_obj_lanes: the same two passes with one THREAD per (latent, sub-chunk of SL = 32 steps) running the reference's
+// loop (ihgp.h:60-78, :212-222) sequentially - no warp scans.  A CTA owns (sequence, LG latents, chunk of CH steps):
+//   A  augmented state from zero over the sub-chunk                 -> summary f_s
+//      carries across the sub-chunks: z <- Z^32 z + f_s with the span-32 coupling E_k(32) (built once per CTA)
+//   FINAL = false: the chunk summary  Z^32 z_in(7) + f_7  -> zsum     (interior chunks only: all sub-chunks are whole)
+//   FINAL = true : B  the literal recurrence from the true carry: per-step loss / gradient terms and the dU weights.
+// Every thread's inputs (u, U'y, raw y(l): 256-byte runs of the latent-major series) are brought into a private
+// shared-memory slot by the copy engine (cp.async.bulk) and the dU weights leave the same way: no per-lane HBM
+// instructions, no uncoalesced wavefronts.  ~115 FP64 instructions per latent-step (the warp-scan kernel: ~650).
+constexpr int SL = 32;                 // steps per thread
+constexpr int NSUBC = CH / SL;         // sub-chunks per chunk
+constexpr int LOG2_SL = 5;
+constexpr int UP3 = 3 * SL + 2;        // slot pitch in doubles ([u | U'y -> dU weight | y(l)] + pad): UP3 / 2 odd => conflict-free 16-byte loads
+
+template <int D>
+struct ObjLC {
+    double M[D * D], K[D], HA[D], dM[3][D * D], dK[3][D];
+};
+
+// z <- Z^32 z + f   on the augmented state [x; dx_0; dx_1; dx_2];  cp = [P = M^32 | E_0(32) | E_1(32) | E_2(32)]
+template <int D>
+__device__ __forceinline__ void advance32(const double* __restrict__ cp, const double* __restrict__ f, double (&z)[4][D]) {
+    double P[D * D], zn[4][D];
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) P[i] = cp[i];
+    mv<D>(P, z[0], zn[0]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double E[D * D];
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) E[i] = cp[(1 + k) * D * D + i];
+        mv<D>(P, z[1 + k], zn[1 + k]);
+        mv_acc<D>(E, z[0], zn[1 + k]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int q = 0; q < D; ++q) z[a][q] = zn[a][q] + f[a * D + q];
+}
+
+// one step of the augmented recurrence (ihgp.h:71-77): dx_k+ = dAKHA_k x + AKHA dx_k + dK_k u uses the PRE-step x
+template <int D>
+__device__ __forceinline__ void aug_step(const ObjLC<D>& c, double uj, double (&z)[4][D]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double t1[D], xn[D];
+        mv<D>(c.dM[k], z[0], t1);
+        mv<D>(c.M, z[1 + k], xn);
+#pragma unroll
+        for (int q = 0; q < D; ++q) z[1 + k][q] = xn[q] + fma(c.dK[k][q], uj, t1[q]);
+    }
+    double xn[D];
+    mv<D>(c.M, z[0], xn);
+#pragma unroll
+    for (int q = 0; q < D; ++q) z[0][q] = xn[q] + c.K[q] * uj;
+}
+
+template <int D, int LG, bool FINAL>
+__global__ void __launch_bounds__(NSUBC * LG) k_obj_lanes(const double* __restrict__ u, const double* __restrict__ w,
+                                                         const double* __restrict__ yl, const LatentConsts* __restrict__ consts,
+                                                         const double* __restrict__ S, double sigma, int L, long long N, long long T,
+                                                         long long nC, long long c_cnt, long long cpc,
+                                                         const double* __restrict__ zin, double* __restrict__ zsum,
+                                                         double* __restrict__ wgt, double* __restrict__ part,
+                                                         double* __restrict__ xT, double* __restrict__ dxT) {
+    constexpr int NT = NSUBC * LG;
+    constexpr int PITCH = FINAL ? UP3 : SL + 2;
+    extern __shared__ double slots[];                 // [NT][PITCH]
+    __shared__ double exch[NSUBC][LG][4 * D];         // sub-chunk summaries, then (FINAL) the sub-chunks' partial sums
+    __shared__ double cpl[LG][4 * D * D];
+    __shared__ unsigned long long bar;
+    const int tid = threadIdx.x, s = tid / LG, li = tid % LG;
+    const int nLG = L / LG;
+    const long long nG = (c_cnt + cpc - 1) / cpc;
+    const long long bid = blockIdx.x;
+    const int lgi = (int)(bid % nLG);
+    const long long gi = (bid / nLG) % nG;
+    const long long n = bid / ((long long)nLG * nG);
+    const int l = lgi * LG + li;
+    const LatentConsts* lc = consts + l;
+    if (tid == 0) {
+        mbar_init(&bar, NT);
+        mbar_fence_init();
+    }
+    ObjLC<D> c;
+    load_mat<D>(lc->AKHA, c.M);
+    load_vec<D>(lc->K, c.K);
+    load_vec<D>(lc->HA, c.HA);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { load_mat<D>(lc->dAKHA[k], c.dM[k]); load_vec<D>(lc->dK[k], c.dK[k]); }
+    if (s == 0) {
+        // span-32 transition of the augmented state: P = M^32 and E_k(32) by doubling, E(2n) = E(n) M^n + M^n E(n)
+        double P[D * D];
+        load_mat<D>(lc->powM[LOG2_SL], P);
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) cpl[li][i] = P[i];
+        for (int k = 0; k < 3; ++k) {
+            double E[D * D];
+#pragma unroll
+            for (int i = 0; i < D * D; ++i) E[i] = c.dM[k][i];
+            for (int lev = 0; lev < LOG2_SL; ++lev) {
+                double Mn[D * D], a[D * D];
+                load_mat<D>(lc->powM[lev], Mn);
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int j = 0; j < D; ++j) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int q = 0; q < D; ++q) acc += E[i * D + q] * Mn[q * D + j] + Mn[i * D + q] * E[q * D + j];
+                        a[i * D + j] = acc;
+                    }
+#pragma unroll
+                for (int i = 0; i < D * D; ++i) E[i] = a[i];
+            }
+#pragma unroll
+            for (int i = 0; i < D * D; ++i) cpl[li][(1 + k) * D * D + i] = E[i];
+        }
+    }
+    __syncthreads();
+    const double Si = __ldg(&lc->S), logSi = __ldg(&lc->logS), hak = __ldg(&lc->hak);
+    const double c1 = (1.0 - hak) / Si;                          // moihgp.h:510-511
+    const double rsS = FINAL ? 1.0 / sqrt(__ldg(S + l)) : 0.0;
+    const double rsig = 1.0 / sigma;
+    double hda0[3], dSk[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { hda0[k] = __ldg(&lc->HdA[k][0]); dSk[k] = __ldg(&lc->dS[k]); }
+    const size_t so = ((size_t)n * L + l) * T;
+    const bool al = ((reinterpret_cast<size_t>(u) & 15) == 0) &&
+                    (!FINAL || (((reinterpret_cast<size_t>(w) | reinterpret_cast<size_t>(yl) | reinterpret_cast<size_t>(wgt)) & 15) == 0));
+    double* slot = slots + (size_t)tid * PITCH;
+    const long long c_lo = gi * cpc, c_hi = min(c_cnt, c_lo + cpc);
+    for (long long ch = c_lo; ch < c_hi; ++ch) {
+        const long long ts = ch * CH + (long long)s * SL;
+        const int len = (int)max(0LL, min((long long)SL, T - ts));
+        const bool bulk = al && len == SL && (((so + ts) & 1) == 0);
+        constexpr unsigned RUN = SL * (unsigned)sizeof(double);
+        if (FINAL) bulk_wait_read<0>();               // the previous chunk's weight store has read this slot
+        fence_async_smem();
+        if (bulk) {
+            mbar_expect_tx(&bar, FINAL ? 3 * RUN : RUN);
+            bulk_g2s(slot, u + so + ts, RUN, &bar);
+            if (FINAL) {
+                bulk_g2s(slot + SL, w + so + ts, RUN, &bar);
+                bulk_g2s(slot + 2 * SL, yl + so + ts, RUN, &bar);
+            }
+        } else {
+            for (int j = 0; j < SL; ++j) {
+                slot[j] = j < len ? __ldg(u + so + ts + j) : 0.0;
+                if (FINAL) {
+                    slot[SL + j] = j < len ? __ldg(w + so + ts + j) : 0.0;
+                    slot[2 * SL + j] = j < len ? __ldg(yl + so + ts + j) : 0.0;
+                }
+            }
+            mbar_arrive(&bar);
+        }
+        const size_t ci = (((size_t)n * L + l) * nC + ch) * 4 * D;
+        double z[4][D];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int q = 0; q < D; ++q) z[a][q] = FINAL ? zin[ci + a * D + q] : 0.0;
+        mbar_wait(&bar, (unsigned)((ch - c_lo) & 1));
+        // ---- A: from zero ------------------------------------------------------------------------------------------
+        {
+            double f[4][D];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int q = 0; q < D; ++q) f[a][q] = 0.0;
+#pragma unroll 4
+            for (int j = 0; j < SL; j += 2) {
+                const double2 u2 = reinterpret_cast<const double2*>(slot)[j >> 1];
+                if (j < len) aug_step<D>(c, u2.x, f);
+                if (j + 1 < len) aug_step<D>(c, u2.y, f);
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int q = 0; q < D; ++q) exch[s][li][a * D + q] = f[a][q];
+        }
+        __syncthreads();
+        for (int k = 0; k < s; ++k) advance32<D>(cpl[li], exch[k][li], z);
+        if (!FINAL) {
+            if (s == NSUBC - 1) {
+                advance32<D>(cpl[li], exch[NSUBC - 1][li], z);
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int q = 0; q < D; ++q) zsum[ci + a * D + q] = z[a][q];
+            }
+            __syncthreads();
+            continue;
+        }
+        // ---- B: the literal recurrence from the true carry ----------------------------------------------------------
+        double sv2 = 0.0, svd[3] = {0.0, 0.0, 0.0}, spw = 0.0;
+#pragma unroll 2
+        for (int j = 0; j < SL; j += 2) {
+            const double2 u2 = reinterpret_cast<const double2*>(slot)[j >> 1];
+            const double2 w2 = reinterpret_cast<const double2*>(slot + SL)[j >> 1];
+            const double2 y2 = reinterpret_cast<const double2*>(slot + 2 * SL)[j >> 1];
+            double wg[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double uj = h ? u2.y : u2.x, wj = h ? w2.y : w2.x, yj = h ? y2.y : y2.x;
+                double hax = c.HA[0] * z[0][0];
+#pragma unroll
+                for (int q = 1; q < D; ++q) hax = fma(c.HA[q], z[0][q], hax);
+                const double v = uj - hax;                                           // ihgp.h:214
+                const double pv = (yj - hax) * c1;                                   // moihgp.h:510-511 (raw y(l), Q8)
+                wg[h] = fma(pv, rsS, -wj * rsig);                                    // moihgp.h:546-550 (rank-1 form)
+                if (j + h < len) {
+                    sv2 = fma(v, v, sv2);
+                    spw = fma(pv, wj, spw);                                          // moihgp.h:558-560
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        double hd = c.HA[0] * z[1 + k][0];
+#pragma unroll
+                        for (int q = 1; q < D; ++q) hd = fma(c.HA[q], z[1 + k][q], hd);
+                        const double dv = -hda0[k] * z[0][0] - hd;                   // ihgp.h:218 (Q20 de facto)
+                        svd[k] = fma(v, dv, svd[k]);
+                    }
+                    aug_step<D>(c, uj, z);
+                }
+            }
+            reinterpret_cast<double2*>(slot + SL)[j >> 1] = make_double2(wg[0], wg[1]);
+        }
+        if (len > 0 && ts + len == T) {                                              // this thread owns step T-1
+            if (xT) {
+#pragma unroll
+                for (int q = 0; q < D; ++q) xT[((size_t)n * L + l) * D + q] = z[0][q];
+            }
+            if (dxT) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+#pragma unroll
+                    for (int q = 0; q < D; ++q) dxT[(((size_t)n * L + l) * 3 + k) * D + q] = z[1 + k][q];
+            }
+        }
+        // the dU weights leave through the copy engine
+        if (bulk) {
+            fence_async_smem();
+            bulk_s2g(wgt + so + ts, slot + SL, RUN);
+            bulk_commit();
+        } else {
+            for (int j = 0; j < len; ++j) wgt[so + ts + j] = slot[SL + j];
+        }
+        // per-chunk partial sums (ihgp.h:215, :219), fixed order over the sub-chunks
+        __syncthreads();                              // everyone is done with the forward summaries in exch
+        {
+            const double q2 = sv2 / Si;
+            exch[s][li][0] = 0.5 * (q2 + (double)len * logSi);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) exch[s][li][1 + k] = (svd[k] - 0.5 * (q2 - (double)len) * dSk[k]) / Si;
+            exch[s][li][4] = spw;
+        }
+        __syncthreads();
+        if (s == 0) {
+            double* pp = part + (((size_t)ch * N + n) * L + l) * NPART;
+#pragma unroll
+            for (int jj = 0; jj < 5; ++jj) {
+                double a = exch[0][li][jj];
+#pragma unroll
+                for (int k = 1; k < NSUBC; ++k) a += exch[k][li][jj];
+                pp[jj] = a;
+            }
+        }
+        __syncthreads();
+    }
+    if (FINAL) bulk_wait_read<0>();
+}
+
+template <int D, bool FINAL>
+void launch_obj_lanes(const ObjArgs& a, long long nC, long long c_cnt, cudaStream_t st) {
+    constexpr int LG = 8, NT = NSUBC * LG;
+    const size_t smem = sizeof(double) * NT * (FINAL ? UP3 : SL + 2);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_obj_lanes<D, LG, FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_done = true;
+    }
+    const int nLG = a.L / LG;
+    long long groups = (148LL * 32 + a.N * nLG - 1) / (a.N * nLG);
+    if (groups < 1) groups = 1;
+    if (groups > c_cnt) groups = c_cnt;
+    const long long cpc = (c_cnt + groups - 1) / groups;
+    const long long nG = (c_cnt + cpc - 1) / cpc;
+    k_obj_lanes<D, LG, FINAL><<<(unsigned)(a.N * nG * nLG), NT, smem, st>>>(a.u, a.w, a.yl, a.consts, a.S, a.sigma, a.L, a.N, a.T, nC, c_cnt, cpc,
+                                                                            a.zin, a.zsum, a.wgt, a.part, a.xT, a.dxT);
 }
 
 // Cross-chunk coupling matrices by doubling: for a span of n steps  E_k(n) = sum_i M^(n-1-i) dM_k M^i,  and
@@ -659,9 +953,18 @@ cudaError_t run_objective(const ObjArgs& a, cudaStream_t st) {
     double* Ek = a.Ek;
     // phase 0: the whole evaluation; phase 1 ("begin"): summaries + the block's end state from a zero carry-in;
     // phase 2 ("finish"): from the true carry-in, reusing the projected series and the summaries of phase 1
+    // thread-per-sub-chunk kernels when the latents come in whole groups of 8, else the warp-scan kernel
+    const bool lanes = a.L % 8 == 0 && getenv("MOIHGP_OBJ_WARP") == nullptr;        // A/B switch, read per call
     if (a.phase != 2 && (nC > 1 || a.phase == 1)) {
-        k_obj_scan<D, false><<<grid, 128, 0, st>>>(a.u, a.w, a.yl, a.consts, a.S, a.sigma, a.L, a.N, a.T, nC, 0, nC, cpw, nullptr, a.zsum,
-                                                   nullptr, nullptr, nullptr, nullptr);
+        if (lanes) {
+            // interior chunks (whole) by k_obj_lanes; the last chunk of the sequence (possibly ragged) by the warp-scan kernel
+            if (nC > 1) launch_obj_lanes<D, false>(a, nC, nC - 1, st);
+            k_obj_scan<D, false><<<(unsigned)((a.N * a.L + 3) / 4), 128, 0, st>>>(a.u, a.w, a.yl, a.consts, a.S, a.sigma, a.L, a.N, a.T, nC, nC - 1, 1, 1,
+                                                                                 nullptr, a.zsum, nullptr, nullptr, nullptr, nullptr);
+        } else {
+            k_obj_scan<D, false><<<grid, 128, 0, st>>>(a.u, a.w, a.yl, a.consts, a.S, a.sigma, a.L, a.N, a.T, nC, 0, nC, cpw, nullptr, a.zsum,
+                                                       nullptr, nullptr, nullptr, nullptr);
+        }
         mark(a.mk, "k_obj_scan_summaries");
     }
     k_obj_coupling<D><<<(3 * a.L + 63) / 64, 64, 0, st>>>(a.consts, a.L, Ek);
@@ -671,8 +974,9 @@ cudaError_t run_objective(const ObjArgs& a, cudaStream_t st) {
         if (a.zend) k_obj_block_end<D><<<(unsigned)((a.N * a.L + 127) / 128), 128, 0, st>>>(a.consts, Ek, a.L, a.N, nC, a.zsum, a.zin, a.zend);
         return cudaGetLastError();
     }
-    k_obj_scan<D, true><<<grid, 128, 0, st>>>(a.u, a.w, a.yl, a.consts, a.S, a.sigma, a.L, a.N, a.T, nC, 0, nC, cpw, a.zin, nullptr, a.wgt,
-                                              a.part, a.xT, a.dxT);
+    if (lanes) launch_obj_lanes<D, true>(a, nC, nC, st);
+    else k_obj_scan<D, true><<<grid, 128, 0, st>>>(a.u, a.w, a.yl, a.consts, a.S, a.sigma, a.L, a.N, a.T, nC, 0, nC, cpw, a.zin, nullptr, a.wgt,
+                                                   a.part, a.xT, a.dxT);
     mark(a.mk, "k_obj_scan_final");
     const size_t nsplit = obj_gu_splits(a.N, a.T);
     const long long slabs = a.N * ((a.T + GK - 1) / GK);
@@ -702,7 +1006,10 @@ size_t obj_gu_splits(long long N, long long T) {
     return (size_t)s;
 }
 
-int obj_launch_count(long long T) { return (T + CH - 1) / CH > 1 ? 7 : 6; }
+int obj_launch_count(long long T, int L) {
+    const bool many = (T + CH - 1) / CH > 1;
+    return many ? (L % 8 == 0 ? 8 : 7) : 6;
+}
 
 cudaError_t launch_objective(int dim, const ObjArgs& a, cudaStream_t st) {
     return dim == 2 ? run_objective<2>(a, st) : run_objective<3>(a, st);

@@ -516,3 +516,27 @@ def test_scan_final_kernels_agree(cuda_lib, kernel, p, L, N, T, monkeypatch):
             assert rel_err(a[k], b[k]) < 1e-12, (k, mode)
         if mode == 1 or np.max(np.abs(b["Xs"])) < 1e100:
             assert rel_err(a["Xs"], b["Xs"]) < (1e-12 if mode == 1 else 1e-7), mode
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel,p,L,N,T", [("Matern32", 64, 32, 1, 5000), ("Matern52", 16, 8, 3, 1300), ("Matern32", 32, 16, 2, 256),
+                                            ("Matern52", 24, 8, 2, 33), ("Matern32", 48, 24, 1, 4097)])
+def test_objective_kernels_agree(cuda_lib, kernel, p, L, N, T, monkeypatch):
+    """The two implementations of the objective's scan (thread per sub-chunk, warp per chunk) give the same loss,
+    gradient and final state to rounding."""
+    from multioutputihgp_b200 import MOIHGPSequences
+    from oracle.gen_golden import make_data, make_params
+    rng = np.random.default_rng(T + L)
+    m = MOIHGPSequences(0.1, p, L, kernel, True)
+    m.update(make_params(rng, p, L, kernel))
+    Y = np.stack([make_data(rng, p, L, T) for _ in range(N)])
+    x0 = 0.3 * rng.standard_normal((N, L, m.igp_dim))
+    dx0 = 0.1 * rng.standard_normal((N, L, 3, m.igp_dim))
+    monkeypatch.delenv("MOIHGP_OBJ_WARP", raising=False)
+    la, ga, xa, dxa = m.objective(Y, x0=x0, dx0=dx0, want_state=True)
+    monkeypatch.setenv("MOIHGP_OBJ_WARP", "1")
+    lb, gb, xb, dxb = m.objective(Y, x0=x0, dx0=dx0, want_state=True)
+    monkeypatch.delenv("MOIHGP_OBJ_WARP", raising=False)
+    assert abs(la - lb) <= 1e-12 * abs(lb)
+    assert rel_err(ga, gb) < 1e-11
+    assert rel_err(xa, xb) < 1e-12 and rel_err(dxa, dxb) < 1e-11
