@@ -461,11 +461,16 @@ __global__ void __launch_bounds__(NSUBC * LG) k_obj_lanes(const double* __restri
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int q = 0; q < D; ++q) f[a][q] = 0.0;
+            if (len == SL) {                          // whole sub-chunk: straight-line code
 #pragma unroll 4
-            for (int j = 0; j < SL; j += 2) {
-                const double2 u2 = reinterpret_cast<const double2*>(slot)[j >> 1];
-                if (j < len) aug_step<D>(c, u2.x, f);
-                if (j + 1 < len) aug_step<D>(c, u2.y, f);
+                for (int j = 0; j < SL; j += 2) {
+                    const double2 u2 = reinterpret_cast<const double2*>(slot)[j >> 1];
+                    aug_step<D>(c, u2.x, f);
+                    aug_step<D>(c, u2.y, f);
+                }
+            } else {
+#pragma unroll 1
+                for (int j = 0; j < len; ++j) aug_step<D>(c, slot[j], f);
             }
 #pragma unroll
             for (int a = 0; a < 4; ++a)
@@ -487,36 +492,39 @@ __global__ void __launch_bounds__(NSUBC * LG) k_obj_lanes(const double* __restri
         }
         // ---- B: the literal recurrence from the true carry ----------------------------------------------------------
         double sv2 = 0.0, svd[3] = {0.0, 0.0, 0.0}, spw = 0.0;
-#pragma unroll 2
-        for (int j = 0; j < SL; j += 2) {
-            const double2 u2 = reinterpret_cast<const double2*>(slot)[j >> 1];
-            const double2 w2 = reinterpret_cast<const double2*>(slot + SL)[j >> 1];
-            const double2 y2 = reinterpret_cast<const double2*>(slot + 2 * SL)[j >> 1];
-            double wg[2];
+        // one step: loss / gradient terms on the PRE-step state, the dU weight, then the recurrence
+        auto step_b = [&](double uj, double wj, double yj) -> double {
+            double hax = c.HA[0] * z[0][0];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const double uj = h ? u2.y : u2.x, wj = h ? w2.y : w2.x, yj = h ? y2.y : y2.x;
-                double hax = c.HA[0] * z[0][0];
+            for (int q = 1; q < D; ++q) hax = fma(c.HA[q], z[0][q], hax);
+            const double v = uj - hax;                                               // ihgp.h:214
+            const double pv = (yj - hax) * c1;                                       // moihgp.h:510-511 (raw y(l), Q8)
+            sv2 = fma(v, v, sv2);
+            spw = fma(pv, wj, spw);                                                  // moihgp.h:558-560
 #pragma unroll
-                for (int q = 1; q < D; ++q) hax = fma(c.HA[q], z[0][q], hax);
-                const double v = uj - hax;                                           // ihgp.h:214
-                const double pv = (yj - hax) * c1;                                   // moihgp.h:510-511 (raw y(l), Q8)
-                wg[h] = fma(pv, rsS, -wj * rsig);                                    // moihgp.h:546-550 (rank-1 form)
-                if (j + h < len) {
-                    sv2 = fma(v, v, sv2);
-                    spw = fma(pv, wj, spw);                                          // moihgp.h:558-560
+            for (int k = 0; k < 3; ++k) {
+                double hd = c.HA[0] * z[1 + k][0];
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        double hd = c.HA[0] * z[1 + k][0];
-#pragma unroll
-                        for (int q = 1; q < D; ++q) hd = fma(c.HA[q], z[1 + k][q], hd);
-                        const double dv = -hda0[k] * z[0][0] - hd;                   // ihgp.h:218 (Q20 de facto)
-                        svd[k] = fma(v, dv, svd[k]);
-                    }
-                    aug_step<D>(c, uj, z);
-                }
+                for (int q = 1; q < D; ++q) hd = fma(c.HA[q], z[1 + k][q], hd);
+                const double dv = -hda0[k] * z[0][0] - hd;                           // ihgp.h:218 (Q20 de facto)
+                svd[k] = fma(v, dv, svd[k]);
             }
-            reinterpret_cast<double2*>(slot + SL)[j >> 1] = make_double2(wg[0], wg[1]);
+            aug_step<D>(c, uj, z);
+            return fma(pv, rsS, -wj * rsig);                                         // moihgp.h:546-550 (rank-1 form)
+        };
+        if (len == SL) {                              // whole sub-chunk: straight-line code
+#pragma unroll 2
+            for (int j = 0; j < SL; j += 2) {
+                const double2 u2 = reinterpret_cast<const double2*>(slot)[j >> 1];
+                const double2 w2 = reinterpret_cast<const double2*>(slot + SL)[j >> 1];
+                const double2 y2 = reinterpret_cast<const double2*>(slot + 2 * SL)[j >> 1];
+                const double g0 = step_b(u2.x, w2.x, y2.x);
+                const double g1 = step_b(u2.y, w2.y, y2.y);
+                reinterpret_cast<double2*>(slot + SL)[j >> 1] = make_double2(g0, g1);
+            }
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < len; ++j) slot[SL + j] = step_b(slot[j], slot[SL + j], slot[2 * SL + j]);
         }
         if (len > 0 && ts + len == T) {                                              // this thread owns step T-1
             if (xT) {
@@ -613,16 +621,22 @@ __global__ void k_obj_coupling(const LatentConsts* __restrict__ consts, int L, d
 
 // zin[c+1] = Z^CH zin[c] + zsum[c] on the augmented state z = [x; dx_0; dx_1; dx_2]:
 //   x' = M^CH x + f_x,   dx_k' = M^CH dx_k + E_k x + f_k.
-// One WARP per (sequence, latent): groups of 256 chunks (lane = 8 consecutive chunks, Kogge-Stone over lanes with the
-// span-(8 * 2^j) transition), groups in sequence.
+// One WARP (= one CTA) per (sequence, latent): groups of 256 chunks (lane = 8 consecutive chunks, Kogge-Stone over lanes
+// with the span-(8 * 2^j) transition), groups in sequence.  The chain is latency-bound (a handful of warps on the whole
+// GPU), so nothing on it may wait for HBM: a group's 256 summaries (one contiguous run) are staged into shared memory
+// with coalesced loads, the carries are written back the same way, and the scan-level matrices sit in shared memory.
 template <int D>
-__global__ void __launch_bounds__(128) k_obj_carry(const LatentConsts* __restrict__ consts, const double* __restrict__ Ek, int L,
-                                                  long long N, long long nC, const double* __restrict__ x0,
-                                                  const double* __restrict__ dx0, const double* __restrict__ zsum,
-                                                  double* __restrict__ zin) {
-    const int lane = threadIdx.x & 31;
-    const long long id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (id >= N * L) return;
+__global__ void __launch_bounds__(32) k_obj_carry(const LatentConsts* __restrict__ consts, const double* __restrict__ Ek, int L,
+                                                 long long N, long long nC, const double* __restrict__ x0,
+                                                 const double* __restrict__ dx0, const double* __restrict__ zsum,
+                                                 double* __restrict__ zin) {
+    constexpr int ZD = 4 * D;                 // doubles per chunk
+    constexpr int BLK = CG * ZD;              // doubles per lane and group
+    constexpr int PITCH = BLK + 2;            // PITCH / 2 odd: conflict-free 16-byte accesses across lanes
+    extern __shared__ double stage[];         // [32][PITCH]
+    __shared__ double lev[5][4 * D * D];      // per scan level: M^(CH 8 2^j), E_k(CH 8 2^j)
+    const int lane = threadIdx.x;
+    const long long id = blockIdx.x;
     const int l = (int)(id % L);
     double MC[D * D], E[3][D * D];
     load_mat<D>(consts[l].powM[LOG2_CH], MC);
@@ -630,7 +644,13 @@ __global__ void __launch_bounds__(128) k_obj_carry(const LatentConsts* __restric
     for (int k = 0; k < 3; ++k)
 #pragma unroll
         for (int i = 0; i < D * D; ++i) E[k][i] = Ek[((size_t)l * 3 + k) * D * D + i];
-    const size_t stride = 4 * D, base = (size_t)id * nC * 4 * D;   // [n][l][chunk][4*D]
+    for (int i = lane; i < 5 * 4 * D * D; i += 32) {
+        const int j = i / (4 * D * D), r = i - j * (4 * D * D);
+        const int m = r / (D * D), e = r - m * (D * D);
+        lev[j][r] = m == 0 ? consts[l].powM[LOG2_CH + LOG2_CG + j][(e / D) * 3 + (e % D)]
+                           : Ek[(((size_t)(LOG2_CG + j) * L + l) * 3 + (m - 1)) * D * D + e];
+    }
+    const size_t base = (size_t)id * nC * ZD;      // [n][l][chunk][4*D]
     const long long nG = (nC + 32 * CG - 1) / (32 * CG);
     double carry[4][D];
 #pragma unroll
@@ -639,27 +659,48 @@ __global__ void __launch_bounds__(128) k_obj_carry(const LatentConsts* __restric
 #pragma unroll
         for (int k = 0; k < 3; ++k) carry[1 + k][q] = dx0 ? dx0[((size_t)id * 3 + k) * D + q] : 0.0;
     }
-    // one chunk: z <- Z^CH z + zsum[c]   (zsum of the last chunk is never used)
-    auto advance = [&](double (&z)[4][D], long long c) {
+    double* mine = stage + lane * PITCH;
+    // one chunk: z <- Z^CH z + f   (the summary of the sequence's last chunk is never used)
+    auto advance = [&](double (&z)[4][D], const double (&f)[ZD]) {
         double zn[4][D];
         mv<D>(MC, z[0], zn[0]);
 #pragma unroll
         for (int k = 0; k < 3; ++k) { mv<D>(MC, z[1 + k], zn[1 + k]); mv_acc<D>(E[k], z[0], zn[1 + k]); }
-        const bool have = c < nC - 1;
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int q = 0; q < D; ++q) z[a][q] = zn[a][q] + (have ? zsum[c * stride + base + a * D + q] : 0.0);
+            for (int q = 0; q < D; ++q) z[a][q] = zn[a][q] + f[a * D + q];
+    };
+    auto load_f = [&](int i, long long c, double (&f)[ZD]) {
+#pragma unroll
+        for (int e = 0; e < ZD; e += 2) {
+            const double2 t2 = *reinterpret_cast<const double2*>(mine + i * ZD + e);
+            f[e] = c < nC - 1 ? t2.x : 0.0;
+            f[e + 1] = c < nC - 1 ? t2.y : 0.0;
+        }
     };
     for (long long g = 0; g < nG; ++g) {
-        const long long c0 = (g * 32 + lane) * CG;
+        const long long cbeg = g * 32 * CG;
+        const int pairs = (int)min((long long)32 * CG, nC - cbeg) * ZD / 2;      // 16-byte units of this group
+        const double2* src = reinterpret_cast<const double2*>(zsum + base + cbeg * ZD);
+        __syncwarp();
+        for (int e = lane; e < pairs; e += 32) {
+            const int blk = e / (BLK / 2), off = e - blk * (BLK / 2);
+            *reinterpret_cast<double2*>(stage + blk * PITCH + 2 * off) = src[e];
+        }
+        __syncwarp();
+        const long long c0 = cbeg + (long long)lane * CG;
         double z[4][D];
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int q = 0; q < D; ++q) z[a][q] = lane == 0 ? carry[a][q] : 0.0;
-#pragma unroll 1
-        for (int i = 0; i < CG; ++i) advance(z, c0 + i);
+#pragma unroll 2
+        for (int i = 0; i < CG; ++i) {
+            double f[ZD];
+            load_f(i, c0 + i, f);
+            advance(z, f);
+        }
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
             const int o = 1 << j;
@@ -668,7 +709,8 @@ __global__ void __launch_bounds__(128) k_obj_carry(const LatentConsts* __restric
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int q = 0; q < D; ++q) zo[a][q] = __shfl_up_sync(FULL, z[a][q], o);
-            load_mat<D>(consts[l].powM[LOG2_CH + LOG2_CG + j], P);
+#pragma unroll
+            for (int i = 0; i < D * D; ++i) P[i] = lev[j][i];
             if (lane >= o) {
 #pragma unroll
                 for (int a = 0; a < 4; ++a) mv_acc<D>(P, zo[a], z[a]);
@@ -676,7 +718,7 @@ __global__ void __launch_bounds__(128) k_obj_carry(const LatentConsts* __restric
                 for (int k = 0; k < 3; ++k) {
                     double Ej[D * D];
 #pragma unroll
-                    for (int i = 0; i < D * D; ++i) Ej[i] = Ek[(((size_t)(LOG2_CG + j) * L + l) * 3 + k) * D * D + i];
+                    for (int i = 0; i < D * D; ++i) Ej[i] = lev[j][(1 + k) * D * D + i];
                     mv_acc<D>(Ej, zo[0], z[1 + k]);
                 }
             }
@@ -690,16 +732,24 @@ __global__ void __launch_bounds__(128) k_obj_carry(const LatentConsts* __restric
                 x[a][q] = lane == 0 ? carry[a][q] : up;
                 carry[a][q] = __shfl_sync(FULL, z[a][q], 31);
             }
-#pragma unroll 1
+#pragma unroll 2
         for (int i = 0; i < CG; ++i) {
-            const long long c = c0 + i;
-            if (c < nC) {
+            double f[ZD];
+            load_f(i, c0 + i, f);
+            double xf[ZD];                                   // the carry INTO chunk c0 + i replaces its summary in the stage
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int q = 0; q < D; ++q) zin[c * stride + base + a * D + q] = x[a][q];
-            }
-            advance(x, c);
+                for (int q = 0; q < D; ++q) xf[a * D + q] = x[a][q];
+#pragma unroll
+            for (int e = 0; e < ZD; e += 2) *reinterpret_cast<double2*>(mine + i * ZD + e) = make_double2(xf[e], xf[e + 1]);
+            advance(x, f);
+        }
+        __syncwarp();
+        double2* dst = reinterpret_cast<double2*>(zin + base + cbeg * ZD);
+        for (int e = lane; e < pairs; e += 32) {
+            const int blk = e / (BLK / 2), off = e - blk * (BLK / 2);
+            dst[e] = *reinterpret_cast<const double2*>(stage + blk * PITCH + 2 * off);
         }
     }
 }
@@ -968,7 +1018,7 @@ cudaError_t run_objective(const ObjArgs& a, cudaStream_t st) {
         mark(a.mk, "k_obj_scan_summaries");
     }
     k_obj_coupling<D><<<(3 * a.L + 63) / 64, 64, 0, st>>>(a.consts, a.L, Ek);
-    k_obj_carry<D><<<(unsigned)((a.N * a.L * 32 + 127) / 128), 128, 0, st>>>(a.consts, Ek, a.L, a.N, nC, a.x0, a.dx0, a.zsum, a.zin);
+    k_obj_carry<D><<<(unsigned)(a.N * a.L), 32, sizeof(double) * 32 * (CG * 4 * D + 2), st>>>(a.consts, Ek, a.L, a.N, nC, a.x0, a.dx0, a.zsum, a.zin);
     mark(a.mk, "k_obj_carry");
     if (a.phase == 1) {
         if (a.zend) k_obj_block_end<D><<<(unsigned)((a.N * a.L + 127) / 128), 128, 0, st>>>(a.consts, Ek, a.L, a.N, nC, a.zsum, a.zin, a.zend);
