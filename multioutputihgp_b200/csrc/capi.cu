@@ -596,13 +596,14 @@ static int objective_phase(moihgp_handle* h, int phase, const double* Y, size_t 
     cudaSetDevice(h->device);
     const int L = h->L, D = h->dim, p = h->p;
     const size_t nC = obj_chunks((long long)T), nsplit = obj_gu_splits((long long)N, (long long)T);
-    double *u, *w, *yl, *rho, *zsum, *zin, *part, *gU, *Ek, *lat;
+    double *u, *w, *yl, *rho, *zsum, *zin, *zsub, *part, *gU, *Ek, *lat;
     int* nanf;
     long long* nanrows;
     const size_t nan_cap = std::min<size_t>(N * T, (size_t)1 << 22);
     if (ws_get(h, "nanrows", nan_cap, &nanrows)) return -1;
     if (ws_get(h, "u", N * L * T, &u) || ws_get(h, "w", N * L * T, &w) || ws_get(h, "yl", N * L * T, &yl) || ws_get(h, "rho", N * project_tiles((long long)T), &rho) ||
-        ws_get(h, "zsum", nC * N * L * 4 * D, &zsum) || ws_get(h, "zin", nC * N * L * 4 * D, &zin) || ws_get(h, "part", nC * N * L * 8, &part) ||
+        ws_get(h, "zsum", nC * N * L * 4 * D, &zsum) || ws_get(h, "zin", nC * N * L * 4 * D, &zin) || ws_get(h, "zsub", nC * 8 * N * L * 4 * D, &zsub) ||
+        ws_get(h, "part", nC * N * L * 8, &part) ||
         ws_get(h, "gU", nsplit * p * L, &gU) || ws_get(h, "Ek", (size_t)L * 27 * 16, &Ek) || ws_get(h, "lat", ((size_t)L + 1) * 8, &lat) ||
         ws_get(h, "nanf", 4, &nanf))
         return -1;
@@ -620,7 +621,7 @@ static int objective_phase(moihgp_handle* h, int phase, const double* Y, size_t 
     a.zend = zend;
     a.Y = Y; a.u = u; a.w = w; a.yl = yl; a.rho = rho; a.wgt = w;   // the weights overwrite w in place (same thread, same index)
     a.consts = h->d_consts; a.U = h->d_U; a.S = h->d_S; a.sigma = h->sigma; a.p = p; a.L = L; a.threading = h->threading;
-    a.N = (long long)N; a.T = (long long)T; a.x0 = x0; a.dx0 = dx0; a.zsum = zsum; a.zin = zin; a.part = part; a.gU_part = gU;
+    a.N = (long long)N; a.T = (long long)T; a.x0 = x0; a.dx0 = dx0; a.zsum = zsum; a.zin = zin; a.zsub = zsub; a.part = part; a.gU_part = gU;
     a.Ek = Ek; a.lat_sums = lat; a.loss = loss; a.grad = grad; a.xT = xT; a.dxT = dxT;
     CK(launch_objective(D, a, h->stream));
     h->launches += obj_launch_count((long long)T, L);

@@ -92,6 +92,7 @@ struct ObjArgs {
     long long N, T;
     const double *x0, *dx0;       // [N][L][D], [N][L][3][D] carried-in state or null
     double *zsum, *zin;           // [nC][N][L][4*D] chunk summaries / carries
+    double* zsub = nullptr;       // [N][nC][8][L][4*D] summaries of the 32-step sub-chunks (k_obj_lanes; workspace, may be null)
     double* part;                 // [nC][N][L][8] per-chunk partial sums
     double* gU_part;              // [nSplit][p][L] split-K partials of dU
     double* Ek;                   // [L][3][D*D] cross-chunk coupling matrices (workspace)

@@ -354,12 +354,12 @@ __global__ void __launch_bounds__(NSUBC * LG) k_obj_lanes(const double* __restri
                                                          const double* __restrict__ S, double sigma, int L, long long N, long long T,
                                                          long long nC, long long c_cnt, long long cpc,
                                                          const double* __restrict__ zin, double* __restrict__ zsum,
-                                                         double* __restrict__ wgt, double* __restrict__ part,
+                                                         double* zsub, double* __restrict__ wgt, double* __restrict__ part,
                                                          double* __restrict__ xT, double* __restrict__ dxT) {
     constexpr int NT = NSUBC * LG;
     constexpr int PITCH = FINAL ? UP3 : SL + 2;
     extern __shared__ double slots[];                 // [NT][PITCH]
-    __shared__ double exch[NSUBC][LG][4 * D];         // sub-chunk summaries, then (FINAL) the sub-chunks' partial sums
+    __shared__ __align__(16) double exch[NSUBC][LG][4 * D];   // sub-chunk summaries, then (FINAL) the partial sums of the sub-chunks
     __shared__ double cpl[LG][4 * D * D];
     __shared__ unsigned long long bar;
     const int tid = threadIdx.x, s = tid / LG, li = tid % LG;
@@ -454,8 +454,13 @@ __global__ void __launch_bounds__(NSUBC * LG) k_obj_lanes(const double* __restri
 #pragma unroll
             for (int q = 0; q < D; ++q) z[a][q] = FINAL ? zin[ci + a * D + q] : 0.0;
         mbar_wait(&bar, (unsigned)((ch - c_lo) & 1));
-        // ---- A: from zero ------------------------------------------------------------------------------------------
-        {
+        // ---- A: from zero (FINAL: the summaries pass has already done it for the interior chunks) ---------------------
+        double* zs = zsub ? zsub + ((((size_t)n * nC + ch) * NSUBC + s) * L + l) * 4 * D : nullptr;
+        if (FINAL && zs && ch < nC - 1) {
+#pragma unroll
+            for (int e = 0; e < 4 * D; e += 2)
+                *reinterpret_cast<double2*>(&exch[s][li][e]) = *reinterpret_cast<const double2*>(zs + e);
+        } else {
             double f[4][D];
 #pragma unroll
             for (int a = 0; a < 4; ++a)
@@ -476,6 +481,11 @@ __global__ void __launch_bounds__(NSUBC * LG) k_obj_lanes(const double* __restri
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int q = 0; q < D; ++q) exch[s][li][a * D + q] = f[a][q];
+            if (!FINAL && zs) {
+#pragma unroll
+                for (int e = 0; e < 4 * D; e += 2)
+                    *reinterpret_cast<double2*>(zs + e) = make_double2(f[e / D][e % D], f[(e + 1) / D][(e + 1) % D]);
+            }
         }
         __syncthreads();
         for (int k = 0; k < s; ++k) advance32<D>(cpl[li], exch[k][li], z);
@@ -587,7 +597,7 @@ void launch_obj_lanes(const ObjArgs& a, long long nC, long long c_cnt, cudaStrea
     const long long cpc = (c_cnt + groups - 1) / groups;
     const long long nG = (c_cnt + cpc - 1) / cpc;
     k_obj_lanes<D, LG, FINAL><<<(unsigned)(a.N * nG * nLG), NT, smem, st>>>(a.u, a.w, a.yl, a.consts, a.S, a.sigma, a.L, a.N, a.T, nC, c_cnt, cpc,
-                                                                            a.zin, a.zsum, a.wgt, a.part, a.xT, a.dxT);
+                                                                            a.zin, a.zsum, a.zsub, a.wgt, a.part, a.xT, a.dxT);
 }
 
 // Cross-chunk coupling matrices by doubling: for a span of n steps  E_k(n) = sum_i M^(n-1-i) dM_k M^i,  and
