@@ -153,6 +153,11 @@ int moihgp_cuda_objective_dev(moihgp_handle* h, const double* Y, size_t N, size_
 int moihgp_cuda_objective_begin_dev(moihgp_handle* h, const double* Y, size_t N, size_t T, double* zend_host);
 int moihgp_cuda_objective_finish_dev(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0, const double* dx0,
                                      double* loss, double* grad, double* xT, double* dxT);
+/* The block transition T(n) of the carry exchange above, per latent: out[L][4][d*d] = [AKHA^n, E_0(n), E_1(n), E_2(n)]
+ * (row-major d x d), E_k(n) = sum_i AKHA^(n-1-i) dAKHA_k AKHA^i, so that for a block of n steps
+ *   x_out = AKHA^n x_in + x_out(0),   dx_k,out = AKHA^n dx_k,in + E_k(n) x_in + dx_k,out(0)      (ihgp.h:71-77 unrolled).
+ * Host arithmetic on the handle's copy of the per-latent constants; no device work. */
+int moihgp_cuda_block_transition(moihgp_handle* h, size_t n, double* out);
 
 #ifdef __cplusplus
 }

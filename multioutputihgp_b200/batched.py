@@ -202,6 +202,13 @@ class MOIHGPSequences(object):
         N, T, _ = Y.shape
         self._check(self._lib.moihgp_cuda_objective_finish_dev(self._h, _ptr(Y), N, T, _ptr(x0), _ptr(dx0), _ptr(loss), _ptr(grad), None, None))
 
+    def block_transition(self, n):
+        """(AKHA^n [L,d,d], E_k(n) [L,3,d,d]): how a block of n steps maps its carry-in (time-sharded evaluation)."""
+        L, d = self.num_latent, self.igp_dim
+        out = np.zeros((L, 4, d, d))
+        self._check(self._lib.moihgp_cuda_block_transition(self._h, int(n), _ptr(out)))
+        return out[:, 0].copy(), out[:, 1:].copy()
+
     def bind(self, Y):
         """Copy the observations to the device once; ``objective_bound`` then evaluates on them at the current parameters
         (the L-BFGS loop calls the objective tens of times on the same data).  ``bind(None)`` releases them."""

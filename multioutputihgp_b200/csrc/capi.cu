@@ -422,6 +422,46 @@ long long moihgp_cuda_latent_consts(moihgp_handle* h, size_t l, double* out, siz
     return (long long)v.size();
 }
 
+int moihgp_cuda_block_transition(moihgp_handle* h, size_t n, double* out) {
+    if (!h || !out) return -2;
+    const int d = h->dim, dd = d * d;
+    auto mul = [&](const double* A, const double* B, double* C) {            // C = A B   (d x d, row-major, C distinct)
+        for (int i = 0; i < d; ++i) for (int j = 0; j < d; ++j) {
+            double s = 0.0;
+            for (int q = 0; q < d; ++q) s += A[i * d + q] * B[q * d + j];
+            C[i * d + j] = s;
+        }
+    };
+    for (int l = 0; l < h->L; ++l) {
+        const LatentConsts& c = h->consts[l];
+        double P[9] = {0}, E[3][9] = {{0}}, Pb[9], Eb[3][9], t1[9], t2[9];
+        for (int i = 0; i < d; ++i) P[i * d + i] = 1.0;
+        for (int k = 0; k < 3; ++k) for (int i = 0; i < d; ++i) for (int j = 0; j < d; ++j) Eb[k][i * d + j] = c.dAKHA[k][i * 3 + j];
+        // bits of n from the least significant: (Pb, Eb) = T(2^j) by doubling, (P, E) = T(bits seen so far);
+        // appending a span b after a span a:  P <- Pb P,  E_k <- Pb E_k + Eb_k P
+        for (int j = 0; (n >> j) != 0 && j < NPOW; ++j) {
+            for (int i = 0; i < d; ++i) for (int q = 0; q < d; ++q) Pb[i * d + q] = c.powM[j][i * 3 + q];
+            if ((n >> j) & 1) {
+                for (int k = 0; k < 3; ++k) {
+                    mul(Pb, E[k], t1);
+                    mul(Eb[k], P, t2);
+                    for (int i = 0; i < dd; ++i) E[k][i] = t1[i] + t2[i];
+                }
+                mul(Pb, P, t1);
+                for (int i = 0; i < dd; ++i) P[i] = t1[i];
+            }
+            for (int k = 0; k < 3; ++k) {                                   // E(2b) = E(b) M^b + M^b E(b)
+                mul(Eb[k], Pb, t1);
+                mul(Pb, Eb[k], t2);
+                for (int i = 0; i < dd; ++i) Eb[k][i] = t1[i] + t2[i];
+            }
+        }
+        double* o = out + (size_t)l * 4 * dd;
+        for (int i = 0; i < dd; ++i) { o[i] = P[i]; for (int k = 0; k < 3; ++k) o[(1 + k) * dd + i] = E[k][i]; }
+    }
+    return 0;
+}
+
 int moihgp_cuda_latent_iters(moihgp_handle* h, size_t l, int* out8) {
     if (!h || !out8 || l >= (size_t)h->L) return -2;
     for (int i = 0; i < 4; ++i) { out8[i] = h->consts[l].iters[i]; out8[4 + i] = h->consts[l].conv[i]; }

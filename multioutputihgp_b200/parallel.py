@@ -126,15 +126,20 @@ def stack_consts(consts):
 
 def carry_in_from_block_ends(consts, block_lengths, ends_x, ends_dx, x0, dx0, rank):
     """True carry-in (x [L,d], dx [L,3,d]) of block `rank`, given every block's end state from a zero carry-in.
-    consts: list of per-latent dicts or the stacked pair of stack_consts(); ends_x [G,L,d], ends_dx [G,L,3,d]."""
-    AK, dAK = consts if isinstance(consts, tuple) else stack_consts(consts)
+    consts: list of per-latent dicts, the stacked pair of stack_consts(), or a callable n -> (P [L,d,d], E [L,3,d,d]);
+    ends_x [G,L,d], ends_dx [G,L,3,d]."""
+    if callable(consts):                                         # n -> (P, E), e.g. MOIHGPSequences.block_transition
+        transition = consts
+    else:
+        AK, dAK = consts if isinstance(consts, tuple) else stack_consts(consts)
+        transition = lambda n_: block_transition(AK, dAK, n_)
     x = np.array(x0, dtype=np.float64).copy()
     dx = np.array(dx0, dtype=np.float64).copy()
     cache = {}
     for g in range(rank):
         n = int(block_lengths[g])
         if n not in cache:
-            cache[n] = block_transition(AK, dAK, n)
+            cache[n] = transition(n)
         P, E = cache[n]                                          # [L,d,d], [L,3,d,d]
         xo = x
         x = np.einsum("lij,lj->li", P, xo) + ends_x[g]
@@ -240,8 +245,7 @@ class TimeShardedDeviceObjective(object):
             out = [torch.empty_like(t) for _ in range(world)]
             dist.all_gather(out, t, group=self.group)
             ends = [o.cpu().numpy() for o in out]
-            consts = stack_consts([m.latent_consts(l) for l in range(L)])
-            xin, dxin = carry_in_from_block_ends(consts, self.block_lengths, [e[:L * d].reshape(L, d) for e in ends],
+            xin, dxin = carry_in_from_block_ends(m.block_transition, self.block_lengths, [e[:L * d].reshape(L, d) for e in ends],
                                                  [e[L * d:].reshape(L, 3, d) for e in ends], x0, dx0, rank)
         x0d = torch.from_numpy(np.ascontiguousarray(xin[None])).to(self.dev)
         dx0d = torch.from_numpy(np.ascontiguousarray(dxin[None])).to(self.dev)

@@ -540,3 +540,29 @@ def test_objective_kernels_agree(cuda_lib, kernel, p, L, N, T, monkeypatch):
     assert abs(la - lb) <= 1e-12 * abs(lb)
     assert rel_err(ga, gb) < 1e-11
     assert rel_err(xa, xb) < 1e-12 and rel_err(dxa, dxb) < 1e-11
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel", ["Matern32", "Matern52"])
+def test_block_transition_matches_the_host_powering(cuda_lib, kernel):
+    """moihgp_cuda_block_transition (binary powering on the library's power tables) against parallel.block_transition
+    (numpy, from AKHA and dAKHA alone) and against the brute-force sum for a short block."""
+    from multioutputihgp_b200 import MOIHGPSequences
+    from multioutputihgp_b200.parallel import block_transition, stack_consts
+    from oracle.gen_golden import make_params
+    rng = np.random.default_rng(5)
+    p, L = 6, 3
+    m = MOIHGPSequences(0.1, p, L, kernel, True)
+    m.update(make_params(rng, p, L, kernel))
+    AK, dAK = stack_consts([m.latent_consts(l) for l in range(L)])
+    for n in (1, 2, 5, 256, 1000, 123456):
+        P, E = m.block_transition(n)
+        Pn, En = block_transition(AK, dAK, n)
+        assert rel_err(P, Pn) < 1e-12 and rel_err(E, En) < 1e-11, n
+    P5, E5 = m.block_transition(5)
+    for l in range(L):
+        M = AK[l]
+        assert rel_err(P5[l], np.linalg.matrix_power(M, 5)) < 1e-13
+        for k in range(3):
+            brute = sum(np.linalg.matrix_power(M, 4 - i) @ dAK[l, k] @ np.linalg.matrix_power(M, i) for i in range(5))
+            assert rel_err(E5[l, k], brute) < 1e-12
