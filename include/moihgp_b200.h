@@ -159,6 +159,25 @@ int moihgp_cuda_objective_finish_dev(moihgp_handle* h, const double* Y, size_t N
  * Host arithmetic on the handle's copy of the per-latent constants; no device work. */
 int moihgp_cuda_block_transition(moihgp_handle* h, size_t n, double* out);
 
+/* The fused filter + smoother + NLL pass on one contiguous BLOCK of a longer sequence sharded in time (forward
+ * carry exchange, then the mirror-image backward exchange for IHGP::backwardSmoother, ihgp.h:108-113).  DEVICE buffers,
+ * chunked-scan path; seq_end = 1 on the block that ends the sequence, otherwise T % 256 == 0.  Three phases per block:
+ *   1  project the block, chunk summaries, forward chain from x0 (normally NULL = zeros).
+ *      host_out[N][L][d + 1] = [state after the block's last step | the block's first projected observation]
+ *      -> caller: x_in(g+1) = AKHA^n_g x_in(g) + x_end_g (moihgp_cuda_block_transition), u_after(g) = first observation of g+1
+ *   2  x0 = true carry-in, u_after [N][L]: forward chain, backward chain from a zero b_end.
+ *      host_out[N][L][d] = backward value at the block's first step
+ *      -> caller, from the last block down: b_end(g) = b_start(g+1), b_start(g) = host_out_g + G^n_g b_end(g)
+ *         (moihgp_cuda_smoother_power)
+ *   3  b_end [N][L][d] (NULL on the last block): backward chain + the final pass: X, Xs [N][T][L][d], nll[N] (the block's
+ *      share: sum the blocks), xT (meaningful on the last block).  x0 / u_after as in phase 2.
+ * With the literal smoother (mode 0) b is Xs itself, with mode 1 it is Xs - X. */
+int moihgp_cuda_fsn_block_dev(moihgp_handle* h, int phase, const double* Y, size_t N, size_t T, int seq_end, int smoother_mode,
+                              const double* x0, const double* u_after, const double* b_end, double* X, double* Xs, double* nll,
+                              double* xT, double* host_out);
+/* G[mode]^n per latent: out[L][d*d] row-major (host arithmetic on the handle's power tables) */
+int moihgp_cuda_smoother_power(moihgp_handle* h, int smoother_mode, size_t n, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -209,6 +209,26 @@ class MOIHGPSequences(object):
         self._check(self._lib.moihgp_cuda_block_transition(self._h, int(n), _ptr(out)))
         return out[:, 0].copy(), out[:, 1:].copy()
 
+    def smoother_power(self, n, mode=SMOOTH_RTS):
+        """G[mode]^n per latent, [L,d,d]: how a backward value crosses a block of n steps (time-sharded smoother)."""
+        L, d = self.num_latent, self.igp_dim
+        out = np.zeros((L, d, d))
+        self._check(self._lib.moihgp_cuda_smoother_power(self._h, int(mode), int(n), _ptr(out)))
+        return out
+
+    def fsn_block(self, phase, Y, seq_end, smoother_mode=SMOOTH_RTS, x0=None, u_after=None, b_end=None, X=None, Xs=None, nll=None, xT=None):
+        """One phase (1, 2, 3) of the fused pass on one block of a sequence sharded in time (torch CUDA tensors).
+        Phase 1 returns (x_end [N,L,d], u_first [N,L]), phase 2 returns b_start [N,L,d], phase 3 fills X / Xs / nll / xT."""
+        N, T, _ = Y.shape
+        L, d = self.num_latent, self.igp_dim
+        host = np.zeros((N, L, d + 1)) if phase == 1 else (np.zeros((N, L, d)) if phase == 2 else None)
+        self._lib.moihgp_cuda_set_stream(self._h, _torch_stream(Y.device))
+        self._check(self._lib.moihgp_cuda_fsn_block_dev(self._h, int(phase), _ptr(Y), N, T, 1 if seq_end else 0, int(smoother_mode), _ptr(x0),
+                                                        _ptr(u_after), _ptr(b_end), _ptr(X), _ptr(Xs), _ptr(nll), _ptr(xT), _ptr(host)))
+        if phase == 1:
+            return host[:, :, :d].copy(), host[:, :, d].copy()
+        return host
+
     def bind(self, Y):
         """Copy the observations to the device once; ``objective_bound`` then evaluates on them at the current parameters
         (the L-BFGS loop calls the objective tens of times on the same data).  ``bind(None)`` releases them."""

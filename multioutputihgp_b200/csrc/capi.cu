@@ -543,6 +543,88 @@ int moihgp_cuda_filter_smoother_nll_dev(moihgp_handle* h, const double* Y, size_
     return 0;
 }
 
+// One contiguous block of a longer sequence sharded in TIME over several devices (chunked-scan path), in three phases
+// with the blocks' carries exchanged by the caller in between (include/moihgp_b200.h).
+int moihgp_cuda_fsn_block_dev(moihgp_handle* h, int phase, const double* Y, size_t N, size_t T, int seq_end, int mode,
+                              const double* x0, const double* u_after, const double* b_end, double* X, double* Xs, double* nll,
+                              double* xT, double* host_out) {
+    if (!h) return -2;
+    if (phase < 1 || phase > 3) return fail(h, "phase must be 1, 2 or 3");
+    if (N == 0 || T == 0) return fail(h, "N and T must be positive");
+    if (mode < 0 || mode > 1) return fail(h, "smoother_mode must be 0 or 1");
+    if (!seq_end && T % 256 != 0) return fail(h, "a block that does not end the sequence must hold a multiple of 256 steps");
+    if (phase == 1 && !Y) return -2;
+    if (phase == 3 && Xs && !X) return fail(h, "Xs needs X");
+    cudaSetDevice(h->device);
+    const int L = h->L, D = h->dim;
+    const size_t nC = scan_chunks((long long)T);
+    double *u, *rho, *fsum, *bsum, *xin, *bin, *Bx, *vsq, *npart, *Wsum, *sbe, *sbi, *xe, *bo;
+    int* nanf;
+    long long* nanrows;
+    const size_t nan_cap = std::min<size_t>(N * T, (size_t)1 << 22);
+    if (ws_get(h, "nanrows", nan_cap, &nanrows)) return -1;
+    if (ws_get(h, "u", N * L * T, &u) || ws_get(h, "rho", N * project_tiles((long long)T), &rho) || ws_get(h, "npart", nll_partials((long long)N), &npart) ||
+        ws_get(h, "fsum", nC * N * L * D, &fsum) || ws_get(h, "bsum", nC * N * L * D, &bsum) || ws_get(h, "xin", nC * N * L * D, &xin) ||
+        ws_get(h, "bin", nC * N * L * D, &bin) || ws_get(h, "Bx", (size_t)L * 2 * 9, &Bx) || ws_get(h, "Wsum", scan_weights_doubles(L), &Wsum) ||
+        ws_get(h, "sbe", N * L * scan_superblocks((long long)T) * D, &sbe) || ws_get(h, "sbi", N * L * scan_superblocks((long long)T) * D, &sbi) ||
+        ws_get(h, "vsq", nC * N * L, &vsq) || ws_get(h, "nanf", 4, &nanf) || ws_get(h, "blk_xe", N * L * D, &xe) || ws_get(h, "blk_bo", N * L * D, &bo))
+        return -1;
+    if (phase == 1) {
+        CK(cudaMemsetAsync(nanf, 0, 2 * sizeof(int), h->stream));
+        CK(launch_project(Y, h->d_U, h->d_S, h->p, L, (long long)N, (long long)T, u, nullptr, nullptr, rho, nanf, nanrows, (long long)nan_cap, h->stream));
+        h->launches += 2;
+    }
+    ScanArgs a;
+    a.u = u; a.consts = h->d_consts; a.L = L; a.N = (long long)N; a.T = (long long)T; a.x0 = x0;
+    a.fsum = fsum; a.bsum = bsum; a.xin = xin; a.bin = bin; a.Bx = Bx; a.Wsum = Wsum; a.sb_end = sbe; a.sb_in = sbi; a.vsq = vsq;
+    a.X = phase == 3 ? X : nullptr; a.Xs = phase == 3 ? Xs : nullptr; a.xT = phase == 3 ? xT : nullptr;
+    a.phase = phase; a.seq_end = seq_end ? 1 : 0; a.u_after = seq_end ? nullptr : u_after; a.b_end = phase == 3 ? b_end : nullptr;
+    a.x_end = phase == 1 ? xe : nullptr; a.b_out = phase == 2 ? bo : nullptr;
+    CK(launch_scan(D, mode, a, h->stream));
+    h->launches += scan_launch_count((long long)T);
+    if (phase == 1 && host_out) {
+        // [N][L][D + 1]: the block's end state from x0, then its first projected observation (the previous block's u_after)
+        std::vector<double> hx(N * L * D), hu(N * L);
+        CK(cudaMemcpyAsync(hx.data(), xe, sizeof(double) * N * L * D, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpy2DAsync(hu.data(), sizeof(double), u, sizeof(double) * T, sizeof(double), N * L, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        for (size_t i = 0; i < N * L; ++i) {
+            for (int q = 0; q < D; ++q) host_out[i * (D + 1) + q] = hx[i * D + q];
+            host_out[i * (D + 1) + D] = hu[i];
+        }
+    }
+    if (phase == 2 && host_out) {
+        CK(cudaMemcpyAsync(host_out, bo, sizeof(double) * N * L * D, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    if (phase == 3 && nll) {
+        CK(launch_nll_reduce(rho, vsq, h->d_consts, h->d_S, h->sigma, h->p, L, (long long)N, (long long)T, npart, nll, h->stream));
+        h->launches += 2;
+    }
+    return 0;
+}
+
+int moihgp_cuda_smoother_power(moihgp_handle* h, int mode, size_t n, double* out) {
+    if (!h || !out || mode < 0 || mode > 1) return -2;
+    const int d = h->dim, dd = d * d;
+    for (int l = 0; l < h->L; ++l) {
+        const LatentConsts& c = h->consts[l];
+        double P[9] = {0}, t1[9];
+        for (int i = 0; i < d; ++i) P[i * d + i] = 1.0;
+        for (int j = 0; (n >> j) != 0 && j < NPOW; ++j) {
+            if (!((n >> j) & 1)) continue;
+            for (int i = 0; i < d; ++i) for (int q = 0; q < d; ++q) {
+                double s_ = 0.0;
+                for (int r = 0; r < d; ++r) s_ += c.powG[mode][j][i * 3 + r] * P[r * d + q];
+                t1[i * d + q] = s_;
+            }
+            for (int i = 0; i < dd; ++i) P[i] = t1[i];
+        }
+        for (int i = 0; i < dd; ++i) out[(size_t)l * dd + i] = P[i];
+    }
+    return 0;
+}
+
 // Host buffers.  Independent sequences are processed in slices, software-pipelined over three streams: the H2D copy of
 // slice i+1 and the D2H copy of slice i-1 overlap the kernels of slice i (PCIe is full duplex), with two sets of
 // device buffers.  (Pinned host memory is needed for the copies to be asynchronous; pageable memory still works.)
@@ -585,7 +667,6 @@ int moihgp_cuda_filter_smoother_nll(moihgp_handle* h, const double* Y, size_t N,
     if (ws_get(h, "nanf", 4, &nanf)) return -1;
     if (h->h_flags_cap < nsl) {
         if (h->h_flags) cudaFreeHost(h->h_flags);
-    if (h->d_bound) cudaFree(h->d_bound);
         h->h_flags = nullptr;
         h->h_flags_cap = 0;
         CK(cudaMallocHost(&h->h_flags, sizeof(int) * nsl));

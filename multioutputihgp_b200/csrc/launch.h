@@ -52,6 +52,14 @@ struct ScanArgs {
     double *X, *Xs;               // [N][T][L][D] outputs (either may be null)
     double* vsq;                  // [nC][N][L] sum of squared innovations (workspace)
     double* xT;                   // [N][L][D] final filtered state or null
+    // ---- one long sequence sharded in TIME over several devices (this call = one contiguous block of it) ----
+    int seq_end = 1;              // 1: the block ends the sequence; 0: more steps follow (then T % 256 == 0)
+    const double* u_after = nullptr;   // [N][L] projected observation of the first step AFTER the block (seq_end == 0)
+    const double* b_end = nullptr;     // [N][L][D] backward value at the first step after the block (null = zeros)
+    double* b_out = nullptr;      // [N][L][D] backward value at the block's FIRST step (the previous block's b_end)
+    double* x_end = nullptr;      // phase 1: [N][L][D] filtered state after the block's last step, from x0
+    int phase = 0;                // 0: whole pass; 1: summaries + forward chain -> x_end; 2: forward chain from the true
+                                  // x0, backward chain from b_end = 0 -> b_out; 3: backward chain from b_end + final pass
     Marker* mk = nullptr;
 };
 size_t scan_chunks(long long T);

@@ -247,7 +247,8 @@ __global__ void __launch_bounds__(32 * LGMAX, 2) k_scan(const double* __restrict
                                                     const double* __restrict__ xin, const double* __restrict__ bin,
                                                     double* __restrict__ fsum, double* __restrict__ bsum,
                                                     double* __restrict__ X, double* __restrict__ Xs,
-                                                    double* __restrict__ vsq_out, double* __restrict__ xT) {
+                                                    double* __restrict__ vsq_out, double* __restrict__ xT,
+                                                    const double* __restrict__ u_after, int seq_end) {
     extern __shared__ double tile[];
     __shared__ double pws[LGMAX][10 * D * D];       // per latent of the CTA: M^(SUB 2^k), then G^(SUB 2^k), k = 0..4
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
@@ -297,7 +298,8 @@ __global__ void __launch_bounds__(32 * LGMAX, 2) k_scan(const double* __restrict
 #pragma unroll
                 for (int i = 0; i < SUB; ++i) uu[i] = tf + i < T ? __ldg(up + tf + i) : 0.0;
             }
-            const double u_next = t0 + CH < T ? __ldg(up + t0 + CH) : 0.0;
+            // the step after the chunk: the next chunk's first, or (block of a longer sequence) the next block's first
+            const double u_next = t0 + CH < T ? __ldg(up + t0 + CH) : (u_after ? __ldg(u_after + (size_t)n * L + l) : 0.0);
             double x_in[D], b_in[D], f_end[D], beta[D], x_last[D], vsq;
             const size_t ci = (((size_t)n * L + l) * nC + c) * D;      // carries are chunk-minor: [n][l][chunk][D]
 #pragma unroll
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(32 * LGMAX, 2) k_scan(const double* __restrict
             }
             double* tX = tileX + lane * GS + wi * D;
             double* tXs = tileXs + lane * GS + wi * D;
-            if (t0 + CH < T) chunk_pass<D, MODE, FINAL, true>(cst, pws[wi], uu, u_next, tf, T, x_in, b_in, lane, f_end, beta, vsq, tX, tXs, RS, x_last);
+            if (t0 + CH < T || !seq_end) chunk_pass<D, MODE, FINAL, true>(cst, pws[wi], uu, u_next, tf, T, x_in, b_in, lane, f_end, beta, vsq, tX, tXs, RS, x_last);
             else chunk_pass<D, MODE, FINAL, false>(cst, pws[wi], uu, u_next, tf, T, x_in, b_in, lane, f_end, beta, vsq, tX, tXs, RS, x_last);
             if (!FINAL) {
                 if (lane == 31) {
@@ -530,7 +532,8 @@ __global__ void __launch_bounds__(128) k_carry(const LatentConsts* __restrict__ 
                                               long long N, long long nC, long long nS, const double* __restrict__ x0,
                                               const double* __restrict__ fsum, const double* __restrict__ bsum,
                                               double* __restrict__ xin, double* __restrict__ bin,
-                                              const double* __restrict__ sb_in, double* __restrict__ sb_end) {
+                                              const double* __restrict__ sb_in, double* __restrict__ sb_end,
+                                              const double* __restrict__ b_end, int seq_end) {
     const int lane = threadIdx.x & 31;
     const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (wid >= N * L * nS) return;
@@ -581,7 +584,13 @@ __global__ void __launch_bounds__(128) k_carry(const LatentConsts* __restrict__ 
                 double xi[D], bn[D];
 #pragma unroll
                 for (int q = 0; q < D; ++q) { xi[q] = xin[c * stride + base + q]; bn[q] = bsum[c * stride + base + q]; }
-                mv_acc<D>(c == nC - 1 ? Bl : Bf, xi, bn);
+                mv_acc<D>((c == nC - 1 && seq_end) ? Bl : Bf, xi, bn);
+                if (c == nC - 1 && b_end) {              // the value entering the block from the right: + G^CH b_end
+                    double be[D];
+#pragma unroll
+                    for (int q = 0; q < D; ++q) be[q] = b_end[(size_t)id * D + q];
+                    mv_acc<D>(TC, be, bn);
+                }
 #pragma unroll
                 for (int q = 0; q < D; ++q) dv[i][q] = bn[q];
             } else {
@@ -637,7 +646,7 @@ __global__ void __launch_bounds__(128) k_carry(const LatentConsts* __restrict__ 
 #pragma unroll
                     for (int q = 0; q < D; ++q) {
                         if (DIR == 0) xin[c * stride + base + q] = x[q];
-                        else bin[c * stride + base + q] = c == nC - 1 ? 0.0 : x[q];
+                        else bin[c * stride + base + q] = c == nC - 1 ? (b_end ? b_end[(size_t)id * D + q] : 0.0) : x[q];
                     }
                 }
                 double xn[D];
@@ -651,6 +660,48 @@ __global__ void __launch_bounds__(128) k_carry(const LatentConsts* __restrict__ 
 #pragma unroll
         for (int q = 0; q < D; ++q) sb_end[(size_t)wid * D + q] = carry[q];
     }
+}
+
+// What leaves a block on the left: the backward value at its first step, b_out = beta0[0] + B xin[0] + G^CH bin[0]
+// (the previous block's b_end).  One thread per (sequence, latent).
+template <int D, int MODE>
+__global__ void __launch_bounds__(128) k_block_start(const LatentConsts* __restrict__ consts, const double* __restrict__ Bx, int L,
+                                                    long long N, long long nC, int seq_end, const double* __restrict__ xin,
+                                                    const double* __restrict__ bsum, const double* __restrict__ bin,
+                                                    double* __restrict__ b_out) {
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= N * L) return;
+    const int l = (int)(id % L);
+    double TC[D * D], B[D * D], xi[D], bi[D], o[D];
+    load_mat<D>(consts[l].powG[MODE][LOG2_CH], TC);
+    const int kind = (nC == 1 && seq_end) ? 1 : 0;
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) B[i] = Bx[((size_t)l * 2 + kind) * D * D + i];
+    const size_t ci = (size_t)id * nC * D;
+#pragma unroll
+    for (int q = 0; q < D; ++q) { xi[q] = xin[ci + q]; bi[q] = bin[ci + q]; o[q] = bsum[ci + q]; }
+    mv_acc<D>(B, xi, o);
+    mv_acc<D>(TC, bi, o);
+#pragma unroll
+    for (int q = 0; q < D; ++q) b_out[(size_t)id * D + q] = o[q];
+}
+
+// Filtered state after the last step of a block of whole chunks: x_end = M^CH xin[nC-1] + fsum[nC-1].  One thread per
+// (sequence, latent).
+template <int D>
+__global__ void __launch_bounds__(128) k_block_end(const LatentConsts* __restrict__ consts, int L, long long N, long long nC,
+                                                  const double* __restrict__ xin, const double* __restrict__ fsum,
+                                                  double* __restrict__ x_end) {
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= N * L) return;
+    double TC[D * D], x[D], o[D];
+    load_mat<D>(consts[(int)(id % L)].powM[LOG2_CH], TC);
+    const size_t ci = ((size_t)id * nC + (nC - 1)) * D;
+#pragma unroll
+    for (int q = 0; q < D; ++q) x[q] = xin[ci + q];
+    mv<D>(TC, x, o);
+#pragma unroll
+    for (int q = 0; q < D; ++q) x_end[(size_t)id * D + q] = o[q] + fsum[ci + q];
 }
 
 // Chain the super-blocks: one thread per (sequence, latent).  forward: in[S+1] = M^span in[S] + end[S], in[0] = x0;
@@ -739,7 +790,7 @@ constexpr int LOG2_SL = 5;
 
 template <int D, int MODE, int LG, bool INTERIOR>
 __device__ __forceinline__ void lanes_chunk(const LC<D>& c, const double (&PM)[D * D], const double (&PG)[D * D],
-                                            const double* __restrict__ up, long long ts, long long T, int s, int li, int tid,
+                                            const double* __restrict__ up, double u_nx, long long ts, long long T, int s, int li, int tid,
                                             const double* x_chunk, const double* b_chunk, double* tile,
                                             unsigned long long* ubar, unsigned uphase,
                                             double (*exch)[LG][D], double (*vred)[LG], double* __restrict__ Xg,
@@ -759,7 +810,6 @@ __device__ __forceinline__ void lanes_chunk(const LC<D>& c, const double (&PM)[D
         mbar_expect_tx(ubar, SL * (unsigned)sizeof(double));
         bulk_g2s(slot, up + ts, SL * (unsigned)sizeof(double), ubar);
     } else mbar_arrive(ubar);
-    const double u_nx = (INTERIOR || ts + SL < T) ? __ldg(up + ts + SL) : 0.0;
     if (!bulk) {                                      // ragged end of the sequence / odd alignment: fill the slot by hand
         for (int j = 0; j < SL; ++j) slot[j] = (INTERIOR || j < len) ? __ldg(up + ts + j) : 0.0;
     }
@@ -947,7 +997,8 @@ __global__ void __launch_bounds__(NSUBC * LG, (D == 2 ? 384 : 256) / (NSUBC * LG
                                                           int L, long long N, long long T, long long nC, long long cpc,
                                                           const double* __restrict__ xin, const double* __restrict__ bin,
                                                           double* __restrict__ X, double* __restrict__ Xs,
-                                                          double* __restrict__ vsq_out, double* __restrict__ xT) {
+                                                          double* __restrict__ vsq_out, double* __restrict__ xT,
+                                                          const double* __restrict__ u_after, int seq_end) {
     extern __shared__ double tile[];                  // the CTA's filtered states: [SL][NT] double2 (D = 2) or [D][SL][NT]
     __shared__ double exch[NSUBC][LG][D];
     __shared__ double vred[NSUBC][LG];
@@ -986,10 +1037,12 @@ __global__ void __launch_bounds__(NSUBC * LG, (D == 2 ? 384 : 256) / (NSUBC * LG
         double* Xsg = Xs ? Xs + go : nullptr;
         double* vdst = vsq_out + ((size_t)c * N + n) * L + l;
         double* xTd = xT ? xT + ((size_t)n * L + l) * D : nullptr;
-        if (c * CH + CH < T)
-            lanes_chunk<D, MODE, LG, true>(cst, PM, PG, up, ts, T, s, li, tid, x_chunk, b_chunk, tile, &ubar, (unsigned)((c - c_lo) & 1), exch, vred, Xg, Xsg, gstride, vec_x, vdst, xTd);
+        // the step after this thread's last one: in the block, or the next block's first (sequence sharded in time)
+        const double u_nx = ts + SL < T ? __ldg(up + ts + SL) : (u_after ? __ldg(u_after + (size_t)n * L + l) : 0.0);
+        if (c * CH + CH < T || !seq_end)
+            lanes_chunk<D, MODE, LG, true>(cst, PM, PG, up, u_nx, ts, T, s, li, tid, x_chunk, b_chunk, tile, &ubar, (unsigned)((c - c_lo) & 1), exch, vred, Xg, Xsg, gstride, vec_x, vdst, xTd);
         else
-            lanes_chunk<D, MODE, LG, false>(cst, PM, PG, up, ts, T, s, li, tid, x_chunk, b_chunk, tile, &ubar, (unsigned)((c - c_lo) & 1), exch, vred, Xg, Xsg, gstride, vec_x, vdst, xTd);
+            lanes_chunk<D, MODE, LG, false>(cst, PM, PG, up, u_nx, ts, T, s, li, tid, x_chunk, b_chunk, tile, &ubar, (unsigned)((c - c_lo) & 1), exch, vred, Xg, Xsg, gstride, vec_x, vdst, xTd);
     }
 }
 
@@ -1011,7 +1064,7 @@ cudaError_t launch_scan_lanes(const ScanArgs& a, long long nC, cudaStream_t st) 
     const long long cpc = (nC + groups - 1) / groups;
     const long long nG = (nC + cpc - 1) / cpc;
     k_scan_lanes<D, MODE, LG><<<(unsigned)(a.N * nG * nLG), NT, smem, st>>>(a.u, a.consts, a.L, a.N, a.T, nC, cpc, a.xin, a.bin, a.X, a.Xs,
-                                                                            a.vsq, a.xT);
+                                                                            a.vsq, a.xT, a.u_after, a.seq_end);
     return cudaGetLastError();
 }
 
@@ -1034,16 +1087,28 @@ cudaError_t run_scan(const ScanArgs& a, cudaStream_t st) {
         if (groups > chunks) groups = chunks;
         return (chunks + groups - 1) / groups;
     };
-    if (nC > 1) {
+    // Phases (a.phase): 0 = the whole pass.  A block of a longer sequence sharded in time runs 1 (summaries + forward
+    // chain from a.x0 -> x_end), 2 (last-chunk summary with the true u_after, forward chain from the true x0, backward
+    // chain from b_end = 0 -> b_out) and 3 (backward chain from the true b_end + the final pass); the carries of the
+    // blocks are exchanged between the phases (capi.cu, multioutputihgp_b200/parallel.py).
+    const int ph = a.phase;
+    const bool sharded = ph != 0;
+    if (ph <= 1 && (nC > 1 || sharded)) {
         // summaries: interior chunks as dot products with tabulated weights, the last chunk by the recurrence itself
         k_scan_weights<D, MODE><<<a.L * (CH + 1), 32, 0, st>>>(a.consts, a.Wsum);
         const long long nI = nC - 1;
-        const long long cpw = per_unit(a.N * a.L, nI);
-        const long long warps = a.N * a.L * ((nI + cpw - 1) / cpw);
-        k_scan_summaries_dot<D><<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(a.u, a.Wsum, a.L, a.N, a.T, nC, cpw, a.fsum, a.bsum);
+        if (nI > 0) {
+            const long long cpw = per_unit(a.N * a.L, nI);
+            const long long warps = a.N * a.L * ((nI + cpw - 1) / cpw);
+            k_scan_summaries_dot<D><<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(a.u, a.Wsum, a.L, a.N, a.T, nC, cpw, a.fsum, a.bsum);
+        }
+    }
+    if ((ph == 0 && nC > 1) || ph == 1 || ph == 2) {
         k_scan<D, MODE, false><<<(unsigned)(a.N * nLG), 32 * lg, 0, st>>>(a.u, a.consts, a.L, a.N, a.T, nC, nLG, nC - 1, 1, 1, nullptr, nullptr,
-                                                                         a.fsum, a.bsum, nullptr, nullptr, nullptr, nullptr);
+                                                                         a.fsum, a.bsum, nullptr, nullptr, nullptr, nullptr, a.u_after, a.seq_end);
         mark(a.mk, "k_scan_summaries");
+    }
+    if ((ph == 0 && nC > 1) || ph == 2) {
         k_response<D, MODE><<<a.L * 2 * D, 32, 0, st>>>(a.consts, r_last, a.Bx);
         mark(a.mk, "k_response");
     }
@@ -1051,19 +1116,29 @@ cudaError_t run_scan(const ScanArgs& a, cudaStream_t st) {
         const long long nGr = (nC + 32 * CG - 1) / (32 * CG), nS = (nGr + SB - 1) / SB;
         const unsigned gw = (unsigned)((a.N * a.L * nS * 32 + 127) / 128), gt = (unsigned)((a.N * a.L + 127) / 128);
         const double* in = nullptr;
+        if (ph <= 2) {
+            if (nS > 1) {
+                k_carry<D, MODE, 0, 0><<<gw, 128, 0, st>>>(a.consts, a.Bx, a.L, a.N, nC, nS, a.x0, a.fsum, a.bsum, a.xin, a.bin, nullptr, a.sb_end, nullptr, a.seq_end);
+                k_carry_super<D, MODE, 0><<<gt, 128, 0, st>>>(a.consts, a.L, a.N, nS, a.x0, a.sb_end, a.sb_in);
+                in = a.sb_in;
+            }
+            k_carry<D, MODE, 0, 1><<<gw, 128, 0, st>>>(a.consts, a.Bx, a.L, a.N, nC, nS, a.x0, a.fsum, a.bsum, a.xin, a.bin, in, nullptr, nullptr, a.seq_end);
+        }
+        if (ph == 1) {
+            if (a.x_end) k_block_end<D><<<gt, 128, 0, st>>>(a.consts, a.L, a.N, nC, a.xin, a.fsum, a.x_end);
+            mark(a.mk, "k_carry");
+            return cudaGetLastError();
+        }
         if (nS > 1) {
-            k_carry<D, MODE, 0, 0><<<gw, 128, 0, st>>>(a.consts, a.Bx, a.L, a.N, nC, nS, a.x0, a.fsum, a.bsum, a.xin, a.bin, nullptr, a.sb_end);
-            k_carry_super<D, MODE, 0><<<gt, 128, 0, st>>>(a.consts, a.L, a.N, nS, a.x0, a.sb_end, a.sb_in);
+            k_carry<D, MODE, 1, 0><<<gw, 128, 0, st>>>(a.consts, a.Bx, a.L, a.N, nC, nS, a.x0, a.fsum, a.bsum, a.xin, a.bin, nullptr, a.sb_end, a.b_end, a.seq_end);
+            k_carry_super<D, MODE, 1><<<gt, 128, 0, st>>>(a.consts, a.L, a.N, nS, a.x0, a.sb_end, a.sb_in);
             in = a.sb_in;
         }
-        k_carry<D, MODE, 0, 1><<<gw, 128, 0, st>>>(a.consts, a.Bx, a.L, a.N, nC, nS, a.x0, a.fsum, a.bsum, a.xin, a.bin, in, nullptr);
-        if (nS > 1) {
-            k_carry<D, MODE, 1, 0><<<gw, 128, 0, st>>>(a.consts, a.Bx, a.L, a.N, nC, nS, a.x0, a.fsum, a.bsum, a.xin, a.bin, nullptr, a.sb_end);
-            k_carry_super<D, MODE, 1><<<gt, 128, 0, st>>>(a.consts, a.L, a.N, nS, a.x0, a.sb_end, a.sb_in);
-        }
-        k_carry<D, MODE, 1, 1><<<gw, 128, 0, st>>>(a.consts, a.Bx, a.L, a.N, nC, nS, a.x0, a.fsum, a.bsum, a.xin, a.bin, in, nullptr);
+        k_carry<D, MODE, 1, 1><<<gw, 128, 0, st>>>(a.consts, a.Bx, a.L, a.N, nC, nS, a.x0, a.fsum, a.bsum, a.xin, a.bin, in, nullptr, a.b_end, a.seq_end);
+        if (a.b_out) k_block_start<D, MODE><<<gt, 128, 0, st>>>(a.consts, a.Bx, a.L, a.N, nC, a.seq_end, a.xin, a.bsum, a.bin, a.b_out);
     }
     mark(a.mk, "k_carry");
+    if (ph == 2) return cudaGetLastError();
     // final pass: thread-per-sub-chunk kernel when the latents come in whole groups of 16 or 8, else the warp-per-chunk one
     const bool force_warp = getenv("MOIHGP_SCAN_FINAL_WARP") != nullptr;   // A/B switch, read per call
     if (!force_warp && a.L % 8 == 0) {
@@ -1074,7 +1149,7 @@ cudaError_t run_scan(const ScanArgs& a, cudaStream_t st) {
     const long long cpc = per_unit(a.N * nLG, nC);
     const long long nG = (nC + cpc - 1) / cpc;
     k_scan<D, MODE, true><<<(unsigned)(a.N * nG * nLG), 32 * lg, smem, st>>>(a.u, a.consts, a.L, a.N, a.T, nC, nLG, 0, nC, cpc, a.xin, a.bin,
-                                                                            nullptr, nullptr, a.X, a.Xs, a.vsq, a.xT);
+                                                                            nullptr, nullptr, a.X, a.Xs, a.vsq, a.xT, a.u_after, a.seq_end);
     mark(a.mk, "k_scan_final");
     return cudaGetLastError();
 }

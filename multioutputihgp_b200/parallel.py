@@ -254,3 +254,82 @@ class TimeShardedDeviceObjective(object):
             dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, group=self.group)
         host = self.buf.cpu().numpy()
         return float(host[0]), host[2:].copy()
+
+
+def forward_carry_in(transition, block_lengths, ends_x, x0, rank):
+    """Filter state entering block `rank`: x_in(g+1) = AKHA^n_g x_in(g) + x_end_g, x_in(0) = x0.  ends_x [G,N,L,d] are the
+    blocks' end states from a ZERO carry-in, transition(n) -> (AKHA^n [L,d,d], ...), x0 [N,L,d]."""
+    x = np.array(x0, dtype=np.float64).copy()
+    for g in range(rank):
+        P = transition(int(block_lengths[g]))[0]
+        x = np.einsum("lij,nlj->nli", P, x) + ends_x[g]
+    return x
+
+
+def backward_carry_in(smoother_power, block_lengths, starts_b, rank):
+    """Backward value entering block `rank` from the right (None on the last block): b_end(g) = b_start(g+1),
+    b_start(g) = starts_b[g] + G^n_g b_end(g); starts_b [G,N,L,d] are the blocks' first-step backward values computed
+    from a ZERO b_end, smoother_power(n) -> G^n [L,d,d].  The mirror image of forward_carry_in."""
+    G_ = len(block_lengths)
+    if rank == G_ - 1:
+        return None
+    b_start = np.array(starts_b[G_ - 1], dtype=np.float64)                # the last block has b_end = 0
+    for g in range(G_ - 2, rank, -1):
+        b_start = starts_b[g] + np.einsum("lij,nlj->nli", smoother_power(int(block_lengths[g])), b_start)
+    return b_start
+
+
+class TimeShardedFilterSmoother(object):
+    """Fused filter + smoother + NLL of ONE long sequence (or N of them) whose contiguous time blocks live on different
+    ranks: forward carry exchange, then the mirror-image backward exchange, two all-gathers of O(L d) doubles and one
+    all-reduce of the NLL.  ``model`` provides ``fsn_block(phase, ...)``, ``block_transition(n)``, ``smoother_power(n, mode)``
+    (``MOIHGPSequences``); every block but the last holds a multiple of 256 steps (``time_block_bounds_aligned``)."""
+
+    def __init__(self, model, block_lengths, smoother_mode=1, group=None, device=None):
+        import torch
+        self.model, self.group, self.mode = model, group, int(smoother_mode)
+        self.block_lengths = [int(b) for b in block_lengths]
+        self.dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+
+    def _gather(self, arr, world):
+        import torch
+        dist = _dist()
+        t = torch.from_numpy(np.ascontiguousarray(arr)).to(self.dev)
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t, group=self.group)
+        return [o.cpu().numpy() for o in out]
+
+    def __call__(self, Y_block, X, Xs, x0=None, nll=None, xT=None):
+        """Y_block [N,n,p], X / Xs [N,n,L,d] (this rank's block, tensors on the device); returns nll [N] of the whole
+        sequence (numpy).  x0 [N,L,d] is the state before the first step of the WHOLE sequence."""
+        import torch
+        dist = _dist()
+        m = self.model
+        N = Y_block.shape[0]
+        L, d = m.num_latent, m.igp_dim
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        world = dist.get_world_size(self.group) if multi else 1
+        rank = dist.get_rank(self.group) if multi else 0
+        last = rank == world - 1
+        x0 = np.zeros((N, L, d)) if x0 is None else np.asarray(x0, dtype=np.float64).reshape(N, L, d)
+        to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.dev)
+        x_end, u_first = m.fsn_block(1, Y_block, last, self.mode)
+        x_in, u_after = x0, None
+        if multi:
+            got = self._gather(np.concatenate([x_end.ravel(), u_first.ravel()]), world)
+            ends = [g_[:N * L * d].reshape(N, L, d) for g_ in got]
+            x_in = forward_carry_in(m.block_transition, self.block_lengths, ends, x0, rank)
+            if not last:
+                u_after = to_dev(got[rank + 1][N * L * d:].reshape(N, L))
+        x_in_dev = to_dev(x_in)
+        b0 = m.fsn_block(2, Y_block, last, self.mode, x0=x_in_dev, u_after=u_after)
+        b_end = None
+        if multi:
+            starts = [g_.reshape(N, L, d) for g_ in self._gather(b0.ravel(), world)]
+            be = backward_carry_in(lambda n_: m.smoother_power(n_, self.mode), self.block_lengths, starts, rank)
+            b_end = None if be is None else to_dev(be)
+        nll_dev = nll if nll is not None else torch.zeros(N, dtype=torch.float64, device=self.dev)
+        m.fsn_block(3, Y_block, last, self.mode, x0=x_in_dev, u_after=u_after, b_end=b_end, X=X, Xs=Xs, nll=nll_dev, xT=xT)
+        if multi:
+            dist.all_reduce(nll_dev, op=dist.ReduceOp.SUM, group=self.group)
+        return nll_dev.cpu().numpy()

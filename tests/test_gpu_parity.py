@@ -566,3 +566,58 @@ def test_block_transition_matches_the_host_powering(cuda_lib, kernel):
         for k in range(3):
             brute = sum(np.linalg.matrix_power(M, 4 - i) @ dAK[l, k] @ np.linalg.matrix_power(M, i) for i in range(5))
             assert rel_err(E5[l, k], brute) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel,p,L,N,cuts", [("Matern32", 8, 4, 1, (0, 512, 1280, 1700)), ("Matern52", 16, 8, 2, (0, 256, 512, 1024)),
+                                               ("Matern32", 12, 5, 1, (0, 768, 800)), ("Matern52", 6, 3, 3, (0, 256, 257)),
+                                               ("Matern32", 64, 32, 1, (0, 2048, 4096, 6000))])
+def test_time_sharded_filter_smoother_blocks_equal_the_whole_sequence(cuda_lib, kernel, p, L, N, cuts):
+    """moihgp_cuda_fsn_block_dev: a sequence cut into contiguous blocks (each on its own handle, as on its own GPU), forward
+    carry exchange, mirror-image backward exchange - filtered states, smoothed states and NLL equal the
+    whole-sequence pass, in both smoother modes."""
+    import torch
+    from multioutputihgp_b200 import MOIHGPSequences
+    from multioutputihgp_b200.parallel import backward_carry_in, forward_carry_in
+    from oracle.gen_golden import make_data, make_params
+    rng = np.random.default_rng(sum(cuts))
+    params = make_params(rng, p, L, kernel)
+    T, G = cuts[-1], len(cuts) - 1
+    lengths = [cuts[g + 1] - cuts[g] for g in range(G)]
+    Y = np.stack([make_data(rng, p, L, T) for _ in range(N)])
+    whole = MOIHGPSequences(0.1, p, L, kernel, True)
+    whole.update(params)
+    whole.set_path("scan")
+    d = whole.igp_dim
+    x0 = 0.3 * rng.standard_normal((N, L, d))
+    dev = torch.device("cuda:0")
+    models = []
+    for g in range(G):
+        m = MOIHGPSequences(0.1, p, L, kernel, True)
+        m.update(params)
+        models.append(m)
+    Yd = [torch.from_numpy(np.ascontiguousarray(Y[:, cuts[g]:cuts[g + 1]])).to(dev) for g in range(G)]
+    to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    for mode in (1, 0):
+        ref = whole.filter_smoother_nll(Y, x0=x0, smoother_mode=mode)
+        ph1 = [models[g].fsn_block(1, Yd[g], g == G - 1, mode) for g in range(G)]
+        ends, ufirst = [a for a, _ in ph1], [b for _, b in ph1]
+        x_in = [forward_carry_in(models[0].block_transition, lengths, ends, x0, g) for g in range(G)]
+        u_after = [to_dev(ufirst[g + 1]) if g < G - 1 else None for g in range(G)]
+        b0 = [models[g].fsn_block(2, Yd[g], g == G - 1, mode, x0=to_dev(x_in[g]), u_after=u_after[g]) for g in range(G)]
+        X = [torch.zeros((N, lengths[g], L, d), dtype=torch.float64, device=dev) for g in range(G)]
+        Xs = [torch.zeros_like(X[g]) for g in range(G)]
+        nll = torch.zeros((G, N), dtype=torch.float64, device=dev)
+        xT = torch.zeros((N, L, d), dtype=torch.float64, device=dev)
+        for g in range(G):
+            be = backward_carry_in(lambda n_: models[0].smoother_power(n_, mode), lengths, b0, g)
+            models[g].fsn_block(3, Yd[g], g == G - 1, mode, x0=to_dev(x_in[g]), u_after=u_after[g], b_end=None if be is None else to_dev(be),
+                                X=X[g], Xs=Xs[g], nll=nll[g], xT=xT if g == G - 1 else None)
+        torch.cuda.synchronize()
+        Xc = np.concatenate([x.cpu().numpy() for x in X], axis=1)
+        Xsc = np.concatenate([x.cpu().numpy() for x in Xs], axis=1)
+        assert rel_err(Xc, ref["X"]) < 1e-12, mode
+        assert rel_err(nll.sum(0).cpu().numpy(), ref["nll"]) < 1e-12, mode
+        assert rel_err(xT.cpu().numpy(), ref["xT"]) < 1e-12, mode
+        if mode == 1 or np.max(np.abs(ref["Xs"])) < 1e100:
+            assert rel_err(Xsc, ref["Xs"]) < (1e-11 if mode == 1 else 1e-7), mode
