@@ -16,3 +16,6 @@ PY
 for T in 1000000 4000000; do
 TS_P=256 TS_L=64 TS_T=$T python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533 scripts/gpu_time_shard.py 2>&1 | grep "time-sharded" | tee -a gpurun_out/time_shard_g$NG.txt
 done
+for T in 2000000 8000000; do
+TS_T=$T python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29535 scripts/gpu_time_shard_fsn.py 2>&1 | grep -E "time-sharded|last rank|Error|error" | tee -a gpurun_out/time_shard_fsn_g$NG.txt
+done

@@ -380,6 +380,23 @@ def test_time_sharded_objective_two_gpus(cuda_lib):
 
 
 @pytest.mark.gpu
+def test_time_sharded_filter_smoother_two_gpus(cuda_lib):
+    """the fused filter + smoother + NLL pass of one long sequence split in time over two GPUs (forward and
+    backward carry all-gathers + NCCL all-reduce of the NLL) equals the single-GPU pass.  Needs two devices."""
+    import subprocess
+    import sys
+    import torch
+    from conftest import ROOT
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, TS_T="70001", TS_P="16", TS_L="8")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29543", os.path.join(ROOT, "scripts", "gpu_time_shard_fsn.py")], capture_output=True, text=True, env=env, timeout=600)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "time-sharded filter+smoother+NLL" in r.stdout and "block borders agree" in r.stdout
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("p,L", [(256, 64), (64, 32), (96, 33), (200, 11)])
 def test_update_polar_factor_on_device(cuda_lib, p, L):
     """MOIHGP::update (moihgp.h:431-447): U = polar factor of the raw block; large blocks go through k_polar.  Checked against

@@ -146,3 +146,148 @@ def test_time_sharded_objective_gloo(tmp_path, world, T):
         z = np.load(os.path.join(str(tmp_path), "trank%d.npz" % r))
         assert abs(float(z["loss"]) - loss) <= 1e-11 * abs(loss)
         assert rel_err(z["grad"], grad) < 1e-10
+
+
+class _OracleBlockModel(object):
+    """CPU stand-in for MOIHGPSequences' time-sharding interface (fsn_block / block_transition / smoother_power), built on
+    the oracle: lets the exchange protocol of TimeShardedFilterSmoother run under gloo without a GPU."""
+
+    def __init__(self, o, params, p, L):
+        self.o, self.num_latent, self.igp_dim = o, L, o.ihgp_consts(0)["AKHA"].shape[0]
+        c = [o.ihgp_consts(l) for l in range(L)]
+        self.M = np.stack([c_["AKHA"] for c_ in c])
+        self.K = np.stack([np.asarray(c_["K"]).ravel() for c_ in c])
+        self.HA = np.stack([np.asarray(c_["HA"]).ravel() for c_ in c])
+        self.G = np.stack([o.smoother_consts(l, 1)[0] for l in range(L)])
+        self.U, self.S = o.U, params[p * L:p * L + L]
+
+    def block_transition(self, n):
+        return np.stack([np.linalg.matrix_power(m_, n) for m_ in self.M]), None
+
+    def smoother_power(self, n, mode):
+        return np.stack([np.linalg.matrix_power(g_, n) for g_ in self.G])
+
+    def fsn_block(self, phase, Y, seq_end, smoother_mode=1, x0=None, u_after=None, b_end=None, X=None, Xs=None, nll=None, xT=None):
+        import torch
+        Ynp = Y.numpy()
+        N, n, _ = Ynp.shape
+        L, d = self.num_latent, self.igp_dim
+        u = (Ynp @ self.U) / np.sqrt(self.S)
+        x_in = np.zeros((N, L, d)) if x0 is None else x0.numpy()
+        r = self.o.filter_smoother_nll(Ynp, x0=x_in, smoother_mode=1)
+        if phase == 1:
+            return r["xT"].copy(), u[:, 0, :].copy()
+        Xf = r["X"]
+        b = np.zeros((N, L, d)) if b_end is None else b_end.numpy().copy()
+        bs = np.zeros((N, n, L, d))
+        for j in range(n - 1, -1, -1):
+            if j + 1 < n:
+                v = u[:, j + 1] - np.einsum("lq,nlq->nl", self.HA, Xf[:, j])
+            elif seq_end:
+                v = np.zeros((N, L))
+            else:
+                v = u_after.numpy() - np.einsum("lq,nlq->nl", self.HA, Xf[:, j])
+            gk = np.einsum("lij,lj->li", self.G, self.K)
+            b = np.einsum("lij,nlj->nli", self.G, b) + gk[None] * v[:, :, None]
+            bs[:, j] = b
+        if phase == 2:
+            return bs[:, 0].copy()
+        X.copy_(torch.from_numpy(Xf))
+        Xs.copy_(torch.from_numpy(Xf + bs))
+        nll.copy_(torch.from_numpy(r["nll"]))
+        if xT is not None:
+            xT.copy_(torch.from_numpy(r["xT"]))
+
+
+def _fsn_worker(rank, world, port, T, out_dir):
+    import torch
+    import torch.distributed as dist
+    from multioutputihgp_b200.parallel import TimeShardedFilterSmoother, time_block_bounds
+    from oracle.binding import OracleMOIHGP
+    from oracle.gen_golden import make_data, make_params
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(91)
+    p, L, N = 6, 3, 2
+    params = make_params(rng, p, L, "Matern32")
+    Y = np.stack([make_data(rng, p, L, T) for _ in range(N)])
+    x0 = 0.2 * rng.standard_normal((N, L, 2))
+    o = OracleMOIHGP(0.1, p, L, "Matern32", threading=True)
+    o.update(params)
+    bounds = [time_block_bounds(T, world, r) for r in range(world)]
+    t0, t1 = bounds[rank]
+    fs = TimeShardedFilterSmoother(_OracleBlockModel(o, params, p, L), [b[1] - b[0] for b in bounds], 1, device=torch.device("cpu"))
+    X = torch.zeros((N, t1 - t0, L, 2), dtype=torch.float64)
+    Xs = torch.zeros_like(X)
+    nll = fs(torch.from_numpy(np.ascontiguousarray(Y[:, t0:t1])), X, Xs, x0=x0)
+    np.savez(os.path.join(out_dir, "frank%d.npz" % rank), X=X.numpy(), Xs=Xs.numpy(), nll=nll, t0=t0, t1=t1)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,T", [(2, 151), (3, 90)])
+def test_time_sharded_filter_smoother_gloo(tmp_path, world, T):
+    """One sequence split in time over the ranks: forward carry exchange, mirror-image backward exchange,
+    NLL all-reduce; every rank's block of X / Xs and the NLL equal the single-process pass over the whole sequence."""
+    import torch.multiprocessing as mp
+    from oracle.binding import OracleMOIHGP
+    from oracle.gen_golden import make_data, make_params
+    mp.spawn(_fsn_worker, args=(world, _free_port(), T, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(91)
+    p, L, N = 6, 3, 2
+    params = make_params(rng, p, L, "Matern32")
+    Y = np.stack([make_data(rng, p, L, T) for _ in range(N)])
+    x0 = 0.2 * rng.standard_normal((N, L, 2))
+    o = OracleMOIHGP(0.1, p, L, "Matern32", threading=True)
+    o.update(params)
+    ref = o.filter_smoother_nll(Y, x0=x0, smoother_mode=1)
+    for r in range(world):
+        z = np.load(os.path.join(str(tmp_path), "frank%d.npz" % r))
+        t0, t1 = int(z["t0"]), int(z["t1"])
+        assert rel_err(z["X"], ref["X"][:, t0:t1]) < 1e-12
+        assert rel_err(z["Xs"], ref["Xs"][:, t0:t1]) < 1e-11
+        assert rel_err(z["nll"], ref["nll"]) < 1e-11
+
+
+def test_carry_algebra_of_the_time_sharded_smoother():
+    """forward_carry_in / backward_carry_in against the plain sequential recursions on random stable systems."""
+    from multioutputihgp_b200.parallel import backward_carry_in, forward_carry_in
+    rng = np.random.default_rng(12)
+    L, d, N = 3, 2, 2
+    M = 0.5 * rng.standard_normal((L, d, d)) * 0.6
+    Gm = 0.5 * rng.standard_normal((L, d, d)) * 0.6
+    lengths = [5, 7, 4]
+    T = sum(lengths)
+    drive_f = rng.standard_normal((T, N, L, d))
+    drive_b = rng.standard_normal((T, N, L, d))
+    x0 = rng.standard_normal((N, L, d))
+    x, xs = x0.copy(), []
+    for t in range(T):
+        xs.append(x.copy())                              # state BEFORE step t
+        x = np.einsum("lij,nlj->nli", M, x) + drive_f[t]
+    b, bs = np.zeros((N, L, d)), [None] * (T + 1)
+    bs[T] = b.copy()
+    for t in range(T - 1, -1, -1):
+        b = np.einsum("lij,nlj->nli", Gm, b) + drive_b[t]
+        bs[t] = b.copy()
+    cuts = np.concatenate([[0], np.cumsum(lengths)])
+    ends, starts = [], []
+    for g in range(3):
+        z = np.zeros((N, L, d))
+        for t in range(cuts[g], cuts[g + 1]):
+            z = np.einsum("lij,nlj->nli", M, z) + drive_f[t]
+        ends.append(z)
+        z = np.zeros((N, L, d))
+        for t in range(cuts[g + 1] - 1, cuts[g] - 1, -1):
+            z = np.einsum("lij,nlj->nli", Gm, z) + drive_b[t]
+        starts.append(z)
+    tr = lambda n: (np.stack([np.linalg.matrix_power(m_, n) for m_ in M]), None)
+    sp = lambda n: np.stack([np.linalg.matrix_power(g_, n) for g_ in Gm])
+    for g in range(3):
+        assert rel_err(forward_carry_in(tr, lengths, ends, x0, g), xs[cuts[g]]) < 1e-13
+        be = backward_carry_in(sp, lengths, starts, g)
+        if g == 2:
+            assert be is None
+        else:
+            assert rel_err(be, bs[cuts[g + 1]]) < 1e-13
