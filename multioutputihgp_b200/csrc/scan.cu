@@ -20,9 +20,12 @@
 //   4. the same three steps run backwards for the smoother, fused in the same kernel.
 // Across chunks: k_scan<.., FINAL=false> produces per-chunk summaries from zero carries,
 // k_response the (constant) linear response of a chunk to its carry-in, k_carry chains them
-// (a length T/256 recurrence per (sequence, latent)), and k_scan<.., FINAL=true> produces the
-// outputs from the true carries.  The input series u[n][l][t] is read with unit stride; the
-// outputs X/Xs [n][t][l][d] are staged in shared memory and written as contiguous rows.
+// (a length T/256 recurrence per (sequence, latent)), and the final pass produces the outputs from
+// the true carries: k_scan_lanes (one thread per 32-step sub-chunk, latents in groups of 16 or 8)
+// or k_scan<.., FINAL=true> (any shape).  The input series u[n][l][t] is read with unit stride; the
+// outputs X/Xs [n][t][l][d] are written as contiguous rows.
+// A block of a longer sequence sharded in time over several devices runs the same kernels in three
+// phases (run_scan; ScanArgs::phase, seq_end, u_after, b_end): SURVEY.md section 8(e).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdlib.h>

@@ -1,11 +1,16 @@
+# 4-GPU evidence: weak-scaling bench under torchrun, time-sharded objective and filter+smoother
 cd ${GRAFT_REPO_ROOT:-.}; mkdir -p gpurun_out
 NG=${1:-4}
-for mode in with without; do
-if [ $mode = without ]; then export BENCH_SKIP_ALLREDUCE=1; else unset BENCH_SKIP_ALLREDUCE; fi
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29551 bench.py --gpus $NG --steps 20 --warmup 3 --no-e2e --no-cpu > gpurun_out/bench_g${NG}_$mode.json 2> gpurun_out/bench_g${NG}_$mode.err
+nvidia-smi -L | wc -l
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus $NG --steps 20 --warmup 3 > gpurun_out/bench_g$NG.json 2> gpurun_out/bench_g$NG.err
+echo "rc=$? bytes=$(wc -c < gpurun_out/bench_g$NG.json)"
 python - <<PY
 import json
-d = json.load(open("gpurun_out/bench_g${NG}_$mode.json"))
-print("$mode all-reduce: gpus", d["n_gpus"], "value %.4g" % d["value"], "ms", round(d["ms_per_step"], 3), "frac", round(d["roofline"]["frac"], 4), d["roofline"]["kernels_ms_event_bracketed"], d["clocks"])
+try:
+    d = json.load(open("gpurun_out/bench_g$NG.json"))
+    print("gpus", d["n_gpus"], "value", d["value"], "ms", d["ms_per_step"], "frac", d["roofline"]["frac"], "e2e", d["e2e"]["value"] if d["e2e"] else None, d["clocks"])
+except Exception as e:
+    print("no json:", e)
 PY
-done
+TS_P=256 TS_L=64 TS_T=4000000 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533 scripts/gpu_time_shard.py 2>&1 | grep "time-sharded" | tee -a gpurun_out/time_shard_g$NG.txt
+TS_T=8000000 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29535 scripts/gpu_time_shard_fsn.py 2>&1 | grep -E "time-sharded|last rank|Error|error" | tee -a gpurun_out/time_shard_fsn_g$NG.txt
