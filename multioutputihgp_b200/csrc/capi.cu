@@ -36,7 +36,10 @@ struct moihgp_handle {
     int kernel = 32, dim = 2, p = 0, L = 0, threading = 0, device = 0, num_param = 0;
     double dt = 0.0, sigma = 1e-2;
     std::vector<double> U, S, igp;            // host copies: [p*L], [L], [L*3]
-    std::vector<LatentConsts> consts;         // host copy of the per-latent constants
+    std::vector<LatentConsts> consts;         // host copy of the per-latent constants (refreshed on demand: mirror())
+    bool consts_fresh = false;
+    double* h_small = nullptr;                // pinned staging of the one-launch objective (k_obj_small)
+    size_t h_small_cap = 0;
     double *d_U = nullptr, *d_S = nullptr, *d_igp = nullptr;
     LatentConsts* d_consts = nullptr;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -140,8 +143,16 @@ int push_model(moihgp_handle* h, bool device_polar = false) {
     CK(cudaMemcpyAsync(h->d_igp, h->igp.data(), sizeof(double) * h->igp.size(), cudaMemcpyHostToDevice, h->stream));
     CK(launch_setup(h->dim, h->d_igp, h->dt, h->L, h->d_consts, h->stream));
     h->launches += 1;
+    h->consts_fresh = false;          // no host round trip here: update() returns while k_setup runs (mirror() fetches on demand)
+    return 0;
+}
+
+// host copy of the per-latent constants, fetched when somebody on the host needs them
+int mirror(moihgp_handle* h) {
+    if (h->consts_fresh) return 0;
     CK(cudaMemcpyAsync(h->consts.data(), h->d_consts, sizeof(LatentConsts) * h->L, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    h->consts_fresh = true;
     return 0;
 }
 
@@ -297,6 +308,7 @@ void moihgp_cuda_destroy(moihgp_handle* h) {
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
     if (h->h_flags) cudaFreeHost(h->h_flags);
+    if (h->h_small) cudaFreeHost(h->h_small);
     if (h->d_bound) cudaFree(h->d_bound);
     for (int i = 0; i < 2; ++i) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_c[i]) cudaEventDestroy(h->ev_c[i]); if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]); }
     delete h;
@@ -410,6 +422,7 @@ int moihgp_cuda_get_U(moihgp_handle* h, double* U) {
 
 long long moihgp_cuda_latent_consts(moihgp_handle* h, size_t l, double* out, size_t cap) {
     if (!h || !out || l >= (size_t)h->L) return -2;
+    if (mirror(h)) return -1;
     const LatentConsts& c = h->consts[l];
     const int d = h->dim;
     std::vector<double> v;
@@ -424,6 +437,7 @@ long long moihgp_cuda_latent_consts(moihgp_handle* h, size_t l, double* out, siz
 
 int moihgp_cuda_block_transition(moihgp_handle* h, size_t n, double* out) {
     if (!h || !out) return -2;
+    if (mirror(h)) return -1;
     const int d = h->dim, dd = d * d;
     auto mul = [&](const double* A, const double* B, double* C) {            // C = A B   (d x d, row-major, C distinct)
         for (int i = 0; i < d; ++i) for (int j = 0; j < d; ++j) {
@@ -464,12 +478,14 @@ int moihgp_cuda_block_transition(moihgp_handle* h, size_t n, double* out) {
 
 int moihgp_cuda_latent_iters(moihgp_handle* h, size_t l, int* out8) {
     if (!h || !out8 || l >= (size_t)h->L) return -2;
+    if (mirror(h)) return -1;
     for (int i = 0; i < 4; ++i) { out8[i] = h->consts[l].iters[i]; out8[4 + i] = h->consts[l].conv[i]; }
     return 0;
 }
 
 int moihgp_cuda_smoother_consts(moihgp_handle* h, size_t l, int mode, double* G, double* P) {
     if (!h || l >= (size_t)h->L || mode < 0 || mode > 1) return -2;
+    if (mirror(h)) return -1;
     const int d = h->dim;
     for (int i = 0; i < d; ++i) for (int j = 0; j < d; ++j) {
         if (G) G[i * d + j] = h->consts[l].G[mode][i * 3 + j];
@@ -505,6 +521,7 @@ int moihgp_cuda_filter_smoother_nll_dev(moihgp_handle* h, const double* Y, size_
         if (ws_get(h, "nanf", 4, &nanf)) return -1;
         CK(cudaMemsetAsync(nanf, 0, 2 * sizeof(int), h->stream));
         double Ssum = 0.0, logs = 0.0;
+        if (mirror(h)) return -1;
         for (int l = 0; l < L; ++l) { Ssum += h->S[l]; logs += h->consts[l].logS; }
         const double m_n = std::max((double)(h->p - L), 0.0);
         ChainArgs c;
@@ -606,6 +623,7 @@ int moihgp_cuda_fsn_block_dev(moihgp_handle* h, int phase, const double* Y, size
 
 int moihgp_cuda_smoother_power(moihgp_handle* h, int mode, size_t n, double* out) {
     if (!h || !out || mode < 0 || mode > 1) return -2;
+    if (mirror(h)) return -1;
     const int d = h->dim, dd = d * d;
     for (int l = 0; l < h->L; ++l) {
         const LatentConsts& c = h->consts[l];
@@ -777,11 +795,52 @@ int moihgp_cuda_objective_finish_dev(moihgp_handle* h, const double* Y, size_t N
     return objective_phase(h, 2, Y, N, T, x0, dx0, loss, grad, xT, dxT, nullptr);
 }
 
+// One short sequence (the streaming learner's window): everything in ONE launch, inputs and outputs through one pinned
+// staging buffer (one H2D, k_obj_small, one D2H).  Y_resident != null: the observations are already on the device.
+// Returns 1 if the kernel met a missing (NaN) output - the caller then takes the general path.
+static int objective_small(moihgp_handle* h, const double* Y, const double* Y_resident, size_t T, const double* x0, const double* dx0,
+                           double* loss, double* grad, double* xT, double* dxT) {
+    const size_t L = h->L, D = h->dim, p = h->p, np = h->num_param;
+    const size_t nY = Y_resident ? 0 : T * p, nx = L * D, ndx = 3 * L * D;
+    const size_t nin = nY + nx + ndx, nout = np + 2 + nx + ndx;
+    if (h->h_small_cap < nin + nout) {
+        if (h->h_small) cudaFreeHost(h->h_small);
+        h->h_small = nullptr;
+        h->h_small_cap = 0;
+        CK(cudaMallocHost(&h->h_small, sizeof(double) * (nin + nout)));
+        h->h_small_cap = nin + nout;
+    }
+    double* dbuf;
+    if (ws_get(h, "small", nin + nout, &dbuf)) return -1;
+    double* hb = h->h_small;
+    if (nY) std::copy(Y, Y + nY, hb);
+    if (x0) std::copy(x0, x0 + nx, hb + nY); else std::fill(hb + nY, hb + nY + nx, 0.0);
+    if (dx0) std::copy(dx0, dx0 + ndx, hb + nY + nx); else std::fill(hb + nY + nx, hb + nin, 0.0);
+    CK(cudaMemcpyAsync(dbuf, hb, sizeof(double) * nin, cudaMemcpyHostToDevice, h->stream));
+    double* dout = dbuf + nin;
+    CK(launch_objective_small((int)D, Y_resident ? Y_resident : dbuf, h->d_U, h->d_S, h->sigma, h->d_consts, (int)p, (int)L, (long long)T,
+                              h->threading, dbuf + nY, dbuf + nY + nx, dout, dout + np + 2, dout + np + 2 + nx, h->stream));
+    h->launches += 1;
+    CK(cudaMemcpyAsync(hb + nin, dout, sizeof(double) * nout, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const double* ho = hb + nin;
+    if (ho[1] != 0.0) return 1;
+    *loss = ho[0];
+    std::copy(ho + 2, ho + 2 + np, grad);
+    if (xT) std::copy(ho + np + 2, ho + np + 2 + nx, xT);
+    if (dxT) std::copy(ho + np + 2 + nx, ho + nout, dxT);
+    return 0;
+}
+
 int moihgp_cuda_objective(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0, const double* dx0, double* loss,
                           double* grad, double* xT, double* dxT) {
     if (!h || !Y || !loss || !grad) return -2;
     if (N == 0 || T == 0) return fail(h, "N and T must be positive");
     cudaSetDevice(h->device);
+    if (N == 1 && h->path != 1 && obj_small_smem(h->p, h->L, (long long)T)) {
+        const int rs = objective_small(h, Y, nullptr, T, x0, dx0, loss, grad, xT, dxT);
+        if (rs <= 0) return rs;                  // 1: missing observations -> the general path below
+    }
     const size_t L = h->L, D = h->dim, p = h->p, np = h->num_param;
     double *dY, *dx = nullptr, *ddx = nullptr, *dout, *dxT_ = nullptr, *ddxT = nullptr;
     if (ws_get(h, "hY", N * T * p, &dY) || ws_get(h, "hout", np + 2, &dout)) return -1;
@@ -831,6 +890,10 @@ int moihgp_cuda_objective_bound(moihgp_handle* h, const double* x0, const double
     if (!h->d_bound) return fail(h, "no data bound: call moihgp_cuda_bind_data first");
     cudaSetDevice(h->device);
     const size_t N = h->bound_N, T = h->bound_T, L = h->L, D = h->dim, np = h->num_param;
+    if (N == 1 && h->path != 1 && obj_small_smem(h->p, h->L, (long long)T)) {
+        const int rs = objective_small(h, nullptr, h->d_bound, T, x0, dx0, loss, grad, xT, dxT);
+        if (rs <= 0) return rs;
+    }
     double *dx = nullptr, *ddx = nullptr, *dout, *dxT_ = nullptr, *ddxT = nullptr;
     if (ws_get(h, "hout", np + 2, &dout)) return -1;
     if (x0 && ws_get(h, "hx0", N * L * D, &dx)) return -1;

@@ -115,6 +115,10 @@ size_t obj_chunks(long long T);
 size_t obj_gu_splits(long long N, long long T);
 int obj_launch_count(long long T, int L);
 cudaError_t launch_objective(int dim, const ObjArgs& a, cudaStream_t st);
+size_t obj_small_smem(int p, int L, long long T);
+cudaError_t launch_objective_small(int dim, const double* Y, const double* U, const double* S, double sigma, const LatentConsts* consts,
+                                   int p, int L, long long T, int threading, const double* x0, const double* dx0, double* out, double* xT,
+                                   double* dxT, cudaStream_t st);
 
 // step.cu  (one observation per call: the legacy gpXX_* entry points)
 struct StepArgs {

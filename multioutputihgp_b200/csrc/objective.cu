@@ -997,6 +997,166 @@ __global__ void __launch_bounds__(256) k_obj_finish(const double* __restrict__ l
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// k_obj_small: the WHOLE objective of one short sequence in ONE kernel launch (one CTA): projection, residual norms, the
+// sensitivity recursion, the dU contraction and the assembly of loss / gradient - what the streaming learner evaluates
+// a handful of times per sample on its window (moihgp_online.h:40-72; BASELINE configs[1]: p = 8, L = 4, window <= 64),
+// where the general path is nothing but launch latency (8 launches, ~65 us of device time for ~5 us of arithmetic).
+// Four lanes per latent: lane 0 of the group carries x, lanes 1..3 carry dx_k (ihgp.h:71-77); the pre-step x is broadcast
+// inside the group each step.  Same quirks as the general path (Q5, Q8, Q9, Q20).  Observations with missing outputs are
+// not handled here: the kernel raises out[1] and the caller re-runs the general path.
+// out = [loss, nan flag, grad[num_param]]; dynamic shared memory: U[p][L], Y[T][p], u[T][L], w -> dU weights [T][L], lat[L][5].
+template <int D>
+__global__ void __launch_bounds__(128) k_obj_small(const double* __restrict__ Y, const double* __restrict__ U, const double* __restrict__ S,
+                                                  double sigma, const LatentConsts* __restrict__ consts, int p, int L, int T, int threading,
+                                                  const double* __restrict__ x0, const double* __restrict__ dx0, double* __restrict__ out,
+                                                  double* __restrict__ xT, double* __restrict__ dxT) {
+    extern __shared__ double sm[];
+    double* sU = sm;
+    double* sY = sU + p * L;
+    double* su = sY + (size_t)T * p;
+    double* sw = su + (size_t)T * L;
+    double* lat = sw + (size_t)T * L;            // [L][5]
+    __shared__ double red[128];
+    __shared__ int bad;
+    const int tid = threadIdx.x;
+    if (tid == 0) bad = 0;
+    for (int i = tid; i < p * L; i += 128) sU[i] = U[i];
+    for (int i = tid; i < T * p; i += 128) sY[i] = Y[i];
+    __syncthreads();
+    // ---- projection  w = U'y, u = S^-1/2 w   (moihgp.h:481-498 without missing data) --------------------------------
+    for (int i = tid; i < T * L; i += 128) {
+        const int t = i / L, l = i - t * L;
+        double a = 0.0;
+        for (int r = 0; r < p; ++r) a = fma(sU[r * L + l], sY[t * p + r], a);
+        sw[i] = a;
+        su[i] = a * (1.0 / sqrt(S[l]));
+    }
+    __syncthreads();
+    // ---- residual norms  rho_t = || (I - U U') y_t ||_2   (moihgp.h:499-501; norm, not squared: Q9) -------------------
+    double rho = 0.0;
+    for (int t = tid; t < T; t += 128) {
+        double ysq = 0.0, wsq = 0.0;
+        for (int r = 0; r < p; ++r) ysq = fma(sY[t * p + r], sY[t * p + r], ysq);
+        for (int l = 0; l < L; ++l) wsq = fma(sw[t * L + l], sw[t * L + l], wsq);
+        double q = ysq - wsq;
+        if (!(ysq == ysq)) bad = 1;              // a missing (NaN) output somewhere in this observation
+        if (!(q >= 1e-4 * ysq)) {                // cancellation: the explicit form
+            q = 0.0;
+            for (int r = 0; r < p; ++r) {
+                double e = sY[t * p + r];
+                for (int l = 0; l < L; ++l) e = fma(-sU[r * L + l], sw[t * L + l], e);
+                q = fma(e, e, q);
+            }
+        }
+        rho += sqrt(q);
+    }
+    red[tid] = rho;
+    __syncthreads();
+    // ---- the recursion: lane (l, c), c = 0: x, c = 1..3: dx_{c-1} ------------------------------------------------------
+    {
+        const int l = min(tid >> 2, L - 1), c = tid & 3;
+        const bool live = (tid >> 2) < L;
+        const LatentConsts* lc = consts + l;
+        double M[D * D], HA[D], Dm[D * D], Dk[D], z[D];
+        load_mat<D>(lc->AKHA, M);
+        load_vec<D>(lc->HA, HA);
+        if (c == 0) {
+#pragma unroll
+            for (int i = 0; i < D * D; ++i) Dm[i] = 0.0;
+            load_vec<D>(lc->K, Dk);
+        } else {
+            load_mat<D>(lc->dAKHA[c - 1], Dm);
+            load_vec<D>(lc->dK[c - 1], Dk);
+        }
+#pragma unroll
+        for (int q = 0; q < D; ++q)
+            z[q] = c == 0 ? (x0 ? x0[l * D + q] : 0.0) : (dx0 ? dx0[(l * 3 + c - 1) * D + q] : 0.0);
+        const double Si = lc->S, logSi = lc->logS, c1 = (1.0 - lc->hak) / Si;
+        const double rsS = 1.0 / sqrt(S[l]), rsig = 1.0 / sigma;
+        const double hda0 = c > 0 ? lc->HdA[c - 1][0] : 0.0, dSk = c > 0 ? lc->dS[c - 1] : 0.0;
+        double sv2 = 0.0, acc = 0.0;             // acc: sum pv * w (c = 0) or sum v * dv_k (c > 0)
+        for (int j = 0; j < T; ++j) {
+            const double uj = su[j * L + l];
+            double x[D];
+#pragma unroll
+            for (int q = 0; q < D; ++q) x[q] = __shfl_sync(FULL, z[q], 0, 4);     // the group's pre-step x
+            double hax = HA[0] * x[0];
+#pragma unroll
+            for (int q = 1; q < D; ++q) hax = fma(HA[q], x[q], hax);
+            const double v = uj - hax;                                           // ihgp.h:214
+            sv2 = fma(v, v, sv2);
+            if (c == 0) {
+                const double wj = sw[j * L + l];
+                const double pv = (sY[j * p + l] - hax) * c1;                    // moihgp.h:510-511 (raw y(l), Q8)
+                acc = fma(pv, wj, acc);                                          // moihgp.h:558-560
+                if (live) sw[j * L + l] = fma(pv, rsS, -wj * rsig);              // moihgp.h:546-550 (rank-1 form)
+            } else {
+                double hd = HA[0] * z[0];
+#pragma unroll
+                for (int q = 1; q < D; ++q) hd = fma(HA[q], z[q], hd);
+                const double dv = -hda0 * x[0] - hd;                             // ihgp.h:218 (Q20 de facto)
+                acc = fma(v, dv, acc);
+            }
+            double t1[D], zn[D];
+            mv<D>(Dm, x, t1);
+            mv<D>(M, z, zn);
+#pragma unroll
+            for (int q = 0; q < D; ++q) z[q] = zn[q] + fma(Dk[q], uj, t1[q]);   // ihgp.h:73-77
+        }
+        if (live) {
+            const double q2 = sv2 / Si;
+            if (c == 0) {
+                lat[l * 5 + 0] = 0.5 * (q2 + (double)T * logSi);                 // ihgp.h:215
+                lat[l * 5 + 4] = acc;
+                if (xT) {
+#pragma unroll
+                    for (int q = 0; q < D; ++q) xT[l * D + q] = z[q];
+                }
+            } else {
+                lat[l * 5 + c] = (acc - 0.5 * (q2 - (double)T) * dSk) / Si;      // ihgp.h:219
+                if (dxT) {
+#pragma unroll
+                    for (int q = 0; q < D; ++q) dxT[(l * 3 + c - 1) * D + q] = z[q];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- dU = Y' W   (moihgp.h:538-552 as the rank-1 sum) ------------------------------------------------------------
+    double* grad = out + 2;
+    const int sizeU = p * L;
+    for (int i = tid; i < sizeU; i += 128) {
+        const int r = i / L, cc = i - r * L;
+        double a = 0.0;
+        for (int t = 0; t < T; ++t) a = fma(sY[t * p + r], sw[t * L + cc], a);
+        grad[i] = a;
+    }
+    // ---- loss and the remaining gradient entries (moihgp.h:553-609), as k_obj_finish ------------------------------------
+    if (tid == 0) {
+        double rho_sum = 0.0;
+        for (int i = 0; i < 128; ++i) rho_sum += red[i];
+        const double steps = (double)T;
+        const double m_n = fmax((double)(p - L), 0.0);
+        double Ssum = 0.0;
+        for (int l = 0; l < L; ++l) Ssum += S[l];
+        double ls = steps * (0.5 * log(Ssum) + 0.5 * m_n * log(sigma)) + 0.5 * rho_sum / sigma;
+        double gsig = 0.5 * (steps * m_n - rho_sum / sigma) / sigma;
+        for (int l = 0; l < L; ++l) {
+            const double* q = lat + l * 5;
+            if (threading) ls += q[0];
+            const double Sl = S[l], rs = sqrt(Sl);
+            const double g2 = q[3];
+            grad[sizeU + l] = steps * 0.5 / Sl - 0.5 * (1.0 / rs / rs / rs) * q[4] - g2 * sigma / Sl / Sl;
+            gsig += g2 / Sl;
+            for (int k = 0; k < 3; ++k) grad[sizeU + L + 1 + 3 * l + k] = q[1 + k];
+        }
+        grad[sizeU + L] = gsig;
+        out[0] = ls;
+        out[1] = bad ? 1.0 : 0.0;
+    }
+}
+
 template <int D>
 cudaError_t run_objective(const ObjArgs& a, cudaStream_t st) {
     const long long nC = (a.T + CH - 1) / CH;
@@ -1069,6 +1229,28 @@ size_t obj_gu_splits(long long N, long long T) {
 int obj_launch_count(long long T, int L) {
     const bool many = (T + CH - 1) / CH > 1;
     return many ? (L % 8 == 0 ? 8 : 7) : 6;
+}
+
+// one short sequence, one launch (k_obj_small): shared memory it needs, 0 if the shape does not qualify
+size_t obj_small_smem(int p, int L, long long T) {
+    if (L > 32 || T > 1024) return 0;                 // beyond ~1000 steps the sequential loop loses to the chunked scan
+    const size_t b = sizeof(double) * ((size_t)p * L + (size_t)T * p + 2 * (size_t)T * L + 5 * (size_t)L);
+    return b <= 96 * 1024 ? b : 0;
+}
+
+cudaError_t launch_objective_small(int dim, const double* Y, const double* U, const double* S, double sigma, const LatentConsts* consts,
+                                   int p, int L, long long T, int threading, const double* x0, const double* dx0, double* out, double* xT,
+                                   double* dxT, cudaStream_t st) {
+    const size_t smem = obj_small_smem(p, L, T);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_obj_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(k_obj_small<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr_done = true;
+    }
+    if (dim == 2) k_obj_small<2><<<1, 128, smem, st>>>(Y, U, S, sigma, consts, p, L, (int)T, threading, x0, dx0, out, xT, dxT);
+    else k_obj_small<3><<<1, 128, smem, st>>>(Y, U, S, sigma, consts, p, L, (int)T, threading, x0, dx0, out, xT, dxT);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_objective(int dim, const ObjArgs& a, cudaStream_t st) {

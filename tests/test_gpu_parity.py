@@ -638,3 +638,45 @@ def test_time_sharded_filter_smoother_blocks_equal_the_whole_sequence(cuda_lib, 
         assert rel_err(xT.cpu().numpy(), ref["xT"]) < 1e-12, mode
         if mode == 1 or np.max(np.abs(ref["Xs"])) < 1e100:
             assert rel_err(Xsc, ref["Xs"]) < (1e-11 if mode == 1 else 1e-7), mode
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel,threading,p,L,T", [("Matern32", False, 8, 4, 1), ("Matern32", True, 8, 4, 64), ("Matern52", True, 16, 8, 300),
+                                                    ("Matern52", False, 5, 5, 17), ("Matern32", True, 40, 12, 129), ("Matern52", True, 3, 1, 40)])
+def test_one_launch_objective_matches_the_general_path_and_the_oracle(cuda_lib, kernel, threading, p, L, T):
+    """k_obj_small (one short sequence, one launch: the streaming learner's window) against the general objective path
+    (forced with set_path('scan')) and the oracle; with a missing observation it hands over to the general path."""
+    from multioutputihgp_b200 import MOIHGPSequences
+    from oracle.binding import OracleMOIHGP
+    from oracle.gen_golden import make_data, make_params
+    rng = np.random.default_rng(100 * p + T)
+    params = make_params(rng, p, L, kernel)
+    Y = make_data(rng, p, L, T)[None]
+    m = MOIHGPSequences(0.1, p, L, kernel, threading)
+    o = OracleMOIHGP(0.1, p, L, kernel, threading)
+    m.update(params)
+    o.update(params)
+    d = m.igp_dim
+    x0 = 0.2 * rng.standard_normal((1, L, d))
+    dx0 = 0.1 * rng.standard_normal((1, L, 3, d))
+    n0 = m.launch_count
+    la, ga, xa, dxa = m.objective(Y, x0=x0, dx0=dx0, want_state=True)
+    assert m.launch_count - n0 == 1                     # really the one-launch kernel
+    m.set_path("scan")
+    lb, gb, xb, dxb = m.objective(Y, x0=x0, dx0=dx0, want_state=True)
+    m.set_path("auto")
+    lo, go, xo, dxo = o.objective(Y, x0=x0, dx0=dx0)
+    for l_, g_, x_, dx_ in ((lb, gb, xb, dxb), (lo, go, xo, dxo)):
+        assert _close(la, l_)
+        assert rel_err(ga, g_) < TOL
+        assert rel_err(xa, x_) < TOL and rel_err(dxa, dx_) < TOL
+    # bound (resident) data takes the same kernel
+    m.bind(Y)
+    lc, gc = m.objective_bound(x0, dx0)
+    m.bind(None)
+    assert lc == la and np.array_equal(gc, ga)
+    if p > L + 2 and T > 2:
+        Yn = Y.copy()
+        Yn[0, T // 2, 0] = np.nan
+        ln, gn = m.objective(Yn, x0=x0, dx0=dx0)[:2]
+        assert np.isnan(ln)                              # as the reference's (moihgp.h:501 multiplies the full y)
