@@ -654,9 +654,9 @@ int moihgp_cuda_filter_smoother_nll(moihgp_handle* h, const double* Y, size_t N,
     if (mode < 0 && Xs) return fail(h, "Xs requested with smoother_mode = none");
     cudaSetDevice(h->device);
     const size_t L = h->L, D = h->dim, p = h->p;
-    // slices: enough chains per slice to keep every SM busy (the many-chains kernels want >= 2 warps per SM), about
-    // eight slices when the batch is large; a multiple of 32 sequences
-    size_t Ns = std::max<size_t>((2 * 148 * 32 + L - 1) / L, (N + 7) / 8);
+    // slices: the call is PCIe-bound (D2H of the states), so what matters is how soon the first results can start to
+    // flow back: slices as small as one warp of chains per SM allows, at most sixteen; a multiple of 32 sequences
+    size_t Ns = std::max<size_t>((148 * 32 + L - 1) / L, (N + 15) / 16);
     Ns = ((Ns + 31) / 32) * 32;
     if (Ns > N) Ns = N;
     const size_t nsl = (N + Ns - 1) / Ns;
