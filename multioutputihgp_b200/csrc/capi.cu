@@ -743,7 +743,7 @@ static int objective_phase(moihgp_handle* h, int phase, const double* Y, size_t 
     if (ws_get(h, "u", N * L * T, &u) || ws_get(h, "w", N * L * T, &w) || ws_get(h, "yl", N * L * T, &yl) || ws_get(h, "rho", N * project_tiles((long long)T), &rho) ||
         ws_get(h, "zsum", nC * N * L * 4 * D, &zsum) || ws_get(h, "zin", nC * N * L * 4 * D, &zin) || ws_get(h, "zsub", nC * 8 * N * L * 4 * D, &zsub) ||
         ws_get(h, "part", nC * N * L * 8, &part) ||
-        ws_get(h, "gU", nsplit * p * L, &gU) || ws_get(h, "Ek", (size_t)L * 27 * 16, &Ek) || ws_get(h, "lat", ((size_t)L + 1) * 8, &lat) ||
+        ws_get(h, "gU", nsplit * p * L, &gU) || ws_get(h, "Ek", (size_t)L * 27 * 16, &Ek) || ws_get(h, "lat", ((size_t)L + 1) * 8 * 16, &lat) ||
         ws_get(h, "nanf", 4, &nanf))
         return -1;
     Marker* mk = h->profiling ? &h->marker : nullptr;

@@ -104,7 +104,7 @@ struct ObjArgs {
     double* part;                 // [nC][N][L][8] per-chunk partial sums
     double* gU_part;              // [nSplit][p][L] split-K partials of dU
     double* Ek;                   // [L][3][D*D] cross-chunk coupling matrices (workspace)
-    double* lat_sums;             // [L+1][8] per-latent reduced sums (workspace)
+    double* lat_sums;             // [L+1][16][8] per-latent partial sums (workspace)
     double *loss, *grad;          // [1], [num_param] outputs (device)
     double *xT, *dxT;             // final state or null
     int phase = 0;                // 0: whole evaluation, 1: begin (summaries + block end from zero carry), 2: finish

@@ -930,20 +930,26 @@ __global__ void __launch_bounds__(256) k_gradU_mma(const double* __restrict__ Y,
 }
 
 // Per-latent reduction of the chunk partials (blocks 0..L-1) and of rho (block L): fixed order.
+constexpr int RSPLIT = 16;        // CTAs per latent in k_obj_reduce (fixed-order partials, summed in k_obj_finish)
 __global__ void __launch_bounds__(256) k_obj_reduce(const double* __restrict__ part, const double* __restrict__ rho, int L,
-                                                   long long N, long long tiles, long long nC, double* __restrict__ lat_sums /*[L+1][8]*/) {
+                                                   long long N, long long tiles, long long nC,
+                                                   double* __restrict__ lat_part /*[L+1][RSPLIT][8]*/) {
     __shared__ double red[256][5];
     const int tid = threadIdx.x;
-    const int l = blockIdx.x;
+    const int l = blockIdx.x / RSPLIT, sp = blockIdx.x % RSPLIT;
     double s[5] = {0, 0, 0, 0, 0};
     if (l < L) {
-        for (long long i = tid; i < nC * N; i += 256) {
+        const long long tot = nC * N, per = (tot + RSPLIT - 1) / RSPLIT;
+        const long long hi = min(tot, (sp + 1) * per);
+        for (long long i = sp * per + tid; i < hi; i += 256) {
             const double* pp = part + ((size_t)i * L + l) * NPART;
 #pragma unroll
             for (int j = 0; j < 5; ++j) s[j] += pp[j];
         }
     } else {
-        for (long long i = tid; i < N * tiles; i += 256) s[0] += rho[i];
+        const long long tot = N * tiles, per = (tot + RSPLIT - 1) / RSPLIT;
+        const long long hi = min(tot, (sp + 1) * per);
+        for (long long i = sp * per + tid; i < hi; i += 256) s[0] += rho[i];
     }
 #pragma unroll
     for (int j = 0; j < 5; ++j) red[tid][j] = s[j];
@@ -955,13 +961,13 @@ __global__ void __launch_bounds__(256) k_obj_reduce(const double* __restrict__ p
         }
         __syncthreads();
     }
-    if (tid < 5) lat_sums[(size_t)l * 8 + tid] = red[0][tid];
+    if (tid < 5) lat_part[((size_t)l * RSPLIT + sp) * 8 + tid] = red[0][tid];
 }
 
 // Assemble loss and gradient [U (p*L row-major) | S (L) | sigma | (mag, len, noise) x L]  (moihgp.h:553-609)
 // grid: enough CTAs of 256 threads to cover the p*L entries of dU (fixed-order sum over the split-K partials);
 // thread 0 of CTA 0 assembles the scalar / per-latent entries.
-__global__ void __launch_bounds__(256) k_obj_finish(const double* __restrict__ lat_sums, const double* __restrict__ gU_part,
+__global__ void __launch_bounds__(256) k_obj_finish(const double* __restrict__ lat_part, const double* __restrict__ gU_part,
                                                    int nsplit, const double* __restrict__ S, double sigma, int p, int L,
                                                    long long N, long long T, int threading, double* __restrict__ loss,
                                                    double* __restrict__ grad) {
@@ -975,6 +981,17 @@ __global__ void __launch_bounds__(256) k_obj_finish(const double* __restrict__ l
             grad[i] = s;
         }
     }
+    // CTA 0: the RSPLIT partials of every per-latent sum in fixed order, then the scalar / per-latent entries
+    __shared__ double lat_sums[65 * 8];
+    if (blockIdx.x == 0) {
+        for (int i = tid; i < (L + 1) * 5; i += 256) {
+            const int l = i / 5, j = i - l * 5;
+            double a = 0.0;
+            for (int sp = 0; sp < RSPLIT; ++sp) a += lat_part[((size_t)l * RSPLIT + sp) * 8 + j];
+            lat_sums[l * 8 + j] = a;
+        }
+    }
+    __syncthreads();
     if (tid == 0 && blockIdx.x == 0) {
         const double steps = (double)N * (double)T;
         const double rho_sum = lat_sums[(size_t)L * 8];
@@ -1207,7 +1224,7 @@ cudaError_t run_objective(const ObjArgs& a, cudaStream_t st) {
     else k_gradU<<<gg, 256, 0, st>>>(a.Y, a.wgt, a.p, a.L, a.N, a.T, per, a.gU_part);
     mark(a.mk, "k_gradU");
     double* lat_sums = a.lat_sums;
-    k_obj_reduce<<<a.L + 1, 256, 0, st>>>(a.part, a.rho, a.L, a.N, (long long)project_tiles(a.T), nC, lat_sums);
+    k_obj_reduce<<<(a.L + 1) * RSPLIT, 256, 0, st>>>(a.part, a.rho, a.L, a.N, (long long)project_tiles(a.T), nC, lat_sums);
     k_obj_finish<<<(a.p * a.L + 255) / 256, 256, 0, st>>>(lat_sums, a.gU_part, (int)nsplit, a.S, a.sigma, a.p, a.L, a.N, a.T, a.threading, a.loss, a.grad);
     mark(a.mk, "k_obj_reduce");
     return cudaGetLastError();
