@@ -169,6 +169,19 @@ public:
         return loss;
     }
 
+    // One long sequence sharded in TIME over several devices (one MOIHGP object per device / process): the
+    // carry algebra a caller needs around moihgp_cuda_objective_begin_dev / _finish_dev and moihgp_cuda_fsn_block_dev.
+    //   blockTransition(n, out): out[L][4][d*d] = [AKHA^n, E_0(n), E_1(n), E_2(n)], row-major
+    //   smootherPower(mode, n, out): out[L][d*d] = G[mode]^n
+    void blockTransition(size_t n, std::vector<double>& out) {
+        out.assign(_num_latent * 4 * _dim * _dim, 0.0);
+        detail::check(_h, moihgp_cuda_block_transition(_h, n, &out[0]), "MOIHGP::blockTransition");
+    }
+    void smootherPower(int smoother_mode, size_t n, std::vector<double>& out) {
+        out.assign(_num_latent * _dim * _dim, 0.0);
+        detail::check(_h, moihgp_cuda_smoother_power(_h, smoother_mode, n, &out[0]), "MOIHGP::smootherPower");
+    }
+
     moihgp_handle* handle() { return _h; }
 
 private:
