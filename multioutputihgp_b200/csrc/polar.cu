@@ -52,11 +52,14 @@ __global__ void __launch_bounds__(1024) k_polar(const double* __restrict__ A /*[
                 double al = 0.0, be = 0.0, ga = 0.0;
                 for (int r = lane; r < p; r += 32) { const double x = wi[r], y = wj[r]; al = fma(x, x, al); be = fma(y, y, be); ga = fma(x, y, ga); }
                 al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
-                if (ga != 0.0) {
-                    my_off = fmax(my_off, fabs(ga) / sqrt(al * be));
+                // relative size of the off-diagonal entry, |ga| / sqrt(al be), compared through squares (no sqrt / division on
+                // this latency chain): >= 1e-15 keeps the sweeps going, <= 3e-17 is not worth a rotation
+                const double g2 = ga * ga, prod = al * be;
+                if (g2 > 1e-30 * prod) my_off = 1.0;
+                if (g2 > 1e-33 * prod) {
                     const double zeta = (be - al) / (2.0 * ga);
-                    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                    const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(fma(zeta, zeta, 1.0)));
+                    const double c = rsqrt(fma(t, t, 1.0)), s = c * t;
                     for (int r = lane; r < p; r += 32) { const double x = wi[r], y = wj[r]; wi[r] = c * x - s * y; wj[r] = s * x + c * y; }
                     double* vi = Vt + (size_t)i * Lp;
                     double* vj = Vt + (size_t)j * Lp;
@@ -65,27 +68,26 @@ __global__ void __launch_bounds__(1024) k_polar(const double* __restrict__ A /*[
             }
             __syncthreads();
         }
-        if (lane == 0 && my_off > 0.0) atomicMax(reinterpret_cast<unsigned long long*>(&off_max), (unsigned long long)__double_as_longlong(my_off));   // non-negative doubles order like integers
+        if (lane == 0 && my_off > 0.0) off_max = 1.0;               // some pair was still above 1e-15 in this sweep
         __syncthreads();
         const double off = off_max;
         __syncthreads();
-        if (off < 1e-15) break;
+        if (off == 0.0) break;
     }
     for (int j = warp; j < Lp; j += nwarps) {
         const double* wj = Wt + (size_t)j * p;
         double q = 0.0;
         for (int r = lane; r < p; r += 32) q = fma(wj[r], wj[r], q);
         q = warp_sum(q);
-        if (lane == 0) nrm[j] = sqrt(q);
+        if (lane == 0) nrm[j] = q > 0.0 ? 1.0 / sqrt(q) : 0.0;       // 1 / singular value (0 for a zero column)
     }
+    __syncthreads();
+    for (int i = tid; i < L * p; i += blockDim.x) Wt[i] *= nrm[i / p];   // W <- W diag(1/s): orthonormal columns
     __syncthreads();
     for (int i = tid; i < p * L; i += blockDim.x) {
         const int r = i / L, c = i - r * L;
         double s = 0.0;
-        for (int k = 0; k < L; ++k) {
-            const double nk = nrm[k];
-            if (nk > 0.0) s = fma(Wt[(size_t)k * p + r] / nk, Vt[(size_t)k * Lp + c], s);
-        }
+        for (int k = 0; k < L; ++k) s = fma(Wt[(size_t)k * p + r], Vt[(size_t)k * Lp + c], s);
         U[i] = s;
     }
 }
