@@ -45,7 +45,10 @@ __global__ void __launch_bounds__(1024) k_polar(const double* __restrict__ A /*[
             for (int pr = warp; pr < Lp / 2; pr += nwarps) {
                 int i, j;
                 if (pr == 0) { i = n1; j = rnd; }
-                else { i = (rnd + pr) % n1; j = (rnd - pr + n1) % n1; }
+                else {                                   // (rnd +- pr) mod n1 with 0 <= rnd, pr < n1
+                    i = rnd + pr; if (i >= n1) i -= n1;
+                    j = rnd - pr; if (j < 0) j += n1;
+                }
                 if (i > j) { const int t = i; i = j; j = t; }
                 double* wi = Wt + (size_t)i * p;
                 double* wj = Wt + (size_t)j * p;
@@ -57,9 +60,13 @@ __global__ void __launch_bounds__(1024) k_polar(const double* __restrict__ A /*[
                 const double g2 = ga * ga, prod = al * be;
                 if (g2 > 1e-30 * prod) my_off = 1.0;
                 if (g2 > 1e-33 * prod) {
-                    const double zeta = (be - al) / (2.0 * ga);
-                    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(fma(zeta, zeta, 1.0)));
-                    const double c = rsqrt(fma(t, t, 1.0)), s = c * t;
+                    // Jacobi angle, |theta| <= pi/4, tan(2 theta) = 2 ga / (be - al), without a division on the chain:
+                    // cos(2 theta) = |d| / h, h = hypot(d, 2 ga);  c = sqrt((1 + cos 2theta) / 2);  s = sin(2 theta) / (2 c)
+                    const double d = be - al;
+                    const double rh = rsqrt(fma(d, d, 4.0 * g2));
+                    const double x = fma(0.5 * fabs(d), rh, 0.5);
+                    const double ic = rsqrt(x);
+                    const double c = x * ic, s = copysign(ga * rh * ic, d * ga);
                     for (int r = lane; r < p; r += 32) { const double x = wi[r], y = wj[r]; wi[r] = c * x - s * y; wj[r] = s * x + c * y; }
                     double* vi = Vt + (size_t)i * Lp;
                     double* vj = Vt + (size_t)j * Lp;
