@@ -23,6 +23,7 @@ import os
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 import numpy as np
@@ -79,7 +80,31 @@ class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
+    def _nvml_loop(self, index):
+        # in-process sampling through NVML every 5 ms (nvidia-smi -lms delivers only a handful of samples in a 0.2 s timed
+        # region); the nvidia-smi stream stays as the fallback
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            hd = nv.nvmlDeviceGetHandleByIndex(index)
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(hd, nv.NVML_CLOCK_SM))
+            bits = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
+            while not self._nv_stop:
+                if self._nv_on:
+                    sm = float(nv.nvmlDeviceGetClockInfo(hd, nv.NVML_CLOCK_SM))
+                    try:
+                        rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(hd))
+                    except Exception:
+                        rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(hd))
+                    self._nv_rows.append((sm, mx, tuple(n for n, b in bits if rs & b)))
+                time.sleep(0.005)
+        except Exception:
+            pass
+
     def __init__(self, index):
+        self._nv_rows, self._nv_stop, self._nv_on = [], False, False
+        self._nv_thread = threading.Thread(target=self._nvml_loop, args=(index,), daemon=True)
+        self._nv_thread.start()
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
@@ -89,6 +114,7 @@ class ClockSampler:
 
     def mark_timed_region_start(self):
         """Samples taken before this point (start-up, warm-up) are dropped."""
+        self._nv_on = True
         self.f.flush()
         try:
             self.skip = sum(1 for _ in open(self.f.name))
@@ -97,6 +123,23 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self._nv_on, self._nv_stop = False, True
+        if len(self._nv_rows) >= 3:
+            if self.p is not None:
+                self.p.terminate()
+                try:
+                    self.p.wait(timeout=5)
+                except Exception:
+                    self.p.kill()
+                try:
+                    os.unlink(self.f.name)
+                except Exception:
+                    pass
+            rows = list(self._nv_rows)
+            reasons = sorted({r for row in rows for r in row[2]})
+            out.update(sm_mhz=float(np.median([r[0] for r in rows])), sm_max_mhz=float(max(r[1] for r in rows)), reasons=reasons,
+                       samples=len(rows), source="nvml")
+            return out
         if self.p is None:
             return out
         self.p.terminate()
