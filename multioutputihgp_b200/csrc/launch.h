@@ -38,6 +38,17 @@ cudaError_t launch_project(const double* Y, const double* U, const double* S, in
 cudaError_t launch_backproject(const double* X, const double* U, const double* S, int p, int L, int d, long long N,
                                long long T, double* Yhat, cudaStream_t stream);
 
+// true the first time it is called with this flag array on the current device: function attributes (dynamic shared
+// memory size) belong to the device's context, so they are set once per device, not once per process
+inline bool first_use_on_device(bool (&done)[64]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+}
+
 // scan.cu
 struct ScanArgs {
     const double* u;              // [N][L][T] projected observations

@@ -22,6 +22,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include "moihgp_device.cuh"
+#include "small_mat.cuh"
 #include "tma.cuh"
 #include "launch.h"
 
@@ -36,34 +37,6 @@ constexpr int LOG2_CH = 8;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int NPART = 8;          // per-chunk partial sums: loss, g0, g1, g2, pv*w (3 spare)
 
-template <int D> __device__ __forceinline__ void load_mat(const double* src9, double* dst) {
-#pragma unroll
-    for (int i = 0; i < D; ++i)
-#pragma unroll
-        for (int j = 0; j < D; ++j) dst[i * D + j] = __ldg(src9 + i * 3 + j);
-}
-template <int D> __device__ __forceinline__ void load_vec(const double* src3, double* dst) {
-#pragma unroll
-    for (int i = 0; i < D; ++i) dst[i] = __ldg(src3 + i);
-}
-template <int D> __device__ __forceinline__ void mv(const double* M, const double* x, double* y) {
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-        double s = M[i * D] * x[0];
-#pragma unroll
-        for (int j = 1; j < D; ++j) s = fma(M[i * D + j], x[j], s);
-        y[i] = s;
-    }
-}
-template <int D> __device__ __forceinline__ void mv_acc(const double* M, const double* x, double* y) {
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-        double s = y[i];
-#pragma unroll
-        for (int j = 0; j < D; ++j) s = fma(M[i * D + j], x[j], s);
-        y[i] = s;
-    }
-}
 
 // Warp-level LTI scan  z+ = M z + r_i  over this lane's SUB steps: returns, per step, the state BEFORE
 // the step (pre[i]) and the lane's end state after the inclusive scan (z_end; lane 31 = chunk end).
@@ -585,11 +558,9 @@ template <int D, bool FINAL>
 void launch_obj_lanes(const ObjArgs& a, long long nC, long long c_cnt, cudaStream_t st) {
     constexpr int LG = 8, NT = NSUBC * LG;
     const size_t smem = sizeof(double) * NT * (FINAL ? UP3 : SL + 2);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {};
+    if (first_use_on_device(attr_done))
         cudaFuncSetAttribute(k_obj_lanes<D, LG, FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_done = true;
-    }
     const int nLG = a.L / LG;
     long long groups = (148LL * 32 + a.N * nLG - 1) / (a.N * nLG);
     if (groups < 1) groups = 1;
@@ -1259,11 +1230,10 @@ cudaError_t launch_objective_small(int dim, const double* Y, const double* U, co
                                    int p, int L, long long T, int threading, const double* x0, const double* dx0, double* out, double* xT,
                                    double* dxT, cudaStream_t st) {
     const size_t smem = obj_small_smem(p, L, T);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {};
+    if (first_use_on_device(attr_done)) {
         cudaFuncSetAttribute(k_obj_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         cudaFuncSetAttribute(k_obj_small<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        attr_done = true;
     }
     if (dim == 2) k_obj_small<2><<<1, 128, smem, st>>>(Y, U, S, sigma, consts, p, L, (int)T, threading, x0, dx0, out, xT, dxT);
     else k_obj_small<3><<<1, 128, smem, st>>>(Y, U, S, sigma, consts, p, L, (int)T, threading, x0, dx0, out, xT, dxT);

@@ -30,6 +30,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include "moihgp_device.cuh"
+#include "small_mat.cuh"
 #include "tma.cuh"
 #include "launch.h"
 
@@ -49,16 +50,6 @@ struct LC {                       // per-warp register copy of the latent's cons
     double M[D * D], K[D], HA[D], G[D * D], drv[D * D];
 };
 
-template <int D> __device__ __forceinline__ void load_mat(const double* src9, double* dst) {
-#pragma unroll
-    for (int i = 0; i < D; ++i)
-#pragma unroll
-        for (int j = 0; j < D; ++j) dst[i * D + j] = __ldg(src9 + i * 3 + j);
-}
-template <int D> __device__ __forceinline__ void load_vec(const double* src3, double* dst) {
-#pragma unroll
-    for (int i = 0; i < D; ++i) dst[i] = __ldg(src3 + i);
-}
 template <int D, int MODE>
 __device__ __forceinline__ void load_lc(const LatentConsts* c, LC<D>& o) {
     load_mat<D>(c->AKHA, o.M);
@@ -67,24 +58,6 @@ __device__ __forceinline__ void load_lc(const LatentConsts* c, LC<D>& o) {
     load_mat<D>(c->G[MODE], o.G);
     if (MODE == 0) load_mat<D>(c->ImA, o.drv);
     else load_vec<D>(c->GK, o.drv);
-}
-template <int D> __device__ __forceinline__ void mv(const double* M, const double* x, double* y) {  // y = M x
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-        double s = M[i * D] * x[0];
-#pragma unroll
-        for (int j = 1; j < D; ++j) s = fma(M[i * D + j], x[j], s);
-        y[i] = s;
-    }
-}
-template <int D> __device__ __forceinline__ void mv_acc(const double* M, const double* x, double* y) {  // y += M x
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-        double s = y[i];
-#pragma unroll
-        for (int j = 0; j < D; ++j) s = fma(M[i * D + j], x[j], s);
-        y[i] = s;
-    }
 }
 
 // Where a lane's steps live in the CTA's shared-memory output tile:
@@ -1053,11 +1026,10 @@ template <int D, int MODE, int LG>
 cudaError_t launch_scan_lanes(const ScanArgs& a, long long nC, cudaStream_t st) {
     constexpr int NT = NSUBC * LG;
     const size_t smem = sizeof(double) * D * SL * NT;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {};
+    if (first_use_on_device(attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(k_scan_lanes<D, MODE, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     const int nLG = a.L / LG;
     const long long target = 148LL * 24;
