@@ -107,6 +107,26 @@ for case in range(CASES):
         note("time-sharded X", rel(np.concatenate([q.cpu().numpy() for q in Xb], 1), a["X"]), 1e-11, ctx)
         note("time-sharded Xs", rel(np.concatenate([q.cpu().numpy() for q in Xsb], 1), a["Xs"]), 1e-10, ctx)
         note("time-sharded nll", rel(nllb.sum(0).cpu().numpy(), a["nll"]), 1e-11, ctx)
+# --- host-buffer call in several pipeline slices vs the device-resident call
+for (kernel, p, L, N, T) in (("Matern52", 16, 8, 1300, 40), ("Matern32", 8, 4, 2500, 33)):
+    params = make_params(rng, p, L, kernel)
+    Y = rng.standard_normal((N, T, p))
+    m = MOIHGPSequences(0.1, p, L, kernel, True)
+    m.update(params)
+    d = m.igp_dim
+    x0 = 0.3 * rng.standard_normal((N, L, d))
+    host = m.filter_smoother_nll(Y, x0=x0, smoother_mode=1, want_yhat=True)
+    Xd = torch.zeros((N, T, L, d), dtype=torch.float64, device=dev)
+    Xsd = torch.zeros_like(Xd)
+    Yh = torch.zeros((N, T, p), dtype=torch.float64, device=dev)
+    nd = torch.zeros(N, dtype=torch.float64, device=dev)
+    m.filter_smoother_nll_device(torch.from_numpy(Y).to(dev), x0=torch.from_numpy(x0).to(dev), smoother_mode=1, X=Xd, Xs=Xsd, Yhat=Yh, nll=nd)
+    torch.cuda.synchronize()
+    ctx = (kernel, p, L, N, T)
+    note("host slices vs device X", rel(host["X"], Xd.cpu().numpy()), 1e-13, ctx)
+    note("host slices vs device Xs", rel(host["Xs"], Xsd.cpu().numpy()), 1e-13, ctx)
+    note("host slices vs device Yhat", rel(host["Yhat"], Yh.cpu().numpy()), 1e-13, ctx)
+    note("host slices vs device nll", rel(host["nll"], nd.cpu().numpy()), 1e-13, ctx)
 print("fuzz: %d cases, worst relative differences:" % CASES)
 for k in sorted(worst):
     print("   %-45s %.2e" % (k, worst[k]))
