@@ -393,8 +393,10 @@ int moihgp_cuda_update(moihgp_handle* h, const double* params) {
         double* d_raw;
         if (ws_get(h, "Uraw", (size_t)p * L, &d_raw)) return -1;
         CK(cudaMemcpyAsync(d_raw, params, sizeof(double) * p * L, cudaMemcpyHostToDevice, h->stream));
-        CK(launch_polar(d_raw, p, L, h->d_U, h->stream));
-        h->launches += 1;
+        int* pst;
+        if (ws_get(h, "polar_status", 4, &pst)) return -1;
+        CK(launch_polar(d_raw, p, L, h->d_U, pst, h->stream));
+        h->launches += 2;
     } else {
         polar_factor(params, p, L, h->U.data());
     }

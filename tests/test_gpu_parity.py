@@ -680,3 +680,50 @@ def test_one_launch_objective_matches_the_general_path_and_the_oracle(cuda_lib, 
         Yn[0, T // 2, 0] = np.nan
         ln, gn = m.objective(Yn, x0=x0, dx0=dx0)[:2]
         assert np.isnan(ln)                              # as the reference's (moihgp.h:501 multiplies the full y)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("p,L", [(256, 64), (128, 33), (100, 21), (512, 16)])
+def test_newton_schulz_polar_factor_agrees_with_jacobi(cuda_lib, p, L, monkeypatch):
+    """update() on the device: k_polar_ns (Newton-Schulz, the fast way for a block that is nearly orthonormal, as inside a
+    line search) against k_polar (one-sided Jacobi) on nearly orthonormal, generic, badly scaled and ill-conditioned
+    blocks; a rank-deficient block falls back to Jacobi."""
+    from multioutputihgp_b200 import MOIHGPSequences
+    from oracle.gen_golden import make_params
+    rng = np.random.default_rng(p + L)
+    m = MOIHGPSequences(0.1, p, L, "Matern32", True)
+    base = make_params(rng, p, L, "Matern32")
+    Q, _ = np.linalg.qr(rng.standard_normal((p, L)))
+    sv = np.geomspace(1.0, 1e-5, L)
+    blocks = {
+        "near-orthonormal": Q + 0.01 * rng.standard_normal((p, L)),
+        "generic": rng.standard_normal((p, L)),
+        "scaled": 1e4 * rng.standard_normal((p, L)),
+        "ill-conditioned": (Q * sv) @ np.linalg.qr(rng.standard_normal((L, L)))[0],
+    }
+    for name, B in blocks.items():
+        params = base.copy()
+        params[:p * L] = B.ravel()
+        monkeypatch.delenv("MOIHGP_POLAR_JACOBI", raising=False)
+        m.update(params)
+        U_ns = m.U.copy()
+        monkeypatch.setenv("MOIHGP_POLAR_JACOBI", "1")
+        m.update(params)
+        U_j = m.U.copy()
+        monkeypatch.delenv("MOIHGP_POLAR_JACOBI", raising=False)
+        Wm, _, Vt = np.linalg.svd(B, full_matrices=False)
+        tol = 1e-9 if name != "ill-conditioned" else 1e-7           # the polar factor's conditioning is 1 / sigma_min
+        assert rel_err(U_ns, Wm @ Vt) < tol, name
+        assert rel_err(U_ns, U_j) < tol, name
+        assert np.max(np.abs(U_ns.T @ U_ns - np.eye(L))) < 1e-12, name
+    # rank-deficient: no unique polar factor; the iteration gives up and the Jacobi kernel's answer is the result
+    B = rng.standard_normal((p, L))
+    B[:, -1] = B[:, 0]
+    params = base.copy()
+    params[:p * L] = B.ravel()
+    m.update(params)
+    U_a = m.U.copy()
+    monkeypatch.setenv("MOIHGP_POLAR_JACOBI", "1")
+    m.update(params)
+    monkeypatch.delenv("MOIHGP_POLAR_JACOBI", raising=False)
+    assert np.array_equal(U_a, m.U)
