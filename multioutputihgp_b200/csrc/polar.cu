@@ -5,6 +5,7 @@
 // A V = W diag(s): columns live contiguously in shared memory (Wt[j][r], Vt[j][r]); each sweep is a round-robin
 // tournament of Lp - 1 rounds with Lp / 2 disjoint column pairs, one warp per pair per round.  The polar factor is
 // unique, so the rotation order only moves the result by rounding (~1e-16).
+// k_polar_ns (below) gets the same factor by the Newton-Schulz iteration and runs first; the Jacobi kernel is its fallback.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdlib.h>
