@@ -193,12 +193,30 @@ __global__ void __launch_bounds__(1024) k_polar_ns(const double* __restrict__ A 
     // ---- starting point: as it is when X'X is already close to I, else scaled below the convergence radius --------------
     double E = gram();
     if (!(E * (double)Lp < 0.9)) {
-        // ||A||_2 <= sqrt(||A||_1 ||A||_inf): after the scaling every singular value is <= 1 (< sqrt 3)
-        double cs = 0.0, rs = 0.0;
-        for (int c = tid; c < L; c += nthr) { double a = 0.0; for (int r = 0; r < p; ++r) a += fabs(X[(size_t)r * PX + c]); cs = fmax(cs, a); }
-        for (int r = tid; r < p; r += nthr) { double a = 0.0; for (int c = 0; c < L; ++c) a += fabs(X[(size_t)r * PX + c]); rs = fmax(rs, a); }
-        const double n1 = block_max(cs), ninf = block_max(rs);
-        if (tid == 0) s_scale = (n1 > 0.0 && ninf > 0.0) ? 1.0 / sqrt(n1 * ninf) : 0.0;
+        // scale by the largest singular value: lambda_max(G) by a dozen power iterations on G = X'X = 3 I - 2 C (one warp;
+        // || G v || approaches lambda_max from below, hence the margin; a bad estimate only costs iterations, and past the
+        // convergence radius the loop below hands over to the Jacobi kernel)
+        if (warp == 0) {
+            const double v_init = 1.0 / sqrt((double)L);
+            double v0 = lane < L ? v_init : 0.0, v1 = lane + 32 < L ? v_init : 0.0, lam = 0.0;
+            for (int it = 0; it < 12; ++it) {
+                red[lane] = v0;
+                red[lane + 32] = v1;
+                __syncwarp();
+                double w0 = 0.0, w1 = 0.0;
+                for (int k = 0; k < L; ++k) {
+                    const double vk = red[k];
+                    if (lane < L) w0 = fma((lane == k ? 3.0 : 0.0) - 2.0 * C[(size_t)lane * PX + k], vk, w0);
+                    if (lane + 32 < L) w1 = fma((lane + 32 == k ? 3.0 : 0.0) - 2.0 * C[(size_t)(lane + 32) * PX + k], vk, w1);
+                }
+                lam = sqrt(warp_sum(w0 * w0 + w1 * w1));
+                const double inv = lam > 0.0 ? 1.0 / lam : 0.0;
+                v0 = w0 * inv;
+                v1 = w1 * inv;
+                __syncwarp();
+            }
+            if (lane == 0) s_scale = lam > 0.0 ? 1.0 / sqrt(1.05 * lam) : 0.0;
+        }
         __syncthreads();
         const double sc = s_scale;
         for (int i = tid; i < p * PX; i += nthr) X[i] *= sc;
