@@ -23,13 +23,20 @@ TABLE = {
     "Matern32": [(1, 1, .1), (.5, .5, .1), (2, .3, .05), (.5, .3, .5)],
     "Matern52": [(1, 1, .1), (.5, .5, .1), (.5, .3, .05), (.5, .5, .5)],
 }
+# the same, restricted to hyper-parameters where the LITERAL backward smoother (ihgp.h:105-113) is stable too:
+# rho(G) = 0.32, 0.03, 0.21, 0.40 (Matern-3/2) and 0.35, 0.22, 0.60, 0.22 (Matern-5/2) at dt = 0.1, so that smoothed means can
+# be compared over whole sequences of any length (the default Matern-3/2 entry (1, 1, .1) has rho(G) = 6.39 and overflows)
+LITERAL_STABLE = {
+    "Matern32": [(.5, .5, .1), (2, .3, .05), (.5, .3, .5), (10, 1, .1)],
+    "Matern52": TABLE["Matern52"],
+}
 
 
-def make_params(rng, p, L, kernel):
+def make_params(rng, p, L, kernel, table=None):
     U = (np.eye(p, L) + 0.3 * rng.standard_normal((p, L))).ravel()
     S = rng.uniform(0.5, 2.0, L)
     sigma = 0.05
-    tbl = TABLE[kernel]
+    tbl = (table or TABLE)[kernel]
     igp = np.array([tbl[l % len(tbl)] for l in range(L)], dtype=np.float64).ravel()
     return np.concatenate([U, S, [sigma], igp])
 
@@ -90,6 +97,33 @@ def case(kernel, threading, p, L, T, seed, dt=0.1):
     return out
 
 
+def smoother_case(kernel, p, L, T, seed, dt=0.1):
+    """IHGP::backwardSmoother (ihgp.h:103-114) of the reference over a WHOLE sequence of its own filtered states, for
+    hyper-parameters where its gain is stable (LITERAL_STABLE), so that the fixture pins smoothed means and the
+    smoothed covariance at full length rather than on a 40-step prefix."""
+    rng = np.random.default_rng(seed)
+    params = make_params(rng, p, L, kernel, LITERAL_STABLE)
+    Y = make_data(rng, p, L, T, dt)
+    ref = RefMOIHGP(dt, p, L, kernel, False)
+    ref.update(params)
+    X, _, nll = ref.filter_nll(Y)
+    out = {"kernel": kernel, "p": p, "L": L, "T": T, "dt": dt, "params": params, "Y": Y, "flt_X": X, "flt_nll": nll}
+    Xs = np.zeros_like(X)
+    P = np.zeros((L, ref.d, ref.d))
+    G = np.zeros((L, ref.d, ref.d))
+    for l in range(L):
+        Xs[:, l, :], P[l], G[l] = ref.ihgp_smoother(params[p * L + L + 1 + 3 * l:][:3], X[:, l, :])
+    out.update(sm_Xs=Xs, sm_P=P, sm_G=G)
+    return out
+
+
+SMOOTHER_CASES = [
+    # name, kernel, p, L, T, seed
+    ("lit_m32_p8L4_T700", "Matern32", 8, 4, 700, 21),
+    ("lit_m52_p16L8_T600", "Matern52", 16, 8, 600, 22),
+    ("lit_m32_p5L3_T300", "Matern32", 5, 3, 300, 23),
+]
+
 CASES = [
     # name, kernel, threading, p, L, T, seed
     ("c1_m32_p2L1_T63", "Matern32", True, 2, 1, 63, 1234),     # BASELINE config 1 shape (example_regression.cpp)
@@ -107,4 +141,9 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     for name, kernel, thr, p, L, T, seed in CASES:
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **case(kernel, thr, p, L, T, seed))
+        print("wrote", name)
+    out2 = os.path.join(OUT, "..", "golden_smoother")
+    os.makedirs(out2, exist_ok=True)
+    for name, kernel, p, L, T, seed in SMOOTHER_CASES:
+        np.savez_compressed(os.path.join(out2, name + ".npz"), **smoother_case(kernel, p, L, T, seed))
         print("wrote", name)

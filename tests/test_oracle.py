@@ -51,10 +51,11 @@ def test_oracle_matches_reference_golden(path):
         G, P = o.smoother_consts(l, 0)
         Xs = o.ihgp_smooth(l, 0, g["flt_X"][: min(T, 40), l, :])
         assert rel_err(G, g["sm%d_G" % l]) < TOL
-        if np.all(np.isfinite(g["sm%d_P" % l])) and np.max(np.abs(g["sm%d_P" % l])) < 1e100:
-            assert rel_err(P, g["sm%d_P" % l]) < 1e-7   # iterate #100 of an unconverged map: looser
-        if np.all(np.isfinite(g["sm%d_Xs" % l])) and np.max(np.abs(g["sm%d_Xs" % l])) < 1e100:
-            assert rel_err(Xs, g["sm%d_Xs" % l]) < 1e-7
+        # P is iterate #100 of the reference's un-converged DLyap map (Q2; 2.5e162 for the default Matern-3/2 latent) and the
+        # literal recursion grows like 6.39^n there (Q3) - both are still well-defined numbers and agree far inside TOL
+        assert np.all(np.isfinite(g["sm%d_P" % l])) and np.all(np.isfinite(g["sm%d_Xs" % l]))
+        assert rel_err(P, g["sm%d_P" % l]) < TOL
+        assert rel_err(Xs, g["sm%d_Xs" % l]) < TOL
     # missing observations (moihgp.h:150-178), predict-only (moihgp.h:381-428), single-step likelihoods
     for i in range(3):
         xn, yh, dxn = o.step(g["one_x"], g["nan%d_y" % i], g["one_dx"])
@@ -64,6 +65,31 @@ def test_oracle_matches_reference_golden(path):
     l1, g1 = o.negLogLikelihood(g["one_x"], g["one_y"], g["one_dx"])
     assert abs(l1 - g["one_lik1"]) <= TOL * abs(g["one_lik1"]) and rel_err(g1, g["one_grad"]) < TOL
     assert abs(o.negLogLikelihood(g["one_x"], g["one_y"]) - g["one_lik2"]) <= TOL * abs(g["one_lik2"])
+
+
+def smoother_cases():
+    import glob
+    import os
+    from conftest import ROOT
+    return sorted(glob.glob(os.path.join(ROOT, "tests", "golden_smoother", "*.npz")))
+
+
+@pytest.mark.parametrize("path", smoother_cases(), ids=lambda p: p.split("/")[-1][:-4])
+def test_oracle_matches_reference_smoother_over_whole_sequences(path):
+    """tests/golden_smoother: the reference's IHGP::backwardSmoother (ihgp.h:103-114) run over WHOLE sequences of its own
+    filtered states, hyper-parameters with rho(G) < 1 (oracle/gen_golden.py: LITERAL_STABLE) - means, covariance, gain."""
+    g = load_golden(path)
+    L = int(g["L"])
+    o = OracleMOIHGP(float(g["dt"]), int(g["p"]), L, str(g["kernel"]), False)
+    o.update(g["params"])
+    r = o.filter_smoother_nll(g["Y"], smoother_mode=0)
+    assert rel_err(r["X"][0], g["flt_X"]) < TOL and abs(r["nll"][0] - g["flt_nll"]) <= TOL * abs(g["flt_nll"])
+    assert rel_err(r["Xs"][0], g["sm_Xs"]) < TOL
+    for l in range(L):
+        G, P = o.smoother_consts(l, 0)
+        assert max(abs(np.linalg.eigvals(G))) < 1.0
+        assert rel_err(G, g["sm_G"][l]) < TOL and rel_err(P, g["sm_P"][l]) < TOL
+        assert rel_err(r["Xs"][0][:, l], g["sm_Xs"][:, l]) < TOL, l
 
 
 def test_survey_anchor_values():
