@@ -265,6 +265,47 @@ def cpu_reference_rate(kind, kernel, p, L, N, T, seed, budget_s, nthreads, repea
     return rate, what + ", " + what_impl, dt_, used, ("reference" if use_ref else "port")
 
 
+def workload_setup(name, nseq=0, tlen=0):
+    kind, kernel, p, L, N, T = WORKLOADS[name]
+    if nseq:
+        N = nseq
+    if tlen:
+        T = tlen
+    d = 3 if kernel == "Matern52" else 2
+    seed = 1234 + {"c3": 2, "c4": 3, "c5": 4}[name]   # 1234 + config index
+    metric = METRIC if kind == "fsn" else "latent time-steps/sec (NLL+gradient objective, fp64)"
+    ybytes = 8.0 * N * T * p
+    cfg = {"workload": WORKLOAD_DESC[name], "kernel": kernel, "p": p, "L": L, "d": d, "sequences_per_gpu": N, "T": T,
+           "dt": DT, "pass": "filter + RTS smoother + NLL (writes X, Xs, nll); smoother_mode = RTS (this library's extension: the reference's "
+                             "literal IHGP::backwardSmoother, which the reference arm runs, does the same work per step but is unstable for "
+                             "the default Matern-3/2 latent, SURVEY Q3)" if kind == "fsn" else "NLL + gradient (writes loss, grad[num_param])",
+           "sharding": "sequences over ranks, no data-path collective; all-reduce of the summed NLL only" if kind == "fsn"
+                       else "independent sequences over ranks; fp64 all-reduce of [loss, grad]",
+           "l2": "inputs (%.1f GB/GPU) larger than L2 (126 MB), no flush needed" % (ybytes / 1e9)}
+    return kind, kernel, p, L, N, T, d, seed, metric, cfg
+
+
+def source_hash():
+    """sha256 over the CUDA sources: profiles/traffic.json is only quoted while it describes THESE kernels."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "multioutputihgp_b200", "csrc", "*"))):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(os.path.basename(f).encode())
+            h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+FP64_PEAK_TFLOPS = 37.0   # measured here: scripts/microbench/fp64_rate.cu, profiles/r01/fp64_rate_microbench.txt (DMMA m8n8k4)
+
+
+def objective_flops_per_step(p, L, d):
+    """algorithmic flops of one sequence-step of the NLL + gradient objective"""
+    K = 3
+    return 6.0 * p * L + L * (2 * d * d + 2 * d + K * (4 * d * d + 2 * d) + 4 * K * d + 30)
+
+
 def emit(line):
     """The ONE JSON line goes to the process's real stdout; everything else printed while running (NCCL's version
     banner, library chatter) was redirected to stderr by main()."""
@@ -274,84 +315,17 @@ def emit(line):
 _REAL_STDOUT = 1
 
 
-def main():
-    global _REAL_STDOUT
-    sys.stdout.flush()
-    _REAL_STDOUT = os.dup(1)
-    os.dup2(2, 1)
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
-    ap.add_argument("--nseq", type=int, default=0, help="override sequences per GPU (debug only: not the benchmark config)")
-    ap.add_argument("--tlen", type=int, default=0, help="override T (debug only)")
-    ap.add_argument("--path", default="auto", choices=["auto", "scan", "chain"], help="force a kernel path (debug only)")
-    ap.add_argument("--spw", type=int, default=0, help="many-chains kernels: sequences per warp (debug only; 0 = automatic)")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    a = ap.parse_args()
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    kind, kernel, p, L, N, T = WORKLOADS[a.workload]
-    if a.nseq:
-        N = a.nseq
-    if a.tlen:
-        T = a.tlen
-    d = 3 if kernel == "Matern52" else 2
-    seed = 1234 + {"c3": 2, "c4": 3, "c5": 4}[a.workload]   # 1234 + config index
-    steps, warmup = max(a.steps, 1), max(a.warmup, 3)
-    metric = METRIC if kind == "fsn" else "latent time-steps/sec (NLL+gradient objective, fp64)"
-    ybytes = 8.0 * N * T * p
-    cfg = {"workload": WORKLOAD_DESC[a.workload], "kernel": kernel, "p": p, "L": L, "d": d, "sequences_per_gpu": N, "T": T,
-           "dt": DT, "pass": "filter + RTS smoother + NLL (writes X, Xs, nll)" if kind == "fsn" else "NLL + gradient (writes loss, grad[num_param])",
-           "sharding": "sequences over ranks, no data-path collective; all-reduce of the summed NLL only" if kind == "fsn"
-                       else "independent sequences over ranks; fp64 all-reduce of [loss, grad]",
-           "l2": "inputs (%.1f GB/GPU) larger than L2 (126 MB), no flush needed" % (ybytes / 1e9)}
-    cores = len(os.sched_getaffinity(0))
-
-    # ------------------------------------------------------------------ reference arm (CPU)
-    if a.impl == "reference":
-        if rank != 0:
-            return
-        t0 = time.perf_counter()
-        # every step is the same bounded sample, sized so that warmup + steps of them take about two minutes
-        per = max(1.0, min(10.0, 120.0 / (warmup + steps)))
-        r, what, dts, used, ckind = cpu_reference_rate(kind, kernel, p, L, N, T, seed, budget_s=per, nthreads=cores, repeats=warmup + steps)
-        rates = r[warmup:]
-        samples = [(what, t) for t in dts[warmup:]]
-        value = float(np.mean(rates))
-        sample = samples[-1][0] + " per step"
-        line = {"impl": "reference", "metric": metric, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": warmup,
-                "ms_per_step": 1e3 * float(np.mean([s[1] for s in samples])), "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-                "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": ckind, "sample": sample},
-                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "note": "kind=reference: the reference's own classes (MOIHGP::step v3 + negLogLikelihood(x,y) per observation, then "
-                        "IHGP::backwardSmoother per latent) compiled from /root/reference against the Eigen-API shim (Eigen itself is "
-                        "absent from the image), literal smoother; kind=port: oracle/moihgp_oracle.cpp; wall %.0f s" % (time.perf_counter() - t0)}
-        emit(line)
-        return
-
-    # ------------------------------------------------------------------ our arm (B200)
-    import torch
-    import torch.distributed as dist
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
-    torch.cuda.set_device(local_rank)
+def run_ours(a, wl, torch, dist, rank, local_rank, world, steps, warmup, cores, with_e2e, with_cpu, nseq=0, tlen=0):
+    """One workload on this rank's GPU: device-resident timed region (+ e2e through the host-buffer C ABI, + CPU baseline).
+    Returns the JSON line (rank 0) or None."""
+    kind, kernel, p, L, N, T, d, seed, metric, cfg = workload_setup(wl, nseq, tlen)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     from multioutputihgp_b200 import MOIHGPSequences
     model = MOIHGPSequences(DT, p, L, kernel, threading=True, device=local_rank)
     params, Hmix = model_params(p, L, kernel, seed)
     model.update(params)
-    model.set_path(a.path)
-    model.set_chain_seqs_per_warp(a.spw)
+    model.set_path(a.path if wl == a.workload else "auto")
+    model.set_chain_seqs_per_warp(a.spw if wl == a.workload else 0)
     stab = check_stability(model, L)
 
     Y = make_data_device(torch, dev, Hmix, N, T, p, L, seed, rank)
@@ -437,13 +411,25 @@ def main():
     roof["frac"] = roof["achieved"] / peak
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            roof["traffic"] = json.load(f).get(a.workload, {}).get("fused_pass_dram_bytes_per_step")
+            tj = json.load(f).get(wl, {})
+        # DRAM bytes per step from the ncu --set full capture of this workload; quoted only while the capture describes the
+        # kernels that just ran (same source hash, same size) - otherwise null, never a stale constant
+        if tj.get("source_hash") == source_hash() and not nseq and not tlen:
+            roof["traffic"] = tj.get("fused_pass_dram_bytes_per_step")
+            roof["traffic_source"] = tj.get("source")
+        else:
+            roof["traffic_note"] = "profiles/traffic.json was captured with other kernel sources (hash %s, now %s) or another size" % (tj.get("source_hash"), source_hash())
     except Exception:
         pass
+    if kind == "obj":
+        fl = objective_flops_per_step(p, L, d) * N * T
+        roof["fp64"] = {"flops_per_step": fl, "achieved_tflops": fl / (pass_ms * 1e-3) / 1e12, "peak_tflops": FP64_PEAK_TFLOPS,
+                        "frac": fl / (pass_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
+                        "note": "this pass is FP64-compute-bound (48 flop/B), not HBM-bound: SURVEY 8(d)"}
 
     # ------------------------------------------------------------------ e2e: host buffers through the C ABI
     e2e = None
-    if not a.no_e2e:
+    if with_e2e:
         import psutil
         lib, h = model._lib, model._h
         model.set_stream(None)
@@ -499,7 +485,7 @@ def main():
 
     # ------------------------------------------------------------------ CPU baseline beside it (rank 0, N = 1 only)
     cpu = None
-    if rank == 0 and world == 1 and not a.no_cpu:
+    if rank == 0 and world == 1 and with_cpu:
         r, what, dt_, used, ckind = cpu_reference_rate(kind, kernel, p, L, N, T, seed, budget_s=a.cpu_seconds, nthreads=cores)
         cpu = {"value": r, "unit": UNIT, "cores": used, "kind": ckind, "sample": "%s, %.1f s" % (what, dt_)}
 
@@ -509,6 +495,85 @@ def main():
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "hbm_GBps_alg": balg * units / world / (ms_per_step * 1e-3) / 1e9,
                 ("nll_total" if kind == "fsn" else "loss_total"): result_scalar, "stability": stab}
+        return line
+    return None
+
+
+def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--nseq", type=int, default=0, help="override sequences per GPU (debug only: not the benchmark config)")
+    ap.add_argument("--tlen", type=int, default=0, help="override T (debug only)")
+    ap.add_argument("--path", default="auto", choices=["auto", "scan", "chain"], help="force a kernel path (debug only)")
+    ap.add_argument("--spw", type=int, default=0, help="many-chains kernels: sequences per warp (debug only; 0 = automatic)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the extra configs[3] / configs[4] device passes of the default run")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    steps, warmup = max(a.steps, 1), max(a.warmup, 3)
+    cores = len(os.sched_getaffinity(0))
+    kind, kernel, p, L, N, T, d, seed, metric, cfg = workload_setup(a.workload, a.nseq, a.tlen)
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        t0 = time.perf_counter()
+        # every step is the same bounded sample, sized so that warmup + steps of them take about two minutes
+        per = max(1.0, min(10.0, 120.0 / (warmup + steps)))
+        r, what, dts, used, ckind = cpu_reference_rate(kind, kernel, p, L, N, T, seed, budget_s=per, nthreads=cores, repeats=warmup + steps)
+        rates = r[warmup:]
+        samples = [(what, t) for t in dts[warmup:]]
+        value = float(np.mean(rates))
+        sample = samples[-1][0] + " per step"
+        line = {"impl": "reference", "metric": metric, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": warmup,
+                "ms_per_step": 1e3 * float(np.mean([s[1] for s in samples])), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": ckind, "sample": sample},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "kind=reference: the reference's own classes (MOIHGP::step v3 + negLogLikelihood(x,y) per observation, then "
+                        "IHGP::backwardSmoother per latent) compiled from /root/reference against the Eigen-API shim (Eigen itself is "
+                        "absent from the image), literal smoother; kind=port: oracle/moihgp_oracle.cpp; wall %.0f s" % (time.perf_counter() - t0)}
+        emit(line)
+        return
+
+    # ------------------------------------------------------------------ our arm (B200)
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    line = run_ours(a, a.workload, torch, dist, rank, local_rank, world, steps, warmup, cores, not a.no_e2e, not a.no_cpu, a.nseq, a.tlen)
+    # the other single-GPU BASELINE configurations, device-resident passes only (a second or two each), so that the one
+    # line the driver records also witnesses configs[3] and configs[4]
+    if world == 1 and a.workload == "c3" and not a.no_also and not a.nseq and not a.tlen:
+        also = {}
+        for wl in ("c4", "c5"):
+            torch.cuda.empty_cache()
+            sub = run_ours(a, wl, torch, dist, rank, local_rank, world, min(steps, 10), warmup, cores, False, False)
+            r = sub["roofline"]
+            also[wl] = {"workload": sub["config"]["workload"], "metric": sub["metric"], "value": sub["value"], "unit": sub["unit"],
+                        "ms_per_step": sub["ms_per_step"], "steps": sub["steps"], "gpu_launches": sub["gpu_launches"], "clocks": sub["clocks"],
+                        "roofline": {k: r.get(k) for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "traffic_note",
+                                                           "algorithmic_bytes_per_latent_step", "kernels_ms_event_bracketed", "fp64")}}
+        line["also"] = also
+    if rank == 0:
         emit(line)
     if world > 1:
         dist.destroy_process_group()

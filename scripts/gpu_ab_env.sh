@@ -1,14 +1,17 @@
-# A/B of an environment switch in one GPU session: usage  gpu_ab_env.sh VAR  (runs bench with VAR unset and VAR=0, 3 reps)
+#!/bin/bash
+# A/B of one environment knob over bench workloads (run under gpurun):
+#   scripts/gpu_ab_env.sh <workload> "<bench flags>" VAR v1 v2 ...     ('-' = variable unset)
 cd ${GRAFT_REPO_ROOT:-.}; mkdir -p gpurun_out
-VAR=$1
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-for rep in 1 2 3; do
-for v in default off; do
-if [ $v = off ]; then export $VAR=0; else unset $VAR; fi
-python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu > gpurun_out/ab_$v.json 2>/dev/null
-python - <<PY
+wl=$1; flags=$2; var=$3; shift 3
+for v in "$@"; do
+  if [ "$v" = "-" ]; then unset $var; else export $var=$v; fi
+  python bench.py --workload $wl $flags --no-e2e --no-cpu > gpurun_out/ab_${wl}_${var}_$v.json 2> gpurun_out/ab_${wl}_${var}_$v.err || tail -3 gpurun_out/ab_${wl}_${var}_$v.err
+  python - <<PY
 import json
-d = json.load(open("gpurun_out/ab_$v.json"))
-print("$VAR $v rep$rep", round(d["ms_per_step"], 3), d["roofline"]["kernels_ms_event_bracketed"], d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
+try:
+    d = json.load(open("gpurun_out/ab_${wl}_${var}_$v.json"))
+    print("$wl $var=$v", "ms %.4f" % d["ms_per_step"], "frac %.4f" % d["roofline"]["frac"], d["roofline"]["kernels_ms_event_bracketed"])
+except Exception as e:
+    print("$wl $var=$v failed:", e)
 PY
-done; done
+done
