@@ -8,7 +8,9 @@
  *      (gp32_* at wrapper.cpp:31-326, gp52_* at :329-624) with the same signatures, argument
  *      layouts and (absent) error convention, so that the reference's moihgp/pywrapper.py
  *      (ctypes bindings at pywrapper.py:28-145) loads this library unchanged.  One observation
- *      per call; each call is one small kernel launch on the GPU.
+ *      per call; each call is one small kernel launch on the GPU.  One extension: gpXX_step1 / gpXX_step2 accept
+ *      y == NULL and then take the prediction step with the derivative states (xnew = A x, dxnew_k = dA_k x + A dx_k:
+ *      IHGP::step's NaN branch, ihgp.h:39-47), which the reference's wrapper cannot express.
  *
  *  (2) WHOLE-SEQUENCE symbols (moihgp_cuda_*) - the device boundary moved up to where the
  *      reference's callers loop over observations:
@@ -126,6 +128,12 @@ int moihgp_cuda_filter_smoother_nll(moihgp_handle* h, const double* Y, size_t N,
 /* same, DEVICE buffers already resident in HBM; asynchronous on the handle's stream */
 int moihgp_cuda_filter_smoother_nll_dev(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0,
                                         int smoother_mode, double* X, double* Xs, double* Yhat, double* nll, double* xT);
+
+/* IHGP::backwardSmoother(X, Xprev, P, G) (ihgp.h:103-114) for every latent, over CALLER-SUPPLIED filtered states
+ * X[N][T][L][d] (not necessarily produced by this library): Xs[N][T][L][d] per `smoother_mode` (0 = the reference's
+ * recursion as written, 1 = RTS).  G and P of each latent come from moihgp_cuda_smoother_consts.  HOST / DEVICE buffers. */
+int moihgp_cuda_smooth(moihgp_handle* h, const double* X, size_t N, size_t T, int smoother_mode, double* Xs);
+int moihgp_cuda_smooth_dev(moihgp_handle* h, const double* X, size_t N, size_t T, int smoother_mode, double* Xs);
 
 /* RegressionObjective::operator() / OnlineObjective::operator() window loop over N sequences
  * (moihgp_regression.h:42-50, moihgp_online.h:61-70): loss = sum_n sum_t negLogLikelihood(x, y, dx, grad)

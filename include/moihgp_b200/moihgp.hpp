@@ -2,16 +2,20 @@
 // libmoihgp.so (include/moihgp_b200.h).  Header-only, no dependency beyond the C ABI.
 //
 // Same class and method names, argument meaning and (absent) error behaviour as the reference:
-//   moihgp::MOIHGP<StateSpace>              moihgp/include/moihgp/moihgp.h:76-757
+//   moihgp::IHGP<StateSpace>                moihgp/include/moihgp/ihgp.h:17-263     (public members :243-254)
+//   moihgp::MOIHGP<StateSpace>              moihgp/include/moihgp/moihgp.h:76-757   (public U, S, dA, sigma :741-744)
 //   moihgp::RegressionObjective<StateSpace> moihgp/include/moihgp/moihgp_regression.h:17-70
 //   moihgp::OnlineObjective<StateSpace>     moihgp/include/moihgp/moihgp_online.h:18-115
-// living in namespace moihgp_b200 so that both header sets can be included side by side; a reference build switches
-// with `namespace moihgp = moihgp_b200;`.
+// (the learners MOIHGPRegression / MOIHGPOnlineLearning around LBFGS++ are in learners.hpp) living in namespace
+// moihgp_b200 so that both header sets can be included side by side.  include/moihgp_b200/dropin/ holds headers with the
+// REFERENCE'S OWN include paths (<moihgp/moihgp_regression.h> ...) that alias these classes into namespace moihgp with
+// Eigen types: the reference's cpp_examples compile against them unchanged.
 //
-// The reference's vector type is Eigen::VectorXd.  Eigen is not a dependency here: every class takes the vector type
-// as a template parameter `Vec` (default std::vector<double>) and only needs size(), resize(n), data() and operator[]
-// - which Eigen::VectorXd provides - so `MOIHGP<Matern32StateSpace, Eigen::VectorXd>` gives the reference's exact
-// signatures, and the functors plug into LBFGSpp::LBFGSBSolver::minimize(f, x, fx, lb, ub) unchanged.
+// The reference's vector / matrix types are Eigen::VectorXd / Eigen::MatrixXd.  Eigen is not a dependency here: every
+// class takes them as template parameters `Vec` (default std::vector<double>: needs size(), resize(n), operator[]) and
+// `Mat` (default DenseMatrix below: needs resize(r, c), operator()(i, j)) - which Eigen provides - so
+// `MOIHGP<Matern32StateSpace, Eigen::VectorXd, Eigen::MatrixXd>` gives the reference's exact signatures, and the functors
+// plug into LBFGSpp::LBFGSBSolver::minimize(f, x, fx, lb, ub) unchanged.
 //
 // What runs where: the per-observation methods (step, negLogLikelihood) are one small kernel launch each (the legacy
 // gpXX_* path); the objective functors hand the WHOLE window / data set to moihgp_cuda_objective - one fused device pass
@@ -19,6 +23,8 @@
 #ifndef MOIHGP_B200_MOIHGP_HPP
 #define MOIHGP_B200_MOIHGP_HPP
 
+#include <algorithm>
+#include <cmath>
 #include <cstddef>
 #include <list>
 #include <stdexcept>
@@ -31,8 +37,38 @@ namespace moihgp_b200 {
 
 // StateSpace tags (the reference's duck-typed classes matern32ss.h:13-99 / matern52ss.h:13-110 reduce, on this side of
 // the boundary, to the choice of kernel; their arithmetic runs in the K-setup kernel)
-struct Matern32StateSpace { static constexpr int kernel = MOIHGP_MATERN32; static constexpr int dim = 2; };
-struct Matern52StateSpace { static constexpr int kernel = MOIHGP_MATERN52; static constexpr int dim = 3; };
+// Of the duck type (matern32ss.h:67-91) they keep getDim / getNumParam / getParams / update; F, Pinf, dF, dPinf are
+// internal to K-setup and not exposed.
+template <int KERNEL, int DIM>
+struct StateSpaceTag {
+    static constexpr int kernel = KERNEL;
+    static constexpr int dim = DIM;
+    StateSpaceTag() { _p[0] = 1.0; _p[1] = 1.0; _p[2] = 0.1; }          // matern32ss.h:35 / matern52ss.h:33
+    size_t getDim() const { return DIM; }
+    size_t getNumParam() const { return 3; }
+    template <typename Vec> void update(const Vec& params) { for (int i = 0; i < 3; ++i) _p[i] = params[i]; }
+    std::vector<double> getParams() const { return std::vector<double>(_p, _p + 3); }
+private:
+    double _p[3];
+};
+typedef StateSpaceTag<MOIHGP_MATERN32, 2> Matern32StateSpace;
+typedef StateSpaceTag<MOIHGP_MATERN52, 3> Matern52StateSpace;
+
+// Default matrix type (column-major like Eigen's): just enough for the public members U, A, Q, K, ...
+struct DenseMatrix {
+    DenseMatrix() : _r(0), _c(0) {}
+    DenseMatrix(size_t r, size_t c) : _r(r), _c(c), _d(r * c, 0.0) {}
+    void resize(size_t r, size_t c) { _r = r; _c = c; _d.assign(r * c, 0.0); }
+    size_t rows() const { return _r; }
+    size_t cols() const { return _c; }
+    double& operator()(size_t i, size_t j) { return _d[i + j * _r]; }
+    const double& operator()(size_t i, size_t j) const { return _d[i + j * _r]; }
+    double* data() { return _d.empty() ? NULL : &_d[0]; }
+    const double* data() const { return _d.empty() ? NULL : &_d[0]; }
+private:
+    size_t _r, _c;
+    std::vector<double> _d;
+};
 
 namespace detail {
 template <typename Vec> inline Vec make_vec(size_t n) { Vec v; v.resize(n); for (size_t i = 0; i < n; ++i) v[i] = 0.0; return v; }
@@ -42,12 +78,164 @@ inline void check(moihgp_handle* h, int rc, const char* where) {
 }  // namespace detail
 
 // ------------------------------------------------------------------------------------------------------------------
+// IHGP<StateSpace>   (ihgp.h:17-263): ONE latent infinite-horizon GP.  On this side of the boundary it is a device model
+// with one output and one latent whose mixing is the identity (U = 1, S = 1): Ty = y, yhat = xnew(0), and
+// MOIHGP::negLogLikelihood(x, y) reduces to 1/2 (v^2 / S + log S) exactly (the residual term is identically 0).
+template <typename StateSpace, typename Vec = std::vector<double>, typename Mat = DenseMatrix>
+class IHGP {
+public:
+    IHGP(const double& dt, int device = -1) : _h(NULL), _dim(StateSpace::dim), _num_param(3) {        // ihgp.h:22-34
+        if (moihgp_cuda_create(&_h, StateSpace::kernel, dt, 1, 1, 0, device) != 0 || !_h)
+            throw std::runtime_error("moihgp_cuda_create failed (no B200-class CUDA device? there is no CPU fallback)");
+        refresh();
+    }
+    ~IHGP() { if (_h) moihgp_cuda_destroy(_h); }
+
+    // ihgp.h:37-57.  NaN = missing observation: prediction step xnew = A x, dxnew_k = dA_k x + A dx_k (:39-47)
+    void step(const Vec& x, const double& y, const std::vector<Vec>& dx, Vec& xnew, double& yhat, std::vector<Vec>& dxnew) {
+        double xb[3], dxb[9], xn[3], dxn[9], yy = y, yh = 0.0;
+        pack(x, dx, xb, dxb);
+        gp32_step1(_h, xb, std::isnan(y) ? NULL : &yy, dxb, xn, &yh, dxn);
+        unpack(xn, dxn, xnew, &dxnew);
+        yhat = yh;
+    }
+    // ihgp.h:60-78
+    void step(const Vec& x, const double& y, const std::vector<Vec>& dx, Vec& xnew, std::vector<Vec>& dxnew) {
+        double yhat;
+        step(x, y, dx, xnew, yhat, dxnew);
+    }
+    // ihgp.h:81-93
+    void step(const Vec& x, const double& y, Vec& xnew, double& yhat) {
+        double xb[3], xn[3], yy = y, yh = 0.0;
+        for (size_t i = 0; i < _dim; ++i) xb[i] = x[i];
+        if (std::isnan(y)) gp32_step4(_h, xb, xn, &yh); else gp32_step3(_h, xb, &yy, xn, &yh);
+        xnew.resize(_dim);
+        for (size_t i = 0; i < _dim; ++i) xnew[i] = xn[i];
+        yhat = yh;
+    }
+    // ihgp.h:96-100
+    void step(const Vec& x, Vec& xnew, double& yhat) {
+        double xb[3], xn[3], yh = 0.0;
+        for (size_t i = 0; i < _dim; ++i) xb[i] = x[i];
+        gp32_step4(_h, xb, xn, &yh);
+        xnew.resize(_dim);
+        for (size_t i = 0; i < _dim; ++i) xnew[i] = xn[i];
+        yhat = yh;
+    }
+
+    // ihgp.h:103-114: the reference's recursion as written, on the caller's filtered states X; like the
+    // reference it appends to Xprev and then reverses it.  P, G: smoothed covariance and gain.
+    void backwardSmoother(const std::vector<Vec>& X, std::vector<Vec>& Xprev, Mat& P, Mat& G) {
+        const size_t n = X.size();
+        double g[9], pm[9];
+        detail::check(_h, moihgp_cuda_smoother_consts(_h, 0, MOIHGP_SMOOTH_REFERENCE_LITERAL, g, pm), "IHGP::backwardSmoother");
+        P.resize(_dim, _dim); G.resize(_dim, _dim);
+        for (size_t i = 0; i < _dim; ++i) for (size_t j = 0; j < _dim; ++j) { G(i, j) = g[i * _dim + j]; P(i, j) = pm[i * _dim + j]; }
+        if (n == 0) return;
+        std::vector<double> xin(n * _dim), xout(n * _dim);
+        for (size_t t = 0; t < n; ++t) for (size_t i = 0; i < _dim; ++i) xin[t * _dim + i] = X[t][i];
+        detail::check(_h, moihgp_cuda_smooth(_h, &xin[0], 1, n, MOIHGP_SMOOTH_REFERENCE_LITERAL, &xout[0]), "IHGP::backwardSmoother");
+        for (size_t k = 0; k < n; ++k) {                 // Xprev.push_back(...) from the last step down (:108-112)
+            const size_t t = n - 1 - k;
+            Vec v; v.resize(_dim);
+            for (size_t i = 0; i < _dim; ++i) v[i] = xout[t * _dim + i];
+            Xprev.push_back(v);
+        }
+        std::reverse(Xprev.begin(), Xprev.end());        // :113
+    }
+
+    // ihgp.h:117-201 (K-setup kernel)
+    void update(const Vec& params) {
+        double pb[6] = {1.0, 1.0, 1e-2, params[0], params[1], params[2]};     // U = 1, S = 1, sigma (unused by an IHGP)
+        detail::check(_h, moihgp_cuda_update(_h, pb), "IHGP::update");
+        refresh();
+    }
+    // ihgp.h:204-209
+    double negLogLikelihood(const Vec& x, const double& y) {
+        double xb[3], yy = y;
+        for (size_t i = 0; i < _dim; ++i) xb[i] = x[i];
+        return gp32_lik2(_h, xb, &yy);
+    }
+    // ihgp.h:212-222: loss as above, grad[k] = (v dv_k - 1/2 (v^2/S - 1) dS_k) / S
+    double negLogLikelihood(const Vec& x, const double& y, const std::vector<Vec>& dx, Vec& grad) {
+        double xb[3], dxb[9], g[6], yy = y;
+        pack(x, dx, xb, dxb);
+        gp32_lik1(_h, xb, &yy, dxb, g);                  // g = [dU, dS, dsigma, per-latent gradient (3)]
+        grad.resize(_num_param);
+        for (size_t k = 0; k < _num_param; ++k) grad[k] = g[3 + k];
+        return gp32_lik2(_h, xb, &yy);
+    }
+    Vec getParams() {                                    // ihgp.h:225-228
+        double pb[6];
+        moihgp_cuda_get_params(_h, pb);
+        Vec out = detail::make_vec<Vec>(3);
+        for (int k = 0; k < 3; ++k) out[k] = pb[3 + k];
+        return out;
+    }
+    size_t getNumParam() { return _num_param; }          // ihgp.h:231
+    size_t getDim() { return _dim; }                     // ihgp.h:237
+
+    // ihgp.h:243-254
+    Mat A, Q, K, S, PF, HA, AKHA;
+    std::vector<Mat> dS, dA, dK, dAKHA, HdA;
+
+    moihgp_handle* handle() { return _h; }
+
+private:
+    IHGP(const IHGP&);
+    IHGP& operator=(const IHGP&);
+    void pack(const Vec& x, const std::vector<Vec>& dx, double* xb, double* dxb) const {
+        for (size_t i = 0; i < _dim; ++i) xb[i] = x[i];
+        for (size_t k = 0; k < _num_param; ++k) for (size_t i = 0; i < _dim; ++i) dxb[k * _dim + i] = dx[k][i];
+    }
+    void unpack(const double* xn, const double* dxn, Vec& xnew, std::vector<Vec>* dxnew) const {
+        xnew.resize(_dim);
+        for (size_t i = 0; i < _dim; ++i) xnew[i] = xn[i];
+        if (dxnew) {
+            dxnew->resize(_num_param);
+            for (size_t k = 0; k < _num_param; ++k) { (*dxnew)[k].resize(_dim); for (size_t i = 0; i < _dim; ++i) (*dxnew)[k][i] = dxn[k * _dim + i]; }
+        }
+    }
+    static void put(Mat& m, size_t r, size_t c, const double*& src) {        // row-major flat -> matrix
+        m.resize(r, c);
+        for (size_t i = 0; i < r; ++i) for (size_t j = 0; j < c; ++j) m(i, j) = *src++;
+    }
+    void refresh() {                                     // the public members, from the device's per-latent record
+        double flat[256];
+        const long long n = moihgp_cuda_latent_consts(_h, 0, flat, 256);
+        if (n < 0) throw std::runtime_error("moihgp_cuda_latent_consts failed");
+        const double* s = flat;
+        const size_t d = _dim;
+        put(A, d, d, s); put(Q, d, d, s); put(K, d, 1, s); put(S, 1, 1, s); put(PF, d, d, s); put(HA, 1, d, s); put(AKHA, d, d, s);
+        dS.resize(3); dA.resize(3); dK.resize(3); dAKHA.resize(3); HdA.resize(3);
+        for (int k = 0; k < 3; ++k) { put(dS[k], 1, 1, s); put(dA[k], d, d, s); put(dK[k], d, 1, s); put(dAKHA[k], d, d, s); put(HdA[k], d, 1, s); }
+    }
+    moihgp_handle* _h;
+    size_t _dim, _num_param;
+};
+
+// ------------------------------------------------------------------------------------------------------------------
 // MOIHGP<StateSpace>   (moihgp.h:76-757)
-template <typename StateSpace, typename Vec = std::vector<double> >
+template <typename StateSpace, typename Vec = std::vector<double>, typename Mat = DenseMatrix>
 class MOIHGP {
 public:
     typedef std::vector<Vec> State;                      // x[l]      : IGP state of latent l            (d)
     typedef std::vector<std::vector<Vec> > DState;       // dx[l][k]  : its derivative w.r.t. parameter k (d)
+
+    // moihgp.h:741-744.  U (p x L polar factor), S (L) and sigma mirror the model on the device and are refreshed by the
+    // constructor and by update(); writing to them does not change the model (use update(params)).  dA[r * L + c] is the
+    // p x L unit matrix E_rc of the reference's dU loop (moihgp.h:94-101, :545) - generated on access: the reference
+    // stores all p*L of them (2 GB at p = 256, L = 64).
+    struct UnitMatrices {
+        UnitMatrices() : p(0), L(0) {}
+        size_t size() const { return p * L; }
+        Mat operator[](size_t idx) const { Mat m; m.resize(p, L); for (size_t r = 0; r < p; ++r) for (size_t c = 0; c < L; ++c) m(r, c) = 0.0; m(idx / L, idx % L) = 1.0; return m; }
+        size_t p, L;
+    };
+    Mat U;
+    Vec S;
+    UnitMatrices dA;
+    double sigma;
 
     // moihgp.h:81-136.  U starts as a random near-identity polar factor like the reference's (moihgp.h:103-125) when
     // `random_U` (the default, as the reference), or as the exact identity block otherwise.
@@ -76,6 +264,8 @@ public:
         _dxb.resize(2 * _num_latent * _igp_num_param * _dim);
         _yb.resize(2 * _num_output);
         _pb.resize(_num_param);
+        dA.p = _num_output; dA.L = _num_latent;
+        sync_public();
     }
     ~MOIHGP() { if (_h) moihgp_cuda_destroy(_h); }
 
@@ -108,6 +298,7 @@ public:
     void update(const Vec& params) {
         for (size_t i = 0; i < _num_param; ++i) _pb[i] = params[i];
         detail::check(_h, moihgp_cuda_update(_h, &_pb[0]), "MOIHGP::update");
+        sync_public();
     }
     // moihgp.h:460-611
     double negLogLikelihood(const State& x, const Vec& y, const DState& dx, Vec& grad) {
@@ -187,6 +378,14 @@ public:
 private:
     MOIHGP(const MOIHGP&);
     MOIHGP& operator=(const MOIHGP&);
+    void sync_public() {                                 // U, S, sigma as the device model holds them (moihgp.h:446-449)
+        moihgp_cuda_get_params(_h, &_pb[0]);             // U block = the polar factor
+        U.resize(_num_output, _num_latent);
+        for (size_t r = 0; r < _num_output; ++r) for (size_t c = 0; c < _num_latent; ++c) U(r, c) = _pb[r * _num_latent + c];
+        S.resize(_num_latent);
+        for (size_t l = 0; l < _num_latent; ++l) S[l] = _pb[_num_output * _num_latent + l];
+        sigma = _pb[_num_output * _num_latent + _num_latent];
+    }
     size_t nx() const { return _num_latent * _dim; }
     size_t ndx() const { return _num_latent * _igp_num_param * _dim; }
     void pack_x(const State& x, double* b) const { for (size_t l = 0; l < _num_latent; ++l) for (size_t i = 0; i < _dim; ++i) b[l * _dim + i] = x[l][i]; }
@@ -217,10 +416,10 @@ private:
 // RegressionObjective<StateSpace>   (moihgp_regression.h:17-70): the L-BFGS-B functor over the data set Y.
 // The reference's operator() never calls _gp->update(params) (it optimises a function that is constant in
 // params); `update_params = false` keeps that, `true` evaluates the objective AT params like OnlineObjective does.
-template <typename StateSpace, typename Vec = std::vector<double> >
+template <typename StateSpace, typename Vec = std::vector<double>, typename Mat = DenseMatrix>
 class RegressionObjective {
 public:
-    typedef MOIHGP<StateSpace, Vec> GP;
+    typedef MOIHGP<StateSpace, Vec, Mat> GP;
     RegressionObjective(const size_t& num_data, GP* gp, bool update_params = false) : _gp(gp), _update(update_params), _bound(0) { Y.reserve(num_data); }
 
     // Copy Y to the device once: every later operator() evaluates on that resident copy until rebind() / unbind().
@@ -270,10 +469,10 @@ struct NoBFGSMat {
 
 // ------------------------------------------------------------------------------------------------------------------
 // OnlineObjective<StateSpace>   (moihgp_online.h:18-115): sliding-window objective with the BFGS-proximal term.
-template <typename StateSpace, typename Vec = std::vector<double>, typename BFGSMat = NoBFGSMat<Vec> >
+template <typename StateSpace, typename Vec = std::vector<double>, typename BFGSMat = NoBFGSMat<Vec>, typename Mat = DenseMatrix>
 class OnlineObjective {
 public:
-    typedef MOIHGP<StateSpace, Vec> GP;
+    typedef MOIHGP<StateSpace, Vec, Mat> GP;
     OnlineObjective(GP* gp, const double& gamma, const size_t& windowsize) : _gp(gp), _gamma(gamma), _windowsize(windowsize) {
         oldparams = _gp->getParams();
         _x = typename GP::State(_gp->getNumLatent(), detail::make_vec<Vec>(_gp->getIGPDim()));

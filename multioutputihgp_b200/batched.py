@@ -229,6 +229,19 @@ class MOIHGPSequences(object):
             return host[:, :, :d].copy(), host[:, :, d].copy()
         return host
 
+    def smooth(self, X, smoother_mode=SMOOTH_REFERENCE_LITERAL):
+        """IHGP::backwardSmoother (ihgp.h:103-114) of every latent over caller-supplied filtered states X [N,T,L,d] (or
+        [T,L,d]); returns Xs of the same shape.  Gains / covariances: ``smoother_consts``."""
+        X = _np(X)
+        squeeze = X.ndim == 3
+        if squeeze:
+            X = X[None]
+        N, T, L, d = X.shape
+        assert L == self.num_latent and d == self.igp_dim
+        Xs = np.empty_like(X)
+        self._check(self._lib.moihgp_cuda_smooth(self._h, _ptr(X), N, T, int(smoother_mode), _ptr(Xs)))
+        return Xs[0] if squeeze else Xs
+
     def bind(self, Y):
         """Copy the observations to the device once; ``objective_bound`` then evaluates on them at the current parameters
         (the L-BFGS loop calls the objective tens of times on the same data).  ``bind(None)`` releases them."""

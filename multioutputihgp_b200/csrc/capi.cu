@@ -728,6 +728,31 @@ int moihgp_cuda_filter_smoother_nll(moihgp_handle* h, const double* Y, size_t N,
     return 0;
 }
 
+int moihgp_cuda_smooth_dev(moihgp_handle* h, const double* X, size_t N, size_t T, int mode, double* Xs) {
+    if (!h || !X || !Xs) return -2;
+    if (N == 0 || T == 0) return fail(h, "N and T must be positive");
+    if (mode < 0 || mode > 1) return fail(h, "smoother_mode must be 0 or 1");
+    cudaSetDevice(h->device);
+    CK(launch_smooth_seq(X, h->d_consts, h->L, h->dim, (long long)N, (long long)T, mode, Xs, h->stream));
+    h->launches += 1;
+    return 0;
+}
+
+int moihgp_cuda_smooth(moihgp_handle* h, const double* X, size_t N, size_t T, int mode, double* Xs) {
+    if (!h || !X || !Xs) return -2;
+    if (N == 0 || T == 0) return fail(h, "N and T must be positive");
+    cudaSetDevice(h->device);
+    const size_t n = N * T * (size_t)h->L * h->dim;
+    double *dX, *dXs;
+    if (ws_get(h, "smX", n, &dX) || ws_get(h, "smXs", n, &dXs)) return -1;
+    CK(cudaMemcpyAsync(dX, X, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    const int rc = moihgp_cuda_smooth_dev(h, dX, N, T, mode, dXs);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(Xs, dXs, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 // phase 0: whole evaluation; 1: begin (projection, summaries, block end from a zero carry-in -> zend, device);
 // 2: finish (from the true carry-in; reuses the workspace phase 1 filled)
 static int objective_phase(moihgp_handle* h, int phase, const double* Y, size_t N, size_t T, const double* x0, const double* dx0,

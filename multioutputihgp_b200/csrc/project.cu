@@ -377,6 +377,11 @@ struct RowsSmem {
     }
 };
 
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tma_load_box(void* dst_smem, const CUtensorMap* tm, int col, int row, unsigned long long* bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
                  ::"r"(smem_u32(dst_smem)), "l"(tm), "r"(col), "r"(row), "r"(smem_u32(bar)) : "memory");
@@ -398,7 +403,8 @@ __global__ void __launch_bounds__(32 * NW, 1) k_project_rows(const __grid_consta
     using SMC = RowsSmem<NB>;
     extern __shared__ unsigned char smraw_unaligned[];
     unsigned char* smraw = smraw_unaligned + ((1024u - (smem_u32(smraw_unaligned) & 1023u)) & 1023u);   // swizzle atoms are 1 KB
-    const int tid = threadIdx.x, lane = tid & 31, wi = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int wi = __shfl_sync(FULL, tid >> 5, 0);           // provably warp-uniform: the TMA issue path stays in uniform registers
     const int g4 = lane >> 2, q4 = lane & 3;
     const int P16 = SMC::p16(p);
     const unsigned stage_bytes = (unsigned)SMC::stage_bytes(nbox);
@@ -436,8 +442,9 @@ __global__ void __launch_bounds__(32 * NW, 1) k_project_rows(const __grid_consta
             const int c0 = ipn * KP;
             const int nb_ = min(nbox, (p - c0 + 15) >> 4);                                    // boxes that hold columns < p
             unsigned char* stg = ring + (size_t)ist * stage_bytes;
-            if (lane == 0) {
+            if (elect_one()) {
                 mbar_expect_tx(bars + ist, 2048u * (unsigned)nb_);
+#pragma unroll 4
                 for (int j = 0; j < nb_; ++j) tma_load_box(stg + j * 2048, &tmY, c0 + 16 * j, irow, bars + ist);
             }
             if (++ipn == NP) {

@@ -214,6 +214,38 @@ __global__ void __launch_bounds__(ST) k_lik(LikArgs a) {
     }
 }
 
+// IHGP::backwardSmoother (ihgp.h:108-113) over caller-supplied filtered states X[N][T][L][d] (any X, not necessarily the
+// output of this library's filter): one thread per (sequence, latent) chain walks backwards in time.  The generic,
+// shape-independent form behind moihgp_cuda_smooth; the fused passes use k_smooth_chain / k_scan_lanes instead.
+//   mode 0 (reference, literal): Xs[T-1] = X[T-1],  Xs[j] = X[j+1] + G Xs[j+1] - A X[j+1]
+//   mode 1 (RTS):                Xs[T-1] = X[T-1],  Xs[j] = X[j] + G (Xs[j+1] - A X[j])
+__global__ void __launch_bounds__(128) k_smooth_seq(const double* __restrict__ X, const LatentConsts* __restrict__ consts, int L, int d,
+                                                   long long N, long long T, int mode, double* __restrict__ Xs) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * L) return;
+    const long long n = i / L;
+    const int l = (int)(i - n * L);
+    const LatentConsts& c = consts[l];
+    const size_t stride = (size_t)L * d;
+    const double* x = X + ((size_t)n * T * L + l) * d;
+    double* xs = Xs + ((size_t)n * T * L + l) * d;
+    double s[DMAX], nx[DMAX];
+    for (int a = 0; a < d; ++a) { s[a] = x[(size_t)(T - 1) * stride + a]; nx[a] = s[a]; xs[(size_t)(T - 1) * stride + a] = s[a]; }
+    for (long long j = T - 2; j >= 0; --j) {
+        double cur[DMAX], out[DMAX];
+        for (int a = 0; a < d; ++a) cur[a] = x[(size_t)j * stride + a];
+        const double* drive = mode == 0 ? nx : cur;          // the literal form is driven by X[j+1] (Q3), RTS by X[j]
+        const double* B = mode == 0 ? c.ImA : c.Bs;          // I - A  /  I - G A
+        for (int a = 0; a < d; ++a) {
+            double acc = c.G[mode][a * 3] * s[0];
+            for (int b = 1; b < d; ++b) acc = fma(c.G[mode][a * 3 + b], s[b], acc);
+            for (int b = 0; b < d; ++b) acc = fma(B[a * 3 + b], drive[b], acc);
+            out[a] = acc;
+        }
+        for (int a = 0; a < d; ++a) { s[a] = out[a]; nx[a] = cur[a]; xs[(size_t)j * stride + a] = out[a]; }
+    }
+}
+
 size_t step_smem(int L) { return sizeof(double) * (3 * (size_t)L + 2 * (size_t)L * L + 2 * L) + sizeof(int) * ((size_t)L + 2); }
 size_t lik_smem(int L) { return sizeof(double) * (8 * (size_t)L + ST + 2 * (size_t)L * L + 2 * L) + sizeof(int) * ((size_t)L + 2); }
 
@@ -223,6 +255,13 @@ cudaError_t launch_step(const StepArgs& a, cudaStream_t st) {
     const size_t smem = step_smem(a.L);
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_step<<<1, ST, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_smooth_seq(const double* X, const LatentConsts* consts, int L, int d, long long N, long long T, int mode, double* Xs,
+                              cudaStream_t st) {
+    const long long chains = N * L;
+    k_smooth_seq<<<(unsigned)((chains + 127) / 128), 128, 0, st>>>(X, consts, L, d, N, T, mode, Xs);
     return cudaGetLastError();
 }
 

@@ -19,6 +19,9 @@ void oracle_step2(void* h, const double* x, const double* y, const double* dx, d
 double oracle_lik1(void* h, const double* x, const double* y, const double* dx, double* grad, int literal);
 double oracle_lik2(void* h, const double* x, const double* y, int literal);
 double oracle_objective(void* h, const double* Y, size_t N, size_t T, double* x, double* dx, double* grad, int literal);
+size_t oracle_ihgp_consts(void* h, size_t l, double* out);
+void oracle_smoother_consts(void* h, size_t l, int mode, double* G, double* P);
+void oracle_ihgp_smooth(void* h, size_t l, int mode, const double* X, size_t n, double* Xs);
 void oracle_filter_smoother_nll(void* h, const double* Y, size_t N, size_t T, double* x, double* X, double* Xs, double* Yhat, double* nll,
                                 int smoother_mode, int nthreads);
 }
@@ -188,7 +191,123 @@ static void run(int kernel, size_t p, size_t L, size_t T, bool threading, unsign
     oracle_del(o);
 }
 
+// IHGP<StateSpace> (ihgp.h:17-263): public members, the four step overloads (incl. the NaN prediction branch), both
+// negLogLikelihood overloads, backwardSmoother, update / getParams - against the oracle's single-latent model.
+template <typename SS>
+static void run_ihgp(int kernel, unsigned seed) {
+    using namespace moihgp_b200;
+    std::mt19937 gen(seed);
+    std::normal_distribution<> nrm(0.0, 1.0);
+    const double dt = 0.1;
+    IHGP<SS> gp(dt);
+    void* o = oracle_new(kernel, dt, 1, 1, 0);
+    const size_t d = gp.getDim();
+    Vec prm(3);
+    prm[0] = 0.5; prm[1] = 0.5; prm[2] = 0.1;                                 // rho(G) < 1 in the literal smoother too
+    gp.update(prm);
+    const double op[6] = {1.0, 1.0, 1e-2, prm[0], prm[1], prm[2]};
+    oracle_update(o, op);
+    expect("IHGP::getParams", rel_err(gp.getParams().data(), prm.data(), 3));
+    // public members (ihgp.h:243-254) against the oracle's flat record: A Q K S PF HA AKHA, then per k: dS dA dK dAKHA HdA
+    double flat[256];
+    oracle_ihgp_consts(o, 0, flat);
+    std::vector<double> mine;
+    auto add = [&](const DenseMatrix& m) { for (size_t i = 0; i < m.rows(); ++i) for (size_t j = 0; j < m.cols(); ++j) mine.push_back(m(i, j)); };
+    add(gp.A); add(gp.Q); add(gp.K); add(gp.S); add(gp.PF); add(gp.HA); add(gp.AKHA);
+    for (int k = 0; k < 3; ++k) { add(gp.dS[k]); add(gp.dA[k]); add(gp.dK[k]); add(gp.dAKHA[k]); add(gp.HdA[k]); }
+    expect("IHGP public members A..HdA", rel_err(mine.data(), flat, mine.size()));
+    // steps + likelihoods along a short sequence
+    Vec x(d, 0.0), xn, xo(d, 0.0), xno(d), dxo(3 * d, 0.0), dxno(3 * d), g, go(6);
+    std::vector<Vec> dx(3, Vec(d, 0.0)), dxn;
+    std::vector<Vec> X;
+    double e_x = 0, e_dx = 0, e_y = 0, e_l = 0, e_g = 0;
+    for (int t = 0; t < 60; ++t) {
+        const double y = std::sin(0.3 * t) + 0.1 * nrm(gen);
+        double yh = 0.0, yho = 0.0;
+        const double l1 = gp.negLogLikelihood(x, y, dx, g), l2 = gp.negLogLikelihood(x, y);
+        const double l2o = oracle_lik2(o, xo.data(), &y, 0);
+        oracle_lik1(o, xo.data(), &y, dxo.data(), go.data(), 0);
+        gp.step(x, y, dx, xn, yh, dxn);
+        oracle_step1(o, xo.data(), &y, dxo.data(), xno.data(), &yho, dxno.data());
+        Vec dflat(3 * d);
+        for (int k = 0; k < 3; ++k) for (size_t i = 0; i < d; ++i) dflat[k * d + i] = dxn[k][i];
+        e_x = std::fmax(e_x, rel_err(xn.data(), xno.data(), d));
+        e_dx = std::fmax(e_dx, rel_err(dflat.data(), dxno.data(), 3 * d));
+        e_y = std::fmax(e_y, std::fabs(yh - yho) / std::fmax(std::fabs(yho), 1e-300));
+        e_l = std::fmax(e_l, std::fmax(std::fabs(l1 - l2o), std::fabs(l2 - l2o)) / std::fabs(l2o));
+        e_g = std::fmax(e_g, rel_err(g.data(), go.data() + 3, 3));
+        x = xn; dx = dxn; xo = xno; dxo = dxno;
+        X.push_back(x);
+    }
+    expect("IHGP::step xnew", e_x);
+    expect("IHGP::step dxnew", e_dx);
+    expect("IHGP::step yhat", e_y);
+    expect("IHGP::negLogLikelihood (both overloads) loss", e_l);
+    expect("IHGP::negLogLikelihood grad", e_g);
+    // NaN observation: prediction step xnew = A x, dxnew_k = dA_k x + A dx_k (ihgp.h:39-47), also through step(x, xnew, yhat)
+    {
+        double yh = 0.0, yh4 = 0.0;
+        Vec x4;
+        gp.step(x, std::nan(""), dx, xn, yh, dxn);
+        gp.step(x, x4, yh4);
+        Vec want(d, 0.0), wd(3 * d, 0.0), got(3 * d);
+        for (size_t i = 0; i < d; ++i) for (size_t j = 0; j < d; ++j) want[i] += gp.A(i, j) * x[j];
+        for (int k = 0; k < 3; ++k) for (size_t i = 0; i < d; ++i) {
+            for (size_t j = 0; j < d; ++j) wd[k * d + i] += gp.dA[k](i, j) * x[j] + gp.A(i, j) * dx[k][j];
+            got[k * d + i] = dxn[k][i];
+        }
+        expect("IHGP::step(NaN) xnew = A x", rel_err(xn.data(), want.data(), d), 1e-14);
+        expect("IHGP::step(NaN) dxnew = dA x + A dx", rel_err(got.data(), wd.data(), 3 * d), 1e-13);
+        expect("IHGP::step(x, xnew, yhat)", rel_err(x4.data(), want.data(), d) + std::fabs(yh4 - want[0]) + std::fabs(yh - want[0]), 1e-14);
+    }
+    // backwardSmoother (ihgp.h:103-114) on the filtered states
+    {
+        std::vector<Vec> Xprev;
+        DenseMatrix P, G;
+        gp.backwardSmoother(X, Xprev, P, G);
+        std::vector<double> xin(X.size() * d), xso(X.size() * d), xs(X.size() * d), Go(d * d), Po(d * d), Gm(d * d), Pm(d * d);
+        for (size_t t = 0; t < X.size(); ++t) for (size_t i = 0; i < d; ++i) { xin[t * d + i] = X[t][i]; xs[t * d + i] = Xprev[t][i]; }
+        oracle_ihgp_smooth(o, 0, 0, xin.data(), X.size(), xso.data());
+        oracle_smoother_consts(o, 0, 0, Go.data(), Po.data());
+        for (size_t i = 0; i < d; ++i) for (size_t j = 0; j < d; ++j) { Gm[i * d + j] = G(i, j); Pm[i * d + j] = P(i, j); }
+        expect("IHGP::backwardSmoother Xprev", Xprev.size() == X.size() ? rel_err(xs.data(), xso.data(), xs.size()) : 1.0);
+        expect("IHGP::backwardSmoother G", rel_err(Gm.data(), Go.data(), d * d));
+        expect("IHGP::backwardSmoother P", rel_err(Pm.data(), Po.data(), d * d));
+    }
+    oracle_del(o);
+}
+
+// MOIHGP public members U, S, dA, sigma (moihgp.h:741-744)
+static void run_public_members() {
+    using namespace moihgp_b200;
+    const size_t p = 5, L = 2;
+    MOIHGP<Matern32StateSpace> gp(0.1, p, L, false);
+    Vec prm = gp.getParams();
+    prm[p * L] = 1.7; prm[p * L + 1] = 0.4; prm[p * L + L] = 0.03;
+    for (size_t i = 0; i < p * L; ++i) prm[i] += 0.05 * std::sin(1.0 + i);
+    gp.update(prm);
+    Vec now = gp.getParams();
+    double e = 0.0, orth = 0.0;
+    for (size_t r = 0; r < p; ++r) for (size_t c = 0; c < L; ++c) e = std::fmax(e, std::fabs(gp.U(r, c) - now[r * L + c]));
+    for (size_t a = 0; a < L; ++a) for (size_t b = 0; b < L; ++b) {
+        double s = 0.0;
+        for (size_t r = 0; r < p; ++r) s += gp.U(r, a) * gp.U(r, b);
+        orth = std::fmax(orth, std::fabs(s - (a == b ? 1.0 : 0.0)));
+    }
+    expect("MOIHGP::U == polar factor held by the model", e, 0.0);
+    expect("MOIHGP::U orthonormal columns", orth, 1e-13);
+    expect("MOIHGP::S, sigma", std::fabs(gp.S[0] - 1.7) + std::fabs(gp.S[1] - 0.4) + std::fabs(gp.sigma - 0.03), 0.0);
+    DenseMatrix E = gp.dA[1 * L + 1];
+    double s = 0.0;
+    for (size_t r = 0; r < p; ++r) for (size_t c = 0; c < L; ++c) s += E(r, c);
+    expect("MOIHGP::dA[idx] = unit matrix E_rc", std::fabs(s - 1.0) + std::fabs(E(1, 1) - 1.0) + (gp.dA.size() == p * L ? 0.0 : 1.0), 0.0);
+}
+
 int main() {
+    std::printf("-- IHGP<Matern32>, IHGP<Matern52>\n");
+    run_ihgp<moihgp_b200::Matern32StateSpace>(32, 5);
+    run_ihgp<moihgp_b200::Matern52StateSpace>(52, 6);
+    run_public_members();
     std::printf("-- Matern32, p=2, L=1, T=63 (example_regression shape)\n");
     run<moihgp_b200::Matern32StateSpace>(32, 2, 1, 63, false, 1);
     std::printf("-- Matern32, p=8, L=4, T=300, threading\n");
