@@ -165,13 +165,14 @@ class ClockSampler:
         return out
 
 
-def make_data_device(torch, dev, Hmix, N, T, p, L, seed, rank):
+def make_data_device(torch, dev, Hmix, N, T, p, L, seed, rank, t_offset=0):
     """Synthetic observations after example_regression.cpp:18-28: sinusoidal latents sin(w_l t + phi_n), mixed by Hmix,
-    plus 0.1 * U(-1, 1) noise.  Built block-wise on the device."""
+    plus 0.1 * U(-1, 1) noise.  Built block-wise on the device.  t_offset: first time step (a rank's block of one long
+    sequence sharded in time)."""
     g = torch.Generator(device=dev)
     g.manual_seed(seed + 7919 * rank)
     Y = torch.empty((N, T, p), dtype=torch.float64, device=dev)
-    t = torch.arange(T, dtype=torch.float64, device=dev) * DT
+    t = (torch.arange(T, dtype=torch.float64, device=dev) + float(t_offset)) * DT
     w = 1.0 + 3.0 * torch.arange(L, dtype=torch.float64, device=dev) / max(L - 1, 1)
     H = torch.from_numpy(Hmix).to(dev)
     nb = 128
@@ -315,10 +316,24 @@ def emit(line):
 _REAL_STDOUT = 1
 
 
-def run_ours(a, wl, torch, dist, rank, local_rank, world, steps, warmup, cores, with_e2e, with_cpu, nseq=0, tlen=0):
+def run_ours(a, wl, torch, dist, rank, local_rank, world, steps, warmup, cores, with_e2e, with_cpu, nseq=0, tlen=0, shard="auto"):
     """One workload on this rank's GPU: device-resident timed region (+ e2e through the host-buffer C ABI, + CPU baseline).
-    Returns the JSON line (rank 0) or None."""
+    Returns the JSON line (rank 0) or None.
+    shard: "sequences" = weak scaling (every rank its own sequences); "time" = STRONG scaling of the objective (BASELINE
+    configs[4]: the ONE sequence of T steps is cut into contiguous blocks of time, one per rank; carry exchange by NCCL
+    all-gather + a device kernel, [loss, grad] by NCCL all-reduce); "auto" = time for the objective when world > 1."""
     kind, kernel, p, L, N, T, d, seed, metric, cfg = workload_setup(wl, nseq, tlen)
+    time_shard = kind == "obj" and world > 1 and shard in ("auto", "time")
+    T_total = T
+    if time_shard:
+        from multioutputihgp_b200.parallel import time_block_bounds_aligned
+        bounds = [time_block_bounds_aligned(T_total, world, r) for r in range(world)]
+        t_lo, t_hi = bounds[rank]
+        T = t_hi - t_lo
+        cfg["sharding"] = ("ONE sequence cut into %d contiguous blocks of time (whole 256-step chunks), one per rank: begin -> NCCL all-gather of "
+                           "the block ends (L*d*4 doubles per rank) -> carry-in kernel -> finish -> NCCL all-reduce of [loss, grad]; no host "
+                           "round trip inside an evaluation" % world)
+        cfg["T_per_gpu"] = [b[1] - b[0] for b in bounds]
     dev = torch.device("cuda", local_rank)
     from multioutputihgp_b200 import MOIHGPSequences
     model = MOIHGPSequences(DT, p, L, kernel, threading=True, device=local_rank)
@@ -328,7 +343,15 @@ def run_ours(a, wl, torch, dist, rank, local_rank, world, steps, warmup, cores, 
     model.set_chain_seqs_per_warp(a.spw if wl == a.workload else 0)
     stab = check_stability(model, L)
 
-    Y = make_data_device(torch, dev, Hmix, N, T, p, L, seed, rank)
+    if time_shard:
+        # every rank builds the SAME whole sequence (rank 0's seed) and keeps its block: loss_total is then comparable with
+        # the one-GPU evaluation of the same workload
+        Yfull = make_data_device(torch, dev, Hmix, N, T_total, p, L, seed, 0)
+        Y = Yfull[:, t_lo:t_hi].contiguous()
+        del Yfull
+        torch.cuda.empty_cache()
+    else:
+        Y = make_data_device(torch, dev, Hmix, N, T, p, L, seed, rank)
     if kind == "fsn":
         X = torch.empty((N, T, L, d), dtype=torch.float64, device=dev)
         Xs = torch.empty_like(X)
@@ -343,6 +366,13 @@ def run_ours(a, wl, torch, dist, rank, local_rank, world, steps, warmup, cores, 
             torch.sum(nll, dim=0, keepdim=True, out=out)
             if world > 1 and not os.environ.get("BENCH_SKIP_ALLREDUCE"):      # (diagnosis only: isolates the collective's cost)
                 dist.all_reduce(out)
+    elif time_shard:
+        from multioutputihgp_b200.parallel import TimeShardedDeviceObjective
+        tso = TimeShardedDeviceObjective(model, [b[1] - b[0] for b in bounds], num_sequences=N)
+        out = tso.buf                                                              # [loss, pad, grad...] (all-reduced in enqueue)
+
+        def step():
+            tso.enqueue(Y)
     else:
         out = torch.zeros(2 + model.num_param, dtype=torch.float64, device=dev)   # [loss, pad, grad...] (all-reduced)
 
@@ -382,7 +412,7 @@ def run_ours(a, wl, torch, dist, rank, local_rank, world, steps, warmup, cores, 
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(ms.item())
-    units = float(N) * T * L * world
+    units = float(N) * T_total * L if time_shard else float(N) * T * L * world
     value = units / (ms_per_step * 1e-3)
     result_scalar = float(out[0].item())
 
@@ -429,7 +459,7 @@ def run_ours(a, wl, torch, dist, rank, local_rank, world, steps, warmup, cores, 
 
     # ------------------------------------------------------------------ e2e: host buffers through the C ABI
     e2e = None
-    if with_e2e:
+    if with_e2e and not time_shard:
         import psutil
         lib, h = model._lib, model._h
         model.set_stream(None)
@@ -491,8 +521,8 @@ def run_ours(a, wl, torch, dist, rank, local_rank, world, steps, warmup, cores, 
 
     if rank == 0:
         line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "higher_is_better": True, "scaling": "strong" if time_shard else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": cfg, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "hbm_GBps_alg": balg * units / world / (ms_per_step * 1e-3) / 1e9,
                 ("nll_total" if kind == "fsn" else "loss_total"): result_scalar, "stability": stab}
         return line
@@ -514,6 +544,9 @@ def main():
     ap.add_argument("--tlen", type=int, default=0, help="override T (debug only)")
     ap.add_argument("--path", default="auto", choices=["auto", "scan", "chain"], help="force a kernel path (debug only)")
     ap.add_argument("--spw", type=int, default=0, help="many-chains kernels: sequences per warp (debug only; 0 = automatic)")
+    ap.add_argument("--shard", default="auto", choices=["auto", "time", "sequences"],
+                    help="multi-GPU objective (c5): 'time' = one sequence cut into blocks of time (strong scaling, the default for c5), "
+                         "'sequences' = independent sequences per rank (weak scaling)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the extra configs[3] / configs[4] device passes of the default run")
@@ -559,7 +592,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    line = run_ours(a, a.workload, torch, dist, rank, local_rank, world, steps, warmup, cores, not a.no_e2e, not a.no_cpu, a.nseq, a.tlen)
+    line = run_ours(a, a.workload, torch, dist, rank, local_rank, world, steps, warmup, cores, not a.no_e2e, not a.no_cpu, a.nseq, a.tlen, a.shard)
     # the other single-GPU BASELINE configurations, device-resident passes only (a second or two each), so that the one
     # line the driver records also witnesses configs[3] and configs[4]
     if world == 1 and a.workload == "c3" and not a.no_also and not a.nseq and not a.tlen:
@@ -570,9 +603,21 @@ def main():
             r = sub["roofline"]
             also[wl] = {"workload": sub["config"]["workload"], "metric": sub["metric"], "value": sub["value"], "unit": sub["unit"],
                         "ms_per_step": sub["ms_per_step"], "steps": sub["steps"], "gpu_launches": sub["gpu_launches"], "clocks": sub["clocks"],
+                        "result_total": sub.get("nll_total", sub.get("loss_total")),
                         "roofline": {k: r.get(k) for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "traffic_note",
                                                            "algorithmic_bytes_per_latent_step", "kernels_ms_event_bracketed", "fp64")}}
         line["also"] = also
+    # BASELINE configs[4] as quoted ("NLL+gradient sharded over 8 GPUs with NCCL all-reduce"): the ONE T = 1e6 sequence
+    # sharded in TIME over the ranks of this run - strong scaling, next to the weak-scaling headline
+    if world > 1 and a.workload == "c3" and not a.no_also and not a.nseq and not a.tlen:
+        torch.cuda.empty_cache()
+        sub = run_ours(a, "c5", torch, dist, rank, local_rank, world, min(steps, 20), warmup, cores, False, False, shard="time")
+        if rank == 0:
+            line["also"] = {"c5_time_sharded": {"workload": sub["config"]["workload"], "sharding": sub["config"]["sharding"], "metric": sub["metric"],
+                                                "value": sub["value"], "unit": sub["unit"], "ms_per_step": sub["ms_per_step"], "scaling": sub["scaling"],
+                                                "n_gpus": world, "steps": sub["steps"], "gpu_launches": sub["gpu_launches"], "clocks": sub["clocks"],
+                                                "loss_total": sub.get("loss_total"),
+                                                "kernels_ms_event_bracketed": sub["roofline"]["kernels_ms_event_bracketed"]}}
     if rank == 0:
         emit(line)
     if world > 1:

@@ -161,6 +161,15 @@ int moihgp_cuda_objective_dev(moihgp_handle* h, const double* Y, size_t N, size_
 int moihgp_cuda_objective_begin_dev(moihgp_handle* h, const double* Y, size_t N, size_t T, double* zend_host);
 int moihgp_cuda_objective_finish_dev(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0, const double* dx0,
                                      double* loss, double* grad, double* xT, double* dxT);
+/* The same exchange WITHOUT host round trips (everything asynchronous on the handle's stream, so that the caller's
+ * all-gather - NCCL on the same stream - sits between the two calls):
+ *   begin_async : like begin, the end state goes to DEVICE memory zend_dev[N][L][4][d] (NULL on the last block)
+ *   carry_in_dev: ends_dev[G][N][L][4][d] = every block's end state (all-gathered); block `rank`'s true carry-in
+ *                 z_in(g+1) = T(n_g) z_in(g) + ends_g, chained over g < rank from (x0, dx0) (device, NULL = zeros), is
+ *                 written to xin_dev[N][L][d], dxin_dev[N][L][3][d] - pass them to finish_dev.  block_lengths: G host values. */
+int moihgp_cuda_objective_begin_async(moihgp_handle* h, const double* Y, size_t N, size_t T, double* zend_dev);
+int moihgp_cuda_carry_in_dev(moihgp_handle* h, const double* ends_dev, size_t G, const long long* block_lengths, size_t rank, size_t N,
+                             const double* x0_dev, const double* dx0_dev, double* xin_dev, double* dxin_dev);
 /* The block transition T(n) of the carry exchange above, per latent: out[L][4][d*d] = [AKHA^n, E_0(n), E_1(n), E_2(n)]
  * (row-major d x d), E_k(n) = sum_i AKHA^(n-1-i) dAKHA_k AKHA^i, so that for a block of n steps
  *   x_out = AKHA^n x_in + x_out(0),   dx_k,out = AKHA^n dx_k,in + E_k(n) x_in + dx_k,out(0)      (ihgp.h:71-77 unrolled).

@@ -110,6 +110,10 @@ def load():
     lib.moihgp_cuda_objective_begin_dev.argtypes = [vp, vp, sz, sz, vp]
     lib.moihgp_cuda_objective_finish_dev.restype = ctypes.c_int
     lib.moihgp_cuda_objective_finish_dev.argtypes = obj
+    lib.moihgp_cuda_objective_begin_async.restype = ctypes.c_int
+    lib.moihgp_cuda_objective_begin_async.argtypes = [vp, vp, sz, sz, vp]
+    lib.moihgp_cuda_carry_in_dev.restype = ctypes.c_int
+    lib.moihgp_cuda_carry_in_dev.argtypes = [vp, vp, sz, ctypes.POINTER(ctypes.c_longlong), sz, sz, vp, vp, vp, vp]
     lib.moihgp_cuda_block_transition.restype = ctypes.c_int
     lib.moihgp_cuda_block_transition.argtypes = [vp, sz, vp]
     lib.moihgp_cuda_fsn_block_dev.restype = ctypes.c_int
@@ -132,5 +136,5 @@ LEGACY_NAMES = ["new", "del", "step1", "step2", "step3", "step4", "update", "lik
                 "num_param", "num_igp_param"]
 CUDA_NAMES = ["create", "destroy", "set_stream", "sync", "last_error", "launch_count", "profile", "profile_read", "set_path", "set_chain_seqs_per_warp", "igp_dim", "num_param",
               "num_igp_param", "update", "get_params", "get_U", "latent_consts", "latent_iters", "smoother_consts",
-              "filter_smoother_nll", "filter_smoother_nll_dev", "objective", "objective_dev", "bind_data", "objective_bound", "objective_begin_dev", "objective_finish_dev", "block_transition", "fsn_block_dev", "smoother_power", "smooth", "smooth_dev"]
+              "filter_smoother_nll", "filter_smoother_nll_dev", "objective", "objective_dev", "bind_data", "objective_bound", "objective_begin_dev", "objective_finish_dev", "block_transition", "fsn_block_dev", "smoother_power", "smooth", "smooth_dev", "objective_begin_async", "carry_in_dev"]
 ALL_SYMBOLS = ["gp%s_%s" % (xx, n) for xx in ("32", "52") for n in LEGACY_NAMES] + ["moihgp_cuda_" + n for n in CUDA_NAMES]

@@ -197,6 +197,21 @@ class MOIHGPSequences(object):
         self._check(self._lib.moihgp_cuda_objective_begin_dev(self._h, _ptr(Y), N, T, _ptr(z)))
         return (z[:, :, 0].copy(), z[:, :, 1:].copy()) if want_end else None
 
+    def objective_begin_async(self, Y, zend=None):
+        """Like objective_begin_device, without a host round trip: the block's end state from a zero carry-in goes to the
+        torch CUDA tensor ``zend`` [N,L,4,d] (None on the last block); asynchronous on torch's current stream."""
+        N, T, _ = Y.shape
+        self.set_stream(_torch_stream(Y.device))
+        self._check(self._lib.moihgp_cuda_objective_begin_async(self._h, _ptr(Y), N, T, _ptr(zend)))
+
+    def carry_in_device(self, ends, block_lengths, rank, xin, dxin, x0=None, dx0=None):
+        """This block's true carry-in from the all-gathered block ends ``ends`` [G,N,L,4,d] (torch CUDA tensors throughout):
+        z_in(g+1) = T(n_g) z_in(g) + ends_g chained over g < rank; written to xin [N,L,d], dxin [N,L,3,d]."""
+        G = len(block_lengths)
+        lens = (ctypes.c_longlong * G)(*[int(b) for b in block_lengths])
+        N = xin.shape[0]
+        self._check(self._lib.moihgp_cuda_carry_in_dev(self._h, _ptr(ends), G, lens, int(rank), N, _ptr(x0), _ptr(dx0), _ptr(xin), _ptr(dxin)))
+
     def objective_finish_device(self, Y, loss, grad, x0=None, dx0=None):
         """Step 2: loss / grad of the block from its true carry-in (torch CUDA tensors), reusing step 1's projection."""
         N, T, _ = Y.shape

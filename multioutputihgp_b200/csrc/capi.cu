@@ -816,6 +816,22 @@ int moihgp_cuda_objective_begin_dev(moihgp_handle* h, const double* Y, size_t N,
     return 0;
 }
 
+int moihgp_cuda_objective_begin_async(moihgp_handle* h, const double* Y, size_t N, size_t T, double* zend_dev) {
+    if (!h) return -2;
+    if (zend_dev && T % 256 != 0) return fail(h, "objective_begin: the block end state needs a block length that is a multiple of 256 steps");
+    return objective_phase(h, 1, Y, N, T, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, zend_dev);
+}
+
+int moihgp_cuda_carry_in_dev(moihgp_handle* h, const double* ends_dev, size_t G, const long long* block_lengths, size_t rank, size_t N,
+                             const double* x0_dev, const double* dx0_dev, double* xin_dev, double* dxin_dev) {
+    if (!h || !xin_dev || !dxin_dev || (rank > 0 && (!ends_dev || !block_lengths))) return -2;
+    if (rank >= G || G > 64) return fail(h, "carry_in: need rank < G <= 64 blocks");
+    cudaSetDevice(h->device);
+    CK(launch_block_carry(h->dim, h->d_consts, h->L, (long long)N, (int)rank, block_lengths, ends_dev, x0_dev, dx0_dev, xin_dev, dxin_dev, h->stream));
+    h->launches += 1;
+    return 0;
+}
+
 int moihgp_cuda_objective_finish_dev(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0, const double* dx0,
                                      double* loss, double* grad, double* xT, double* dxT) {
     if (!loss || !grad) return -2;

@@ -126,6 +126,10 @@ size_t obj_chunks(long long T);
 size_t obj_gu_splits(long long N, long long T);
 int obj_launch_count(long long T, int L);
 cudaError_t launch_objective(int dim, const ObjArgs& a, cudaStream_t st);
+// carry-in of time block `rank` from the gathered block ends (device arithmetic of moihgp_cuda_block_transition)
+cudaError_t launch_block_carry(int dim, const LatentConsts* consts, int L, long long N, int rank, const long long* block_lengths,
+                               const double* ends /*[G][N][L][4][D]*/, const double* x0, const double* dx0, double* xin, double* dxin,
+                               cudaStream_t st);
 size_t obj_small_smem(int p, int L, long long T);
 cudaError_t launch_objective_small(int dim, const double* Y, const double* U, const double* S, double sigma, const LatentConsts* consts,
                                    int p, int L, long long T, int threading, const double* x0, const double* dx0, double* out, double* xT,

@@ -151,13 +151,33 @@ class TimeShardedObjective(object):
     """loss, grad of ONE long sequence whose contiguous time blocks live on different ranks.
 
     ``evaluate(Y_block, x0, dx0) -> (loss, grad, xT, dxT)`` is the local evaluator (``MOIHGPSequences.objective`` with
-    ``want_state=True`` on a GPU box); ``consts`` the per-latent constants of the CURRENT hyper-parameters
-    (``[model.latent_consts(l) for l in range(L)]``); ``block_lengths[g]`` the number of time steps of rank g's block."""
+    ``want_state=True`` on a GPU box); ``block_lengths[g]`` the number of time steps of rank g's block.
 
-    def __init__(self, evaluate, consts, block_lengths, num_param, group=None, device=None):
+    ``consts`` gives the block transitions of the model's CURRENT hyper-parameters.  Inside an optimiser loop the
+    parameters change between calls (``model.update(params)`` then ``obj(Y_block)``), so pass something that is evaluated
+    on every call: a callable ``n -> (P [L,d,d], E [L,3,d,d])`` such as ``model.block_transition``, or a zero-argument
+    provider returning the per-latent constant dicts (``lambda: [model.latent_consts(l) for l in range(L)]``).  A plain
+    list of dicts / a stacked (AKHA, dAKHA) pair is taken as fixed - only right while the parameters do not change."""
+
+    def __init__(self, evaluate, consts, block_lengths, num_param, group=None, device=None, num_latent=None, igp_dim=None):
         self.evaluate, self.block_lengths = evaluate, [int(b) for b in block_lengths]
-        self.consts = consts if isinstance(consts, tuple) else stack_consts(consts)
+        self.consts = consts
         self.num_param, self.group, self.device = int(num_param), group, device
+        self.num_latent, self.igp_dim = num_latent, igp_dim
+
+    def _current(self):
+        """(transition or stacked constants of the current parameters, L, d)"""
+        c = self.consts
+        if callable(c):
+            try:
+                c = c()                                  # zero-argument provider of the per-latent constants
+            except TypeError:
+                if self.num_latent is not None and self.igp_dim is not None:
+                    return c, self.num_latent, self.igp_dim
+                P, _ = c(1)                              # n -> (P, E): shapes from one call
+                return c, P.shape[0], P.shape[-1]
+        st = c if isinstance(c, tuple) else stack_consts(c)
+        return st, st[0].shape[0], st[0].shape[-1]
 
     def _gather(self, vec, world):
         import torch
@@ -175,7 +195,7 @@ class TimeShardedObjective(object):
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
         world = dist.get_world_size(self.group) if multi else 1
         rank = dist.get_rank(self.group) if multi else 0
-        L, d = self.consts[0].shape[0], self.consts[0].shape[-1]
+        consts, L, d = self._current()
         x0 = np.zeros((L, d)) if x0 is None else np.asarray(x0, dtype=np.float64).reshape(L, d)
         dx0 = np.zeros((L, 3, d)) if dx0 is None else np.asarray(dx0, dtype=np.float64).reshape(L, 3, d)
         if not multi:
@@ -188,7 +208,7 @@ class TimeShardedObjective(object):
         ends_x = [e[:L * d].reshape(L, d) for e in ends]
         ends_dx = [e[L * d:].reshape(L, 3, d) for e in ends]
         # (3) true carry-in, (4) the block again, (5) all-reduce
-        xin, dxin = carry_in_from_block_ends(self.consts, self.block_lengths, ends_x, ends_dx, x0, dx0, rank)
+        xin, dxin = carry_in_from_block_ends(consts, self.block_lengths, ends_x, ends_dx, x0, dx0, rank)
         loss, grad, _, _ = self.evaluate(Y_block, xin, dxin)
         buf = torch.from_numpy(np.concatenate([[loss], np.asarray(grad, dtype=np.float64)]))
         if self.device is not None:
@@ -215,43 +235,48 @@ def time_block_bounds_aligned(T, world_size, rank, align=256):
 
 
 class TimeShardedDeviceObjective(object):
-    """One-pass variant on the GPU library: ``objective_begin_device`` projects the block and returns its end state from
-    a zero carry-in, the end states are all-gathered, ``objective_finish_device`` evaluates from the true carry-in reusing
-    the projection, and [loss, grad] is all-reduced in place on the device (NCCL).  One pass over the data per rank."""
+    """One-pass variant on the GPU library, with NO host round trip inside an evaluation: ``objective_begin_async``
+    projects the block and leaves its end state from a zero carry-in in device memory, NCCL all-gathers the end states on the
+    same stream, ``carry_in_device`` (a tiny kernel: the block transitions T(n_g) by binary powering on the device's power
+    tables) forms this rank's true carry-in, ``objective_finish_device`` evaluates from it reusing the projection, and
+    [loss, grad] is all-reduced in place.  Everything is queued on torch's current stream; ``__call__`` syncs once, at the
+    end, to hand [loss, grad] to the optimiser; ``enqueue`` does not sync at all."""
 
-    def __init__(self, model, block_lengths, group=None):
+    def __init__(self, model, block_lengths, group=None, num_sequences=1):
         import torch
         self.model, self.group = model, group
         self.block_lengths = [int(b) for b in block_lengths]
         self.dev = torch.device("cuda", torch.cuda.current_device())
-        self.buf = torch.zeros(2 + model.num_param, dtype=torch.float64, device=self.dev)
+        L, d, N, G = model.num_latent, model.igp_dim, int(num_sequences), len(self.block_lengths)
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        self.buf = torch.zeros(2 + model.num_param, **f64)
+        self.ends = torch.zeros((G, N, L, 4, d), **f64)              # all-gathered block ends
+        self.zend = torch.zeros((N, L, 4, d), **f64)                 # this block's end state from a zero carry-in
+        self.xin = torch.zeros((N, L, d), **f64)
+        self.dxin = torch.zeros((N, L, 3, d), **f64)
 
-    def __call__(self, Y_block_dev, x0=None, dx0=None):
-        import torch
+    def enqueue(self, Y_block_dev, x0=None, dx0=None):
+        """Queue one evaluation on the current stream; the result lands in ``self.buf`` = [loss, pad, grad...].
+        x0 / dx0: carried-in state of the WHOLE sequence (torch CUDA tensors or None = zeros)."""
         dist = _dist()
         m = self.model
-        L, d = m.num_latent, m.igp_dim
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
         world = dist.get_world_size(self.group) if multi else 1
         rank = dist.get_rank(self.group) if multi else 0
-        x0 = np.zeros((L, d)) if x0 is None else np.asarray(x0, dtype=np.float64).reshape(L, d)
-        dx0 = np.zeros((L, 3, d)) if dx0 is None else np.asarray(dx0, dtype=np.float64).reshape(L, 3, d)
         last = rank == world - 1
-        end = m.objective_begin_device(Y_block_dev, want_end=not last)
-        xin, dxin = x0, dx0
+        m.objective_begin_async(Y_block_dev, None if last else self.zend)
         if multi:
-            flat = np.zeros(L * d * 4) if last else np.concatenate([end[0][0].ravel(), end[1][0].ravel()])
-            t = torch.from_numpy(flat).to(self.dev)
-            out = [torch.empty_like(t) for _ in range(world)]
-            dist.all_gather(out, t, group=self.group)
-            ends = [o.cpu().numpy() for o in out]
-            xin, dxin = carry_in_from_block_ends(m.block_transition, self.block_lengths, [e[:L * d].reshape(L, d) for e in ends],
-                                                 [e[L * d:].reshape(L, 3, d) for e in ends], x0, dx0, rank)
-        x0d = torch.from_numpy(np.ascontiguousarray(xin[None])).to(self.dev)
-        dx0d = torch.from_numpy(np.ascontiguousarray(dxin[None])).to(self.dev)
-        m.objective_finish_device(Y_block_dev, self.buf[0:1], self.buf[2:], x0=x0d, dx0=dx0d)
+            dist.all_gather_into_tensor(self.ends, self.zend, group=self.group)
+        m.carry_in_device(self.ends, self.block_lengths, rank, self.xin, self.dxin, x0=x0, dx0=dx0)
+        m.objective_finish_device(Y_block_dev, self.buf[0:1], self.buf[2:], x0=self.xin, dx0=self.dxin)
         if multi:
             dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, group=self.group)
+
+    def __call__(self, Y_block_dev, x0=None, dx0=None):
+        import torch
+        to_dev = lambda a, shape: None if a is None else torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(shape))).to(self.dev)
+        N, L, d = self.xin.shape
+        self.enqueue(Y_block_dev, to_dev(x0, (N, L, d)), to_dev(dx0, (N, L, 3, d)))
         host = self.buf.cpu().numpy()
         return float(host[0]), host[2:].copy()
 

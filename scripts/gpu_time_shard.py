@@ -47,7 +47,7 @@ def evaluate_dev(_Yb, x0, dx0):
     return float(h[0]), h[2:].copy(), xT_dev.cpu().numpy()[0], dxT_dev.cpu().numpy()[0]
 
 
-obj = TimeShardedObjective(evaluate_dev, consts, [b[1] - b[0] for b in bounds], m.num_param, device=dev)
+obj = TimeShardedObjective(evaluate_dev, m.block_transition, [b[1] - b[0] for b in bounds], m.num_param, device=dev, num_latent=L, igp_dim=d)
 obj(None)                                             # warm-up
 dist.barrier()
 tic = time.perf_counter()

@@ -840,6 +840,66 @@ def test_one_launch_objective_matches_the_general_path_and_the_oracle(cuda_lib, 
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("kernel,p,L,N,cuts", [("Matern32", 16, 8, 1, (0, 512, 1280, 2048, 2300)), ("Matern52", 8, 4, 2, (0, 256, 768, 1000)),
+                                               ("Matern32", 256, 64, 1, (0, 1024, 2048, 3001))])
+def test_time_sharded_objective_device_side_exchange(cuda_lib, kernel, p, L, N, cuts):
+    """The host-round-trip-free protocol of the time-sharded objective on ONE device (one handle per block, as on its own
+    GPU): objective_begin_async leaves each block's end state in device memory, carry_in_device (binary powering of the block
+    transitions on the device) forms every block's carry-in from the stacked ends, objective_finish_device evaluates from it.
+    The carry-ins equal the host algebra (parallel.carry_in_from_block_ends) and the states of the whole-sequence evaluation;
+    the blocks' [loss, grad] add up to the whole-sequence evaluation and to the oracle's."""
+    import torch
+    from multioutputihgp_b200 import MOIHGPSequences
+    from multioutputihgp_b200.parallel import carry_in_from_block_ends
+    from oracle.binding import OracleMOIHGP
+    from oracle.gen_golden import make_data, make_params
+    rng = np.random.default_rng(sum(cuts) + p)
+    params = make_params(rng, p, L, kernel)
+    T, G = cuts[-1], len(cuts) - 1
+    lengths = [cuts[g + 1] - cuts[g] for g in range(G)]
+    Y = np.stack([make_data(rng, p, L, T) for _ in range(N)])
+    dev = torch.device("cuda:0")
+    models = []
+    for g in range(G):
+        m = MOIHGPSequences(0.1, p, L, kernel, True)
+        m.update(params)
+        models.append(m)
+    d = models[0].igp_dim
+    f64 = dict(dtype=torch.float64, device=dev)
+    x0 = 0.2 * rng.standard_normal((N, L, d))
+    dx0 = 0.1 * rng.standard_normal((N, L, 3, d))
+    x0d, dx0d = torch.from_numpy(x0).to(dev), torch.from_numpy(dx0).to(dev)
+    Yd = [torch.from_numpy(np.ascontiguousarray(Y[:, cuts[g]:cuts[g + 1]])).to(dev) for g in range(G)]
+    ends = torch.zeros((G, N, L, 4, d), **f64)
+    for g in range(G):
+        models[g].objective_begin_async(Yd[g], None if g == G - 1 else ends[g])
+    out = torch.zeros((G, 2 + models[0].num_param), **f64)
+    xin = torch.zeros((G, N, L, d), **f64)
+    dxin = torch.zeros((G, N, L, 3, d), **f64)
+    for g in range(G):
+        models[g].carry_in_device(ends, lengths, g, xin[g], dxin[g], x0=x0d, dx0=dx0d)
+        models[g].objective_finish_device(Yd[g], out[g, 0:1], out[g, 2:], x0=xin[g], dx0=dxin[g])
+    torch.cuda.synchronize()
+    eh = ends.cpu().numpy()
+    for g in range(G):
+        for n in range(N):
+            xh, dxh = carry_in_from_block_ends(models[0].block_transition, lengths, eh[:, n, :, 0], eh[:, n, :, 1:], x0[n], dx0[n], g)
+            assert rel_err(xin[g, n].cpu().numpy(), xh) < 1e-12 and rel_err(dxin[g, n].cpu().numpy(), dxh) < 1e-11, (g, n)
+    whole = MOIHGPSequences(0.1, p, L, kernel, True)
+    whole.update(params)
+    for g in range(1, G):                                   # the carried state is the state the sequence has at the cut
+        _, _, xT, dxT = whole.objective(Y[:, :cuts[g]], x0=x0, dx0=dx0, want_state=True)
+        assert rel_err(xin[g].cpu().numpy(), xT) < 1e-11 and rel_err(dxin[g].cpu().numpy(), dxT) < 1e-10, g
+    lw, gw = whole.objective(Y, x0=x0, dx0=dx0)
+    tot = out.sum(0).cpu().numpy()
+    assert abs(tot[0] - lw) <= 1e-10 * abs(lw) and rel_err(tot[2:], gw) < TOL
+    o = OracleMOIHGP(0.1, p, L, kernel, True)
+    o.update(params)
+    lo, go, _, _ = o.objective(Y, x0=x0, dx0=dx0)
+    assert _close(tot[0], lo) and rel_err(tot[2:], go) < TOL
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("p,L", [(256, 64), (128, 33), (100, 21), (512, 16)])
 def test_newton_schulz_polar_factor_agrees_with_jacobi(cuda_lib, p, L, monkeypatch):
     """update() on the device: k_polar_ns (Newton-Schulz, the fast way for a block that is nearly orthonormal, as inside a

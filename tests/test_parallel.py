@@ -122,7 +122,23 @@ def _time_worker(rank, world, port, T, out_dir):
     obj = TimeShardedObjective(evaluate, consts, [b[1] - b[0] for b in bounds], o.num_param)
     t0, t1 = bounds[rank]
     loss, grad = obj(Y[t0:t1])
-    np.savez(os.path.join(out_dir, "trank%d.npz" % rank), loss=loss, grad=grad)
+    # an optimiser loop changes the parameters between evaluations: with a provider / a callable the block transitions follow
+    params2 = params.copy()
+    params2[p * L + L + 1:] *= 1.3
+    params2[p * L:p * L + L] *= 0.8
+    prov = TimeShardedObjective(evaluate, lambda: [o.ihgp_consts(l) for l in range(L)], [b[1] - b[0] for b in bounds], o.num_param)
+
+    def transition(n):
+        from multioutputihgp_b200.parallel import block_transition, stack_consts
+        AK, dAK = stack_consts([o.ihgp_consts(l) for l in range(L)])
+        return block_transition(AK, dAK, n)
+    call = TimeShardedObjective(evaluate, transition, [b[1] - b[0] for b in bounds], o.num_param)
+    prov(Y[t0:t1])
+    call(Y[t0:t1])
+    o.update(params2)
+    loss2, grad2 = prov(Y[t0:t1])
+    loss3, grad3 = call(Y[t0:t1])
+    np.savez(os.path.join(out_dir, "trank%d.npz" % rank), loss=loss, grad=grad, loss2=loss2, grad2=grad2, loss3=loss3, grad3=grad3)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -142,10 +158,19 @@ def test_time_sharded_objective_gloo(tmp_path, world, T):
     o = OracleMOIHGP(0.1, p, L, "Matern52", threading=True)
     o.update(params)
     loss, grad = o.objective(Y[None])[:2]
+    params2 = params.copy()
+    params2[p * L + L + 1:] *= 1.3
+    params2[p * L:p * L + L] *= 0.8
+    o.update(params2)
+    loss2, grad2 = o.objective(Y[None])[:2]
     for r in range(world):
         z = np.load(os.path.join(str(tmp_path), "trank%d.npz" % r))
         assert abs(float(z["loss"]) - loss) <= 1e-11 * abs(loss)
         assert rel_err(z["grad"], grad) < 1e-10
+        # after update(params2): the provider / callable forms re-derive the block transitions on every call
+        for k in ("2", "3"):
+            assert abs(float(z["loss" + k]) - loss2) <= 1e-11 * abs(loss2), k
+            assert rel_err(z["grad" + k], grad2) < 1e-10, k
 
 
 class _OracleBlockModel(object):
