@@ -76,6 +76,8 @@ enum { MOIHGP_SMOOTH_NONE = -1, MOIHGP_SMOOTH_REFERENCE_LITERAL = 0, MOIHGP_SMOO
  * `threading` only selects the reference's loss semantics (moihgp.h:588 vs :601, forced off for L < 2). */
 int moihgp_cuda_create(moihgp_handle** out, int kernel, double dt, size_t num_output, size_t num_latent,
                        int threading, int device);
+/* Limits the reference does not have: 1 <= num_latent <= min(num_output, 64).  Every entry point runs on the handle's device
+ * and restores the caller's current CUDA device before it returns. */
 void moihgp_cuda_destroy(moihgp_handle* h);
 /* run every kernel of this handle on `cuda_stream` (a cudaStream_t); NULL = the handle's own (non-blocking) stream.
  * To share the legacy default stream pass cudaStreamLegacy ((cudaStream_t)0x1), not 0. */
@@ -96,6 +98,12 @@ int moihgp_cuda_set_path(moihgp_handle* h, int path);
 int moihgp_cuda_set_chain_seqs_per_warp(moihgp_handle* h, int n);
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 long long moihgp_cuda_launch_count(moihgp_handle* h);
+
+/* Missing observations (NaN) are found on the device.  The host-buffer entry points report an overflow of the
+ * re-projection list (> 2^22 rows with missing outputs in one call) through their status; the asynchronous *_dev entry
+ * points cannot (they do not wait for the device) - ask afterwards: *status = 0 none seen, 1 some (handled), 2 overflow (the
+ * rows beyond 2^22 keep u = NaN).  Waits for the handle's stream. */
+int moihgp_cuda_nan_status(moihgp_handle* h, int* status);
 
 size_t moihgp_cuda_igp_dim(moihgp_handle* h);         /* MOIHGP::getIGPDim      moihgp.h:691 */
 size_t moihgp_cuda_num_param(moihgp_handle* h);       /* MOIHGP::getNumParam    moihgp.h:709 */

@@ -107,6 +107,14 @@ class MOIHGPSequences(object):
         return G, P
 
     @property
+    def nan_status(self):
+        """0 / 1 / 2 (none / handled / overflow) for the last whole-sequence call; waits for the stream.  The *_device methods
+        are asynchronous and cannot raise on an overflow of the missing-observation list themselves."""
+        out = ctypes.c_int(0)
+        self._check(self._lib.moihgp_cuda_nan_status(self._h, ctypes.byref(out)))
+        return int(out.value)
+
+    @property
     def launch_count(self):
         return int(self._lib.moihgp_cuda_launch_count(self._h))
 
@@ -136,8 +144,10 @@ class MOIHGPSequences(object):
         self._check(self._lib.moihgp_cuda_sync(self._h))
 
     # ---- fused pass: filter + smoother + NLL ----------------------------------------------------
-    def filter_smoother_nll(self, Y, x0=None, smoother_mode=SMOOTH_RTS, want_states=True, want_yhat=False, want_nll=True):
-        """Y: [N,T,p] (or [T,p]) NumPy array -> dict of NumPy arrays X, Xs, Yhat, nll, xT."""
+    def filter_smoother_nll(self, Y, x0=None, smoother_mode=SMOOTH_REFERENCE_LITERAL, want_states=True, want_yhat=False, want_nll=True):
+        """Y: [N,T,p] (or [T,p]) NumPy array -> dict of NumPy arrays X, Xs, Yhat, nll, xT.
+        smoother_mode defaults to the reference's own recursion (IHGP::backwardSmoother as written, ihgp.h:108-113, SURVEY Q3 -
+        unstable for some hyper-parameters, e.g. the default Matern-3/2 latent); SMOOTH_RTS is this library's extension."""
         Y = _np(Y)
         if Y.ndim == 2:
             Y = Y[None]
@@ -154,7 +164,7 @@ class MOIHGPSequences(object):
                                                               _ptr(Yhat), _ptr(nll), _ptr(xT)))
         return {"X": X, "Xs": Xs, "Yhat": Yhat, "nll": nll, "xT": xT}
 
-    def filter_smoother_nll_device(self, Y, x0=None, smoother_mode=SMOOTH_RTS, X=None, Xs=None, Yhat=None, nll=None, xT=None):
+    def filter_smoother_nll_device(self, Y, x0=None, smoother_mode=SMOOTH_REFERENCE_LITERAL, X=None, Xs=None, Yhat=None, nll=None, xT=None):
         """Device-resident variant: all arguments are torch CUDA float64 tensors (outputs pre-allocated by the
         caller, any may be None); runs asynchronously on torch's current stream."""
         import torch
@@ -224,14 +234,14 @@ class MOIHGPSequences(object):
         self._check(self._lib.moihgp_cuda_block_transition(self._h, int(n), _ptr(out)))
         return out[:, 0].copy(), out[:, 1:].copy()
 
-    def smoother_power(self, n, mode=SMOOTH_RTS):
+    def smoother_power(self, n, mode=SMOOTH_REFERENCE_LITERAL):
         """G[mode]^n per latent, [L,d,d]: how a backward value crosses a block of n steps (time-sharded smoother)."""
         L, d = self.num_latent, self.igp_dim
         out = np.zeros((L, d, d))
         self._check(self._lib.moihgp_cuda_smoother_power(self._h, int(mode), int(n), _ptr(out)))
         return out
 
-    def fsn_block(self, phase, Y, seq_end, smoother_mode=SMOOTH_RTS, x0=None, u_after=None, b_end=None, X=None, Xs=None, nll=None, xT=None):
+    def fsn_block(self, phase, Y, seq_end, smoother_mode=SMOOTH_REFERENCE_LITERAL, x0=None, u_after=None, b_end=None, X=None, Xs=None, nll=None, xT=None):
         """One phase (1, 2, 3) of the fused pass on one block of a sequence sharded in time (torch CUDA tensors).
         Phase 1 returns (x_end [N,L,d], u_first [N,L]), phase 2 returns b_start [N,L,d], phase 3 fills X / Xs / nll / xT."""
         N, T, _ = Y.shape

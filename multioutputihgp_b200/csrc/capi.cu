@@ -23,6 +23,8 @@
 
 using namespace moihgp;
 
+extern "C" void moihgp_cuda_destroy(moihgp_handle* h);
+
 namespace {
 
 struct Buf {
@@ -63,6 +65,17 @@ struct moihgp_handle {
 };
 
 namespace {
+
+// Every entry point runs on the handle's device and leaves the CALLER'S current device as it found it (a single process
+// may hold handles on several GPUs next to its own allocations).
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -162,12 +175,14 @@ int create(moihgp_handle** out, int kernel, double dt, size_t p, size_t L, int t
     moihgp_handle* h = new moihgp_handle();
     auto bail = [&](const std::string& m) {
         std::fprintf(stderr, "libmoihgp (B200): %s\n", m.c_str());
-        delete h;
+        moihgp_cuda_destroy(h);                  // frees whatever was allocated so far (stream, device / pinned buffers)
         return -1;
     };
+    h->device = -1;                              // until a valid device is known (destroy() then frees nothing on a device)
     if (kernel != 32 && kernel != 52) return bail("kernel must be 32 (Matern-3/2) or 52 (Matern-5/2)");
     if (p == 0 || L == 0 || L > p) return bail("need 1 <= num_latent <= num_output");
-    if (L > 64) return bail("num_latent > 64 is not supported by the per-observation kernels");
+    // the tensor-pipe projection and the per-observation kernels keep one latent block / an L x L system per CTA
+    if (L > 64) return bail("num_latent > 64 is not supported (shared-memory budget of the projection and per-observation kernels)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return bail("no CUDA device: this library has no CPU fallback");
     if (device < 0) cudaGetDevice(&device);
@@ -175,7 +190,7 @@ int create(moihgp_handle** out, int kernel, double dt, size_t p, size_t L, int t
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     if (prop.major != 10) return bail(std::string("device '") + prop.name + "' is not compute capability 10.x (built for sm_100a only)");
-    cudaSetDevice(device);
+    DeviceGuard guard(device);
     h->kernel = kernel; h->dim = kernel == 32 ? 2 : 3; h->p = (int)p; h->L = (int)L; h->dt = dt; h->device = device;
     h->threading = L < 2 ? 0 : (threading ? 1 : 0);                       // moihgp.h:128-135
     h->num_param = (int)(p * L + L + 1 + 3 * L);                          // moihgp.h:93
@@ -221,7 +236,7 @@ StageLayout stage_layout(const moihgp_handle* h) {
 }
 
 int step_call(moihgp_handle* h, const double* x, const double* y, const double* dx, double* xnew, double* yhat, double* dxnew) {
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     const StageLayout s = stage_layout(h);
     const size_t Ld = (size_t)h->L * h->dim;
     std::memcpy(h->h_stage + s.x, x, sizeof(double) * Ld);
@@ -244,7 +259,7 @@ int step_call(moihgp_handle* h, const double* x, const double* y, const double* 
 }
 
 int lik_call(moihgp_handle* h, const double* x, const double* y, const double* dx, double* loss, double* grad) {
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     const StageLayout s = stage_layout(h);
     const size_t Ld = (size_t)h->L * h->dim;
     std::memcpy(h->h_stage + s.x, x, sizeof(double) * Ld);
@@ -299,8 +314,9 @@ int moihgp_cuda_create(moihgp_handle** out, int kernel, double dt, size_t p, siz
 
 void moihgp_cuda_destroy(moihgp_handle* h) {
     if (!h) return;
-    cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
+    if (h->device < 0) { delete h; return; }     // creation failed before a device was chosen: nothing lives on a device
+    DeviceGuard guard(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto& kv : h->ws) if (kv.second.p) cudaFree(kv.second.p);
     cudaFree(h->d_U); cudaFree(h->d_S); cudaFree(h->d_igp); cudaFree(h->d_consts); cudaFree(h->d_stage);
     if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -379,13 +395,28 @@ const char* moihgp_cuda_profile_read(moihgp_handle* h) {
 
 const char* moihgp_cuda_last_error(moihgp_handle* h) { return h ? h->err.c_str() : "null handle"; }
 long long moihgp_cuda_launch_count(moihgp_handle* h) { return h ? h->launches : 0; }
-size_t moihgp_cuda_igp_dim(moihgp_handle* h) { return (size_t)h->dim; }
-size_t moihgp_cuda_num_param(moihgp_handle* h) { return (size_t)h->num_param; }
-size_t moihgp_cuda_num_igp_param(moihgp_handle* h) { return 3; }
+size_t moihgp_cuda_igp_dim(moihgp_handle* h) { return h ? (size_t)h->dim : 0; }
+size_t moihgp_cuda_num_param(moihgp_handle* h) { return h ? (size_t)h->num_param : 0; }
+size_t moihgp_cuda_num_igp_param(moihgp_handle* h) { return h ? 3 : 0; }
+
+// 0: no missing observation seen by the last whole-sequence call on this handle, 1: some (re-projected, moihgp.h:167-178),
+// 2: more than 2^22 rows with missing outputs - the rows beyond that were NOT re-projected (their u is NaN).
+int moihgp_cuda_nan_status(moihgp_handle* h, int* status) {
+    if (!h || !status) return -2;
+    DeviceGuard guard(h->device);
+    *status = 0;
+    auto it = h->ws.find("nanf");
+    if (it == h->ws.end() || !it->second.p) return 0;
+    int flag[2] = {0, 0};
+    CK(cudaMemcpyAsync(flag, it->second.p, sizeof(flag), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *status = flag[0];
+    return 0;
+}
 
 int moihgp_cuda_update(moihgp_handle* h, const double* params) {
     if (!h || !params) return -2;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     const int p = h->p, L = h->L;
     // moihgp.h:436-446: polar factor of the U block - on the device when the block is large (k_polar), else host Jacobi
     const bool dev_polar = (size_t)p * L >= 2048 && polar_smem_bytes(p, L) <= 200 * 1024;
@@ -502,7 +533,7 @@ int moihgp_cuda_filter_smoother_nll_dev(moihgp_handle* h, const double* Y, size_
     if (N == 0 || T == 0) return fail(h, "N and T must be positive");
     if (mode < -1 || mode > 1) return fail(h, "smoother_mode must be -1, 0 or 1");
     if (mode < 0 && Xs) return fail(h, "Xs requested with smoother_mode = none");
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     const int L = h->L, D = h->dim;
     const size_t nC = scan_chunks((long long)T);
     double* Xtmp = nullptr;
@@ -574,7 +605,7 @@ int moihgp_cuda_fsn_block_dev(moihgp_handle* h, int phase, const double* Y, size
     if (!seq_end && T % 256 != 0) return fail(h, "a block that does not end the sequence must hold a multiple of 256 steps");
     if (phase == 1 && !Y) return -2;
     if (phase == 3 && Xs && !X) return fail(h, "Xs needs X");
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     const int L = h->L, D = h->dim;
     const size_t nC = scan_chunks((long long)T);
     double *u, *rho, *fsum, *bsum, *xin, *bin, *Bx, *vsq, *npart, *Wsum, *sbe, *sbi, *xe, *bo;
@@ -654,7 +685,7 @@ int moihgp_cuda_filter_smoother_nll(moihgp_handle* h, const double* Y, size_t N,
     if (N == 0 || T == 0) return fail(h, "N and T must be positive");
     if (mode < -1 || mode > 1) return fail(h, "smoother_mode must be -1, 0 or 1");
     if (mode < 0 && Xs) return fail(h, "Xs requested with smoother_mode = none");
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     const size_t L = h->L, D = h->dim, p = h->p;
     // slices: the call is PCIe-bound (D2H of the states), so what matters is how soon the first results can start to
     // flow back: slices as small as one warp of chains per SM allows, at most sixteen; a multiple of 32 sequences
@@ -732,7 +763,7 @@ int moihgp_cuda_smooth_dev(moihgp_handle* h, const double* X, size_t N, size_t T
     if (!h || !X || !Xs) return -2;
     if (N == 0 || T == 0) return fail(h, "N and T must be positive");
     if (mode < 0 || mode > 1) return fail(h, "smoother_mode must be 0 or 1");
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     CK(launch_smooth_seq(X, h->d_consts, h->L, h->dim, (long long)N, (long long)T, mode, Xs, h->stream));
     h->launches += 1;
     return 0;
@@ -741,7 +772,7 @@ int moihgp_cuda_smooth_dev(moihgp_handle* h, const double* X, size_t N, size_t T
 int moihgp_cuda_smooth(moihgp_handle* h, const double* X, size_t N, size_t T, int mode, double* Xs) {
     if (!h || !X || !Xs) return -2;
     if (N == 0 || T == 0) return fail(h, "N and T must be positive");
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     const size_t n = N * T * (size_t)h->L * h->dim;
     double *dX, *dXs;
     if (ws_get(h, "smX", n, &dX) || ws_get(h, "smXs", n, &dXs)) return -1;
@@ -759,7 +790,7 @@ static int objective_phase(moihgp_handle* h, int phase, const double* Y, size_t 
                            double* loss, double* grad, double* xT, double* dxT, double* zend) {
     if (!h || !Y) return -2;
     if (N == 0 || T == 0) return fail(h, "N and T must be positive");
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     const int L = h->L, D = h->dim, p = h->p;
     const size_t nC = obj_chunks((long long)T), nsplit = obj_gu_splits((long long)N, (long long)T);
     double *u, *w, *yl, *rho, *zsum, *zin, *zsub, *part, *gU, *Ek, *lat;
@@ -826,7 +857,7 @@ int moihgp_cuda_carry_in_dev(moihgp_handle* h, const double* ends_dev, size_t G,
                              const double* x0_dev, const double* dx0_dev, double* xin_dev, double* dxin_dev) {
     if (!h || !xin_dev || !dxin_dev || (rank > 0 && (!ends_dev || !block_lengths))) return -2;
     if (rank >= G || G > 64) return fail(h, "carry_in: need rank < G <= 64 blocks");
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     CK(launch_block_carry(h->dim, h->d_consts, h->L, (long long)N, (int)rank, block_lengths, ends_dev, x0_dev, dx0_dev, xin_dev, dxin_dev, h->stream));
     h->launches += 1;
     return 0;
@@ -879,7 +910,7 @@ int moihgp_cuda_objective(moihgp_handle* h, const double* Y, size_t N, size_t T,
                           double* grad, double* xT, double* dxT) {
     if (!h || !Y || !loss || !grad) return -2;
     if (N == 0 || T == 0) return fail(h, "N and T must be positive");
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     if (N == 1 && h->path != 1 && obj_small_smem(h->p, h->L, (long long)T)) {
         const int rs = objective_small(h, Y, nullptr, T, x0, dx0, loss, grad, xT, dxT);
         if (rs <= 0) return rs;                  // 1: missing observations -> the general path below
@@ -915,7 +946,7 @@ int moihgp_cuda_objective(moihgp_handle* h, const double* Y, size_t N, size_t T,
 // LineSearchMoreThuente.h:212,295), so the H2D copy of Y is paid once.
 int moihgp_cuda_bind_data(moihgp_handle* h, const double* Y, size_t N, size_t T) {
     if (!h) return -2;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     CK(cudaStreamSynchronize(h->stream));
     if (h->d_bound) { cudaFree(h->d_bound); h->d_bound = nullptr; }
     h->bound_N = h->bound_T = 0;
@@ -931,7 +962,7 @@ int moihgp_cuda_bind_data(moihgp_handle* h, const double* Y, size_t N, size_t T)
 int moihgp_cuda_objective_bound(moihgp_handle* h, const double* x0, const double* dx0, double* loss, double* grad, double* xT, double* dxT) {
     if (!h || !loss || !grad) return -2;
     if (!h->d_bound) return fail(h, "no data bound: call moihgp_cuda_bind_data first");
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     const size_t N = h->bound_N, T = h->bound_T, L = h->L, D = h->dim, np = h->num_param;
     if (N == 1 && h->path != 1 && obj_small_smem(h->p, h->L, (long long)T)) {
         const int rs = objective_small(h, nullptr, h->d_bound, T, x0, dx0, loss, grad, xT, dxT);

@@ -598,16 +598,13 @@ cudaError_t run_chain_ns(const ChainArgs& a, cudaStream_t st) {
     for (int r = 0; r < P; ++r) for (int l = 0; l < L; ++l) pc.U[r][l] = a.U_host[(size_t)r * L + l];
     for (int l = 0; l < L; ++l) pc.rs[l] = 1.0 / std::sqrt(a.S_host[l]);
     const unsigned grid = (unsigned)((a.N + NS - 1) / NS);
-    static bool attr_done[64] = {};          // per device: function attributes belong to the device's context
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    static std::atomic<int> attr_done[64];          // per device: function attributes belong to the device's context
+    if (AttrOnce once(attr_done); once) {
         cudaFuncSetAttribute(k_filter_chain<P, L, D, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS::BYTES);
         cudaFuncSetAttribute(k_smooth_chain<L, D, 0, SNS, SRM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS::BYTES);
         cudaFuncSetAttribute(k_smooth_chain<L, D, 1, SNS, SRM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS::BYTES);
         cudaFuncSetAttribute(k_smooth_chain<L, D, 0, NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmoothCfg<L, D, NS, 1>::BYTES);
         cudaFuncSetAttribute(k_smooth_chain<L, D, 1, NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmoothCfg<L, D, NS, 1>::BYTES);
-        if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     k_filter_chain<P, L, D, NS><<<grid, 32, FS::BYTES, st>>>(a.Y, pc, a.consts, a.sigma, a.nll_const, a.N, a.T, a.x0, a.X, a.nll, a.xT, a.nan_flag);
     mark(a.mk, "k_filter_chain");

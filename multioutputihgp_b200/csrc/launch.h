@@ -2,6 +2,8 @@
 // include/moihgp_b200.h).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -38,16 +40,30 @@ cudaError_t launch_project(const double* Y, const double* U, const double* S, in
 cudaError_t launch_backproject(const double* X, const double* U, const double* S, int p, int L, int d, long long N,
                                long long T, double* Yhat, cudaStream_t stream);
 
-// true the first time it is called with this flag array on the current device: function attributes (dynamic shared
-// memory size) belong to the device's context, so they are set once per device, not once per process
-inline bool first_use_on_device(bool (&done)[64]) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) return true;
-    if (done[dev]) return false;
-    done[dev] = true;
-    return true;
-}
+// Function attributes (dynamic shared memory size) belong to the device's context: they are set once per device, not once
+// per process.  `if (AttrOnce once(flags); once) { cudaFuncSetAttribute(...); }` runs the body on the first use on the
+// current device; concurrent host threads are serialised and nobody sees the flag before the attributes are set.
+struct AttrOnce {
+    std::atomic<int>* flag = nullptr;
+    bool first = true;
+    explicit AttrOnce(std::atomic<int> (&flags)[64]) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64) {
+            flag = &flags[dev];
+            first = flag->load(std::memory_order_acquire) == 0;
+        }
+        if (first) mutex().lock();
+    }
+    ~AttrOnce() {
+        if (first) {
+            if (flag) flag->store(1, std::memory_order_release);
+            mutex().unlock();
+        }
+    }
+    explicit operator bool() const { return first; }
+    static std::mutex& mutex() { static std::mutex m; return m; }
+};
 
 // scan.cu
 struct ScanArgs {

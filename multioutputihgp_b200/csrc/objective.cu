@@ -558,8 +558,8 @@ template <int D, bool FINAL>
 void launch_obj_lanes(const ObjArgs& a, long long nC, long long c_cnt, cudaStream_t st) {
     constexpr int LG = 8, NT = NSUBC * LG;
     const size_t smem = sizeof(double) * NT * (FINAL ? UP3 : SL + 2);
-    static bool attr_done[64] = {};
-    if (first_use_on_device(attr_done))
+    static std::atomic<int> attr_done[64];
+    if (AttrOnce once(attr_done); once)
         cudaFuncSetAttribute(k_obj_lanes<D, LG, FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int nLG = a.L / LG;
     long long groups = (148LL * 32 + a.N * nLG - 1) / (a.N * nLG);
@@ -1230,8 +1230,8 @@ cudaError_t launch_objective_small(int dim, const double* Y, const double* U, co
                                    int p, int L, long long T, int threading, const double* x0, const double* dx0, double* out, double* xT,
                                    double* dxT, cudaStream_t st) {
     const size_t smem = obj_small_smem(p, L, T);
-    static bool attr_done[64] = {};
-    if (first_use_on_device(attr_done)) {
+    static std::atomic<int> attr_done[64];
+    if (AttrOnce once(attr_done); once) {
         cudaFuncSetAttribute(k_obj_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         cudaFuncSetAttribute(k_obj_small<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     }

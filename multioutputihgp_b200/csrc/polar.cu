@@ -260,8 +260,8 @@ size_t polar_ns_smem_bytes(int p, int L) {
 cudaError_t launch_polar(const double* A, int p, int L, double* U, int* status, cudaStream_t st) {
     const size_t smem = polar_smem_bytes(p, L);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
-    static bool attr_done[64] = {};          // per device: function attributes belong to the device's context
-    if (first_use_on_device(attr_done)) {
+    static std::atomic<int> attr_done[64];          // per device: function attributes belong to the device's context
+    if (AttrOnce once(attr_done); once) {
         cudaFuncSetAttribute(k_polar, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_polar_ns, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     }

@@ -631,19 +631,23 @@ __global__ void __launch_bounds__(128) k_nan_fix(const double* __restrict__ Y, c
 }
 
 // Back-projection of the filtered function values: Yhat[n][t][r] = sum_l U[r][l] sqrt(S_l) X[n][t][l][0]
-// (ihgp.h:51 yhat = xnew(0); moihgp.h:222-225).  grid: (ceil(T / PT), N)
+// (ihgp.h:51 yhat = xnew(0); moihgp.h:222-225).  grid: ceil(T / PT) * N CTAs.  U_SMEM: U sqrt(S) staged in shared memory; for
+// shapes where it does not fit next to the tile of function values (p L > ~20 000) it is read through the L1/L2 instead.
+template <bool U_SMEM>
 __global__ void __launch_bounds__(PT) k_backproject(const double* __restrict__ X, const double* __restrict__ U,
                                                    const double* __restrict__ S, int p, int L, int d, long long T,
                                                    double* __restrict__ Yhat) {
     extern __shared__ double sm[];
-    double* us = sm;                 // [p][L] scaled by sqrt(S)
-    double* fs = us + (size_t)p * L; // [PT][L + 1]
+    double* fs = sm;                          // [PT][L + 1]
+    double* sq = fs + (size_t)PT * (L + 1);   // [L] sqrt(S)
+    double* us = sq + L;                      // [p][L] scaled by sqrt(S)   (U_SMEM only)
     const int tid = threadIdx.x;
     const long long tiles = (T + PT - 1) / PT;
     const long long n = blockIdx.x / tiles;
     const long long t0 = (blockIdx.x - n * tiles) * PT;
     const int rows = (int)min((long long)PT, T - t0);
-    for (int i = tid; i < p * L; i += PT) us[i] = U[i] * sqrt(S[i % L]);
+    for (int i = tid; i < L; i += PT) sq[i] = sqrt(S[i]);
+    if (U_SMEM) for (int i = tid; i < p * L; i += PT) us[i] = U[i] * sqrt(S[i % L]);
     const double* Xn = X + ((size_t)n * T + t0) * L * d;
     for (int i = tid; i < rows * L; i += PT) fs[(i / L) * (L + 1) + (i % L)] = Xn[(size_t)i * d];
     __syncthreads();
@@ -651,7 +655,8 @@ __global__ void __launch_bounds__(PT) k_backproject(const double* __restrict__ X
     for (int i = tid; i < rows * p; i += PT) {
         const int row = i / p, r = i - row * p;
         double s = 0.0;
-        for (int l = 0; l < L; ++l) s = fma(us[r * L + l], fs[row * (L + 1) + l], s);
+        if (U_SMEM) for (int l = 0; l < L; ++l) s = fma(us[r * L + l], fs[row * (L + 1) + l], s);
+        else for (int l = 0; l < L; ++l) s = fma(__ldg(U + (size_t)r * L + l) * sq[l], fs[row * (L + 1) + l], s);
         Yo[i] = s;
     }
 }
@@ -661,13 +666,8 @@ cudaError_t run_project_mma(const double* Y, const double* U, const double* S, i
                             double* w, double* yl, double* rho_part, int* nan_info, long long* nan_rows, long long nan_cap,
                             cudaStream_t stream) {
     using SMC = MmaSmem<NB>;
-    static bool attr_done[64] = {};          // per device: function attributes belong to the device's context
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-        cudaFuncSetAttribute(k_project_mma<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMC::BYTES);
-        if (dev >= 0 && dev < 64) attr_done[dev] = true;
-    }
+    static std::atomic<int> attr_done[64];          // per device: function attributes belong to the device's context
+    if (AttrOnce once(attr_done); once) cudaFuncSetAttribute(k_project_mma<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMC::BYTES);
     const unsigned grid = (unsigned)(((T + PT - 1) / PT) * N);
     k_project_mma<NB><<<grid, MT, SMC::BYTES, stream>>>(Y, U, S, p, L, T, u, w, yl, rho_part, nan_info, nan_rows, nan_cap);
     return cudaGetLastError();
@@ -693,8 +693,8 @@ cudaError_t run_project_rows(const CUtensorMap& tm, const double* Y, const doubl
                              long long nan_cap, cudaStream_t stream) {
     using SMC = RowsSmem<NB>;
     const size_t smem = SMC::bytes(p, nbox, NW, NST);
-    static bool attr_done[64] = {};
-    if (first_use_on_device(attr_done)) cudaFuncSetAttribute(k_project_rows<NB, NW, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    static std::atomic<int> attr_done[64];
+    if (AttrOnce once(attr_done); once) cudaFuncSetAttribute(k_project_rows<NB, NW, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     const long long ups = (T + RU - 1) / RU, total = ups * N;
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(227 * 1024) / (smem + 1024)));
     const long long grid = std::min<long long>((total + NW - 1) / NW, 148LL * per_sm);
@@ -777,10 +777,15 @@ cudaError_t launch_project(const double* Y, const double* U, const double* S, in
 
 cudaError_t launch_backproject(const double* X, const double* U, const double* S, int p, int L, int d, long long N,
                                long long T, double* Yhat, cudaStream_t stream) {
-    const size_t smem = sizeof(double) * ((size_t)p * L + (size_t)PT * (L + 1));
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k_backproject, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t base = sizeof(double) * ((size_t)PT * (L + 1) + L), full = base + sizeof(double) * (size_t)p * L;
     const unsigned grid = (unsigned)(((T + PT - 1) / PT) * N);
-    k_backproject<<<grid, PT, smem, stream>>>(X, U, S, p, L, d, T, Yhat);
+    if (full <= 200 * 1024) {
+        if (full > 48 * 1024) cudaFuncSetAttribute(k_backproject<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)full);
+        k_backproject<true><<<grid, PT, full, stream>>>(X, U, S, p, L, d, T, Yhat);
+    } else {
+        if (base > 48 * 1024) cudaFuncSetAttribute(k_backproject<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
+        k_backproject<false><<<grid, PT, base, stream>>>(X, U, S, p, L, d, T, Yhat);
+    }
     return cudaGetLastError();
 }
 

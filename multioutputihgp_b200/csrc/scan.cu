@@ -1026,8 +1026,8 @@ template <int D, int MODE, int LG>
 cudaError_t launch_scan_lanes(const ScanArgs& a, long long nC, cudaStream_t st) {
     constexpr int NT = NSUBC * LG;
     const size_t smem = sizeof(double) * D * SL * NT;
-    static bool attr_done[64] = {};
-    if (first_use_on_device(attr_done)) {
+    static std::atomic<int> attr_done[64];
+    if (AttrOnce once(attr_done); once) {
         cudaError_t e = cudaFuncSetAttribute(k_scan_lanes<D, MODE, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }

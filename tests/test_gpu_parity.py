@@ -223,17 +223,17 @@ def test_many_chains_path_full_T_properties(cuda_lib):
     m.update(make_params(rng, p, L, "Matern52"))
     m.set_path("chain")
     Y1, Y2 = rng.standard_normal((N, T, p)), rng.standard_normal((N, T, p))
-    full = m.filter_smoother_nll(Y1)
+    full = m.filter_smoother_nll(Y1, smoother_mode=1)
     a = m.filter_smoother_nll(Y1[:, :cut], smoother_mode=-1)
     b = m.filter_smoother_nll(Y1[:, cut:], x0=a["xT"], smoother_mode=-1)
     assert rel_err(np.concatenate([a["X"], b["X"]], axis=1), full["X"]) < TOL
     assert rel_err(a["nll"] + b["nll"], full["nll"]) < TOL
-    r2 = m.filter_smoother_nll(Y2)
-    r3 = m.filter_smoother_nll(0.7 * Y1 - 1.9 * Y2)
+    r2 = m.filter_smoother_nll(Y2, smoother_mode=1)
+    r3 = m.filter_smoother_nll(0.7 * Y1 - 1.9 * Y2, smoother_mode=1)
     for k in ("X", "Xs"):
         assert rel_err(r3[k], 0.7 * full[k] - 1.9 * r2[k]) < 1e-11
     m.set_path("scan")
-    rs = m.filter_smoother_nll(Y1)
+    rs = m.filter_smoother_nll(Y1, smoother_mode=1)
     for k in ("X", "Xs", "nll"):
         assert rel_err(rs[k], full[k]) < 1e-11, k
 
@@ -388,8 +388,8 @@ def test_filter_is_linear_in_the_observations(cuda_lib):
     m = MOIHGPSequences(0.1, p, L, "Matern32", True)
     m.update(make_params(rng, p, L, "Matern32"))
     Y1, Y2 = rng.standard_normal((N, T, p)), rng.standard_normal((N, T, p))
-    r1, r2 = m.filter_smoother_nll(Y1), m.filter_smoother_nll(Y2)
-    r3 = m.filter_smoother_nll(0.7 * Y1 - 1.9 * Y2)
+    r1, r2 = m.filter_smoother_nll(Y1, smoother_mode=1), m.filter_smoother_nll(Y2, smoother_mode=1)
+    r3 = m.filter_smoother_nll(0.7 * Y1 - 1.9 * Y2, smoother_mode=1)
     for k in ("X", "Xs"):
         assert rel_err(r3[k], 0.7 * r1[k] - 1.9 * r2[k]) < 1e-11
 
@@ -404,7 +404,7 @@ def test_device_resident_entry_points(cuda_lib):
     m = MOIHGPSequences(0.1, p, L, "Matern52", True)
     m.update(make_params(rng, p, L, "Matern52"))
     Y = np.stack([make_data(rng, p, L, T) for _ in range(N)])
-    host = m.filter_smoother_nll(Y)
+    host = m.filter_smoother_nll(Y)                  # default smoother mode: the reference's literal recursion
     dev = torch.device("cuda:0")
     Yd = torch.from_numpy(Y).to(dev)
     X = torch.empty((N, T, L, 3), dtype=torch.float64, device=dev)
@@ -897,6 +897,25 @@ def test_time_sharded_objective_device_side_exchange(cuda_lib, kernel, p, L, N, 
     o.update(params)
     lo, go, _, _ = o.objective(Y, x0=x0, dx0=dx0)
     assert _close(tot[0], lo) and rel_err(tot[2:], go) < TOL
+
+
+@pytest.mark.gpu
+def test_backprojection_with_a_mixing_matrix_larger_than_shared_memory(cuda_lib):
+    """Yhat = U sqrt(S) x(0) (moihgp.h:222-225) at p = 512, L = 64: U (256 KB) does not fit into shared memory."""
+    from multioutputihgp_b200 import MOIHGPSequences
+    from oracle.binding import OracleMOIHGP
+    from oracle.gen_golden import make_data, make_params
+    rng = np.random.default_rng(512)
+    p, L, T = 512, 64, 300
+    params = make_params(rng, p, L, "Matern32")
+    Y = make_data(rng, p, L, T)[None]
+    m = MOIHGPSequences(0.1, p, L, "Matern32", True)
+    o = OracleMOIHGP(0.1, p, L, "Matern32", True)
+    m.update(params)
+    o.update(params)
+    r = m.filter_smoother_nll(Y, smoother_mode=-1, want_yhat=True)
+    ro = o.filter_smoother_nll(Y, smoother_mode=-1, want_yhat=True)
+    assert rel_err(r["Yhat"], ro["Yhat"]) < TOL and rel_err(r["X"], ro["X"]) < TOL and rel_err(r["nll"], ro["nll"]) < TOL
 
 
 @pytest.mark.gpu
