@@ -160,6 +160,25 @@ int moihgp_cuda_objective_bound(moihgp_handle* h, const double* x0, const double
 int moihgp_cuda_objective_dev(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0, const double* dx0,
                               double* loss, double* grad, double* xT, double* dxT);
 
+/* The streaming learner with its data resident on the device (OnlineObjective, moihgp_online.h:18-115):
+ *   online_begin        window of `windowsize` observations, moving mean, carried state (zeros), proximal term (identity
+ *                       around the current parameters) - all in device memory
+ *   online_push         OnlineObjective::push_back(y)   moihgp_online.h:75-93: append, recompute the mean, slide the window
+ *                       and advance the carried state with the new front element (Q12).  ma_given = NULL: the window mean
+ *                       (the reference's C++ learner); else the caller's centre (online_learning.py keeps an exponential
+ *                       mean).  ma_out (or NULL) receives the centre in use.
+ *   online_set_proximal oldparams and the matrix B of the term 1/2 dparams' B dparams (:42-54); B = NULL: the identity;
+ *                       oldparams = NULL: no proximal term on the device (the caller adds its own)
+ *   online_objective    OnlineObjective::operator()     moihgp_online.h:40-72 at `params`: update + window loop + proximal
+ *                       term; ONE CUDA-graph launch per evaluation (H2D params, polar factor, K-setup, window objective,
+ *                       proximal term, D2H [loss, grad]).  The model then holds `params`, as after moihgp_cuda_update.
+ *   online_get_state    the state carried in front of the window. */
+int moihgp_cuda_online_begin(moihgp_handle* h, size_t windowsize);
+int moihgp_cuda_online_push(moihgp_handle* h, const double* y, const double* ma_given, double* ma_out);
+int moihgp_cuda_online_set_proximal(moihgp_handle* h, const double* oldparams, const double* B);
+int moihgp_cuda_online_objective(moihgp_handle* h, const double* params, double* loss, double* grad);
+int moihgp_cuda_online_get_state(moihgp_handle* h, double* x, double* dx);
+
 /* ONE long sequence sharded over several devices in TIME (one process per GPU): every device holds a contiguous block of
  * T steps, DEVICE buffers.  begin projects the block and returns (HOST, zend[N][L][4][d] = [x; dx_0; dx_1; dx_2]) its end
  * state from a ZERO carry-in - needs T % 256 == 0; pass NULL on the last block, whose end state nobody needs.  The caller

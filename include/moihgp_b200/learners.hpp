@@ -159,6 +159,7 @@ public:
         dx = dxnew;                                      // zeros, as the reference (:181)
         _obj->bfgs_mat = _solver->getBFGSMat();
         _obj->oldparams = _params;
+        _obj->prepare();                                 // the proximal term goes to the device once per sample
         double fx;
         _solver->minimize(*_obj, _params, fx, _lb, _ub);
         return yhat;

@@ -373,6 +373,30 @@ public:
         detail::check(_h, moihgp_cuda_smoother_power(_h, smoother_mode, n, &out[0]), "MOIHGP::smootherPower");
     }
 
+    // Device-resident streaming learner (moihgp_cuda_online_*: window, moving mean, carried state and proximal term in HBM;
+    // one CUDA-graph launch per objective evaluation).  Used by OnlineObjective; false / exception-free probes return false
+    // when the shape does not qualify (the caller then keeps the window on the host).
+    bool onlineBegin(size_t windowsize) { return moihgp_cuda_online_begin(_h, windowsize) == 0; }
+    void onlinePush(const Vec& y, Vec& ma) {
+        pack_y(y, &_yb[0]);
+        detail::check(_h, moihgp_cuda_online_push(_h, &_yb[0], NULL, &_yb[_num_output]), "MOIHGP::onlinePush");
+        unpack_y(&_yb[_num_output], ma);
+    }
+    void onlineSetProximal(const Vec& oldparams, const double* B) {
+        for (size_t i = 0; i < _num_param; ++i) _pb[i] = oldparams[i];
+        detail::check(_h, moihgp_cuda_online_set_proximal(_h, &_pb[0], B), "MOIHGP::onlineSetProximal");
+    }
+    double onlineObjective(const Vec& params, Vec& grad) {
+        std::vector<double> pin(_num_param);
+        for (size_t i = 0; i < _num_param; ++i) pin[i] = params[i];
+        double loss = 0.0;
+        detail::check(_h, moihgp_cuda_online_objective(_h, &pin[0], &loss, &_pb[0]), "MOIHGP::onlineObjective");
+        grad.resize(_num_param);
+        for (size_t i = 0; i < _num_param; ++i) grad[i] = _pb[i];
+        sync_public();                                   // the model now holds params (host mirror only, no device traffic)
+        return loss;
+    }
+
     moihgp_handle* handle() { return _h; }
 
 private:
@@ -469,20 +493,56 @@ struct NoBFGSMat {
 
 // ------------------------------------------------------------------------------------------------------------------
 // OnlineObjective<StateSpace>   (moihgp_online.h:18-115): sliding-window objective with the BFGS-proximal term.
+// Device-resident: the window, its moving mean, the carried state (_x, _dx) and the proximal matrix live on the
+// device (moihgp_cuda_online_*); push_back is one small kernel (+ one step kernel when the window slides), operator() is ONE
+// CUDA-graph launch.  The public members Y, ma, oldparams, bfgs_mat keep the reference's meaning; Y and ma are host copies.
+// When the shape does not qualify for the resident path (window > 1024 steps, very large p * L) the window stays on the host
+// and every evaluation hands it to moihgp_cuda_objective, as before.
 template <typename StateSpace, typename Vec = std::vector<double>, typename BFGSMat = NoBFGSMat<Vec>, typename Mat = DenseMatrix>
 class OnlineObjective {
 public:
     typedef MOIHGP<StateSpace, Vec, Mat> GP;
-    OnlineObjective(GP* gp, const double& gamma, const size_t& windowsize) : _gp(gp), _gamma(gamma), _windowsize(windowsize) {
+    OnlineObjective(GP* gp, const double& gamma, const size_t& windowsize) : _gp(gp), _gamma(gamma), _windowsize(windowsize), _prox_m(-1) {
         oldparams = _gp->getParams();
         _x = typename GP::State(_gp->getNumLatent(), detail::make_vec<Vec>(_gp->getIGPDim()));
         _dx = typename GP::DState(_gp->getNumLatent(), std::vector<Vec>(_gp->getNumIGPParam(), detail::make_vec<Vec>(_gp->getIGPDim())));
         ma = detail::make_vec<Vec>(_gp->getNumOutput());
+        _resident = _gp->onlineBegin(windowsize);
+    }
+
+    // Upload the proximal term (oldparams, B) once per streamed sample - MOIHGPOnlineLearning::step calls it right after
+    // setting bfgs_mat / oldparams (moihgp_online.h:182-183).  B's column j is bfgs_mat.apply_Hv(e_j, gamma) (:45-48); the
+    // identity while the BFGS matrix holds no correction (:50-53).  operator() calls it by itself when oldparams changed.
+    void prepare() {
+        if (!_resident) return;
+        const size_t np = _gp->getNumParam();
+        if (bfgs_mat.get_m() > 0) {
+            std::vector<double> B(np * np);
+            Vec e = detail::make_vec<Vec>(np), col = detail::make_vec<Vec>(np);
+            for (size_t j = 0; j < np; ++j) {
+                e[j] = 1.0;
+                bfgs_mat.apply_Hv(e, _gamma, col);
+                e[j] = 0.0;
+                for (size_t i = 0; i < np; ++i) B[i * np + j] = col[i];
+            }
+            _gp->onlineSetProximal(oldparams, &B[0]);
+        } else {
+            _gp->onlineSetProximal(oldparams, NULL);
+        }
+        _prox_old.assign(np, 0.0);
+        for (size_t i = 0; i < np; ++i) _prox_old[i] = oldparams[i];
+        _prox_m = bfgs_mat.get_m();
     }
 
     // moihgp_online.h:40-72
     double operator()(const Vec& params, Vec& grad) {
         const size_t np = _gp->getNumParam(), p = _gp->getNumOutput();
+        if (_resident && !Y.empty()) {
+            bool stale = _prox_m != (int)bfgs_mat.get_m() || _prox_old.size() != np;
+            for (size_t i = 0; i < np && !stale; ++i) stale = _prox_old[i] != oldparams[i];
+            if (stale) prepare();
+            return _gp->onlineObjective(params, grad);   // update(params) + window loop + proximal term: one graph launch
+        }
         Vec dparams = detail::make_vec<Vec>(np), Bp = detail::make_vec<Vec>(np);
         for (size_t i = 0; i < np; ++i) dparams[i] = params[i] - oldparams[i];
         _gp->update(params);                                                     // :43
@@ -509,6 +569,11 @@ public:
     void push_back(const Vec& y) {
         const size_t p = _gp->getNumOutput();
         Y.push_back(y);
+        if (_resident) {
+            _gp->onlinePush(y, ma);                      // mean, slide and carried-state step on the device
+            while (Y.size() > _windowsize) Y.pop_front();
+            return;
+        }
         for (size_t r = 0; r < p; ++r) ma[r] = 0.0;
         for (typename std::list<Vec>::const_iterator it = Y.begin(); it != Y.end(); ++it) for (size_t r = 0; r < p; ++r) ma[r] += (*it)[r];
         for (size_t r = 0; r < p; ++r) ma[r] /= double(Y.size());
@@ -524,6 +589,8 @@ public:
         }
     }
 
+    bool resident() const { return _resident; }
+
     Vec oldparams;                                       // moihgp_online.h:96-99
     BFGSMat bfgs_mat;
     std::list<Vec> Y;
@@ -533,6 +600,9 @@ private:
     GP* _gp;
     double _gamma;
     size_t _windowsize;
+    bool _resident;
+    int _prox_m;
+    std::vector<double> _prox_old;
     typename GP::State _x;
     typename GP::DState _dx;
     std::vector<double> _buf;

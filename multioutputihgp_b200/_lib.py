@@ -78,6 +78,16 @@ def load():
     lib.moihgp_cuda_profile.argtypes = [vp, ctypes.c_int]
     lib.moihgp_cuda_profile_read.restype = ctypes.c_char_p
     lib.moihgp_cuda_profile_read.argtypes = [vp]
+    lib.moihgp_cuda_online_begin.restype = ctypes.c_int
+    lib.moihgp_cuda_online_begin.argtypes = [vp, sz]
+    lib.moihgp_cuda_online_push.restype = ctypes.c_int
+    lib.moihgp_cuda_online_push.argtypes = [vp, vp, vp, vp]
+    lib.moihgp_cuda_online_set_proximal.restype = ctypes.c_int
+    lib.moihgp_cuda_online_set_proximal.argtypes = [vp, vp, vp]
+    lib.moihgp_cuda_online_objective.restype = ctypes.c_int
+    lib.moihgp_cuda_online_objective.argtypes = [vp, vp, vp, vp]
+    lib.moihgp_cuda_online_get_state.restype = ctypes.c_int
+    lib.moihgp_cuda_online_get_state.argtypes = [vp, vp, vp]
     lib.moihgp_cuda_nan_status.restype = ctypes.c_int
     lib.moihgp_cuda_nan_status.argtypes = [vp, c_int_p]
     lib.moihgp_cuda_launch_count.restype = ctypes.c_longlong
@@ -138,5 +148,6 @@ LEGACY_NAMES = ["new", "del", "step1", "step2", "step3", "step4", "update", "lik
                 "num_param", "num_igp_param"]
 CUDA_NAMES = ["create", "destroy", "set_stream", "sync", "last_error", "launch_count", "profile", "profile_read", "set_path", "set_chain_seqs_per_warp", "igp_dim", "num_param",
               "num_igp_param", "update", "get_params", "get_U", "latent_consts", "latent_iters", "smoother_consts",
-              "filter_smoother_nll", "filter_smoother_nll_dev", "objective", "objective_dev", "bind_data", "objective_bound", "objective_begin_dev", "objective_finish_dev", "block_transition", "fsn_block_dev", "smoother_power", "smooth", "smooth_dev", "objective_begin_async", "carry_in_dev", "nan_status"]
+              "filter_smoother_nll", "filter_smoother_nll_dev", "objective", "objective_dev", "bind_data", "objective_bound", "objective_begin_dev", "objective_finish_dev", "block_transition", "fsn_block_dev", "smoother_power", "smooth", "smooth_dev", "objective_begin_async", "carry_in_dev", "nan_status", "online_begin", "online_push", "online_set_proximal",
+              "online_objective", "online_get_state"]
 ALL_SYMBOLS = ["gp%s_%s" % (xx, n) for xx in ("32", "52") for n in LEGACY_NAMES] + ["moihgp_cuda_" + n for n in CUDA_NAMES]

@@ -267,6 +267,38 @@ class MOIHGPSequences(object):
         self._check(self._lib.moihgp_cuda_smooth(self._h, _ptr(X), N, T, int(smoother_mode), _ptr(Xs)))
         return Xs[0] if squeeze else Xs
 
+    # ---- device-resident streaming learner (moihgp_cuda_online_*) -----------------------------------------------
+    def online_begin(self, windowsize):
+        """Window, moving mean, carried state and proximal term in device memory; False if the shape does not qualify."""
+        return self._lib.moihgp_cuda_online_begin(self._h, int(windowsize)) == 0
+
+    def online_push(self, y, ma_given=None, want_ma=False):
+        """OnlineObjective::push_back (moihgp_online.h:75-93); ``ma_given``: the caller's own centre instead of the window mean."""
+        y = _np(y)
+        ma_given = None if ma_given is None else _np(ma_given)
+        ma = np.empty(self.num_output) if want_ma else None
+        self._check(self._lib.moihgp_cuda_online_push(self._h, _ptr(y), _ptr(ma_given), _ptr(ma)))
+        return ma
+
+    def online_set_proximal(self, oldparams=None, B=None):
+        """1/2 dparams' B dparams around ``oldparams`` (B None: identity); ``oldparams`` None: no proximal term on the device."""
+        oldparams = None if oldparams is None else _np(oldparams)
+        B = None if B is None else _np(B)
+        self._check(self._lib.moihgp_cuda_online_set_proximal(self._h, _ptr(oldparams), _ptr(B)))
+
+    def online_objective(self, params):
+        """OnlineObjective::operator() (moihgp_online.h:40-72) at ``params`` on the resident window: one CUDA-graph launch."""
+        params = _np(params)
+        loss, grad = np.zeros(1), np.zeros(self.num_param)
+        self._check(self._lib.moihgp_cuda_online_objective(self._h, _ptr(params), _ptr(loss), _ptr(grad)))
+        return float(loss[0]), grad
+
+    def online_state(self):
+        L, d = self.num_latent, self.igp_dim
+        x, dx = np.zeros((L, d)), np.zeros((L, 3, d))
+        self._check(self._lib.moihgp_cuda_online_get_state(self._h, _ptr(x), _ptr(dx)))
+        return x, dx
+
     def bind(self, Y):
         """Copy the observations to the device once; ``objective_bound`` then evaluates on them at the current parameters
         (the L-BFGS loop calls the objective tens of times on the same data).  ``bind(None)`` releases them."""

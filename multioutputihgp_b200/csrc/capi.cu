@@ -62,6 +62,18 @@ struct moihgp_handle {
     int chain_spw = 0;                        // many-chains kernels: sequences per warp (0 = automatic)
     std::string prof_text;
     std::string err;
+    // ---- device-resident streaming learner (moihgp_online.h:18-115): window, moving mean, carried state, proximal term ----
+    struct Online {
+        size_t W = 0, count = 0;
+        double *d_win = nullptr, *d_ma = nullptr, *d_ynew = nullptr, *d_magiven = nullptr, *d_front = nullptr;
+        double *d_x = nullptr, *d_dx = nullptr, *d_x2 = nullptr, *d_dx2 = nullptr;     // carried state (and the step's output)
+        double *d_params = nullptr, *d_old = nullptr, *d_B = nullptr, *d_out = nullptr;
+        double *h_params = nullptr, *h_out = nullptr, *h_y = nullptr;                  // pinned
+        int *d_count = nullptr, *d_pst = nullptr;
+        bool has_B = false, has_prox = true, use_graph = true;
+        std::map<long long, int> seen;                    // evaluations per (window length, proximal kind)
+        std::map<long long, cudaGraphExec_t> graphs;
+    } on;
 };
 
 namespace {
@@ -326,6 +338,17 @@ void moihgp_cuda_destroy(moihgp_handle* h) {
     if (h->h_flags) cudaFreeHost(h->h_flags);
     if (h->h_small) cudaFreeHost(h->h_small);
     if (h->d_bound) cudaFree(h->d_bound);
+    for (auto& kv : h->on.graphs) cudaGraphExecDestroy(kv.second);
+    {
+        moihgp_handle::Online& o = h->on;
+        double* dev[] = {o.d_win, o.d_ma, o.d_ynew, o.d_magiven, o.d_front, o.d_x, o.d_dx, o.d_x2, o.d_dx2, o.d_params, o.d_old, o.d_B, o.d_out};
+        for (double* q : dev) if (q) cudaFree(q);
+        if (o.d_count) cudaFree(o.d_count);
+        if (o.d_pst) cudaFree(o.d_pst);
+        if (o.h_params) cudaFreeHost(o.h_params);
+        if (o.h_out) cudaFreeHost(o.h_out);
+        if (o.h_y) cudaFreeHost(o.h_y);
+    }
     for (int i = 0; i < 2; ++i) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_c[i]) cudaEventDestroy(h->ev_c[i]); if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]); }
     delete h;
 }
@@ -987,6 +1010,187 @@ int moihgp_cuda_objective_bound(moihgp_handle* h, const double* x0, const double
     std::copy(host.begin() + 2, host.end(), grad);
     return 0;
 }
+
+}  // extern "C"
+
+// =============================================================================================
+// Device-resident streaming learner (moihgp_online.h:40-93, :173-187).  The window of observations, its moving
+// mean, the state carried in front of the window and the proximal matrix live in HBM; one objective evaluation is
+//   H2D params -> polar factor -> K-setup -> one-launch window objective -> proximal term -> D2H [loss, grad, U]
+// queued on the handle's stream and, from the second evaluation of a given window length on, replayed as ONE CUDA graph.
+static int online_enqueue(moihgp_handle* h, size_t T, bool has_B) {
+    moihgp_handle::Online& o = h->on;
+    const int p = h->p, L = h->L, np = h->num_param, pL = p * L;
+    CK(cudaMemcpyAsync(o.d_params, o.h_params, sizeof(double) * np, cudaMemcpyHostToDevice, h->stream));
+    CK(launch_polar(o.d_params, p, L, h->d_U, o.d_pst, h->stream));                                     // moihgp.h:436-446
+    CK(cudaMemcpyAsync(h->d_S, o.d_params + pL, sizeof(double) * L, cudaMemcpyDeviceToDevice, h->stream));   // moihgp.h:448
+    CK(launch_setup(h->dim, o.d_params + pL + L + 1, h->dt, L, h->d_consts, h->stream));                // moihgp.h:450-456
+    CK(launch_objective_small(h->dim, o.d_win, h->d_U, h->d_S, 0.0, h->d_consts, p, L, (long long)T, h->threading, o.d_x, o.d_dx, o.d_out,
+                              nullptr, nullptr, h->stream, o.d_ma, o.d_params + pL + L));               // moihgp_online.h:57-70
+    CK(launch_online_prox(o.d_params, o.has_prox ? o.d_old : nullptr, has_B ? o.d_B : nullptr, np, pL, h->d_U, o.d_out, h->stream));   // moihgp_online.h:42-54
+    CK(cudaMemcpyAsync(o.h_out, o.d_out, sizeof(double) * (2 + np + pL), cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+}
+
+extern "C" {
+
+int moihgp_cuda_online_begin(moihgp_handle* h, size_t windowsize) {
+    if (!h) return -2;
+    if (windowsize < 1) windowsize = 1;                                   // moihgp_online.h:144-151
+    if (!obj_small_smem(h->p, h->L, (long long)windowsize)) return fail(h, "online_begin: window too long / model too large for the one-launch objective");
+    if (polar_smem_bytes(h->p, h->L) > 200 * 1024) return fail(h, "online_begin: p * L too large for the one-CTA polar factor");
+    DeviceGuard guard(h->device);
+    CK(cudaStreamSynchronize(h->stream));
+    moihgp_handle::Online& o = h->on;
+    for (auto& kv : o.graphs) cudaGraphExecDestroy(kv.second);
+    o.graphs.clear();
+    o.seen.clear();
+    const size_t p = h->p, L = h->L, D = h->dim, np = h->num_param, pL = p * L;
+    auto dalloc = [&](double** q, size_t n) { if (*q) cudaFree(*q); *q = nullptr; return cudaMalloc(q, sizeof(double) * std::max<size_t>(n, 2)); };
+    CK(dalloc(&o.d_win, (windowsize + 1) * p)); CK(dalloc(&o.d_ma, p)); CK(dalloc(&o.d_ynew, p)); CK(dalloc(&o.d_magiven, p)); CK(dalloc(&o.d_front, p));
+    CK(dalloc(&o.d_x, L * D)); CK(dalloc(&o.d_dx, L * 3 * D)); CK(dalloc(&o.d_x2, L * D)); CK(dalloc(&o.d_dx2, L * 3 * D));
+    CK(dalloc(&o.d_params, np)); CK(dalloc(&o.d_old, np)); CK(dalloc(&o.d_out, 2 + np + pL));
+    if (o.d_B) { cudaFree(o.d_B); o.d_B = nullptr; }
+    if (!o.d_count) CK(cudaMalloc(&o.d_count, 4 * sizeof(int)));
+    if (!o.d_pst) CK(cudaMalloc(&o.d_pst, 4 * sizeof(int)));
+    if (o.h_params) cudaFreeHost(o.h_params);
+    if (o.h_out) cudaFreeHost(o.h_out);
+    if (o.h_y) cudaFreeHost(o.h_y);
+    CK(cudaMallocHost(&o.h_params, sizeof(double) * np));
+    CK(cudaMallocHost(&o.h_out, sizeof(double) * (2 + np + pL)));
+    CK(cudaMallocHost(&o.h_y, sizeof(double) * 2 * p));
+    CK(cudaMemsetAsync(o.d_count, 0, 4 * sizeof(int), h->stream));
+    CK(cudaMemsetAsync(o.d_x, 0, sizeof(double) * L * D, h->stream));
+    CK(cudaMemsetAsync(o.d_dx, 0, sizeof(double) * L * 3 * D, h->stream));
+    CK(cudaMemsetAsync(o.d_ma, 0, sizeof(double) * p, h->stream));
+    // the proximal term starts from the current parameters and the identity (moihgp_online.h:31, :50-53)
+    std::vector<double> cur(np);
+    moihgp_cuda_get_params(h, cur.data());
+    CK(cudaMemcpyAsync(o.d_old, cur.data(), sizeof(double) * np, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    o.W = windowsize; o.count = 0; o.has_B = false; o.has_prox = true;
+    const char* e = std::getenv("MOIHGP_ONLINE_GRAPH");
+    o.use_graph = !(e && e[0] == '0');
+    return 0;
+}
+
+// OnlineObjective::push_back(y)  moihgp_online.h:75-93.  ma_given = NULL: the moving mean is the mean of the window (the
+// element about to be dropped included, as the reference computes it); otherwise the caller's own centre is used
+// (online_learning.py:54-64 keeps an exponential mean).  ma_out (may be NULL) receives the centre in use.
+int moihgp_cuda_online_push(moihgp_handle* h, const double* y, const double* ma_given, double* ma_out) {
+    if (!h || !y) return -2;
+    moihgp_handle::Online& o = h->on;
+    if (o.W == 0) return fail(h, "online_push: call moihgp_cuda_online_begin first");
+    DeviceGuard guard(h->device);
+    const size_t p = h->p, L = h->L, D = h->dim;
+    std::memcpy(o.h_y, y, sizeof(double) * p);
+    if (ma_given) std::memcpy(o.h_y + p, ma_given, sizeof(double) * p);
+    CK(cudaMemcpyAsync(o.d_ynew, o.h_y, sizeof(double) * p, cudaMemcpyHostToDevice, h->stream));
+    if (ma_given) CK(cudaMemcpyAsync(o.d_magiven, o.h_y + p, sizeof(double) * p, cudaMemcpyHostToDevice, h->stream));
+    CK(launch_online_push(o.d_ynew, ma_given ? o.d_magiven : nullptr, (int)p, (int)o.W, o.d_win, o.d_count, o.d_ma, o.d_front, h->stream));
+    h->launches += 1;
+    if (o.count + 1 > o.W) {
+        // the window slid: the carried state advances with the NEW front element (Q12), step v2 (moihgp_online.h:89)
+        StepArgs a;
+        a.consts = h->d_consts; a.U = h->d_U; a.S = h->d_S; a.sigma = h->sigma; a.p = h->p; a.L = h->L; a.dim = h->dim; a.threading = h->threading;
+        a.x = o.d_x; a.y = o.d_front; a.dx = o.d_dx; a.xnew = o.d_x2; a.yhat = nullptr; a.dxnew = o.d_dx2; a.scratch = nullptr;
+        CK(launch_step(a, h->stream));
+        h->launches += 1;
+        CK(cudaMemcpyAsync(o.d_x, o.d_x2, sizeof(double) * L * D, cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(o.d_dx, o.d_dx2, sizeof(double) * L * 3 * D, cudaMemcpyDeviceToDevice, h->stream));
+    } else {
+        o.count += 1;
+    }
+    if (ma_out) {
+        CK(cudaMemcpyAsync(o.h_y, o.d_ma, sizeof(double) * p, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        std::memcpy(ma_out, o.h_y, sizeof(double) * p);
+    }
+    return 0;
+}
+
+// The proximal term 1/2 dparams' B dparams (moihgp_online.h:42-54): oldparams [num_param] and the matrix B [num_param]^2
+// row-major, e.g. column j = bfgs_mat.apply_Hv(e_j, gamma) (NULL = the identity, the reference's choice while the BFGS
+// matrix holds no correction).  Set once per streamed sample (moihgp_online.h:182-183).
+int moihgp_cuda_online_set_proximal(moihgp_handle* h, const double* oldparams, const double* B) {
+    if (!h) return -2;
+    moihgp_handle::Online& o = h->on;
+    if (o.W == 0) return fail(h, "online_set_proximal: call moihgp_cuda_online_begin first");
+    DeviceGuard guard(h->device);
+    const size_t np = h->num_param;
+    if (!oldparams) {                                   // no proximal term on the device: the caller adds its own
+        CK(cudaStreamSynchronize(h->stream));
+        o.has_prox = false; o.has_B = false;
+        return 0;
+    }
+    o.has_prox = true;
+    CK(cudaMemcpyAsync(o.d_old, oldparams, sizeof(double) * np, cudaMemcpyHostToDevice, h->stream));
+    if (B) {
+        if (!o.d_B) CK(cudaMalloc(&o.d_B, sizeof(double) * np * np));
+        CK(cudaMemcpyAsync(o.d_B, B, sizeof(double) * np * np, cudaMemcpyHostToDevice, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));              // the caller's buffers may be reused right away
+    o.has_B = B != nullptr;
+    return 0;
+}
+
+// OnlineObjective::operator()(params, grad)  moihgp_online.h:40-72 on the resident window: update(params) + the window loop
+// of step v2 + negLogLikelihood(x, y, dx, grad) from the carried state + the proximal term.  loss[1], grad[num_param] (host).
+// The model afterwards holds `params` (polar factor taken), exactly as after moihgp_cuda_update(params).
+int moihgp_cuda_online_objective(moihgp_handle* h, const double* params, double* loss, double* grad) {
+    if (!h || !params || !loss || !grad) return -2;
+    moihgp_handle::Online& o = h->on;
+    if (o.W == 0 || o.count == 0) return fail(h, "online_objective: no window (online_begin / online_push first)");
+    DeviceGuard guard(h->device);
+    const int p = h->p, L = h->L, np = h->num_param, pL = p * L;
+    std::memcpy(o.h_params, params, sizeof(double) * np);
+    const long long key = (long long)o.count * 4 + (o.has_prox ? 2 : 0) + (o.has_B ? 1 : 0);
+    const int seen = o.seen[key]++;
+    auto it = o.graphs.find(key);
+    if (o.use_graph && it == o.graphs.end() && seen >= 1) {
+        // second evaluation with this window length: record the sequence once (the first one ran eagerly and set every
+        // function attribute / workspace), replay it from now on
+        cudaGraph_t g = nullptr;
+        cudaGraphExec_t ge = nullptr;
+        if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const int rc = online_enqueue(h, o.count, o.has_B);
+            const cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
+            if (rc == 0 && ce == cudaSuccess && g && cudaGraphInstantiate(&ge, g, 0) == cudaSuccess) it = o.graphs.emplace(key, ge).first;
+            if (g) cudaGraphDestroy(g);
+        }
+        cudaGetLastError();                              // a failed capture falls back to the eager sequence below
+    }
+    if (it != o.graphs.end()) { CK(cudaGraphLaunch(it->second, h->stream)); h->launches += 5; }
+    else { if (online_enqueue(h, o.count, o.has_B)) return -1; h->launches += 5; }
+    CK(cudaStreamSynchronize(h->stream));
+    if (o.h_out[1] != 0.0) return fail(h, "online_objective: missing (NaN) outputs in the window are not handled on the resident path");
+    *loss = o.h_out[0];
+    std::memcpy(grad, o.h_out + 2, sizeof(double) * np);
+    // host mirror of the model (moihgp_cuda_get_params / get_U): the polar factor came back with the result
+    std::copy(o.h_out + 2 + np, o.h_out + 2 + np + pL, h->U.begin());
+    for (int l = 0; l < L; ++l) h->S[l] = params[pL + l];
+    h->sigma = params[pL + L];
+    for (int i = 0; i < 3 * L; ++i) h->igp[i] = params[pL + L + 1 + i];
+    h->consts_fresh = false;
+    return 0;
+}
+
+// the state carried in front of the window (OnlineObjective::_x, _dx): x [L][d], dx [L][3][d]
+int moihgp_cuda_online_get_state(moihgp_handle* h, double* x, double* dx) {
+    if (!h) return -2;
+    moihgp_handle::Online& o = h->on;
+    if (o.W == 0) return fail(h, "online_get_state: call moihgp_cuda_online_begin first");
+    DeviceGuard guard(h->device);
+    const size_t L = h->L, D = h->dim;
+    if (x) CK(cudaMemcpyAsync(x, o.d_x, sizeof(double) * L * D, cudaMemcpyDeviceToHost, h->stream));
+    if (dx) CK(cudaMemcpyAsync(dx, o.d_dx, sizeof(double) * L * 3 * D, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+}  // extern "C"
+
+extern "C" {
 
 // ---------------------------------------------------------------------------------------------
 // legacy symbols (src/wrapper.cpp:31-624).  Same signatures; errors cannot be returned, so they abort.

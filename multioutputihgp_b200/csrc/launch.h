@@ -149,7 +149,12 @@ cudaError_t launch_block_carry(int dim, const LatentConsts* consts, int L, long 
 size_t obj_small_smem(int p, int L, long long T);
 cudaError_t launch_objective_small(int dim, const double* Y, const double* U, const double* S, double sigma, const LatentConsts* consts,
                                    int p, int L, long long T, int threading, const double* x0, const double* dx0, double* out, double* xT,
-                                   double* dxT, cudaStream_t st);
+                                   double* dxT, cudaStream_t st, const double* centre = nullptr, const double* sigma_dev = nullptr);
+// streaming learner, device-resident (moihgp_online.h:75-93 window maintenance; :45-54 proximal term)
+cudaError_t launch_online_push(const double* y_new, const double* ma_given /*or null*/, int p, int W, double* win /*[W+1][p]*/, int* count,
+                               double* ma, double* front_centred, cudaStream_t st);
+cudaError_t launch_online_prox(const double* params, const double* oldparams, const double* B /*[np][np] or null*/, int np, int pL,
+                               const double* U, double* out /*[loss, flag, grad[np], U[pL]]*/, cudaStream_t st);
 
 // step.cu  (one observation per call: the legacy gpXX_* entry points)
 struct StepArgs {

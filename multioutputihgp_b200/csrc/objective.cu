@@ -996,9 +996,12 @@ __global__ void __launch_bounds__(256) k_obj_finish(const double* __restrict__ l
 // out = [loss, nan flag, grad[num_param]]; dynamic shared memory: U[p][L], Y[T][p], u[T][L], w -> dU weights [T][L], lat[L][5].
 template <int D>
 __global__ void __launch_bounds__(128) k_obj_small(const double* __restrict__ Y, const double* __restrict__ U, const double* __restrict__ S,
-                                                  double sigma, const LatentConsts* __restrict__ consts, int p, int L, int T, int threading,
+                                                  double sigma_host, const LatentConsts* __restrict__ consts, int p, int L, int T, int threading,
                                                   const double* __restrict__ x0, const double* __restrict__ dx0, double* __restrict__ out,
-                                                  double* __restrict__ xT, double* __restrict__ dxT) {
+                                                  double* __restrict__ xT, double* __restrict__ dxT,
+                                                  const double* __restrict__ centre /*[p] subtracted from every observation, or null*/,
+                                                  const double* __restrict__ sigma_dev /*sigma on the device (CUDA-graph replays), or null*/) {
+    const double sigma = sigma_dev ? *sigma_dev : sigma_host;
     extern __shared__ double sm[];
     double* sU = sm;
     double* sY = sU + p * L;
@@ -1010,7 +1013,7 @@ __global__ void __launch_bounds__(128) k_obj_small(const double* __restrict__ Y,
     const int tid = threadIdx.x;
     if (tid == 0) bad = 0;
     for (int i = tid; i < p * L; i += 128) sU[i] = U[i];
-    for (int i = tid; i < T * p; i += 128) sY[i] = Y[i];
+    for (int i = tid; i < T * p; i += 128) sY[i] = centre ? Y[i] - centre[i % p] : Y[i];     // moihgp_online.h:63 (y - ma)
     __syncthreads();
     // ---- projection  w = U'y, u = S^-1/2 w   (moihgp.h:481-498 without missing data) --------------------------------
     for (int i = tid; i < T * L; i += 128) {
@@ -1228,15 +1231,15 @@ size_t obj_small_smem(int p, int L, long long T) {
 
 cudaError_t launch_objective_small(int dim, const double* Y, const double* U, const double* S, double sigma, const LatentConsts* consts,
                                    int p, int L, long long T, int threading, const double* x0, const double* dx0, double* out, double* xT,
-                                   double* dxT, cudaStream_t st) {
+                                   double* dxT, cudaStream_t st, const double* centre, const double* sigma_dev) {
     const size_t smem = obj_small_smem(p, L, T);
     static std::atomic<int> attr_done[64];
     if (AttrOnce once(attr_done); once) {
         cudaFuncSetAttribute(k_obj_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         cudaFuncSetAttribute(k_obj_small<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     }
-    if (dim == 2) k_obj_small<2><<<1, 128, smem, st>>>(Y, U, S, sigma, consts, p, L, (int)T, threading, x0, dx0, out, xT, dxT);
-    else k_obj_small<3><<<1, 128, smem, st>>>(Y, U, S, sigma, consts, p, L, (int)T, threading, x0, dx0, out, xT, dxT);
+    if (dim == 2) k_obj_small<2><<<1, 128, smem, st>>>(Y, U, S, sigma, consts, p, L, (int)T, threading, x0, dx0, out, xT, dxT, centre, sigma_dev);
+    else k_obj_small<3><<<1, 128, smem, st>>>(Y, U, S, sigma, consts, p, L, (int)T, threading, x0, dx0, out, xT, dxT, centre, sigma_dev);
     return cudaGetLastError();
 }
 

@@ -11,10 +11,9 @@
 // the reference's results are whatever iterate the loop stops on.  This file is compiled with
 // -fmad=false so that the stop decisions see the same roundings as the host compiler's.
 //
-// Work split inside the warp: lane 0 builds A, Q, runs DARE and derives S, K, PF, HA, AKHA;
-// lanes 0..2 then each handle one hyper-parameter (block expm, QLyap, DLyap, dS, dK, dAKHA, HdA),
-// lane 3 the literal smoother constants, lane 4 the rts_correct ones, lanes 5..7 the 2^k power
-// tables of AKHA / G used by the chunked scans.
+// Work split: one CTA per latent, six warps with one job each (see k_setup below) - the independent pieces (the three
+// hyper-parameters' DLyap iterations, both smoothers, the block exponential, the 2^k power tables of AKHA / G used by the
+// chunked scans) run concurrently instead of as serialised divergent lanes of one warp.
 #include <cuda_runtime.h>
 #include <math.h>
 #include "moihgp_device.cuh"
@@ -269,19 +268,41 @@ template <int D> __device__ void power_table(const double* M, double (*tab)[9]) 
     }
 }
 
+// One CTA per latent, SIX warps, lane 0 of each doing one of the independent jobs (different code paths in different warps
+// run concurrently; as lanes of one warp they would be serialised):
+//   phase A   warp 0: state space, A = expm(dt F), Q, the literal DARE, gains             (ihgp.h:120-133)
+//             warp 1: the 2d x 2d block exponential behind dA of the lengthscale (:163-167) - needs only F, dF, dt
+//   phase B   warps 0..2: one hyper-parameter each (QLyap, literal DLyap, dS, dK, dAKHA, HdA)   (:136-200)
+//             warp 3: literal smoother constants + G^(2^k) table, warp 4: rts_correct ones + table, warp 5: AKHA^(2^k) table
+// Every quantity is computed by the same instruction sequence as before: results are bit-identical, only the schedule changed.
 template <int D>
-__global__ void __launch_bounds__(128) k_setup(const double* __restrict__ igp_params /*[L][3]*/, double dt, int L,
+__global__ void __launch_bounds__(192) k_setup(const double* __restrict__ igp_params /*[L][3]*/, double dt, int L,
                                               LatentConsts* __restrict__ out) {
     constexpr int DD = D * D;
-    __shared__ WarpScratch<D> scratch[4];
+    __shared__ WarpScratch<D> w;
+    __shared__ double dA_len[DD];                  // dA of the lengthscale, from warp 1's block exponential
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int l = blockIdx.x * 4 + warp;
-    if (l >= L) return;
-    WarpScratch<D>& w = scratch[warp];
+    const int l = blockIdx.x;
     LatentConsts& o = out[l];
     const double* prm = igp_params + 3 * l;
 
-    if (lane == 0) {
+    if (warp == 1 && lane == 0) {
+        StateSpace<D> ss1;                          // the same state space as warp 0 builds (deterministic), privately
+        state_space(ss1, prm[0], prm[1], prm[2]);
+        if (!all_zero<DD>(ss1.dF1)) {
+            constexpr int E = 2 * D;
+            double FF[E * E], EX[E * E];
+            for (int i = 0; i < E * E; ++i) FF[i] = 0.0;
+            for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) {     // ihgp.h:163-166
+                FF[i * E + j] = ss1.F[i * D + j] * dt;
+                FF[(D + i) * E + D + j] = ss1.F[i * D + j] * dt;
+                FF[(D + i) * E + j] = ss1.dF1[i * D + j] * dt;
+            }
+            expm<E>(FF, EX);                                          // ihgp.h:167
+            for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) dA_len[i * D + j] = EX[(D + i) * E + j];
+        }
+    }
+    if (warp == 0 && lane == 0) {
         state_space(w.ss, prm[0], prm[1], prm[2]);
         double tF[DD], t1[DD], t2[DD];
         scl<DD>(w.ss.F, dt, tF);
@@ -314,11 +335,12 @@ __global__ void __launch_bounds__(128) k_setup(const double* __restrict__ igp_pa
         for (int i = 0; i < 3; ++i) o.params[i] = prm[i];
         o.dim = D;
     }
-    __syncwarp();
+    __syncthreads();
+    if (lane != 0) return;
 
-    if (lane < 3) {
-        // ---- one hyper-parameter per lane: ihgp.h:136-200 --------------------------------------
-        const int idx = lane;
+    if (warp < 3) {
+        // ---- one hyper-parameter per warp: ihgp.h:136-200 --------------------------------------
+        const int idx = warp;
         double AT[DD], dA[DD], dAT[DD], dQ[DD], QL[DD], t1[DD], t2[DD];
         tr<D, D>(w.A, AT);
         // exact-zero tests of ihgp.h:141,144,152: dF is non-zero only for the lengthscale (idx 1),
@@ -338,16 +360,7 @@ __global__ void __launch_bounds__(128) k_setup(const double* __restrict__ igp_pa
                 for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) QL[i * D + j] = (w.AK[i] * w.AK[j]) * dR + dQ[i * D + j];
             }
         } else {
-            constexpr int E = 2 * D;
-            double FF[E * E], EX[E * E];
-            for (int i = 0; i < E * E; ++i) FF[i] = 0.0;
-            for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) {     // :163-166
-                FF[i * E + j] = w.ss.F[i * D + j] * dt;
-                FF[(D + i) * E + D + j] = w.ss.F[i * D + j] * dt;
-                FF[(D + i) * E + j] = w.ss.dF1[i * D + j] * dt;
-            }
-            expm<E>(FF, EX);                                          // :167
-            for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) dA[i * D + j] = EX[(D + i) * E + j];
+            cpy<DD>(dA_len, dA);                                      // :163-167, computed by warp 1 in phase A
             tr<D, D>(dA, dAT);                                        // :168
             double a[DD], b[DD], c[DD];
             mm<D, D, D>(dA, w.ss.Pinf, t1); mm<D, D, D>(t1, AT, a);   // dA Pinf A'
@@ -382,7 +395,7 @@ __global__ void __launch_bounds__(128) k_setup(const double* __restrict__ igp_pa
         o.dS[idx] = dS;
         store_mat<D>(dA, o.dA[idx]); store_mat<D>(dAKHA, o.dAKHA[idx]);
         store_vec<D>(dK, o.dK[idx]); store_vec<D>(HdA, o.HdA[idx]);
-    } else if (lane == 3) {
+    } else if (warp == 3) {
         // ---- reference_literal smoother constants: ihgp.h:105-107 (Q3) ---------------------------
         double PPs[DD], t1[DD], APF[DD], sym[DD], X[DD], G[DD], C[DD], P[DD];
         mm<D, D, D>(w.A, w.PF, APF);
@@ -401,9 +414,9 @@ __global__ void __launch_bounds__(128) k_setup(const double* __restrict__ igp_pa
         int it = 0;
         dlyap_literal<D>(G, C, P, &it);                               // :107
         o.smooth_iters = it;
-        cpy<DD>(G, w.G[0]);
         store_mat<D>(G, o.G[0]); store_mat<D>(P, o.Ps[0]);
-    } else if (lane == 4) {
+        power_table<D>(G, o.powG[0]);               // G^(2^k) for the chunked scans
+    } else if (warp == 4) {
         // ---- rts_correct smoother constants (OUR extension) -------------
         //   PPc = A PF A' + Q,  G = PF A' PPc^-1,  P_s = G P_s G' + PF - G PPc G'  (exact solve)
         double AT[DD], t1[DD], PPc[DD], PFAT[DD], G[DD], C[DD];
@@ -431,25 +444,21 @@ __global__ void __launch_bounds__(128) k_setup(const double* __restrict__ igp_pa
         solve_lu<N2, 1>(Mx, rv, pv);
         double GK[D];
         for (int i = 0; i < D; ++i) { double s = 0.0; for (int k = 0; k < D; ++k) s += G[i * D + k] * w.K[k]; GK[i] = s; }
-        cpy<DD>(G, w.G[1]);
         double GA[DD], Bs[DD];
         mm<D, D, D>(G, w.A, GA);
         for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) Bs[i * D + j] = (i == j ? 1.0 : 0.0) - GA[i * D + j];
         store_mat<D>(G, o.G[1]); store_mat<D>(pv, o.Ps[1]); store_vec<D>(GK, o.GK); store_mat<D>(Bs, o.Bs);
+        power_table<D>(G, o.powG[1]);
+    } else if (warp == 5) {
+        power_table<D>(w.AKHA, o.powM);             // AKHA^(2^k) for the chunked scans
     }
-    __syncwarp();
-    // ---- 2^k power tables for the chunked scans ---------------------------------------------------
-    if (lane == 5) power_table<D>(w.AKHA, o.powM);
-    else if (lane == 6) power_table<D>(w.G[0], o.powG[0]);
-    else if (lane == 7) power_table<D>(w.G[1], o.powG[1]);
 }
 
 }  // namespace
 
 cudaError_t launch_setup(int dim, const double* d_igp_params, double dt, int L, LatentConsts* d_out, cudaStream_t stream) {
-    const int blocks = (L + 3) / 4;
-    if (dim == 2) k_setup<2><<<blocks, 128, 0, stream>>>(d_igp_params, dt, L, d_out);
-    else k_setup<3><<<blocks, 128, 0, stream>>>(d_igp_params, dt, L, d_out);
+    if (dim == 2) k_setup<2><<<L, 192, 0, stream>>>(d_igp_params, dt, L, d_out);
+    else k_setup<3><<<L, 192, 0, stream>>>(d_igp_params, dt, L, d_out);
     return cudaGetLastError();
 }
 

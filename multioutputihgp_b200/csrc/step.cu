@@ -258,6 +258,75 @@ cudaError_t launch_step(const StepArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// OnlineObjective::push_back (moihgp_online.h:75-93) on the device-resident window: append y, recompute the moving mean over
+// every element held (the one about to be dropped included, as the reference does), drop the oldest element when the window
+// is over-full, and leave the NEW front element minus the mean in front_centred (the observation the carried state is then
+// advanced with).  win holds the window oldest-first, contiguously.  count[0] = elements held, count[1] = 1 if
+// an element was dropped by this push.
+__global__ void __launch_bounds__(128) k_online_push(const double* __restrict__ y_new, const double* __restrict__ ma_given, int p, int W,
+                                                    double* __restrict__ win, int* __restrict__ count, double* __restrict__ ma,
+                                                    double* __restrict__ front_centred) {
+    const int tid = threadIdx.x;
+    const int n = count[0] + 1;                                  // after the push_back (:77)
+    for (int r = tid; r < p; r += 128) {
+        win[(size_t)(n - 1) * p + r] = y_new[r];
+        if (ma_given) { ma[r] = ma_given[r]; continue; }         // the caller's own centre (online_learning.py:54-64: an EMA)
+        double s = 0.0;
+        for (int k = 0; k < n; ++k) s += win[(size_t)k * p + r];  // ma += *it, oldest first (:79-82)
+        ma[r] = s / double(n);                                   // :83
+    }
+    __syncthreads();
+    const bool drop = n > W;                                     // :84 (at most one element per push: n <= W + 1)
+    if (drop) {
+        for (int r = tid; r < p; r += 128) {
+            for (int k = 0; k + 1 < n; ++k) win[(size_t)k * p + r] = win[(size_t)(k + 1) * p + r];   // pop_front (:88)
+            front_centred[r] = win[r] - ma[r];                   // Y.front() - ma (:89), after the pop
+        }
+    }
+    __syncthreads();
+    if (tid == 0) { count[0] = drop ? n - 1 : n; count[1] = drop ? 1 : 0; }
+}
+
+// Proximal term of OnlineObjective::operator() (moihgp_online.h:42-54) added to the window objective:
+//   dparams = params - oldparams,  Bp = B dparams (B = null: the identity, :50-53),  loss += 1/2 dparams' Bp,  grad += Bp;
+// also appends the model's polar factor U to the output block so that ONE device-to-host copy refreshes the host mirror.
+__global__ void __launch_bounds__(256) k_online_prox(const double* __restrict__ params, const double* __restrict__ oldparams,
+                                                    const double* __restrict__ B, int np, int pL, const double* __restrict__ U,
+                                                    double* __restrict__ out) {
+    __shared__ double red[256];
+    const int tid = threadIdx.x;
+    double part = 0.0;
+    for (int i = tid; oldparams && i < np; i += 256) {           // oldparams = null: no proximal term (the caller adds its own)
+        double bp;
+        if (B) {
+            bp = 0.0;
+            for (int j = 0; j < np; ++j) bp += B[(size_t)i * np + j] * (params[j] - oldparams[j]);
+        } else bp = params[i] - oldparams[i];
+        part += (params[i] - oldparams[i]) * bp;
+        out[2 + i] += bp;
+    }
+    for (int i = tid; i < pL; i += 256) out[2 + np + i] = U[i];
+    red[tid] = part;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int i = 0; i < 256; ++i) s += red[i];                // fixed order
+        out[0] += 0.5 * s;
+    }
+}
+
+cudaError_t launch_online_push(const double* y_new, const double* ma_given, int p, int W, double* win, int* count, double* ma,
+                               double* front_centred, cudaStream_t st) {
+    k_online_push<<<1, 128, 0, st>>>(y_new, ma_given, p, W, win, count, ma, front_centred);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_online_prox(const double* params, const double* oldparams, const double* B, int np, int pL, const double* U, double* out,
+                               cudaStream_t st) {
+    k_online_prox<<<1, 256, 0, st>>>(params, oldparams, B, np, pL, U, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_smooth_seq(const double* X, const LatentConsts* consts, int L, int d, long long N, long long T, int mode, double* Xs,
                               cudaStream_t st) {
     const long long chains = N * L;

@@ -2,9 +2,11 @@
 
 Same constructor, ``step(y)`` protocol, parameter bounds, EMA mean, sliding window and SciPy
 L-BFGS-B settings (maxiter=5, maxls=3) as the reference.  The difference is where the work runs:
-the objective evaluates the whole window with ONE call into the CUDA library
-(``MOIHGPSequences.objective``) instead of 2 x window ctypes calls per evaluation
-(online_learning.py:83-89), and the filter steps use the legacy per-observation symbols.
+the window, the state carried in front of it and the model stay RESIDENT on the device
+(``moihgp_cuda_online_*``): one objective evaluation is one CUDA-graph launch (parameters in,
+polar factor, K-setup, whole-window objective, loss and gradient out) instead of 2 x window ctypes
+calls (online_learning.py:83-89); the filter steps use the legacy per-observation symbols.
+A window with missing observations takes the reference's per-observation loop.
 """
 import numpy as np
 try:
@@ -43,6 +45,9 @@ class MOIHGPOnlineLearning:
         self.windowsize = 1 if windowsize is None else windowsize
         self.ma = None
         self.dma = np.zeros((num_output,), dtype=np.float64)
+        self._resident = self._seq.online_begin(self.windowsize)
+        if self._resident:
+            self._seq.online_set_proximal(None)           # the proximal term stays here (hess_inv solve, as the reference's)
 
     @staticmethod
     def _seq_kernel(kernel):
@@ -69,9 +74,15 @@ class MOIHGPOnlineLearning:
                     self.ma[i] = 0.5 * yi + 0.5 * ma_old[i]
             self.dma = self.ma - ma_old
         self.buffer.append(y)
-        while len(self.buffer) > self.windowsize:                            # online_learning.py:66-68 (Q12)
-            self.buffer.pop(0)
-            self.xinit, _, self.dxinit = self.moihgp.step(self.xinit, y=self.buffer[0] - self.ma, dx=self.dxinit)
+        if self._resident:
+            # window slide + carried-state step on the device, with this learner's own centre (the exponential mean)
+            self._seq.online_push(y, ma_given=self.ma)
+            while len(self.buffer) > self.windowsize:
+                self.buffer.pop(0)
+        else:
+            while len(self.buffer) > self.windowsize:                        # online_learning.py:66-68 (Q12)
+                self.buffer.pop(0)
+                self.xinit, _, self.dxinit = self.moihgp.step(self.xinit, y=self.buffer[0] - self.ma, dx=self.dxinit)
         xnew, yhat, dxnew = self.moihgp.step(self.x, y=y - self.ma, dx=self.dx)
         yhat += self.ma
         self.x = xnew
@@ -79,11 +90,17 @@ class MOIHGPOnlineLearning:
         oldparams = self.moihgp.params.copy()
         window = np.array(self.buffer) - self.ma
         has_nan = bool(np.isnan(window).any())
+        if self._resident and has_nan:
+            self.xinit, self.dxinit = self._seq.online_state()
 
         def objective(params, eval_gradient=True):                           # online_learning.py:74-98
             dparams = params - oldparams
-            self._update(params)
             p = np.linalg.solve(self.hess_inv, dparams)
+            if self._resident and not has_nan:
+                l, g = self._seq.online_objective(params)                    # update(params) + window loop: one graph launch
+                loss = self.gamma * 0.5 * dparams.dot(p) + l
+                return (loss, self.gamma * p + g) if eval_gradient else loss
+            self._update(params)
             if has_nan:
                 # missing observations: per-observation symbols, exactly the reference's loop
                 xt, dxt = self.xinit, self.dxinit
