@@ -512,6 +512,33 @@ def run_ours(a, wl, torch, dist, rank, local_rank, world, steps, warmup, cores, 
         e2e = {"value": float(Ne) * T * L * world / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * float(te.item()), "sequences_per_gpu": Ne,
                "api": api, "steps": ke, "result_check": abs(got - ref_val) <= 1e-9 * abs(ref_val)}
+        if kind == "fsn":
+            # second figure: the same call returning only the function-value component H x of the filtered / smoothed states
+            # ([N,T,L]: what predict-style callers consume) - d times fewer bytes from the device to the host
+            del Xh, Xsh
+            Fh = torch.empty((Ne, T, L), dtype=torch.float64, pin_memory=True)
+            Fsh = torch.empty((Ne, T, L), dtype=torch.float64, pin_memory=True)
+
+            def e2e_values_step():
+                rc = lib.moihgp_cuda_filter_smoother_nll_values(h, Yh.data_ptr(), Ne, T, None, 1, Fh.data_ptr(), Fsh.data_ptr(), None, nllh.data_ptr(), None)
+                if rc != 0:
+                    raise SystemExit("e2e (values) call failed: " + lib.moihgp_cuda_last_error(h).decode())
+            e2e_values_step()
+            sync_all()
+            t0 = time.perf_counter()
+            for _ in range(ke):
+                e2e_values_step()
+            sync_all()
+            tv = torch.tensor([(time.perf_counter() - t0) / ke], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+            e2e["function_values_only"] = {"value": float(Ne) * T * L * world / float(tv.item()), "unit": UNIT, "ms_per_step": 1e3 * float(tv.item()),
+                                           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(8 * Ne * (2 * T * L + 1)),
+                                           "api": "moihgp_cuda_filter_smoother_nll_values (host buffers, pinned): F, Fs [N,T,L] + nll",
+                                           "result_check": abs(float(nllh.sum().item()) - ref_val) <= 1e-9 * abs(ref_val)}
+            e2e["host_topology_note"] = ("the timed copies run at PCIe speed (D2H of X, Xs dominates); with N ranks the pinned traffic of all "
+                                         "ranks shares one host memory system - on this pool every GPU reports CPU affinity 0-31 / NUMA node 0, "
+                                         "so there is no second node to bind to")
 
     # ------------------------------------------------------------------ CPU baseline beside it (rank 0, N = 1 only)
     cpu = None

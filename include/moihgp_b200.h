@@ -133,6 +133,10 @@ int moihgp_cuda_smoother_consts(moihgp_handle* h, size_t l, int mode, double* G,
  * x0 [N][L][d] carried-in state (NULL = zeros); X, Xs, Yhat, nll, xT may each be NULL. */
 int moihgp_cuda_filter_smoother_nll(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0,
                                     int smoother_mode, double* X, double* Xs, double* Yhat, double* nll, double* xT);
+/* same pass, but only the FUNCTION-VALUE component H x = x(0) of every filtered / smoothed state crosses PCIe:
+ * F, Fs [N][T][L] (what predict-style callers consume: yhat = U sqrt(S) x(0), moihgp.h:222-225) - d times fewer bytes out. */
+int moihgp_cuda_filter_smoother_nll_values(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0,
+                                           int smoother_mode, double* F, double* Fs, double* Yhat, double* nll, double* xT);
 /* same, DEVICE buffers already resident in HBM; asynchronous on the handle's stream */
 int moihgp_cuda_filter_smoother_nll_dev(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0,
                                         int smoother_mode, double* X, double* Xs, double* Yhat, double* nll, double* xT);

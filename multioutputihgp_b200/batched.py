@@ -164,6 +164,23 @@ class MOIHGPSequences(object):
                                                               _ptr(Yhat), _ptr(nll), _ptr(xT)))
         return {"X": X, "Xs": Xs, "Yhat": Yhat, "nll": nll, "xT": xT}
 
+    def filter_smoother_nll_values(self, Y, x0=None, smoother_mode=SMOOTH_REFERENCE_LITERAL, want_yhat=False):
+        """The same pass returning only the function-value component H x = x(0) of the filtered / smoothed states,
+        F and Fs [N,T,L] (d times fewer bytes across PCIe), plus nll, xT and optionally Yhat."""
+        Y = _np(Y)
+        if Y.ndim == 2:
+            Y = Y[None]
+        N, T, p = Y.shape
+        L, d = self.num_latent, self.igp_dim
+        x0 = None if x0 is None else _np(x0).reshape(N, L, d)
+        F = np.empty((N, T, L))
+        Fs = np.empty((N, T, L)) if smoother_mode >= 0 else None
+        Yhat = np.empty((N, T, p)) if want_yhat else None
+        nll, xT = np.empty(N), np.empty((N, L, d))
+        self._check(self._lib.moihgp_cuda_filter_smoother_nll_values(self._h, _ptr(Y), N, T, _ptr(x0), smoother_mode, _ptr(F), _ptr(Fs),
+                                                                     _ptr(Yhat), _ptr(nll), _ptr(xT)))
+        return {"F": F, "Fs": Fs, "Yhat": Yhat, "nll": nll, "xT": xT}
+
     def filter_smoother_nll_device(self, Y, x0=None, smoother_mode=SMOOTH_REFERENCE_LITERAL, X=None, Xs=None, Yhat=None, nll=None, xT=None):
         """Device-resident variant: all arguments are torch CUDA float64 tensors (outputs pre-allocated by the
         caller, any may be None); runs asynchronously on torch's current stream."""

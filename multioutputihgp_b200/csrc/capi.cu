@@ -702,8 +702,10 @@ int moihgp_cuda_smoother_power(moihgp_handle* h, int mode, size_t n, double* out
 // Host buffers.  Independent sequences are processed in slices, software-pipelined over three streams: the H2D copy of
 // slice i+1 and the D2H copy of slice i-1 overlap the kernels of slice i (PCIe is full duplex), with two sets of
 // device buffers.  (Pinned host memory is needed for the copies to be asynchronous; pageable memory still works.)
-int moihgp_cuda_filter_smoother_nll(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0, int mode, double* X,
-                                    double* Xs, double* Yhat, double* nll, double* xT) {
+// values_only: X / Xs receive the FUNCTION-VALUE component H x = x(0) of every state only, [N][T][L] (what predict-style
+// callers consume: yhat = U sqrt(S) x(0), moihgp.h:222-225) - d times fewer bytes across PCIe.
+static int fsn_host(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0, int mode, double* X,
+                    double* Xs, double* Yhat, double* nll, double* xT, bool values_only) {
     if (!h || !Y) return -2;
     if (N == 0 || T == 0) return fail(h, "N and T must be positive");
     if (mode < -1 || mode > 1) return fail(h, "smoother_mode must be -1, 0 or 1");
@@ -726,8 +728,9 @@ int moihgp_cuda_filter_smoother_nll(moihgp_handle* h, const double* Y, size_t N,
         }
     }
     const int nbuf = nsl > 1 ? 2 : 1;
-    double *dY[2] = {}, *dx0[2] = {}, *dX[2] = {}, *dXs[2] = {}, *dYh[2] = {}, *dnll[2] = {}, *dxT[2] = {};
-    static const char* names[2][7] = {{"hY0", "hx00", "hX0", "hXs0", "hYh0", "hnll0", "hxT0"}, {"hY1", "hx01", "hX1", "hXs1", "hYh1", "hnll1", "hxT1"}};
+    double *dY[2] = {}, *dx0[2] = {}, *dX[2] = {}, *dXs[2] = {}, *dYh[2] = {}, *dnll[2] = {}, *dxT[2] = {}, *dF[2] = {}, *dFs[2] = {};
+    static const char* names[2][9] = {{"hY0", "hx00", "hX0", "hXs0", "hYh0", "hnll0", "hxT0", "hF0", "hFs0"},
+                                      {"hY1", "hx01", "hX1", "hXs1", "hYh1", "hnll1", "hxT1", "hF1", "hFs1"}};
     for (int b = 0; b < nbuf; ++b) {
         if (ws_get(h, names[b][0], Ns * T * p, &dY[b])) return -1;
         if (x0 && ws_get(h, names[b][1], Ns * L * D, &dx0[b])) return -1;
@@ -736,6 +739,8 @@ int moihgp_cuda_filter_smoother_nll(moihgp_handle* h, const double* Y, size_t N,
         if (Yhat && ws_get(h, names[b][4], Ns * T * p, &dYh[b])) return -1;
         if (nll && ws_get(h, names[b][5], Ns, &dnll[b])) return -1;
         if (xT && ws_get(h, names[b][6], Ns * L * D, &dxT[b])) return -1;
+        if (values_only && X && ws_get(h, names[b][7], Ns * T * L, &dF[b])) return -1;
+        if (values_only && Xs && ws_get(h, names[b][8], Ns * T * L, &dFs[b])) return -1;
     }
     int* nanf;
     if (ws_get(h, "nanf", 4, &nanf)) return -1;
@@ -768,8 +773,19 @@ int moihgp_cuda_filter_smoother_nll(moihgp_handle* h, const double* Y, size_t N,
         CK(cudaMemcpyAsync(&flags[i], nanf, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaEventRecord(h->ev_c[b], h->stream));
         CK(cudaStreamWaitEvent(h->s_out, h->ev_c[b], 0));
-        if (X) CK(cudaMemcpyAsync(X + n0 * T * L * D, dX[b], sizeof(double) * ns * T * L * D, cudaMemcpyDeviceToHost, h->s_out));
-        if (Xs) CK(cudaMemcpyAsync(Xs + n0 * T * L * D, dXs[b], sizeof(double) * ns * T * L * D, cudaMemcpyDeviceToHost, h->s_out));
+        if (values_only) {
+            // component 0 of every state, compacted on the device (in place is not possible: strides differ), then copied out
+            if (X) CK(launch_extract_values(dX[b], dF[b], (long long)(ns * T * L), (int)D, h->stream));
+            if (Xs) CK(launch_extract_values(dXs[b], dFs[b], (long long)(ns * T * L), (int)D, h->stream));
+            h->launches += (X ? 1 : 0) + (Xs ? 1 : 0);
+            CK(cudaEventRecord(h->ev_c[b], h->stream));
+            CK(cudaStreamWaitEvent(h->s_out, h->ev_c[b], 0));
+            if (X) CK(cudaMemcpyAsync(X + n0 * T * L, dF[b], sizeof(double) * ns * T * L, cudaMemcpyDeviceToHost, h->s_out));
+            if (Xs) CK(cudaMemcpyAsync(Xs + n0 * T * L, dFs[b], sizeof(double) * ns * T * L, cudaMemcpyDeviceToHost, h->s_out));
+        } else {
+            if (X) CK(cudaMemcpyAsync(X + n0 * T * L * D, dX[b], sizeof(double) * ns * T * L * D, cudaMemcpyDeviceToHost, h->s_out));
+            if (Xs) CK(cudaMemcpyAsync(Xs + n0 * T * L * D, dXs[b], sizeof(double) * ns * T * L * D, cudaMemcpyDeviceToHost, h->s_out));
+        }
         if (Yhat) CK(cudaMemcpyAsync(Yhat + n0 * T * p, dYh[b], sizeof(double) * ns * T * p, cudaMemcpyDeviceToHost, h->s_out));
         if (nll) CK(cudaMemcpyAsync(nll + n0, dnll[b], sizeof(double) * ns, cudaMemcpyDeviceToHost, h->s_out));
         if (xT) CK(cudaMemcpyAsync(xT + n0 * L * D, dxT[b], sizeof(double) * ns * L * D, cudaMemcpyDeviceToHost, h->s_out));
@@ -780,6 +796,16 @@ int moihgp_cuda_filter_smoother_nll(moihgp_handle* h, const double* Y, size_t N,
     for (size_t i = 0; i < nsl; ++i)
         if (flags[i] == 2) return fail(h, "more than 2^22 observations with missing (NaN) outputs in one call: split the batch");
     return 0;
+}
+
+int moihgp_cuda_filter_smoother_nll(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0, int mode, double* X,
+                                    double* Xs, double* Yhat, double* nll, double* xT) {
+    return fsn_host(h, Y, N, T, x0, mode, X, Xs, Yhat, nll, xT, false);
+}
+
+int moihgp_cuda_filter_smoother_nll_values(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0, int mode, double* F,
+                                           double* Fs, double* Yhat, double* nll, double* xT) {
+    return fsn_host(h, Y, N, T, x0, mode, F, Fs, Yhat, nll, xT, true);
 }
 
 int moihgp_cuda_smooth_dev(moihgp_handle* h, const double* X, size_t N, size_t T, int mode, double* Xs) {

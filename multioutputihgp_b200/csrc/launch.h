@@ -178,6 +178,7 @@ struct LikArgs {
     double* scratch;
 };
 cudaError_t launch_lik(const LikArgs& a, cudaStream_t st);
+cudaError_t launch_extract_values(const double* X, double* F, long long n, int d, cudaStream_t st);
 // IHGP::backwardSmoother over caller-supplied filtered states (generic: one thread per chain)
 cudaError_t launch_smooth_seq(const double* X, const LatentConsts* consts, int L, int d, long long N, long long T, int mode, double* Xs,
                               cudaStream_t st);

@@ -315,6 +315,16 @@ __global__ void __launch_bounds__(256) k_online_prox(const double* __restrict__ 
     }
 }
 
+// F[i] = X[i][0]: the function-value component H x of every state (H = e0', matern32ss.h:22)
+__global__ void __launch_bounds__(256) k_extract_values(const double* __restrict__ X, double* __restrict__ F, long long n, int d) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) F[i] = X[i * d];
+}
+cudaError_t launch_extract_values(const double* X, double* F, long long n, int d, cudaStream_t st) {
+    const long long blocks = (n + 255) / 256;
+    k_extract_values<<<(unsigned)(blocks < 148 * 16 ? (blocks < 1 ? 1 : blocks) : 148 * 16), 256, 0, st>>>(X, F, n, d);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_online_push(const double* y_new, const double* ma_given, int p, int W, double* win, int* count, double* ma,
                                double* front_centred, cudaStream_t st) {
     k_online_push<<<1, 128, 0, st>>>(y_new, ma_given, p, W, win, count, ma, front_centred);

@@ -919,6 +919,25 @@ def test_backprojection_with_a_mixing_matrix_larger_than_shared_memory(cuda_lib)
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("kernel,p,L,N,T,path", [("Matern52", 16, 8, 70, 300, "chain"), ("Matern32", 8, 4, 3, 1000, "scan"), ("Matern32", 64, 32, 1, 700, "scan")])
+def test_function_values_only_output(cuda_lib, kernel, p, L, N, T, path):
+    """moihgp_cuda_filter_smoother_nll_values: the same pass, only the function-value component H x = x(0) of the filtered and
+    smoothed states comes back ([N,T,L]); equal to component 0 of the full output, several pipeline slices included."""
+    from multioutputihgp_b200 import MOIHGPSequences
+    from oracle.gen_golden import make_data, make_params
+    rng = np.random.default_rng(N + T)
+    m = MOIHGPSequences(0.1, p, L, kernel, True)
+    m.update(make_params(rng, p, L, kernel))
+    m.set_path(path)
+    Y = np.stack([make_data(rng, p, L, T) for _ in range(N)])
+    x0 = 0.2 * rng.standard_normal((N, L, m.igp_dim))
+    full = m.filter_smoother_nll(Y, x0=x0, smoother_mode=1, want_yhat=True)
+    val = m.filter_smoother_nll_values(Y, x0=x0, smoother_mode=1, want_yhat=True)
+    assert np.array_equal(val["F"], full["X"][..., 0]) and np.array_equal(val["Fs"], full["Xs"][..., 0])
+    assert np.array_equal(val["nll"], full["nll"]) and np.array_equal(val["xT"], full["xT"]) and np.array_equal(val["Yhat"], full["Yhat"])
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("p,L", [(256, 64), (128, 33), (100, 21), (512, 16)])
 def test_newton_schulz_polar_factor_agrees_with_jacobi(cuda_lib, p, L, monkeypatch):
     """update() on the device: k_polar_ns (Newton-Schulz, the fast way for a block that is nearly orthonormal, as inside a
