@@ -41,7 +41,10 @@ namespace moihgp {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int STAGES = 4;
+#ifndef MOIHGP_FSTAGES
+#define MOIHGP_FSTAGES 4
+#endif
+constexpr int STAGES = MOIHGP_FSTAGES;
 
 template <int P, int L>
 struct ProjConsts {          // passed by value: lives in the constant bank
@@ -441,7 +444,12 @@ __global__ void __launch_bounds__(32, 14) k_filter_chain(const double* __restric
     }
 }
 
-constexpr int SSTAGES = 5;        // smoother ring: 3 loads in flight, 1 tile being processed, 1 tile being stored
+#ifndef MOIHGP_SSTAGES
+#define MOIHGP_SSTAGES 4
+#endif
+// Measured on B200, config 3 (profiles/r02/ab_smoother_ring_depth.txt): 3 / 4 / 5 / 6 stages = 4.35 / 4.0 / 4.43 / 4.17 ms -
+// four stages (9 one-warp CTAs per SM instead of 7) bring the smoother to the measured copy bandwidth (25.8 GB in 4.0 ms).
+constexpr int SSTAGES = MOIHGP_SSTAGES;   // smoother ring: SSTAGES - 2 loads in flight, 1 tile being processed, 1 tile being stored
 
 template <int L, int D, int NS_, int RM_>
 struct SmoothCfg {
