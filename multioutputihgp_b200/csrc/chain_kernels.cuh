@@ -41,8 +41,11 @@ namespace moihgp {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
+// Ring depth of the filter's cp.async tiles.  Measured on B200, config 3 (profiles/r02/ab_smoother_ring_depth.txt):
+// 2 / 3 / 4 / 6 stages = 3.62 / 3.75 / 3.84 / 5.17 ms - one tile in flight per warp is enough (seven warps per SM keep
+// 28 KB of reads outstanding) and deeper rings only crowd the stores out; evict-first stores (__stcs) for X changed nothing.
 #ifndef MOIHGP_FSTAGES
-#define MOIHGP_FSTAGES 4
+#define MOIHGP_FSTAGES 2
 #endif
 constexpr int STAGES = MOIHGP_FSTAGES;
 
