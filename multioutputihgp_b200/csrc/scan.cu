@@ -27,6 +27,7 @@
 // A block of a longer sequence sharded in time over several devices runs the same kernels in three
 // phases (run_scan; ScanArgs::phase, seq_end, u_after, b_end): SURVEY.md section 8(e).
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <math.h>
 #include <stdlib.h>
 #include "moihgp_device.cuh"
@@ -1032,7 +1033,7 @@ cudaError_t launch_scan_lanes(const ScanArgs& a, long long nC, cudaStream_t st) 
         if (e != cudaSuccess) return e;
     }
     const int nLG = a.L / LG;
-    const long long target = 148LL * 24;
+    const long long target = 148LL * 96;           // swept 6 .. 192 on config 4: flat, 96 best by 1 % (profiles/r02)
     long long groups = (target + a.N * nLG - 1) / (a.N * nLG);
     if (groups < 1) groups = 1;
     if (groups > nC) groups = nC;
@@ -1055,7 +1056,7 @@ cudaError_t run_scan(const ScanArgs& a, cudaStream_t st) {
         cudaFuncSetAttribute(k_scan<D, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
     // chunks per CTA / warp: enough CTAs to fill the machine several times over, as few prologues as that allows
-    const long long target = 148LL * 16;
+    const long long target = 148LL * 16;           // swept 4 .. 128 on config 4: 16 and above are equal, below it the machine is not filled
     auto per_unit = [&](long long units, long long chunks) {
         long long groups = (target + units - 1) / units;
         if (groups < 1) groups = 1;
