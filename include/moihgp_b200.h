@@ -223,6 +223,22 @@ int moihgp_cuda_block_transition(moihgp_handle* h, size_t n, double* out);
 int moihgp_cuda_fsn_block_dev(moihgp_handle* h, int phase, const double* Y, size_t N, size_t T, int seq_end, int smoother_mode,
                               const double* x0, const double* u_after, const double* b_end, double* X, double* Xs, double* nll,
                               double* xT, double* host_out);
+/* The same three phases WITHOUT host round trips (asynchronous on the handle's stream; the caller's all-gathers - NCCL on
+ * the same stream - sit between the calls):
+ *   fsn_block_async: like fsn_block_dev, the phase's output goes to DEVICE memory dev_out ([N][L][d + 1] after phase 1,
+ *                    [N][L][d] after phase 2)
+ *   fsn_carry_dev  : direction 0 (after phase 1): gathered_dev[G][N][L][d + 1] -> out_dev[N][L][d] = this block's true x_in
+ *                    (chained over the blocks before `rank` from x0_dev, NULL = zeros) and u_after_dev[N][L] = the next
+ *                    block's first projected observation (untouched on the last block);
+ *                    direction 1 (after phase 2): gathered_dev[G][N][L][d] -> out_dev[N][L][d] = this block's b_end
+ *                    (untouched on the last block).  The arithmetic of moihgp_cuda_block_transition /
+ *                    moihgp_cuda_smoother_power in a one-thread-per-(sequence, latent) kernel.  block_lengths: G host values. */
+int moihgp_cuda_fsn_block_async(moihgp_handle* h, int phase, const double* Y, size_t N, size_t T, int seq_end, int smoother_mode,
+                                const double* x0, const double* u_after, const double* b_end, double* X, double* Xs, double* nll,
+                                double* xT, double* dev_out);
+int moihgp_cuda_fsn_carry_dev(moihgp_handle* h, int direction, int smoother_mode, const double* gathered_dev, size_t G,
+                              const long long* block_lengths, size_t rank, size_t N, const double* x0_dev, double* out_dev,
+                              double* u_after_dev);
 /* G[mode]^n per latent: out[L][d*d] row-major (host arithmetic on the handle's power tables) */
 int moihgp_cuda_smoother_power(moihgp_handle* h, int smoother_mode, size_t n, double* out);
 

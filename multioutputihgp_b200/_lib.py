@@ -132,6 +132,10 @@ def load():
     lib.moihgp_cuda_block_transition.argtypes = [vp, sz, vp]
     lib.moihgp_cuda_fsn_block_dev.restype = ctypes.c_int
     lib.moihgp_cuda_fsn_block_dev.argtypes = [vp, ctypes.c_int, vp, sz, sz, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.moihgp_cuda_fsn_block_async.restype = ctypes.c_int
+    lib.moihgp_cuda_fsn_block_async.argtypes = [vp, ctypes.c_int, vp, sz, sz, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.moihgp_cuda_fsn_carry_dev.restype = ctypes.c_int
+    lib.moihgp_cuda_fsn_carry_dev.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, sz, ctypes.POINTER(ctypes.c_longlong), sz, sz, vp, vp, vp]
     lib.moihgp_cuda_smoother_power.restype = ctypes.c_int
     lib.moihgp_cuda_smoother_power.argtypes = [vp, ctypes.c_int, sz, vp]
     for name in ("moihgp_cuda_smooth", "moihgp_cuda_smooth_dev"):
@@ -150,6 +154,6 @@ LEGACY_NAMES = ["new", "del", "step1", "step2", "step3", "step4", "update", "lik
                 "num_param", "num_igp_param"]
 CUDA_NAMES = ["create", "destroy", "set_stream", "sync", "last_error", "launch_count", "profile", "profile_read", "set_path", "set_chain_seqs_per_warp", "igp_dim", "num_param",
               "num_igp_param", "update", "get_params", "get_U", "latent_consts", "latent_iters", "smoother_consts",
-              "filter_smoother_nll", "filter_smoother_nll_values", "filter_smoother_nll_dev", "objective", "objective_dev", "bind_data", "objective_bound", "objective_begin_dev", "objective_finish_dev", "block_transition", "fsn_block_dev", "smoother_power", "smooth", "smooth_dev", "objective_begin_async", "carry_in_dev", "nan_status", "online_begin", "online_push", "online_set_proximal",
+              "filter_smoother_nll", "filter_smoother_nll_values", "filter_smoother_nll_dev", "objective", "objective_dev", "bind_data", "objective_bound", "objective_begin_dev", "objective_finish_dev", "block_transition", "fsn_block_dev", "fsn_block_async", "fsn_carry_dev", "smoother_power", "smooth", "smooth_dev", "objective_begin_async", "carry_in_dev", "nan_status", "online_begin", "online_push", "online_set_proximal",
               "online_objective", "online_get_state"]
 ALL_SYMBOLS = ["gp%s_%s" % (xx, n) for xx in ("32", "52") for n in LEGACY_NAMES] + ["moihgp_cuda_" + n for n in CUDA_NAMES]

@@ -271,6 +271,24 @@ class MOIHGPSequences(object):
             return host[:, :, :d].copy(), host[:, :, d].copy()
         return host
 
+    def fsn_block_async(self, phase, Y, seq_end, smoother_mode=SMOOTH_REFERENCE_LITERAL, x0=None, u_after=None, b_end=None, X=None, Xs=None,
+                        nll=None, xT=None, out=None):
+        """fsn_block without a host round trip: the phase's output goes to the torch CUDA tensor ``out`` ([N,L,d+1] after
+        phase 1, [N,L,d] after phase 2); asynchronous on torch's current stream."""
+        N, T, _ = Y.shape
+        self._lib.moihgp_cuda_set_stream(self._h, _torch_stream(Y.device))
+        self._check(self._lib.moihgp_cuda_fsn_block_async(self._h, int(phase), _ptr(Y), N, T, 1 if seq_end else 0, int(smoother_mode), _ptr(x0),
+                                                          _ptr(u_after), _ptr(b_end), _ptr(X), _ptr(Xs), _ptr(nll), _ptr(xT), _ptr(out)))
+
+    def fsn_carry_device(self, direction, gathered, block_lengths, rank, out, smoother_mode=SMOOTH_REFERENCE_LITERAL, x0=None, u_after=None):
+        """The carry exchanges of the time-sharded pass on the device (torch CUDA tensors): direction 0 turns the all-gathered
+        phase-1 outputs [G,N,L,d+1] into this block's x_in (``out`` [N,L,d]) and ``u_after`` [N,L]; direction 1 turns the
+        all-gathered phase-2 outputs [G,N,L,d] into this block's b_end (``out`` [N,L,d]; untouched on the last block)."""
+        G = len(block_lengths)
+        lens = (ctypes.c_longlong * G)(*[int(b) for b in block_lengths])
+        self._check(self._lib.moihgp_cuda_fsn_carry_dev(self._h, int(direction), int(smoother_mode), _ptr(gathered), G, lens, int(rank), out.shape[0],
+                                                        _ptr(x0), _ptr(out), _ptr(u_after)))
+
     def smooth(self, X, smoother_mode=SMOOTH_REFERENCE_LITERAL):
         """IHGP::backwardSmoother (ihgp.h:103-114) of every latent over caller-supplied filtered states X [N,T,L,d] (or
         [T,L,d]); returns Xs of the same shape.  Gains / covariances: ``smoother_consts``."""

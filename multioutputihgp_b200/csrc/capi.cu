@@ -618,9 +618,9 @@ int moihgp_cuda_filter_smoother_nll_dev(moihgp_handle* h, const double* Y, size_
 
 // One contiguous block of a longer sequence sharded in TIME over several devices (chunked-scan path), in three phases
 // with the blocks' carries exchanged by the caller in between (include/moihgp_b200.h).
-int moihgp_cuda_fsn_block_dev(moihgp_handle* h, int phase, const double* Y, size_t N, size_t T, int seq_end, int mode,
-                              const double* x0, const double* u_after, const double* b_end, double* X, double* Xs, double* nll,
-                              double* xT, double* host_out) {
+static int fsn_block_impl(moihgp_handle* h, int phase, const double* Y, size_t N, size_t T, int seq_end, int mode,
+                          const double* x0, const double* u_after, const double* b_end, double* X, double* Xs, double* nll,
+                          double* xT, double* host_out, double* dev_out) {
     if (!h) return -2;
     if (phase < 1 || phase > 3) return fail(h, "phase must be 1, 2 or 3");
     if (N == 0 || T == 0) return fail(h, "N and T must be positive");
@@ -670,10 +670,42 @@ int moihgp_cuda_fsn_block_dev(moihgp_handle* h, int phase, const double* Y, size
         CK(cudaMemcpyAsync(host_out, bo, sizeof(double) * N * L * D, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
+    // the same values left in DEVICE memory, asynchronously on the handle's stream (no host round trip: the caller's
+    // all-gather - NCCL on the same stream - follows directly)
+    if (phase == 1 && dev_out) {
+        CK(cudaMemcpy2DAsync(dev_out, sizeof(double) * (D + 1), xe, sizeof(double) * D, sizeof(double) * D, N * L, cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpy2DAsync(dev_out + D, sizeof(double) * (D + 1), u, sizeof(double) * T, sizeof(double), N * L, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    if (phase == 2 && dev_out) CK(cudaMemcpyAsync(dev_out, bo, sizeof(double) * N * L * D, cudaMemcpyDeviceToDevice, h->stream));
     if (phase == 3 && nll) {
         CK(launch_nll_reduce(rho, vsq, h->d_consts, h->d_S, h->sigma, h->p, L, (long long)N, (long long)T, npart, nll, h->stream));
         h->launches += 2;
     }
+    return 0;
+}
+
+int moihgp_cuda_fsn_block_dev(moihgp_handle* h, int phase, const double* Y, size_t N, size_t T, int seq_end, int mode,
+                              const double* x0, const double* u_after, const double* b_end, double* X, double* Xs, double* nll,
+                              double* xT, double* host_out) {
+    return fsn_block_impl(h, phase, Y, N, T, seq_end, mode, x0, u_after, b_end, X, Xs, nll, xT, host_out, nullptr);
+}
+
+int moihgp_cuda_fsn_block_async(moihgp_handle* h, int phase, const double* Y, size_t N, size_t T, int seq_end, int mode,
+                                const double* x0, const double* u_after, const double* b_end, double* X, double* Xs, double* nll,
+                                double* xT, double* dev_out) {
+    return fsn_block_impl(h, phase, Y, N, T, seq_end, mode, x0, u_after, b_end, X, Xs, nll, xT, nullptr, dev_out);
+}
+
+int moihgp_cuda_fsn_carry_dev(moihgp_handle* h, int direction, int mode, const double* gathered_dev, size_t G, const long long* block_lengths,
+                              size_t rank, size_t N, const double* x0_dev, double* out_dev, double* u_after_dev) {
+    if (!h || !gathered_dev || !block_lengths || !out_dev) return -2;
+    if (direction < 0 || direction > 1) return fail(h, "direction must be 0 (forward) or 1 (backward)");
+    if (mode < 0 || mode > 1) return fail(h, "smoother_mode must be 0 or 1");
+    if (G == 0 || G > 64 || rank >= G) return fail(h, "need 1 <= G <= 64 blocks and rank < G");
+    DeviceGuard guard(h->device);
+    CK(launch_fsn_carry(h->dim, direction, mode, h->d_consts, h->L, (long long)N, (int)rank, (int)G, block_lengths, gathered_dev, x0_dev, out_dev,
+                        u_after_dev, h->stream));
+    h->launches += 1;
     return 0;
 }
 

@@ -146,6 +146,10 @@ cudaError_t launch_objective(int dim, const ObjArgs& a, cudaStream_t st);
 cudaError_t launch_block_carry(int dim, const LatentConsts* consts, int L, long long N, int rank, const long long* block_lengths,
                                const double* ends /*[G][N][L][4][D]*/, const double* x0, const double* dx0, double* xin, double* dxin,
                                cudaStream_t st);
+// the two carry exchanges of the time-sharded filter + smoother pass on the device (scan.cu)
+cudaError_t launch_fsn_carry(int dim, int direction, int mode, const LatentConsts* consts, int L, long long N, int rank, int G,
+                             const long long* block_lengths, const double* gathered, const double* x0, double* out, double* u_after,
+                             cudaStream_t st);
 size_t obj_small_smem(int p, int L, long long T);
 cudaError_t launch_objective_small(int dim, const double* Y, const double* U, const double* S, double sigma, const LatentConsts* consts,
                                    int p, int L, long long T, int threading, const double* x0, const double* dx0, double* out, double* xT,

@@ -381,9 +381,10 @@ __global__ void __launch_bounds__(128) k_scan_summaries_dot(const double* __rest
     const double* up = u + ((size_t)n * L + l) * T;
     const bool vec = (reinterpret_cast<size_t>(up) & 15) == 0;      // chunk starts are multiples of 256 steps
     const long long c_hi = min(nI, (g + 1) * cpw);
-    for (long long c = g * cpw; c < c_hi; ++c) {
+    // software pipeline: the loads of chunk c + 1 are in flight while chunk c is reduced (one chunk per warp in flight
+    // leaves 32 KB per SM outstanding - not enough to cover the HBM latency at full bandwidth)
+    auto load_chunk = [&](long long c, double (&uu)[SUB], double& u_next) {
         const long long tb = c * CH + 2 * lane;
-        double uu[SUB];
         if (vec) {
 #pragma unroll
             for (int i = 0; i < SUB; i += 2) {
@@ -395,7 +396,16 @@ __global__ void __launch_bounds__(128) k_scan_summaries_dot(const double* __rest
 #pragma unroll
             for (int i = 0; i < SUB; i += 2) { uu[i] = __ldg(up + tb + 32 * i); uu[i + 1] = __ldg(up + tb + 32 * i + 1); }
         }
-        const double u_next = __ldg(up + (c + 1) * CH);
+        u_next = __ldg(up + (c + 1) * CH);
+    };
+    double un[SUB], un_next = 0.0;
+    if (g * cpw < c_hi) load_chunk(g * cpw, un, un_next);
+    for (long long c = g * cpw; c < c_hi; ++c) {
+        double uu[SUB];
+#pragma unroll
+        for (int i = 0; i < SUB; ++i) uu[i] = un[i];
+        const double u_next = un_next;
+        if (c + 1 < c_hi) load_chunk(c + 1, un, un_next);
         double acc[2 * D];
 #pragma unroll
         for (int k = 0; k < 2 * D; ++k) {
@@ -708,24 +718,31 @@ __global__ void __launch_bounds__(128) k_carry_super(const LatentConsts* __restr
 
 // nll[n] = sum_t [ 1/2 log(sum S) + 1/2 m_n log(sigma) + 1/2 rho_t / sigma ]            moihgp.h:653
 //        + sum_l sum_t 1/2 ( v^2 / S_l + log S_l )                                       ihgp.h:207, moihgp.h:675,684
-// Two stages, fixed order (deterministic): NSPLIT CTAs per sequence, then one thread per sequence.
-constexpr int NSPLIT = 64;
+// Two stages, fixed order (deterministic): nll_nsplit(N) CTAs per sequence, then one thread per sequence.
+// The split count follows the number of sequences: few long sequences (config 4: one sequence, 625 000 + 1 250 000 terms)
+// get 1024 CTAs per sequence, many sequences 64 (k_nll_partial 56 -> 9 us at config 4).
+__host__ __device__ inline int nll_nsplit(long long N) { return N >= 16 ? 64 : 1024; }
 __global__ void __launch_bounds__(256) k_nll_partial(const double* __restrict__ rho_part, const double* __restrict__ vsq,
                                                     const LatentConsts* __restrict__ consts, double sigma, int L, long long N,
-                                                    long long tiles, long long nC, double* __restrict__ part) {
+                                                    long long tiles, long long nC, int nsplit, double* __restrict__ part) {
     __shared__ double red[256];
-    const long long n = blockIdx.x / NSPLIT;
-    const int sp = blockIdx.x % NSPLIT;
+    __shared__ double hinvS[64];                                         // 1 / (2 S_l)
+    const long long n = blockIdx.x / nsplit;
+    const int sp = blockIdx.x % nsplit;
     const int tid = threadIdx.x;
+    const bool inv_sm = L <= 64;
+    if (inv_sm && tid < L) hinvS[tid] = 0.5 / consts[tid].S;
+    __syncthreads();
     double acc = 0.0;
-    const long long tb = (tiles + NSPLIT - 1) / NSPLIT;
+    const long long tb = (tiles + nsplit - 1) / nsplit;
     for (long long i = sp * tb + tid; i < min(tiles, (sp + 1) * tb); i += 256) acc += rho_part[n * tiles + i];
     acc *= 0.5 / sigma;
-    const long long cb = (nC + NSPLIT - 1) / NSPLIT;
+    const long long cb = (nC + nsplit - 1) / nsplit;
     for (long long i = sp * cb * L + tid; i < min(nC, (sp + 1) * cb) * L; i += 256) {
         const long long c = i / L;
         const int l = (int)(i - c * L);
-        acc += 0.5 * vsq[((size_t)c * N + n) * L + l] / consts[l].S;
+        const double v = vsq[((size_t)c * N + n) * L + l];
+        acc += inv_sm ? v * hinvS[l] : 0.5 * v / consts[l].S;
     }
     red[tid] = acc;
     __syncthreads();
@@ -733,15 +750,15 @@ __global__ void __launch_bounds__(256) k_nll_partial(const double* __restrict__ 
         if (tid < o) red[tid] += red[tid + o];
         __syncthreads();
     }
-    if (tid == 0) part[n * NSPLIT + sp] = red[0];
+    if (tid == 0) part[n * nsplit + sp] = red[0];
 }
 __global__ void __launch_bounds__(128) k_nll_reduce(const double* __restrict__ part, const LatentConsts* __restrict__ consts,
                                                    const double* __restrict__ S, double sigma, int p, int L, long long N,
-                                                   long long T, double* __restrict__ nll) {
+                                                   long long T, int nsplit, double* __restrict__ nll) {
     const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     double acc = 0.0;
-    for (int i = 0; i < NSPLIT; ++i) acc += part[n * NSPLIT + i];
+    for (int i = 0; i < nsplit; ++i) acc += part[n * nsplit + i];
     double Ssum = 0.0, logs = 0.0;
     for (int l = 0; l < L; ++l) { Ssum += S[l]; logs += consts[l].logS; }
     const double m_n = fmax((double)(p - L), 0.0);                       // moihgp.h:652
@@ -1152,11 +1169,112 @@ cudaError_t launch_nll_reduce(const double* rho_part, const double* vsq, const L
                               int p, int L, long long N, long long T, double* part, double* nll, cudaStream_t st) {
     const long long nC = (T + CH - 1) / CH;
     const long long tiles = (long long)project_tiles(T);
-    k_nll_partial<<<(unsigned)(N * NSPLIT), 256, 0, st>>>(rho_part, vsq, consts, sigma, L, N, tiles, nC, part);
-    k_nll_reduce<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(part, consts, S, sigma, p, L, N, T, nll);
+    const int nsplit = nll_nsplit(N);
+    k_nll_partial<<<(unsigned)(N * nsplit), 256, 0, st>>>(rho_part, vsq, consts, sigma, L, N, tiles, nC, nsplit, part);
+    k_nll_reduce<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(part, consts, S, sigma, p, L, N, T, nsplit, nll);
     return cudaGetLastError();
 }
 
-size_t nll_partials(long long N) { return (size_t)N * NSPLIT; }
+size_t nll_partials(long long N) { return (size_t)N * nll_nsplit(N); }
+
+// ---- one long sequence sharded in TIME (moihgp_cuda_fsn_block_*): the two carry exchanges on the device ----------------
+// forward  (DIR 0): gathered[g][n][l][D + 1] = [end state of block g from a zero carry-in | first projected observation of g];
+//                   x_in(g+1) = AKHA^n_g x_in(g) + x_end_g chained over g < rank from x0 -> out[n][l][D];
+//                   u_after[n][l] = first observation of block rank + 1 (untouched on the last block)
+// backward (DIR 1): gathered[g][n][l][D] = backward value at block g's first step from a ZERO b_end;
+//                   b_start(G-1) = gathered[G-1], b_start(g) = gathered[g] + G^n_g b_start(g+1); out = b_start(rank + 1)
+//                   (untouched on the last block, whose b_end is not used)
+// Powers by binary powering on the latent's 2^k tables (all powers of one matrix commute, so the order of the factors is
+// free).  One thread per (sequence, latent) - the arithmetic of parallel.forward_carry_in / backward_carry_in.
+struct FsnBlockLens { long long n[64]; };
+
+template <int D>
+__global__ void __launch_bounds__(128) k_fsn_carry(const LatentConsts* __restrict__ consts, int L, long long N, int rank, int G, int dir, int mode,
+                                                  FsnBlockLens lens, const double* __restrict__ gathered, const double* __restrict__ x0,
+                                                  double* __restrict__ out, double* __restrict__ u_after) {
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= N * L) return;
+    const LatentConsts& c = consts[id % L];
+    double P[D * D];
+    long long have = -1;
+    auto power = [&](long long n) {                       // P = M^n, M = AKHA (forward) or G[mode] (backward)
+        if (n == have) return;
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) P[i] = (i / D == i % D) ? 1.0 : 0.0;
+        for (int j = 0; (n >> j) != 0 && j < NPOW; ++j) {
+            if (!((n >> j) & 1)) continue;
+            const double* B = dir == 0 ? c.powM[j] : c.powG[mode][j];
+            double t[D * D];
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    double a = 0.0;
+#pragma unroll
+                    for (int q = 0; q < D; ++q) a += B[i * 3 + q] * P[q * D + k];
+                    t[i * D + k] = a;
+                }
+#pragma unroll
+            for (int i = 0; i < D * D; ++i) P[i] = t[i];
+        }
+        have = n;
+    };
+    double v[D];
+    if (dir == 0) {
+        const int W = D + 1;
+#pragma unroll
+        for (int q = 0; q < D; ++q) v[q] = x0 ? x0[id * D + q] : 0.0;
+        for (int g = 0; g < rank; ++g) {
+            power(lens.n[g]);
+            const double* e = gathered + ((size_t)g * N * L + id) * W;
+            double vn[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                double a = 0.0;
+#pragma unroll
+                for (int q = 0; q < D; ++q) a += P[i * D + q] * v[q];
+                vn[i] = a + e[i];
+            }
+#pragma unroll
+            for (int i = 0; i < D; ++i) v[i] = vn[i];
+        }
+#pragma unroll
+        for (int q = 0; q < D; ++q) out[id * D + q] = v[q];
+        if (u_after && rank + 1 < G) u_after[id] = gathered[((size_t)(rank + 1) * N * L + id) * W + D];
+    } else {
+        if (rank >= G - 1) return;
+        const double* e = gathered + ((size_t)(G - 1) * N * L + id) * D;
+#pragma unroll
+        for (int q = 0; q < D; ++q) v[q] = e[q];
+        for (int g = G - 2; g > rank; --g) {
+            power(lens.n[g]);
+            e = gathered + ((size_t)g * N * L + id) * D;
+            double vn[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                double a = 0.0;
+#pragma unroll
+                for (int q = 0; q < D; ++q) a += P[i * D + q] * v[q];
+                vn[i] = e[i] + a;
+            }
+#pragma unroll
+            for (int i = 0; i < D; ++i) v[i] = vn[i];
+        }
+#pragma unroll
+        for (int q = 0; q < D; ++q) out[id * D + q] = v[q];
+    }
+}
+
+cudaError_t launch_fsn_carry(int dim, int direction, int mode, const LatentConsts* consts, int L, long long N, int rank, int G,
+                             const long long* block_lengths, const double* gathered, const double* x0, double* out, double* u_after,
+                             cudaStream_t st) {
+    if (G < 1 || G > 64 || rank < 0 || rank >= G) return cudaErrorInvalidValue;
+    FsnBlockLens lens;
+    for (int g = 0; g < 64; ++g) lens.n[g] = g < G ? block_lengths[g] : 0;
+    const unsigned grid = (unsigned)((N * L + 127) / 128);
+    if (dim == 3) k_fsn_carry<3><<<grid, 128, 0, st>>>(consts, L, N, rank, G, direction, mode, lens, gathered, x0, out, u_after);
+    else k_fsn_carry<2><<<grid, 128, 0, st>>>(consts, L, N, rank, G, direction, mode, lens, gathered, x0, out, u_after);
+    return cudaGetLastError();
+}
 
 }  // namespace moihgp

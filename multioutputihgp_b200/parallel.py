@@ -324,6 +324,57 @@ class TimeShardedFilterSmoother(object):
         dist.all_gather(out, t, group=self.group)
         return [o.cpu().numpy() for o in out]
 
+    def _all_gather(self, out, inp):
+        """out[G, ...] <- every rank's inp, on the current stream (NCCL); gloo (CPU tests) takes the list form"""
+        dist = _dist()
+        if dist.get_backend(self.group) == "gloo":
+            dist.all_gather(list(out.unbind(0)), inp, group=self.group)
+        else:
+            dist.all_gather_into_tensor(out, inp, group=self.group)
+
+    def _buffers(self, N):
+        import torch
+        if getattr(self, "_bufN", None) != N:
+            L, d, G = self.model.num_latent, self.model.igp_dim, len(self.block_lengths)
+            f64 = dict(dtype=torch.float64, device=self.dev)
+            self._p1, self._g1 = torch.zeros((N, L, d + 1), **f64), torch.zeros((G, N, L, d + 1), **f64)
+            self._p2, self._g2 = torch.zeros((N, L, d), **f64), torch.zeros((G, N, L, d), **f64)
+            self._xin, self._uaf, self._bend = torch.zeros((N, L, d), **f64), torch.zeros((N, L), **f64), torch.zeros((N, L, d), **f64)
+            self._nll = torch.zeros(N, **f64)
+            self._bufN = N
+        return self
+
+    def enqueue(self, Y_block, X, Xs, x0=None, nll=None, xT=None):
+        """The whole exchange queued on torch's current stream with NO host round trip: phase 1 -> NCCL all-gather ->
+        forward carry kernel -> phase 2 -> all-gather -> backward carry kernel -> phase 3 -> all-reduce of the NLL.
+        x0: torch CUDA tensor [N,L,d] (state before the first step of the WHOLE sequence) or None.  Returns the device
+        tensor that will hold the NLL [N] of the whole sequence."""
+        dist = _dist()
+        m = self.model
+        N = Y_block.shape[0]
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        world = dist.get_world_size(self.group) if multi else 1
+        rank = dist.get_rank(self.group) if multi else 0
+        last = rank == world - 1
+        b = self._buffers(N)
+        nll_dev = nll if nll is not None else b._nll
+        if not multi:
+            m.fsn_block_async(1, Y_block, True, self.mode, out=b._p1)
+            m.fsn_block_async(2, Y_block, True, self.mode, x0=x0, out=b._p2)
+            m.fsn_block_async(3, Y_block, True, self.mode, x0=x0, X=X, Xs=Xs, nll=nll_dev, xT=xT)
+            return nll_dev
+        m.fsn_block_async(1, Y_block, last, self.mode, out=b._p1)
+        self._all_gather(b._g1, b._p1)
+        m.fsn_carry_device(0, b._g1, self.block_lengths, rank, b._xin, self.mode, x0=x0, u_after=b._uaf)
+        u_after = None if last else b._uaf
+        m.fsn_block_async(2, Y_block, last, self.mode, x0=b._xin, u_after=u_after, out=b._p2)
+        self._all_gather(b._g2, b._p2)
+        m.fsn_carry_device(1, b._g2, self.block_lengths, rank, b._bend, self.mode)
+        m.fsn_block_async(3, Y_block, last, self.mode, x0=b._xin, u_after=u_after, b_end=None if last else b._bend, X=X, Xs=Xs,
+                          nll=nll_dev, xT=xT)
+        dist.all_reduce(nll_dev, op=dist.ReduceOp.SUM, group=self.group)
+        return nll_dev
+
     def __call__(self, Y_block, X, Xs, x0=None, nll=None, xT=None):
         """Y_block [N,n,p], X / Xs [N,n,L,d] (this rank's block, tensors on the device); returns nll [N] of the whole
         sequence (numpy).  x0 [N,L,d] is the state before the first step of the WHOLE sequence."""

@@ -525,6 +525,75 @@ def test_time_sharded_objective_two_gpus(cuda_lib):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("kernel,p,L,N,cuts", [("Matern32", 8, 4, 1, (0, 512, 1280, 1700)), ("Matern52", 16, 8, 2, (0, 256, 512, 1024)),
+                                               ("Matern32", 64, 32, 1, (0, 2048, 4096, 6000))])
+def test_time_sharded_filter_smoother_device_side_exchange(cuda_lib, kernel, p, L, N, cuts):
+    """The host-round-trip-free protocol of the time-sharded filter + smoother pass on ONE device (one handle per block, as on
+    its own GPU): fsn_block_async leaves the phase outputs in device memory, fsn_carry_device (binary powering on the
+    device) turns the stacked outputs into every block's x_in / u_after and b_end.  The carries equal the host algebra
+    (parallel.forward_carry_in / backward_carry_in); X, Xs, NLL equal the oracle's pass over the whole sequence."""
+    import torch
+    from multioutputihgp_b200 import MOIHGPSequences
+    from multioutputihgp_b200.parallel import backward_carry_in, forward_carry_in
+    from oracle.binding import OracleMOIHGP
+    from oracle.gen_golden import make_data, make_params
+    rng = np.random.default_rng(sum(cuts) + 7)
+    params = make_params(rng, p, L, kernel)
+    T, G = cuts[-1], len(cuts) - 1
+    lengths = [cuts[g + 1] - cuts[g] for g in range(G)]
+    Y = np.stack([make_data(rng, p, L, T) for _ in range(N)])
+    dev = torch.device("cuda:0")
+    f64 = dict(dtype=torch.float64, device=dev)
+    models = []
+    for g in range(G):
+        m = MOIHGPSequences(0.1, p, L, kernel, True)
+        m.update(params)
+        models.append(m)
+    d = models[0].igp_dim
+    x0 = 0.3 * rng.standard_normal((N, L, d))
+    x0d = torch.from_numpy(x0).to(dev)
+    Yd = [torch.from_numpy(np.ascontiguousarray(Y[:, cuts[g]:cuts[g + 1]])).to(dev) for g in range(G)]
+    ro = OracleMOIHGP(0.1, p, L, kernel, True)
+    ro.update(params)
+    for mode in (1, 0):
+        g1 = torch.zeros((G, N, L, d + 1), **f64)
+        g2 = torch.zeros((G, N, L, d), **f64)
+        xin = torch.zeros((G, N, L, d), **f64)
+        uaf = torch.zeros((G, N, L), **f64)
+        bend = torch.zeros((G, N, L, d), **f64)
+        for g in range(G):
+            models[g].fsn_block_async(1, Yd[g], g == G - 1, mode, out=g1[g])
+        for g in range(G):
+            models[g].fsn_carry_device(0, g1, lengths, g, xin[g], mode, x0=x0d, u_after=uaf[g])
+            models[g].fsn_block_async(2, Yd[g], g == G - 1, mode, x0=xin[g], u_after=None if g == G - 1 else uaf[g], out=g2[g])
+        X = [torch.zeros((N, lengths[g], L, d), **f64) for g in range(G)]
+        Xs = [torch.zeros_like(X[g]) for g in range(G)]
+        nll = torch.zeros((G, N), **f64)
+        for g in range(G):
+            models[g].fsn_carry_device(1, g2, lengths, g, bend[g], mode)
+            models[g].fsn_block_async(3, Yd[g], g == G - 1, mode, x0=xin[g], u_after=None if g == G - 1 else uaf[g],
+                                      b_end=None if g == G - 1 else bend[g], X=X[g], Xs=Xs[g], nll=nll[g])
+        torch.cuda.synchronize()
+        h1, h2 = g1.cpu().numpy(), g2.cpu().numpy()
+        for g in range(G):
+            xh = forward_carry_in(models[0].block_transition, lengths, list(h1[..., :d]), x0, g)
+            assert rel_err(xin[g].cpu().numpy(), xh) < 1e-12, (mode, g)
+            if g < G - 1:
+                assert np.array_equal(uaf[g].cpu().numpy(), h1[g + 1][..., d]), (mode, g)
+                bh = backward_carry_in(lambda n_: models[0].smoother_power(n_, mode), lengths, list(h2), g)
+                bd = bend[g].cpu().numpy()                   # literal mode: a latent with rho(G) > 1 overflows on both sides (Q3)
+                assert np.array_equal(np.isfinite(bd), np.isfinite(bh)), (mode, g)
+                for l in range(L):
+                    if np.isfinite(bh[:, l]).all() and np.max(np.abs(bh[:, l])) < 1e100:
+                        assert rel_err(bd[:, l], bh[:, l]) < 1e-12, (mode, g, l)
+        r = ro.filter_smoother_nll(Y, x0=x0, smoother_mode=mode)
+        Xc = np.concatenate([x.cpu().numpy() for x in X], axis=1)
+        Xsc = np.concatenate([x.cpu().numpy() for x in Xs], axis=1)
+        assert rel_err(Xc, r["X"]) < TOL and rel_err(nll.sum(0).cpu().numpy(), r["nll"]) < TOL, mode
+        _assert_smoothed({"Xs": Xsc}, r, mode, ("oracle", mode))
+
+
+@pytest.mark.gpu
 def test_time_sharded_filter_smoother_two_gpus(cuda_lib):
     """the fused filter + smoother + NLL pass of one long sequence split in time over two GPUs (forward and
     backward carry all-gathers + NCCL all-reduce of the NLL) equals the single-GPU pass.  Needs two devices."""

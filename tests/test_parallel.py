@@ -224,6 +224,31 @@ class _OracleBlockModel(object):
             xT.copy_(torch.from_numpy(r["xT"]))
 
 
+    # the host-round-trip-free interface (TimeShardedFilterSmoother.enqueue) on CPU tensors
+    def fsn_block_async(self, phase, Y, seq_end, smoother_mode=1, x0=None, u_after=None, b_end=None, X=None, Xs=None, nll=None, xT=None, out=None):
+        import torch
+        r = self.fsn_block(phase, Y, seq_end, smoother_mode, x0=x0, u_after=u_after, b_end=b_end, X=X, Xs=Xs, nll=nll, xT=xT)
+        if phase == 1:
+            out.copy_(torch.from_numpy(np.concatenate([r[0], r[1][..., None]], axis=-1)))
+        elif phase == 2:
+            out.copy_(torch.from_numpy(r))
+
+    def fsn_carry_device(self, direction, gathered, block_lengths, rank, out, smoother_mode=1, x0=None, u_after=None):
+        import torch
+        from multioutputihgp_b200.parallel import backward_carry_in, forward_carry_in
+        g = gathered.numpy()
+        d = self.igp_dim
+        if direction == 0:
+            x0n = np.zeros(g.shape[1:3] + (d,)) if x0 is None else x0.numpy()
+            out.copy_(torch.from_numpy(forward_carry_in(self.block_transition, block_lengths, list(g[..., :d]), x0n, rank)))
+            if u_after is not None and rank + 1 < len(block_lengths):
+                u_after.copy_(torch.from_numpy(g[rank + 1][..., d].copy()))
+        else:
+            be = backward_carry_in(lambda n_: self.smoother_power(n_, smoother_mode), block_lengths, list(g), rank)
+            if be is not None:
+                out.copy_(torch.from_numpy(be))
+
+
 def _fsn_worker(rank, world, port, T, out_dir):
     import torch
     import torch.distributed as dist
@@ -245,8 +270,12 @@ def _fsn_worker(rank, world, port, T, out_dir):
     fs = TimeShardedFilterSmoother(_OracleBlockModel(o, params, p, L), [b[1] - b[0] for b in bounds], 1, device=torch.device("cpu"))
     X = torch.zeros((N, t1 - t0, L, 2), dtype=torch.float64)
     Xs = torch.zeros_like(X)
-    nll = fs(torch.from_numpy(np.ascontiguousarray(Y[:, t0:t1])), X, Xs, x0=x0)
-    np.savez(os.path.join(out_dir, "frank%d.npz" % rank), X=X.numpy(), Xs=Xs.numpy(), nll=nll, t0=t0, t1=t1)
+    Yb = torch.from_numpy(np.ascontiguousarray(Y[:, t0:t1]))
+    nll = fs(Yb, X, Xs, x0=x0)
+    # the same exchange with everything left in (device) tensors: enqueue
+    X2, Xs2 = torch.zeros_like(X), torch.zeros_like(Xs)
+    nll2 = fs.enqueue(Yb, X2, Xs2, x0=torch.from_numpy(x0)).numpy().copy()
+    np.savez(os.path.join(out_dir, "frank%d.npz" % rank), X=X.numpy(), Xs=Xs.numpy(), nll=nll, t0=t0, t1=t1, X2=X2.numpy(), Xs2=Xs2.numpy(), nll2=nll2)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -273,6 +302,7 @@ def test_time_sharded_filter_smoother_gloo(tmp_path, world, T):
         assert rel_err(z["X"], ref["X"][:, t0:t1]) < 1e-12
         assert rel_err(z["Xs"], ref["Xs"][:, t0:t1]) < 1e-11
         assert rel_err(z["nll"], ref["nll"]) < 1e-11
+        assert rel_err(z["X2"], ref["X"][:, t0:t1]) < 1e-12 and rel_err(z["Xs2"], ref["Xs"][:, t0:t1]) < 1e-11 and rel_err(z["nll2"], ref["nll"]) < 1e-11
 
 
 def test_carry_algebra_of_the_time_sharded_smoother():
