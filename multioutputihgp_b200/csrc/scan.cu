@@ -39,10 +39,13 @@ namespace moihgp {
 
 namespace {
 
-constexpr int SUB = 8;            // steps per lane
-constexpr int CH = 32 * SUB;      // steps per warp-chunk
-constexpr int LOG2_SUB = 3;       // powM[LOG2_SUB + k] = M^(SUB * 2^k)
-constexpr int LOG2_CH = 8;        // powM[LOG2_CH]     = M^CH
+#ifndef MOIHGP_SCAN_LOG2_SUB
+#define MOIHGP_SCAN_LOG2_SUB 3
+#endif
+constexpr int LOG2_SUB = MOIHGP_SCAN_LOG2_SUB;   // powM[LOG2_SUB + k] = M^(SUB * 2^k)
+constexpr int SUB = 1 << LOG2_SUB;               // steps per lane
+constexpr int CH = 32 * SUB;                     // steps per warp-chunk
+constexpr int LOG2_CH = 5 + LOG2_SUB;            // powM[LOG2_CH]     = M^CH
 constexpr int LGMAX = 8;          // latents (warps) per CTA
 constexpr unsigned FULL = 0xffffffffu;
 
