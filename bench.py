@@ -197,7 +197,7 @@ def check_stability(model, L):
     return worst
 
 
-def cpu_reference_rate(kind, kernel, p, L, N, T, seed, budget_s, nthreads, repeats=1):
+def cpu_reference_rate(kind, kernel, p, L, N, T, seed, budget_s, nthreads, repeats=1, force_port=False):
     """Time the CPU implementation of the same pass on the host cores, on a bounded sample of the workload: as many
     sequences (full length when the workload has many, a T-prefix when it is one long sequence) as fit in ~budget_s
     seconds.  Filter + smoother + NLL: the reference's OWN classes (MOIHGP::step / negLogLikelihood / IHGP::
@@ -211,7 +211,7 @@ def cpu_reference_rate(kind, kernel, p, L, N, T, seed, budget_s, nthreads, repea
     params, Hmix = model_params(p, L, kernel, seed)
     rng = np.random.default_rng(seed)
     many = N >= nthreads
-    use_ref = kind == "fsn" and binding.ref_pass_available()
+    use_ref = kind == "fsn" and binding.ref_pass_available() and not force_port
     if use_ref:
         Ts = T if many else min(T, 4000)
     else:
@@ -545,6 +545,14 @@ def run_ours(a, wl, torch, dist, rank, local_rank, world, steps, warmup, cores, 
     if rank == 0 and world == 1 and with_cpu:
         r, what, dt_, used, ckind = cpu_reference_rate(kind, kernel, p, L, N, T, seed, budget_s=a.cpu_seconds, nthreads=cores)
         cpu = {"value": r, "unit": UNIT, "cores": used, "kind": ckind, "sample": "%s, %.1f s" % (what, dt_)}
+        if ckind == "reference":
+            # next to the reference's own classes (eager Eigen-style temporaries on the shim): the oracle port of the same
+            # algorithm (oracle/moihgp_oracle.cpp, plain loops), on one core and on all of them
+            port = {}
+            for tag, nt in (("1_core", 1), ("all_cores", cores)):
+                rp, whatp, dtp, usedp, _ = cpu_reference_rate(kind, kernel, p, L, N, T, seed, budget_s=min(3.0, a.cpu_seconds), nthreads=nt, force_port=True)
+                port[tag] = {"value": rp, "unit": UNIT, "cores": usedp, "sample": "%s, %.1f s" % (whatp, dtp)}
+            cpu["oracle_port"] = port
 
     if rank == 0:
         line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,

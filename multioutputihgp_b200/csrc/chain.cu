@@ -15,6 +15,9 @@ cudaError_t launch_chain_16x16(int dim, const ChainArgs& a, cudaStream_t st);
 cudaError_t launch_chain_32x4(int dim, const ChainArgs& a, cudaStream_t st);
 cudaError_t launch_chain_32x8(int dim, const ChainArgs& a, cudaStream_t st);
 cudaError_t launch_chain_32x16(int dim, const ChainArgs& a, cudaStream_t st);
+cudaError_t launch_chain_4x2(int dim, const ChainArgs& a, cudaStream_t st);
+cudaError_t launch_chain_4x4(int dim, const ChainArgs& a, cudaStream_t st);
+cudaError_t launch_chain_32x2(int dim, const ChainArgs& a, cudaStream_t st);
 
 namespace {
 struct Shape { int p, L; cudaError_t (*fn)(int, const ChainArgs&, cudaStream_t); };
@@ -29,6 +32,9 @@ const Shape kShapes[] = {
     {32, 4, launch_chain_32x4},
     {32, 8, launch_chain_32x8},
     {32, 16, launch_chain_32x16},
+    {4, 2, launch_chain_4x2},
+    {4, 4, launch_chain_4x4},
+    {32, 2, launch_chain_32x2},
 };
 }  // namespace
 

@@ -281,7 +281,10 @@ __global__ void __launch_bounds__(32, 14) k_filter_chain(const double* __restric
             const double ysq = quad_transpose_reduce(sy, lane);
             const double wsq = quad_transpose_reduce(sw, lane);
             double q = ysq - wsq;                                                 // || (I - U U') y ||^2
-            const bool bad = owner && !(q >= 1e-4 * ysq);                         // cancellation (or NaN): evaluate explicitly
+            // P == L: U is square and orthogonal, (I - U U') y vanishes identically and the explicit form would return
+            // rounding noise for EVERY row: rho = 0 unless the row holds a NaN
+            if (P == L && ysq == ysq) q = 0.0;
+            const bool bad = owner && !(q >= 1e-4 * ysq) && !(P == L && ysq == ysq);   // cancellation (or NaN): evaluate explicitly
             if (__any_sync(FULL, bad)) {
                 // explicit  || y - U (U' y) ||^2  of row `lane` (moihgp.h:651), w read back from the exchange tile
                 __syncwarp();

@@ -1032,7 +1032,8 @@ __global__ void __launch_bounds__(128) k_obj_small(const double* __restrict__ Y,
         for (int l = 0; l < L; ++l) wsq = fma(sw[t * L + l], sw[t * L + l], wsq);
         double q = ysq - wsq;
         if (!(ysq == ysq)) bad = 1;              // a missing (NaN) output somewhere in this observation
-        if (!(q >= 1e-4 * ysq)) {                // cancellation: the explicit form
+        if (p == L && ysq == ysq) q = 0.0;       // square orthogonal U: the residual vanishes identically
+        else if (!(q >= 1e-4 * ysq)) {           // cancellation: the explicit form
             q = 0.0;
             for (int r = 0; r < p; ++r) {
                 double e = sY[t * p + r];

@@ -318,8 +318,11 @@ __global__ void __launch_bounds__(MT, NB <= 4 ? 3 : 2) k_project_mma(const doubl
         wsq += __shfl_xor_sync(FULL, wsq, 1); wsq += __shfl_xor_sync(FULL, wsq, 2);
         const double q = ysq - wsq;
         const long long t = rb == 0 ? tA : tB;
-        bad_row[rb] = t < T && !(q >= 1e-4 * ysq);
-        if (q4 == 0 && t < T && !bad_row[rb]) rho_sum += sqrt(q);
+        // p == L: U is square and orthogonal, (I - U U') y vanishes identically - the difference is pure cancellation and
+        // the explicit form would only return rounding noise (1e-16 ||y||), for every row: rho = 0 unless y holds a NaN
+        const bool square_ok = p == L && ysq == ysq;
+        bad_row[rb] = t < T && !(q >= 1e-4 * ysq) && !square_ok;
+        if (q4 == 0 && t < T && !bad_row[rb] && q >= 1e-4 * ysq) rho_sum += sqrt(q);
     }
     if (bad_row[0] || bad_row[1]) any_bad = 1;
     __syncthreads();
@@ -491,6 +494,7 @@ __global__ void __launch_bounds__(32 * NW, 1) k_project_rows(const __grid_consta
             const double q = ysq - wsq;
             if (t < T) {
                 if (q >= 1e-4 * ysq) rho = sqrt(q);
+                else if (p == L && ysq == ysq) rho = 0.0;      // square orthogonal U: (I - U U') y vanishes identically (see k_project_mma)
                 else {
                     // explicit || y - U (U' y) ||_2 (moihgp.h:651) for a row whose norm difference cancelled (or is NaN),
                     // straight from global memory.  Rare.

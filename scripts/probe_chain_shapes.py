@@ -1,0 +1,45 @@
+"""Many-chains path vs chunked-scan path for every instantiated (p, L) shape: device-resident fused pass (filter + RTS
+smoother + NLL) on synthetic data, CUDA events, ms per pass and latent-steps/s.  Run on a B200; prints one line per shape."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from bench import DT, model_params
+from multioutputihgp_b200 import MOIHGPSequences
+
+dev = torch.device("cuda:0")
+# (32, 32), (64, 8), (64, 16) were instantiated and measured in round 2: the scan path is 2 - 4x faster there
+shapes = [(4, 2), (4, 4), (8, 2), (8, 4), (8, 8), (16, 2), (16, 4), (16, 8), (16, 16), (32, 2), (32, 4), (32, 8), (32, 16), (32, 32)]
+T = 4096
+for kernel in ("Matern32", "Matern52"):
+    for p, L in shapes:
+        N = max(256, int(2.5e8 / (T * L)) // 32 * 32)
+        params, Hmix = model_params(p, L, kernel, 4321)
+        m = MOIHGPSequences(DT, p, L, kernel, threading=True, device=0)
+        m.update(params)
+        d = m.igp_dim
+        Y = torch.randn((N, T, p), dtype=torch.float64, device=dev)
+        X = torch.empty((N, T, L, d), dtype=torch.float64, device=dev)
+        Xs = torch.empty_like(X)
+        nll = torch.empty(N, dtype=torch.float64, device=dev)
+        out = {}
+        for path in ("chain", "scan"):
+            m.set_path(path)
+            for _ in range(2):
+                m.filter_smoother_nll_device(Y, smoother_mode=1, X=X, Xs=Xs, nll=nll)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                m.filter_smoother_nll_device(Y, smoother_mode=1, X=X, Xs=Xs, nll=nll)
+            e1.record()
+            torch.cuda.synchronize()
+            out[path] = e0.elapsed_time(e1) / 5
+        balg = 8.0 * (p / L + 2 * d) * N * T * L
+        print("%s p=%2d L=%2d N=%5d T=%d: chain %.3f ms (%.2f TB/s alg, %.0f%% of 6553 GB/s), scan %.3f ms -> chain is %.2fx"
+              % (kernel, p, L, N, T, out["chain"], balg / out["chain"] / 1e9, 100 * balg / out["chain"] / 1e6 / 6553.3, out["scan"], out["scan"] / out["chain"]))
+        del Y, X, Xs, m
+        torch.cuda.empty_cache()

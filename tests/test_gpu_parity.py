@@ -179,6 +179,9 @@ CHAIN_CONFIGS = [
     ("Matern32", 16, 2, 17, 60, 31),
     ("Matern52", 8, 8, 5, 120, 32),
     ("Matern32", 8, 2, 33, 50, 33),
+    ("Matern52", 4, 2, 17, 90, 36),              # round 2: four-output shapes and (32, 2)
+    ("Matern32", 4, 4, 9, 130, 37),
+    ("Matern32", 32, 2, 18, 70, 41),
 ]
 
 
@@ -652,6 +655,7 @@ def test_bound_data_objective_equals_host_buffer_objective(cuda_lib):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("path,kernel,p,L,N,T", [("chain", "Matern52", 16, 8, 5, 203), ("chain", "Matern32", 8, 4, 9, 37),
+                                                 ("chain", "Matern52", 4, 2, 37, 45), ("chain", "Matern32", 32, 2, 19, 70), ("chain", "Matern52", 4, 4, 9, 66),
                                                  ("scan", "Matern52", 16, 8, 3, 515), ("scan", "Matern32", 5, 3, 2, 257)])
 def test_outputs_stay_inside_their_buffers(cuda_lib, path, kernel, p, L, N, T):
     """Ragged N / T through the device entry points with every output placed between guard zones: the guards are intact
