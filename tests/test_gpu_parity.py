@@ -164,6 +164,58 @@ def test_cuda_matches_oracle(cuda_lib, kernel, threading, p, L, N, T, seed):
     assert rel_err(xT, xo) < TOL and rel_err(dxT, dxo) < TOL
 
 
+@pytest.mark.parametrize("seed", list(range(100, 124)))
+def test_random_shapes_match_oracle(cuda_lib, seed):
+    """Differential test on seeded random shapes (odd p, p == L, L not a multiple of 8, T across chunk borders, N across
+    warp borders, random carried-in state, both kernels, both threading values): every output of the fused pass and of the
+    objective against the CPU oracle, on every kernel path that serves the shape."""
+    from multioutputihgp_b200 import MOIHGPSequences
+    from oracle.binding import OracleMOIHGP
+    from oracle.gen_golden import make_data, make_params
+    rng = np.random.default_rng(seed)
+    kernel = ("Matern32", "Matern52")[int(rng.integers(2))]
+    threading = bool(rng.integers(2))
+    p = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 9, 12, 16, 17, 24, 32, 33, 48]))
+    L = int(rng.integers(1, min(p, 20) + 1))
+    if seed % 4 == 0:                                   # every fourth case lands on a many-chains shape
+        p, L = [(4, 2), (4, 4), (8, 4), (16, 8), (32, 2), (16, 16)][(seed // 4) % 6]
+    N = int(rng.choice([1, 2, 3, 5, 9, 33, 150]))
+    T = int(rng.choice([1, 2, 31, 32, 33, 255, 256, 257, 300, 511, 513, 700, 1025]))
+    if N * T * L > 400000:
+        N = max(1, 400000 // (T * L))
+    params = make_params(rng, p, L, kernel)
+    Y = np.stack([make_data(rng, p, L, T) for _ in range(N)])
+    m = MOIHGPSequences(0.1, p, L, kernel, threading)
+    o = OracleMOIHGP(0.1, p, L, kernel, threading)
+    m.update(params)
+    o.update(params)
+    d = m.igp_dim
+    x0 = 0.2 * rng.standard_normal((N, L, d))
+    dx0 = 0.1 * rng.standard_normal((N, L, 3, d))
+    what = (kernel, threading, p, L, N, T)
+    paths = ["scan"]
+    try:
+        m.set_path("chain")
+        m.filter_smoother_nll(Y[:1, :1], smoother_mode=-1, want_states=False)
+        paths.append("chain")
+    except RuntimeError:
+        pass
+    mode = int(rng.integers(2))
+    ro = o.filter_smoother_nll(Y, x0=x0, smoother_mode=mode, want_yhat=True)
+    for path in paths + ["auto"]:
+        m.set_path(path)
+        r = m.filter_smoother_nll(Y, x0=x0, smoother_mode=mode, want_yhat=True)
+        for k in ("X", "Yhat", "nll", "xT"):
+            assert rel_err(r[k], ro[k]) < TOL, (what, path, k)
+        _assert_smoothed(r, ro, mode, (what, path))
+    m.set_path("auto")
+    loss, grad, xT, dxT = m.objective(Y, x0=x0, dx0=dx0, want_state=True)
+    lo, go, xo, dxo = o.objective(Y, x0=x0, dx0=dx0)
+    assert _close(loss, lo), what
+    assert rel_err(grad, go) < TOL, what
+    assert rel_err(xT, xo) < TOL and rel_err(dxT, dxo) < TOL, what
+
+
 CHAIN_CONFIGS = [
     # kernel, p, L, N, T, seed      shapes instantiated for the many-chains kernels (chain.cu); ragged N and T on purpose
     ("Matern52", 16, 8, 9, 1037, 21),
