@@ -137,7 +137,9 @@ int moihgp_cuda_filter_smoother_nll(moihgp_handle* h, const double* Y, size_t N,
  * F, Fs [N][T][L] (what predict-style callers consume: yhat = U sqrt(S) x(0), moihgp.h:222-225) - d times fewer bytes out. */
 int moihgp_cuda_filter_smoother_nll_values(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0,
                                            int smoother_mode, double* F, double* Fs, double* Yhat, double* nll, double* xT);
-/* same, DEVICE buffers already resident in HBM; asynchronous on the handle's stream */
+/* same, DEVICE buffers already resident in HBM; asynchronous on the handle's stream: no host synchronisation, also right
+ * after moihgp_cuda_update, so the call can be captured into a CUDA graph once its workspaces exist (one warm-up call with
+ * the same sizes on the same stream; moihgp_cuda_set_stream refuses to move the handle onto a stream that is capturing) */
 int moihgp_cuda_filter_smoother_nll_dev(moihgp_handle* h, const double* Y, size_t N, size_t T, const double* x0,
                                         int smoother_mode, double* X, double* Xs, double* Yhat, double* nll, double* xT);
 

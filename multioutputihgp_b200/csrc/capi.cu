@@ -357,6 +357,11 @@ int moihgp_cuda_set_stream(moihgp_handle* h, void* s) {
     if (!h) return -2;
     cudaStream_t ns = s ? static_cast<cudaStream_t>(s) : h->own_stream;
     if (ns != h->stream) {
+        // moving the handle waits for the old stream - not possible while the new stream is being captured into a CUDA
+        // graph (the wait would invalidate the capture): refuse, the caller moves the handle once BEFORE the capture
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(ns, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive)
+            return fail(h, "set_stream: the new stream is capturing - move the handle to it (any call on that stream) before the capture begins");
         cudaStreamSynchronize(h->stream);      // work queued on the old stream finishes before the handle moves
         h->stream = ns;
     }
@@ -576,13 +581,12 @@ int moihgp_cuda_filter_smoother_nll_dev(moihgp_handle* h, const double* Y, size_
         int* nanf;
         if (ws_get(h, "nanf", 4, &nanf)) return -1;
         CK(cudaMemsetAsync(nanf, 0, 2 * sizeof(int), h->stream));
-        double Ssum = 0.0, logs = 0.0;
-        if (mirror(h)) return -1;
-        for (int l = 0; l < L; ++l) { Ssum += h->S[l]; logs += h->consts[l].logS; }
+        double Ssum = 0.0;                         // no mirror(h): nothing here waits for K-setup (asynchronous, capturable)
+        for (int l = 0; l < L; ++l) Ssum += h->S[l];
         const double m_n = std::max((double)(h->p - L), 0.0);
         ChainArgs c;
         c.Y = Y; c.U_host = h->U.data(); c.S_host = h->S.data(); c.consts = h->d_consts; c.sigma = h->sigma;
-        c.nll_const = (double)T * (0.5 * std::log(Ssum) + 0.5 * m_n * std::log(h->sigma) + 0.5 * logs);
+        c.nll_const = 0.5 * std::log(Ssum) + 0.5 * m_n * std::log(h->sigma);
         c.N = (long long)N; c.T = (long long)T; c.mode = mode < 0 ? 1 : mode; c.x0 = x0; c.X = X; c.Xs = Xs; c.nll = nll; c.xT = xT; c.mk = mk; c.nan_flag = nanf; c.seqs_per_warp = h->chain_spw;
         CK(launch_chain(h->p, L, D, c, h->stream));
         h->launches += Xs ? 2 : 1;

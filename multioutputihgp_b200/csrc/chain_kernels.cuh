@@ -445,7 +445,12 @@ __global__ void __launch_bounds__(32, 14) k_filter_chain(const double* __restric
             double rho = 0.0;
             for (int q = 0; q < 32; ++q)
                 if ((q & 3) < RB && (8 * (q & 3) + (q >> 2)) / L == s) rho += xch[q];
-            nll[n] = 0.5 * rho / sigma + part + nll_const;
+            // + T (1/2 log sum S + 1/2 m_n log sigma + 1/2 sum_l log S_l)   moihgp.h:652-653, ihgp.h:207: the first two terms
+            // come from the host (parameters), the innovation variances S_l from K-setup's records - read here so that the
+            // host never has to wait for them
+            double logs = 0.0;
+            for (int l = 0; l < L; ++l) logs += __ldg(&consts[l].logS);
+            nll[n] = 0.5 * rho / sigma + part + (double)T * (nll_const + 0.5 * logs);
         }
     }
 }

@@ -103,7 +103,7 @@ struct ChainArgs {
     const double* Y;              // [N][T][p], 16-byte aligned
     const double *U_host, *S_host;    // host copies (become constant-bank kernel parameters)
     const LatentConsts* consts;   // device
-    double sigma, nll_const;      // nll_const = T * (1/2 log sum S + 1/2 m_n log sigma + 1/2 sum_l log S_l)
+    double sigma, nll_const;      // nll_const = 1/2 log sum S + 1/2 m_n log sigma (per step; the kernel adds 1/2 sum_l log S_l from the device records)
     long long N, T;
     int mode;                     // smoother mode 0 / 1 (used when Xs != null)
     const double* x0;

@@ -216,6 +216,46 @@ def test_random_shapes_match_oracle(cuda_lib, seed):
     assert rel_err(xT, xo) < TOL and rel_err(dxT, dxo) < TOL, what
 
 
+@pytest.mark.parametrize("path,kernel,p,L,N,T", [("chain", "Matern52", 16, 8, 160, 300), ("scan", "Matern32", 12, 5, 2, 1500)])
+def test_device_pass_right_after_update_is_capturable_in_a_cuda_graph(cuda_lib, path, kernel, p, L, N, T):
+    """The *_dev entry points are asynchronous on the caller's stream: right after update(params) - K-setup still in flight
+    - the fused pass neither waits for the device nor touches the host, so it can be captured into a CUDA graph and replayed
+    on new data (the many-chains path used to synchronise to fetch log S).  Replays equal the oracle."""
+    import torch
+    from multioutputihgp_b200 import MOIHGPSequences
+    from oracle.binding import OracleMOIHGP
+    from oracle.gen_golden import make_data, make_params
+    rng = np.random.default_rng(N + T)
+    dev = torch.device("cuda:0")
+    m = MOIHGPSequences(0.1, p, L, kernel, True)
+    o = OracleMOIHGP(0.1, p, L, kernel, True)
+    m.set_path(path)
+    d = m.igp_dim
+    f64 = dict(dtype=torch.float64, device=dev)
+    Y = torch.zeros((N, T, p), **f64)
+    X, Xs, nll = torch.zeros((N, T, L, d), **f64), torch.zeros((N, T, L, d), **f64), torch.zeros(N, **f64)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        m.update(make_params(rng, p, L, kernel))
+        m.filter_smoother_nll_device(Y, smoother_mode=1, X=X, Xs=Xs, nll=nll)      # warm-up ON the capture stream: workspaces, attributes
+        torch.cuda.synchronize()
+        params = make_params(rng, p, L, kernel)
+        m.update(params)                                                          # new parameters: K-setup is queued, nothing waits
+        o.update(params)
+        with torch.cuda.graph(g, stream=side):
+            m.filter_smoother_nll_device(Y, smoother_mode=1, X=X, Xs=Xs, nll=nll)
+    for rep in range(2):
+        Yh = np.stack([make_data(rng, p, L, T) for _ in range(N)])
+        Y.copy_(torch.from_numpy(Yh))
+        g.replay()
+        torch.cuda.synchronize()
+        ro = o.filter_smoother_nll(Yh, smoother_mode=1)
+        assert rel_err(X.cpu().numpy(), ro["X"]) < TOL and rel_err(Xs.cpu().numpy(), ro["Xs"]) < TOL, rep
+        assert rel_err(nll.cpu().numpy(), ro["nll"]) < TOL, rep
+
+
 CHAIN_CONFIGS = [
     # kernel, p, L, N, T, seed      shapes instantiated for the many-chains kernels (chain.cu); ragged N and T on purpose
     ("Matern52", 16, 8, 9, 1037, 21),
