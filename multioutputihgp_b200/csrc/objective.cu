@@ -270,13 +270,15 @@ __global__ void __launch_bounds__(128, 3) k_obj_scan(const double* __restrict__ 
 //      carries across the sub-chunks: z <- Z^32 z + f_s with the span-32 coupling E_k(32) (built once per CTA)
 //   FINAL = false: the chunk summary  Z^32 z_in(7) + f_7  -> zsum     (interior chunks only: all sub-chunks are whole)
 //   FINAL = true : B  the literal recurrence from the true carry: per-step loss / gradient terms and the dU weights.
-// Every thread's inputs (u, U'y, raw y(l): 256-byte runs of the latent-major series) are brought into a private
+// Every thread's inputs (u in the summaries pass; U'y and raw y(l) in the final pass: 256-byte runs of the latent-major series) are brought into a private
 // shared-memory slot by the copy engine (cp.async.bulk) and the dU weights leave the same way: no per-lane HBM
 // instructions, no uncoalesced wavefronts.  ~115 FP64 instructions per latent-step (the warp-scan kernel: ~650).
 constexpr int SL = 32;                 // steps per thread
 constexpr int NSUBC = CH / SL;         // sub-chunks per chunk
 constexpr int LOG2_SL = 5;
-constexpr int UP3 = 3 * SL + 2;        // slot pitch in doubles ([u | U'y -> dU weight | y(l)] + pad): UP3 / 2 odd => conflict-free 16-byte loads
+constexpr int UP3 = 2 * SL + 2;        // slot pitch in doubles of the final pass ([U'y -> dU weight | y(l)] + pad): UP3 / 2 odd => conflict-free
+                                       // 16-byte loads.  u = S^-1/2 U'y is formed from U'y in the kernel (the same product k_project
+                                       // forms, bit for bit): a third less shared memory per CTA = six instead of four CTAs per SM
 
 template <int D>
 struct ObjLC {
@@ -392,8 +394,8 @@ __global__ void __launch_bounds__(NSUBC * LG) k_obj_lanes(const double* __restri
 #pragma unroll
     for (int k = 0; k < 3; ++k) { hda0[k] = __ldg(&lc->HdA[k][0]); dSk[k] = __ldg(&lc->dS[k]); }
     const size_t so = ((size_t)n * L + l) * T;
-    const bool al = ((reinterpret_cast<size_t>(u) & 15) == 0) &&
-                    (!FINAL || (((reinterpret_cast<size_t>(w) | reinterpret_cast<size_t>(yl) | reinterpret_cast<size_t>(wgt)) & 15) == 0));
+    const bool al = FINAL ? (((reinterpret_cast<size_t>(w) | reinterpret_cast<size_t>(yl) | reinterpret_cast<size_t>(wgt)) & 15) == 0)
+                          : ((reinterpret_cast<size_t>(u) & 15) == 0);
     double* slot = slots + (size_t)tid * PITCH;
     const long long c_lo = gi * cpc, c_hi = min(c_cnt, c_lo + cpc);
     for (long long ch = c_lo; ch < c_hi; ++ch) {
@@ -404,19 +406,13 @@ __global__ void __launch_bounds__(NSUBC * LG) k_obj_lanes(const double* __restri
         if (FINAL) bulk_wait_read<0>();               // the previous chunk's weight store has read this slot
         fence_async_smem();
         if (bulk) {
-            mbar_expect_tx(&bar, FINAL ? 3 * RUN : RUN);
-            bulk_g2s(slot, u + so + ts, RUN, &bar);
-            if (FINAL) {
-                bulk_g2s(slot + SL, w + so + ts, RUN, &bar);
-                bulk_g2s(slot + 2 * SL, yl + so + ts, RUN, &bar);
-            }
+            mbar_expect_tx(&bar, FINAL ? 2 * RUN : RUN);
+            bulk_g2s(slot, (FINAL ? w : u) + so + ts, RUN, &bar);
+            if (FINAL) bulk_g2s(slot + SL, yl + so + ts, RUN, &bar);
         } else {
             for (int j = 0; j < SL; ++j) {
-                slot[j] = j < len ? __ldg(u + so + ts + j) : 0.0;
-                if (FINAL) {
-                    slot[SL + j] = j < len ? __ldg(w + so + ts + j) : 0.0;
-                    slot[2 * SL + j] = j < len ? __ldg(yl + so + ts + j) : 0.0;
-                }
+                slot[j] = j < len ? __ldg((FINAL ? w : u) + so + ts + j) : 0.0;
+                if (FINAL) slot[SL + j] = j < len ? __ldg(yl + so + ts + j) : 0.0;
             }
             mbar_arrive(&bar);
         }
@@ -443,12 +439,12 @@ __global__ void __launch_bounds__(NSUBC * LG) k_obj_lanes(const double* __restri
 #pragma unroll 4
                 for (int j = 0; j < SL; j += 2) {
                     const double2 u2 = reinterpret_cast<const double2*>(slot)[j >> 1];
-                    aug_step<D>(c, u2.x, f);
-                    aug_step<D>(c, u2.y, f);
+                    aug_step<D>(c, FINAL ? u2.x * rsS : u2.x, f);                 // final pass: the slot holds U'y
+                    aug_step<D>(c, FINAL ? u2.y * rsS : u2.y, f);
                 }
             } else {
 #pragma unroll 1
-                for (int j = 0; j < len; ++j) aug_step<D>(c, slot[j], f);
+                for (int j = 0; j < len; ++j) aug_step<D>(c, FINAL ? slot[j] * rsS : slot[j], f);
             }
 #pragma unroll
             for (int a = 0; a < 4; ++a)
@@ -476,7 +472,8 @@ __global__ void __launch_bounds__(NSUBC * LG) k_obj_lanes(const double* __restri
         // ---- B: the literal recurrence from the true carry ----------------------------------------------------------
         double sv2 = 0.0, svd[3] = {0.0, 0.0, 0.0}, spw = 0.0;
         // one step: loss / gradient terms on the PRE-step state, the dU weight, then the recurrence
-        auto step_b = [&](double uj, double wj, double yj) -> double {
+        auto step_b = [&](double wj, double yj) -> double {
+            const double uj = wj * rsS;                                              // moihgp.h:181, as k_project forms it
             double hax = c.HA[0] * z[0][0];
 #pragma unroll
             for (int q = 1; q < D; ++q) hax = fma(c.HA[q], z[0][q], hax);
@@ -498,16 +495,15 @@ __global__ void __launch_bounds__(NSUBC * LG) k_obj_lanes(const double* __restri
         if (len == SL) {                              // whole sub-chunk: straight-line code
 #pragma unroll 2
             for (int j = 0; j < SL; j += 2) {
-                const double2 u2 = reinterpret_cast<const double2*>(slot)[j >> 1];
-                const double2 w2 = reinterpret_cast<const double2*>(slot + SL)[j >> 1];
-                const double2 y2 = reinterpret_cast<const double2*>(slot + 2 * SL)[j >> 1];
-                const double g0 = step_b(u2.x, w2.x, y2.x);
-                const double g1 = step_b(u2.y, w2.y, y2.y);
-                reinterpret_cast<double2*>(slot + SL)[j >> 1] = make_double2(g0, g1);
+                const double2 w2 = reinterpret_cast<const double2*>(slot)[j >> 1];
+                const double2 y2 = reinterpret_cast<const double2*>(slot + SL)[j >> 1];
+                const double g0 = step_b(w2.x, y2.x);
+                const double g1 = step_b(w2.y, y2.y);
+                reinterpret_cast<double2*>(slot)[j >> 1] = make_double2(g0, g1);
             }
         } else {
 #pragma unroll 1
-            for (int j = 0; j < len; ++j) slot[SL + j] = step_b(slot[j], slot[SL + j], slot[2 * SL + j]);
+            for (int j = 0; j < len; ++j) slot[j] = step_b(slot[j], slot[SL + j]);
         }
         if (len > 0 && ts + len == T) {                                              // this thread owns step T-1
             if (xT) {
@@ -524,10 +520,10 @@ __global__ void __launch_bounds__(NSUBC * LG) k_obj_lanes(const double* __restri
         // the dU weights leave through the copy engine
         if (bulk) {
             fence_async_smem();
-            bulk_s2g(wgt + so + ts, slot + SL, RUN);
+            bulk_s2g(wgt + so + ts, slot, RUN);
             bulk_commit();
         } else {
-            for (int j = 0; j < len; ++j) wgt[so + ts + j] = slot[SL + j];
+            for (int j = 0; j < len; ++j) wgt[so + ts + j] = slot[j];
         }
         // per-chunk partial sums (ihgp.h:215, :219), fixed order over the sub-chunks
         __syncthreads();                              // everyone is done with the forward summaries in exch
