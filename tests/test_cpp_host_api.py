@@ -131,6 +131,23 @@ def test_reference_examples_run_unchanged_on_the_gpu(cuda_lib, example):
     print(r.stdout[-600:], r.stderr[-1000:])
     assert r.returncode == 0
     assert ("Iteration count:" in r.stdout) if example == "example_regression" else (r.stdout.count("Elapsed time per step") == 63)
+    # the same program built against the UNMODIFIED reference headers (CPU, tests/cpp/Makefile: ref_example_*), run beside it on
+    # the box's host: same iteration count of the reference's own L-BFGS-B loop, and the two wall times for the record
+    ref = os.path.join(CPP, "_build", "ref_" + example)
+    if os.path.exists(ref):
+        import re
+        import time
+        t0 = time.perf_counter()
+        rr = subprocess.run([ref], capture_output=True, text=True, timeout=600)
+        t_ref = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        subprocess.run([exe], capture_output=True, text=True, timeout=600)
+        t_gpu = time.perf_counter() - t0
+        assert rr.returncode == 0
+        if example == "example_regression":
+            it = lambda txt: int(re.search(r"Iteration count: (\d+)", txt).group(1))
+            assert it(r.stdout) == it(rr.stdout), (r.stdout[-200:], rr.stdout[-200:])
+        print("%s: GPU drop-in %.2f s wall (incl. CUDA start-up), CPU reference build (-O0, Eigen-API shim) %.2f s" % (example, t_gpu, t_ref))
 
 
 @pytest.mark.gpu
