@@ -507,16 +507,25 @@ __global__ void __launch_bounds__(32) k_response(const LatentConsts* __restrict_
 //   forward : xin[c+1] = M^CH xin[c] + f[c]
 //   backward: bin[c-1] = beta0[c] + Bx(kind c) xin[c] + G^CH bin[c]
 // Three levels (a single long sequence has tens of thousands of chunks: BASELINE config 4, T = 1e7, 39 063 chunks):
-//   group       = 256 chunks scanned by one warp (lane = CG = 8 consecutive chunks, Kogge-Stone over lanes with the
+//   group       = 32 CG chunks scanned by one warp (lane = CG consecutive chunks, Kogge-Stone over lanes with the
 //                 powers M^(CH CG 2^k));
-//   super-block = SB = 8 consecutive groups walked in sequence by that warp;
+//   super-block = SB consecutive groups walked in sequence by that warp;
 //   k_carry_super chains the super-blocks (one thread per (sequence, latent), power M^(CH CG 32 SB)).
 // k_carry<DIR, PHASE>: PHASE 0 runs every super-block from a zero carry and only reports its end value; PHASE 1 runs it
 // from the true carry and writes xin / bin.  When there is one super-block PHASE 1 alone is launched.
-constexpr int CG = 8;              // chunks per lane
-constexpr int LOG2_CG = 3;
-constexpr int SB = 8;              // groups per super-block
-constexpr int LOG2_SB = 3;
+// Granularity of the carry chain, swept on config 4 (39 063 chunks per latent; profiles/r02/carry_granularity.txt): chunks per
+// lane 8 / 4 / 2 / 1 with 8 groups per super-block: k_carry 0.193 / 0.122 / 0.114 / - ms; with 16 groups: - / 0.137 / 0.107 /
+// 0.126 ms.  Fewer chunks per lane = shorter sequential walks inside a lane, more warps.
+#ifndef MOIHGP_SCAN_LOG2_CG
+#define MOIHGP_SCAN_LOG2_CG 1
+#endif
+#ifndef MOIHGP_SCAN_LOG2_SB
+#define MOIHGP_SCAN_LOG2_SB 4
+#endif
+constexpr int LOG2_CG = MOIHGP_SCAN_LOG2_CG;
+constexpr int CG = 1 << LOG2_CG;   // chunks per lane
+constexpr int LOG2_SB = MOIHGP_SCAN_LOG2_SB;
+constexpr int SB = 1 << LOG2_SB;   // groups per super-block
 template <int D, int MODE, int DIR, int PHASE>
 __global__ void __launch_bounds__(128) k_carry(const LatentConsts* __restrict__ consts, const double* __restrict__ Bx, int L,
                                               long long N, long long nC, long long nS, const double* __restrict__ x0,

@@ -132,10 +132,14 @@ def test_reference_examples_run_unchanged_on_the_gpu(cuda_lib, example):
     assert r.returncode == 0
     assert ("Iteration count:" in r.stdout) if example == "example_regression" else (r.stdout.count("Elapsed time per step") == 63)
     # the same program built against the UNMODIFIED reference headers (CPU, tests/cpp/Makefile: ref_example_*), run beside it on
-    # the box's host: same iteration count of the reference's own L-BFGS-B loop, and the two wall times for the record
+    # the box's host, for the record (wall times, iteration counts).  The counts are NOT asserted equal: the shipped
+    # example_regression.cpp:22-26 writes two values into a one-element vector and multiplies a 2 x 2 matrix with it - out of
+    # bounds under real Eigen, a 4-element observation under the Eigen-API shim, on which the reference's own loss is NaN (its
+    # L-BFGS-B loop then idles through max_iterations = 1000) while the drop-in reads the first num_output entries and gets a
+    # finite loss.  With well-formed data the two builds agree iterate by iterate:
+    # test_reference_learners_under_lbfgspp_follow_the_cpu_reference.
     ref = os.path.join(CPP, "_build", "ref_" + example)
     if os.path.exists(ref):
-        import re
         import time
         t0 = time.perf_counter()
         rr = subprocess.run([ref], capture_output=True, text=True, timeout=600)
@@ -144,10 +148,8 @@ def test_reference_examples_run_unchanged_on_the_gpu(cuda_lib, example):
         subprocess.run([exe], capture_output=True, text=True, timeout=600)
         t_gpu = time.perf_counter() - t0
         assert rr.returncode == 0
-        if example == "example_regression":
-            it = lambda txt: int(re.search(r"Iteration count: (\d+)", txt).group(1))
-            assert it(r.stdout) == it(rr.stdout), (r.stdout[-200:], rr.stdout[-200:])
-        print("%s: GPU drop-in %.2f s wall (incl. CUDA start-up), CPU reference build (-O0, Eigen-API shim) %.2f s" % (example, t_gpu, t_ref))
+        print("%s: GPU drop-in %.2f s wall (incl. CUDA start-up), CPU reference build (-O0, Eigen-API shim) %.2f s; reference says: %s"
+              % (example, t_gpu, t_ref, rr.stdout.strip().splitlines()[0] if rr.stdout.strip() else ""))
 
 
 @pytest.mark.gpu
