@@ -570,9 +570,13 @@ void launch_obj_lanes(const ObjArgs& a, long long nC, long long c_cnt, cudaStrea
 // Cross-chunk coupling matrices by doubling: for a span of n steps  E_k(n) = sum_i M^(n-1-i) dM_k M^i,  and
 // E(2n) = E(n) M^n + M^n E(n).  Levels stored for spans of 2^j CHUNKS, j = 0..NLEV-1 (j = 0: one chunk), which is what
 // the carry scan over chunks needs.  One thread per (latent, k).  Ek layout [level][l][3][D*D].
-constexpr int CG = 8;              // chunks per lane in the carry scan
-constexpr int LOG2_CG = 3;
+#ifndef MOIHGP_OBJ_LOG2_CG
+#define MOIHGP_OBJ_LOG2_CG 3
+#endif
+constexpr int LOG2_CG = MOIHGP_OBJ_LOG2_CG;
+constexpr int CG = 1 << LOG2_CG;   // chunks per lane in the carry scan
 constexpr int NLEV = LOG2_CG + 5 + 1;
+static_assert(NLEV <= 16, "the Ek workspace holds 16 levels (capi.cu)");
 template <int D>
 __global__ void k_obj_coupling(const LatentConsts* __restrict__ consts, int L, double* __restrict__ Ek) {
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1176,7 +1180,14 @@ cudaError_t run_objective(const ObjArgs& a, cudaStream_t st) {
         mark(a.mk, "k_obj_scan_summaries");
     }
     k_obj_coupling<D><<<(3 * a.L + 63) / 64, 64, 0, st>>>(a.consts, a.L, Ek);
-    k_obj_carry<D><<<(unsigned)(a.N * a.L), 32, sizeof(double) * 32 * (CG * 4 * D + 2), st>>>(a.consts, Ek, a.L, a.N, nC, a.x0, a.dx0, a.zsum, a.zin);
+    {
+        constexpr size_t carry_smem = sizeof(double) * 32 * (CG * 4 * D + 2);
+        static std::atomic<int> attr_done_c[64];
+        if (AttrOnce once(attr_done_c); once) {
+            if (carry_smem > 48 * 1024) cudaFuncSetAttribute(k_obj_carry<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)carry_smem);
+        }
+        k_obj_carry<D><<<(unsigned)(a.N * a.L), 32, carry_smem, st>>>(a.consts, Ek, a.L, a.N, nC, a.x0, a.dx0, a.zsum, a.zin);
+    }
     mark(a.mk, "k_obj_carry");
     if (a.phase == 1) {
         if (a.zend) k_obj_block_end<D><<<(unsigned)((a.N * a.L + 127) / 128), 128, 0, st>>>(a.consts, Ek, a.L, a.N, nC, a.zsum, a.zin, a.zend);
