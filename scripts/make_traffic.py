@@ -27,10 +27,11 @@ def parse(path):
     rows = [l for l in open(path) if l.startswith('"')]
     per = {}
     for r in csv.DictReader(rows):
-        name = re.sub(r"\(.*", "", r["Kernel Name"])
-        name = re.sub(r"^void ", "", name).replace("moihgp::<unnamed>::", "").replace("<unnamed>::", "")
-        short = re.sub(r"<.*", "", name)
-        if short.startswith("k_setup") or short.startswith("k_polar") or not short.startswith("k_"):
+        m_ = re.search(r"\b(k_[A-Za-z0-9_]+)", re.sub(r"\(.*", "", r["Kernel Name"]))     # e.g. "void unnamed>::k_filter_chain<16, 8, 3, 4>(...)"
+        if not m_:
+            continue
+        short = m_.group(1)
+        if short.startswith("k_setup") or short.startswith("k_polar"):
             continue
         k = per.setdefault(short, {"launches": 0, "dram_bytes_read": 0.0, "dram_bytes_write": 0.0, "duration_ms_under_ncu": 0.0})
         val = float(r["Metric Value"].replace(",", ""))
