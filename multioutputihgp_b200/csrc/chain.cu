@@ -38,15 +38,37 @@ const Shape kShapes[] = {
 };
 }  // namespace
 
+// the instantiated shape that serves a model with p outputs and L latents: (p, L) itself, or the next larger
+// instantiated P with the same L (padded variant of k_filter_chain: zero columns, zero rows of U), else null
+static const Shape* find_shape(int p, int L) {
+    const Shape* best = nullptr;
+    for (const Shape& s : kShapes) {
+        if (s.L != L || s.p < p) continue;
+        if (s.p != p && p < L) continue;
+        if (!best || s.p < best->p) best = &s;
+    }
+    return best;
+}
+
 bool chain_supported(int p, int L, int dim) {
     if (dim != 2 && dim != 3) return false;
-    for (const Shape& s : kShapes) if (s.p == p && s.L == L) return true;
-    return false;
+    return find_shape(p, L) != nullptr;
+}
+
+// the automatic path choice: every served shape but (P = 32, L = 16), where the chunked-scan path ties or wins
+// (profiles/r02/chain_vs_scan_by_shape_v2_square_fix.txt, chain_vs_scan_padded_p.txt: 0.74 - 1.05x)
+bool chain_preferred(int p, int L, int dim) {
+    if (dim != 2 && dim != 3) return false;
+    const Shape* s = find_shape(p, L);
+    return s != nullptr && !(s->p == 32 && s->L == 16);
 }
 
 cudaError_t launch_chain(int p, int L, int dim, const ChainArgs& a, cudaStream_t st) {
-    for (const Shape& s : kShapes) if (s.p == p && s.L == L) return s.fn(dim, a, st);
-    return cudaErrorInvalidValue;
+    const Shape* s = find_shape(p, L);
+    if (!s) return cudaErrorInvalidValue;
+    ChainArgs b = a;
+    b.p = p;
+    return s->fn(dim, b, st);
 }
 
 }  // namespace moihgp

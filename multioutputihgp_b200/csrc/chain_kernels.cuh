@@ -59,6 +59,10 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
@@ -145,12 +149,16 @@ struct FilterCfg {
 
 // grid: ceil(N / NS) CTAs of ONE warp.  NS < 32 / L leaves lanes idle in phase 2 but puts more warps in flight
 // (the recurrence is latency-bound: see DESIGN.md).
-template <int P, int L, int D, int NS_>
+// PADP: the model has p < P outputs: rows of Y are p doubles apart in global memory and land in the first p columns of the
+// P-column tile rows (16-byte copies when p is even, 8-byte copies when it is odd and the rows are only 8-byte aligned); the other columns are zeroed once and U has zero rows
+// there (run_chain_ns), so every later stage - tensor-pipe projection, squared norms, explicit residual, missing-data
+// projection - sees a P-output model whose extra outputs are identically zero and carry no weight.
+template <int P, int L, int D, int NS_, bool PADP>
 __global__ void __launch_bounds__(32, 14) k_filter_chain(const double* __restrict__ Y, const __grid_constant__ ProjConsts<P, L> pc,
                                                     const LatentConsts* __restrict__ consts, double sigma, double nll_const,
                                                     long long N, long long T, const double* __restrict__ x0,
                                                     double* __restrict__ X, double* __restrict__ nll, double* __restrict__ xT,
-                                                    int* __restrict__ nan_flag) {
+                                                    int* __restrict__ nan_flag, int p_real) {
     using C = FilterCfg<P, L, D, NS_>;
     constexpr int NS = C::NS, CH = C::CH, KB = C::KB, NB = C::NB, LD = C::LD, R = C::R, RB = C::RB;
     static_assert(P % 4 == 0 && (CH & (CH - 1)) == 0 && CH <= 32, "P must be 4, 8, 16, 32 or 64");
@@ -205,20 +213,36 @@ __global__ void __launch_bounds__(32, 14) k_filter_chain(const double* __restric
     // ---- cp.async producer: tile of round r into stage r % STAGES ----------------------------------
     // pass k of a round covers rows lr + RPP * k (lr = lane / CH), chunk lc16 = lane % CH of each
     const int lr = lane / CH, lc16 = lane % CH;
-    const size_t seq_stride = (size_t)T * C::ROWB;                             // bytes between sequences of Y
+    const size_t growb = PADP ? (size_t)p_real * 8 : (size_t)C::ROWB;          // bytes between rows of Y in global memory
+    const bool col_ok = !PADP || 2 * lc16 < p_real;                            // this lane's 16-byte chunk holds real outputs
+    const bool odd_p = PADP && (p_real & 1);
+    // one 16-byte chunk of a row: whole (even p), or its 8-byte halves that hold real outputs (odd p)
+    auto copy_chunk = [&](unsigned char* dst, const unsigned char* src) {
+        if (!col_ok) return;
+        if (!odd_p) cp_async16(dst, src);
+        else {
+            cp_async8(dst, src);
+            if (2 * lc16 + 1 < p_real) cp_async8(dst + 8, src + 8);
+        }
+    };
+    const size_t seq_stride = (size_t)T * growb;                               // bytes between sequences of Y
     const unsigned char* Ybytes = reinterpret_cast<const unsigned char*>(Y) + (size_t)n0 * seq_stride;
-    const size_t lane_src = (size_t)(lr / L) * seq_stride + (size_t)(lr % L) * C::ROWB + lc16 * 16;
+    const size_t lane_src = (size_t)(lr / L) * seq_stride + (size_t)(lr % L) * growb + lc16 * 16;
+    if (PADP) {                                                                // the pad columns stay zero for the whole kernel
+        for (int i = lane; i < STAGES * C::TILE / 16; i += 32) reinterpret_cast<double2*>(ytile)[i] = make_double2(0.0, 0.0);
+        __syncwarp();
+    }
     auto issue = [&](long long r) {
         if (r < rounds) {
             unsigned char* st = ytile + (size_t)(r % STAGES) * C::TILE;
             const long long t0 = r * L;
             if (nvalid == NS && t0 + L <= T) {
-                const unsigned char* src = Ybytes + (size_t)t0 * C::ROWB + lane_src;
+                const unsigned char* src = Ybytes + (size_t)t0 * growb + lane_src;
 #pragma unroll
                 for (int k = 0; k < C::PASSES; ++k) {
                     const int row = lr + C::RPP * k;
-                    cp_async16(st + row * C::ROWB + ((lc16 ^ C::swz(row)) << 4),
-                               src + (size_t)((C::RPP * k) / L) * seq_stride + (size_t)((C::RPP * k) % L) * C::ROWB);
+                    copy_chunk(st + row * C::ROWB + ((lc16 ^ C::swz(row)) << 4),
+                               src + (size_t)((C::RPP * k) / L) * seq_stride + (size_t)((C::RPP * k) % L) * growb);
                 }
             } else {
                 // ragged: rows beyond T / sequences beyond N re-read the last valid row / sequence (never used)
@@ -227,8 +251,8 @@ __global__ void __launch_bounds__(32, 14) k_filter_chain(const double* __restric
                 for (int k = 0; k < C::PASSES; ++k) {
                     const int row = lr + C::RPP * k;
                     const int rs_ = min(row / L, nvalid - 1), ri = min(row % L, rows - 1);
-                    cp_async16(st + row * C::ROWB + ((lc16 ^ C::swz(row)) << 4),
-                               Ybytes + (size_t)rs_ * seq_stride + (size_t)(t0 + ri) * C::ROWB + lc16 * 16);
+                    copy_chunk(st + row * C::ROWB + ((lc16 ^ C::swz(row)) << 4),
+                               Ybytes + (size_t)rs_ * seq_stride + (size_t)(t0 + ri) * growb + lc16 * 16);
                 }
             }
         }
@@ -614,18 +638,21 @@ cudaError_t run_chain_ns(const ChainArgs& a, cudaStream_t st) {
     constexpr int SRM = (NS >= 2 && NS == 32 / L) ? 2 : 1;           // ... rounds twice as long: 2x longer contiguous runs per bulk copy
     using SS = SmoothCfg<L, D, SNS, SRM>;
     ProjConsts<P, L> pc;
-    for (int r = 0; r < P; ++r) for (int l = 0; l < L; ++l) pc.U[r][l] = a.U_host[(size_t)r * L + l];
+    const int p_real = a.p > 0 ? a.p : P;
+    for (int r = 0; r < P; ++r) for (int l = 0; l < L; ++l) pc.U[r][l] = r < p_real ? a.U_host[(size_t)r * L + l] : 0.0;
     for (int l = 0; l < L; ++l) pc.rs[l] = 1.0 / std::sqrt(a.S_host[l]);
     const unsigned grid = (unsigned)((a.N + NS - 1) / NS);
     static std::atomic<int> attr_done[64];          // per device: function attributes belong to the device's context
     if (AttrOnce once(attr_done); once) {
-        cudaFuncSetAttribute(k_filter_chain<P, L, D, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS::BYTES);
+        cudaFuncSetAttribute(k_filter_chain<P, L, D, NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS::BYTES);
+        cudaFuncSetAttribute(k_filter_chain<P, L, D, NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS::BYTES);
         cudaFuncSetAttribute(k_smooth_chain<L, D, 0, SNS, SRM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS::BYTES);
         cudaFuncSetAttribute(k_smooth_chain<L, D, 1, SNS, SRM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS::BYTES);
         cudaFuncSetAttribute(k_smooth_chain<L, D, 0, NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmoothCfg<L, D, NS, 1>::BYTES);
         cudaFuncSetAttribute(k_smooth_chain<L, D, 1, NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmoothCfg<L, D, NS, 1>::BYTES);
     }
-    k_filter_chain<P, L, D, NS><<<grid, 32, FS::BYTES, st>>>(a.Y, pc, a.consts, a.sigma, a.nll_const, a.N, a.T, a.x0, a.X, a.nll, a.xT, a.nan_flag);
+    if (p_real == P) k_filter_chain<P, L, D, NS, false><<<grid, 32, FS::BYTES, st>>>(a.Y, pc, a.consts, a.sigma, a.nll_const, a.N, a.T, a.x0, a.X, a.nll, a.xT, a.nan_flag, P);
+    else k_filter_chain<P, L, D, NS, true><<<grid, 32, FS::BYTES, st>>>(a.Y, pc, a.consts, a.sigma, a.nll_const, a.N, a.T, a.x0, a.X, a.nll, a.xT, a.nan_flag, p_real);
     mark(a.mk, "k_filter_chain");
     if (a.Xs) {
         static const bool long_rounds = []() { const char* e = std::getenv("MOIHGP_SMOOTH_LONG_ROUNDS"); return !(e && e[0] == '0'); }();

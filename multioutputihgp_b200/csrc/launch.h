@@ -101,6 +101,7 @@ cudaError_t launch_nll_reduce(const double* rho_part, const double* vsq, const L
 // chain.cu  (many-chains path: thread per (sequence, latent), sequential in time)
 struct ChainArgs {
     const double* Y;              // [N][T][p], 16-byte aligned
+    int p = 0;                    // outputs of the model (0 = the instantiated P); p < P runs the padded variant (p even)
     const double *U_host, *S_host;    // host copies (become constant-bank kernel parameters)
     const LatentConsts* consts;   // device
     double sigma, nll_const;      // nll_const = 1/2 log sum S + 1/2 m_n log sigma (per step; the kernel adds 1/2 sum_l log S_l from the device records)
@@ -112,7 +113,8 @@ struct ChainArgs {
     int seqs_per_warp = 0;        // 0 = automatic
     Marker* mk = nullptr;
 };
-bool chain_supported(int p, int L, int dim);
+bool chain_supported(int p, int L, int dim);     // a many-chains instantiation serves the shape (exactly, or p padded to the next width)
+bool chain_preferred(int p, int L, int dim);     // ... and it is the faster path for many sequences (automatic choice)
 cudaError_t launch_chain(int p, int L, int dim, const ChainArgs& a, cudaStream_t st);
 
 // objective.cu

@@ -13,6 +13,8 @@ from multioutputihgp_b200 import MOIHGPSequences
 dev = torch.device("cuda:0")
 # (32, 32), (64, 8), (64, 16) were instantiated and measured in round 2: the scan path is 2 - 4x faster there
 shapes = [(4, 2), (4, 4), (8, 2), (8, 4), (8, 8), (16, 2), (16, 4), (16, 8), (16, 16), (32, 2), (32, 4), (32, 8), (32, 16), (32, 32)]
+if len(sys.argv) > 1 and sys.argv[1] == "padded":      # p between the instantiated widths: the padded variant of k_filter_chain
+    shapes = [(6, 2), (6, 4), (10, 4), (12, 4), (12, 8), (14, 8), (20, 4), (24, 8), (28, 16), (30, 2), (5, 2), (7, 4), (11, 8), (13, 4), (25, 8)]
 T = 4096
 for kernel in ("Matern32", "Matern52"):
     for p, L in shapes:

@@ -274,6 +274,20 @@ CHAIN_CONFIGS = [
     ("Matern52", 4, 2, 17, 90, 36),              # round 2: four-output shapes and (32, 2)
     ("Matern32", 4, 4, 9, 130, 37),
     ("Matern32", 32, 2, 18, 70, 41),
+    ("Matern32", 6, 2, 19, 75, 45),              # round 2: p between the instantiated widths (padded variant of k_filter_chain)
+    ("Matern52", 6, 4, 9, 130, 46),
+    ("Matern52", 10, 4, 11, 99, 47),
+    ("Matern32", 12, 8, 6, 140, 48),
+    ("Matern52", 14, 2, 33, 40, 49),
+    ("Matern32", 20, 16, 3, 170, 50),
+    ("Matern52", 30, 4, 10, 61, 51),
+    ("Matern32", 26, 8, 5, 88, 52),
+    ("Matern52", 3, 2, 21, 66, 53),              # odd p: rows of Y only 8-byte aligned (8-byte copies into the tile)
+    ("Matern32", 5, 4, 9, 131, 54),
+    ("Matern52", 9, 8, 5, 77, 55),
+    ("Matern32", 13, 4, 10, 64, 56),
+    ("Matern52", 27, 8, 6, 90, 57),
+    ("Matern32", 31, 2, 17, 35, 58),
 ]
 
 
@@ -536,6 +550,9 @@ NAN_CONFIGS = [
     ("Matern52", 16, 8, 6, 300, "chain"),
     ("Matern52", 16, 8, 6, 300, "scan"),
     ("Matern32", 8, 4, 9, 120, "chain"),
+    ("Matern52", 12, 4, 9, 90, "chain"),      # padded variant of the many-chains filter
+    ("Matern32", 6, 2, 19, 70, "chain"),
+    ("Matern52", 11, 4, 9, 85, "chain"),      # ... with odd p
     ("Matern32", 5, 3, 3, 280, "scan"),       # odd p: scalar projection kernel
     ("Matern32", 64, 32, 1, 600, "scan"),     # tensor-pipe projection kernel, large L
 ]
@@ -747,7 +764,7 @@ def test_bound_data_objective_equals_host_buffer_objective(cuda_lib):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("path,kernel,p,L,N,T", [("chain", "Matern52", 16, 8, 5, 203), ("chain", "Matern32", 8, 4, 9, 37),
-                                                 ("chain", "Matern52", 4, 2, 37, 45), ("chain", "Matern32", 32, 2, 19, 70), ("chain", "Matern52", 4, 4, 9, 66),
+                                                 ("chain", "Matern52", 4, 2, 37, 45), ("chain", "Matern52", 10, 4, 11, 57), ("chain", "Matern32", 22, 8, 5, 43), ("chain", "Matern52", 7, 2, 19, 41), ("chain", "Matern32", 32, 2, 19, 70), ("chain", "Matern52", 4, 4, 9, 66),
                                                  ("scan", "Matern52", 16, 8, 3, 515), ("scan", "Matern32", 5, 3, 2, 257)])
 def test_outputs_stay_inside_their_buffers(cuda_lib, path, kernel, p, L, N, T):
     """Ragged N / T through the device entry points with every output placed between guard zones: the guards are intact
