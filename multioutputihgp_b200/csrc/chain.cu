@@ -18,6 +18,10 @@ cudaError_t launch_chain_32x16(int dim, const ChainArgs& a, cudaStream_t st);
 cudaError_t launch_chain_4x2(int dim, const ChainArgs& a, cudaStream_t st);
 cudaError_t launch_chain_4x4(int dim, const ChainArgs& a, cudaStream_t st);
 cudaError_t launch_chain_32x2(int dim, const ChainArgs& a, cudaStream_t st);
+cudaError_t launch_chain_4x1(int dim, const ChainArgs& a, cudaStream_t st);
+cudaError_t launch_chain_8x1(int dim, const ChainArgs& a, cudaStream_t st);
+cudaError_t launch_chain_16x1(int dim, const ChainArgs& a, cudaStream_t st);
+cudaError_t launch_chain_32x1(int dim, const ChainArgs& a, cudaStream_t st);
 
 namespace {
 struct Shape { int p, L; cudaError_t (*fn)(int, const ChainArgs&, cudaStream_t); };
@@ -35,6 +39,10 @@ const Shape kShapes[] = {
     {4, 2, launch_chain_4x2},
     {4, 4, launch_chain_4x4},
     {32, 2, launch_chain_32x2},
+    {4, 1, launch_chain_4x1},
+    {8, 1, launch_chain_8x1},
+    {16, 1, launch_chain_16x1},
+    {32, 1, launch_chain_32x1},
 };
 }  // namespace
 
@@ -50,15 +58,18 @@ static const Shape* find_shape(int p, int L) {
     return best;
 }
 
+// L = 1 with state dimension 3: a sequence-round of X is 3 doubles, which the 16-byte copy-out of the staging tile cannot
+// tile - Matern-5/2 models with a single latent take the chunked-scan path
 bool chain_supported(int p, int L, int dim) {
     if (dim != 2 && dim != 3) return false;
+    if (L == 1 && dim == 3) return false;
     return find_shape(p, L) != nullptr;
 }
 
 // the automatic path choice: every served shape but (P = 32, L = 16), where the chunked-scan path ties or wins
 // (profiles/r02/chain_vs_scan_by_shape_v2_square_fix.txt, chain_vs_scan_padded_p.txt: 0.74 - 1.05x)
 bool chain_preferred(int p, int L, int dim) {
-    if (dim != 2 && dim != 3) return false;
+    if (!chain_supported(p, L, dim)) return false;
     const Shape* s = find_shape(p, L);
     return s != nullptr && !(s->p == 32 && s->L == 16);
 }

@@ -130,7 +130,7 @@ struct FilterCfg {
     static constexpr int NB = LP / 8;
     static constexpr int XROW = LP;                    // exchange tile row pitch (doubles): 16-byte fragment stores of two
                                                        // adjacent rows cover one 128-byte line
-    static constexpr int XSEQ = L * XROW + L;          // per-sequence pitch (doubles): staggers the sequences of a half-warp
+    static constexpr int XSEQ = L * XROW + L + (L & 1);   // per-sequence pitch (doubles): staggers the sequences of a half-warp; even (16-byte stores)
     static constexpr int LD = L * D;                   // doubles per time step of X
     static constexpr int RUN = L * LD;                 // doubles per sequence-round of X
     static constexpr int OSEQ = staging_pitch(L, D);   // staging tile per-sequence pitch (doubles), 16B-aligned
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(32, 14) k_filter_chain(const double* __restric
                 for (int l = 0; l < L; l += 2) {
                     const double2 t = *reinterpret_cast<const double2*>(wr + l);
                     w[l] = t.x;
-                    w[l + 1] = t.y;
+                    if (l + 1 < L) w[l + 1] = t.y;
                 }
                 double qe = 0.0;
 #pragma unroll

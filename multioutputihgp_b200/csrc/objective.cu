@@ -974,8 +974,21 @@ __global__ void __launch_bounds__(256) k_obj_finish(const double* __restrict__ l
         }
     }
     __syncthreads();
-    if (tid == 0 && blockIdx.x == 0) {
-        const double steps = (double)N * (double)T;
+    if (blockIdx.x != 0) return;
+    // the per-latent entries in parallel (thread l), the two scalars by thread 0 in latent order - the same operations in the
+    // same order as a single thread would do them, without 64 latents' worth of divisions queued behind one lane
+    __shared__ double gs_term[64];
+    const double steps = (double)N * (double)T;
+    for (int l = tid; l < L; l += 256) {
+        const double* q = lat_sums + (size_t)l * 8;
+        const double Sl = S[l], rs = sqrt(Sl);
+        const double g2 = q[3];
+        grad[sizeU + l] = steps * 0.5 / Sl - 0.5 * (1.0 / rs / rs / rs) * q[4] - g2 * sigma / Sl / Sl;   // :555-562, :591
+        gs_term[l] = g2 / Sl;                                                              // :592
+        for (int k = 0; k < 3; ++k) grad[sizeU + L + 1 + 3 * l + k] = q[1 + k];            // :608-609
+    }
+    __syncthreads();
+    if (tid == 0) {
         const double rho_sum = lat_sums[(size_t)L * 8];
         const double m_n = fmax((double)(p - L), 0.0);                                     // moihgp.h:502
         double Ssum = 0.0;
@@ -983,13 +996,8 @@ __global__ void __launch_bounds__(256) k_obj_finish(const double* __restrict__ l
         double ls = steps * (0.5 * log(Ssum) + 0.5 * m_n * log(sigma)) + 0.5 * rho_sum / sigma;   // moihgp.h:503
         double gsig = 0.5 * (steps * m_n - rho_sum / sigma) / sigma;                       // moihgp.h:563
         for (int l = 0; l < L; ++l) {
-            const double* q = lat_sums + (size_t)l * 8;
-            if (threading) ls += q[0];                                                     // moihgp.h:588 vs :601 (Q5)
-            const double Sl = S[l], rs = sqrt(Sl);
-            const double g2 = q[3];
-            grad[sizeU + l] = steps * 0.5 / Sl - 0.5 * (1.0 / rs / rs / rs) * q[4] - g2 * sigma / Sl / Sl;   // :555-562, :591
-            gsig += g2 / Sl;                                                               // :592
-            for (int k = 0; k < 3; ++k) grad[sizeU + L + 1 + 3 * l + k] = q[1 + k];        // :608-609
+            if (threading) ls += lat_sums[(size_t)l * 8];                                  // moihgp.h:588 vs :601 (Q5)
+            gsig += gs_term[l];
         }
         grad[sizeU + L] = gsig;
         *loss = ls;

@@ -15,8 +15,12 @@ dev = torch.device("cuda:0")
 shapes = [(4, 2), (4, 4), (8, 2), (8, 4), (8, 8), (16, 2), (16, 4), (16, 8), (16, 16), (32, 2), (32, 4), (32, 8), (32, 16), (32, 32)]
 if len(sys.argv) > 1 and sys.argv[1] == "padded":      # p between the instantiated widths: the padded variant of k_filter_chain
     shapes = [(6, 2), (6, 4), (10, 4), (12, 4), (12, 8), (14, 8), (20, 4), (24, 8), (28, 16), (30, 2), (5, 2), (7, 4), (11, 8), (13, 4), (25, 8)]
+kernels = ("Matern32", "Matern52")
+if len(sys.argv) > 1 and sys.argv[1] == "one":         # one latent: Matern-3/2 only (chain.cu)
+    shapes = [(2, 1), (4, 1), (7, 1), (8, 1), (16, 1), (32, 1)]
+    kernels = ("Matern32",)
 T = 4096
-for kernel in ("Matern32", "Matern52"):
+for kernel in kernels:
     for p, L in shapes:
         N = max(256, int(2.5e8 / (T * L)) // 32 * 32)
         params, Hmix = model_params(p, L, kernel, 4321)

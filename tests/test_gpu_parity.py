@@ -288,6 +288,11 @@ CHAIN_CONFIGS = [
     ("Matern32", 13, 4, 10, 64, 56),
     ("Matern52", 27, 8, 6, 90, 57),
     ("Matern32", 31, 2, 17, 35, 58),
+    ("Matern32", 4, 1, 40, 77, 59),              # one latent (Matern-3/2): rounds of one step, 32 sequences per warp
+    ("Matern32", 2, 1, 70, 63, 60),              # the shape of the reference's own examples (p = 2, L = 1)
+    ("Matern32", 7, 1, 33, 130, 61),
+    ("Matern32", 16, 1, 37, 41, 62),
+    ("Matern32", 29, 1, 65, 33, 63),
 ]
 
 
@@ -553,6 +558,7 @@ NAN_CONFIGS = [
     ("Matern52", 12, 4, 9, 90, "chain"),      # padded variant of the many-chains filter
     ("Matern32", 6, 2, 19, 70, "chain"),
     ("Matern52", 11, 4, 9, 85, "chain"),      # ... with odd p
+    ("Matern32", 3, 1, 40, 60, "chain"),      # one latent
     ("Matern32", 5, 3, 3, 280, "scan"),       # odd p: scalar projection kernel
     ("Matern32", 64, 32, 1, 600, "scan"),     # tensor-pipe projection kernel, large L
 ]
@@ -764,7 +770,7 @@ def test_bound_data_objective_equals_host_buffer_objective(cuda_lib):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("path,kernel,p,L,N,T", [("chain", "Matern52", 16, 8, 5, 203), ("chain", "Matern32", 8, 4, 9, 37),
-                                                 ("chain", "Matern52", 4, 2, 37, 45), ("chain", "Matern52", 10, 4, 11, 57), ("chain", "Matern32", 22, 8, 5, 43), ("chain", "Matern52", 7, 2, 19, 41), ("chain", "Matern32", 32, 2, 19, 70), ("chain", "Matern52", 4, 4, 9, 66),
+                                                 ("chain", "Matern52", 4, 2, 37, 45), ("chain", "Matern52", 10, 4, 11, 57), ("chain", "Matern32", 22, 8, 5, 43), ("chain", "Matern52", 7, 2, 19, 41), ("chain", "Matern32", 2, 1, 45, 50), ("chain", "Matern32", 32, 2, 19, 70), ("chain", "Matern52", 4, 4, 9, 66),
                                                  ("scan", "Matern52", 16, 8, 3, 515), ("scan", "Matern32", 5, 3, 2, 257)])
 def test_outputs_stay_inside_their_buffers(cuda_lib, path, kernel, p, L, N, T):
     """Ragged N / T through the device entry points with every output placed between guard zones: the guards are intact
