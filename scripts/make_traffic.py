@@ -58,6 +58,12 @@ def main():
         p = os.path.join(src, "traffic_%s.csv" % wl)
         if not os.path.exists(p):
             continue
+        # a capture older than the newest CUDA source does not describe the kernels the hash below stands for
+        import glob
+        newest = max(os.path.getmtime(x) for x in glob.glob(os.path.join(ROOT, "multioutputihgp_b200", "csrc", "*")) if x.endswith((".cu", ".cuh", ".h")))
+        if os.path.getmtime(p) < newest and "--force" not in sys.argv:
+            print("%s: capture is older than the CUDA sources - re-run scripts/gpu_traffic.sh (or pass --force)" % wl)
+            continue
         per = parse(p)
         total = sum(k["dram_bytes_read"] + k["dram_bytes_write"] for k in per.values())
         out[wl] = {"workload": WORK[wl], "source_hash": source_hash(),
