@@ -53,10 +53,26 @@ class MOIHGPSequences(object):
         self.num_param = int(self._lib.moihgp_cuda_num_param(h))
         self.num_igp_param = int(self._lib.moihgp_cuda_num_igp_param(h))
 
+    @classmethod
+    def adopt(cls, model):
+        """The whole-sequence interface on the handle of an existing per-observation model (``pywrapper.MOIHGP``): ONE model on
+        the device, shared - ``update`` through either object is seen by both.  ``model`` keeps ownership of the handle (and
+        is kept alive by the returned object)."""
+        import ctypes as _ct
+        self = cls.__new__(cls)
+        self._lib = _lib.load()
+        self._h = _ct.c_void_p(model.handle)
+        self._owner = model
+        self.dt, self.num_output, self.num_latent, self.kernel = model.dt, model.num_output, model.num_latent, None
+        self.igp_dim = int(self._lib.moihgp_cuda_igp_dim(self._h))
+        self.num_param = int(self._lib.moihgp_cuda_num_param(self._h))
+        self.num_igp_param = int(self._lib.moihgp_cuda_num_igp_param(self._h))
+        return self
+
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and getattr(self, "_owner", None) is None:
             self._lib.moihgp_cuda_destroy(self._h)
-            self._h = None
+        self._h = None
 
     def _check(self, rc):
         if rc != 0:

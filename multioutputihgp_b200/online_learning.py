@@ -26,9 +26,9 @@ class MOIHGPOnlineLearning:
 
     def __init__(self, dt, num_output, num_latent, gamma, x_init=None, windowsize=None, kernel="Matern32", threading=False):
         self.moihgp = MOIHGP(dt, num_output, num_latent, kernel=kernel, threading=threading)
-        # whole-window objective on the GPU; kept in lock-step with self.moihgp through update()
-        self._seq = MOIHGPSequences(dt, num_output, num_latent, kernel=self._seq_kernel(kernel), threading=threading)
-        self._seq.update(self.moihgp.params.copy())
+        # whole-window objective on the GPU, on the SAME device model as self.moihgp (one handle: one update serves both)
+        self._seq = MOIHGPSequences.adopt(self.moihgp)
+        self._held = None                                  # the parameters the device model holds, when known
         self.num_output = num_output
         self.num_latent = num_latent
         self.ihgp_dim = self.moihgp.igp_dim
@@ -58,8 +58,10 @@ class MOIHGPOnlineLearning:
         return kernel
 
     def _update(self, params):
-        self.moihgp.update(params)
+        if self._held is not None and np.array_equal(self._held, params):
+            return                                         # the model already holds them (left there by the last evaluation)
         self._seq.update(params)
+        self._held = np.array(params, dtype=np.float64, copy=True)
 
     def step(self, y=None):
         if self.ma is None:                                                  # online_learning.py:54-64
@@ -98,6 +100,7 @@ class MOIHGPOnlineLearning:
             p = np.linalg.solve(self.hess_inv, dparams)
             if self._resident and not has_nan:
                 l, g = self._seq.online_objective(params)                    # update(params) + window loop: one graph launch
+                self._held = np.array(params, dtype=np.float64, copy=True)
                 loss = self.gamma * 0.5 * dparams.dot(p) + l
                 return (loss, self.gamma * p + g) if eval_gradient else loss
             self._update(params)

@@ -48,6 +48,11 @@ class MOIHGP(object):
         self.__params_p, self.__grad_p, self.__x_p, self.__y_p = p(self.__params), p(self.__grad), p(self.__x), p(self.__y)
         self.__dx_p, self.__xnew_p, self.__yhat_p, self.__dxnew_p = p(self.__dx), p(self.__xnew), p(self.__yhat), p(self.__dxnew)
 
+    @property
+    def handle(self):
+        """the library handle (what gpXX_new returned): the moihgp_cuda_* entry points accept it too"""
+        return self.__obj
+
     def __del__(self):
         if getattr(self, "_MOIHGP__obj", None):
             self.__del(self.__obj)
