@@ -88,7 +88,8 @@ class ClockSampler:
             nv.nvmlInit()
             hd = nv.nvmlDeviceGetHandleByIndex(index)
             mx = float(nv.nvmlDeviceGetMaxClockInfo(hd, nv.NVML_CLOCK_SM))
-            bits = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
+            bits = (("gpu_idle", 0x1), ("applications_clocks_setting", 0x2), ("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sync_boost", 0x10),
+                    ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("hw_power_brake_slowdown", 0x80), ("display_clock_setting", 0x100))
             while not self._nv_stop:
                 if self._nv_on:
                     sm = float(nv.nvmlDeviceGetClockInfo(hd, nv.NVML_CLOCK_SM))
@@ -96,7 +97,11 @@ class ClockSampler:
                         rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(hd))
                     except Exception:
                         rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(hd))
-                    self._nv_rows.append((sm, mx, tuple(n for n, b in bits if rs & b)))
+                    try:
+                        pw = nv.nvmlDeviceGetPowerUsage(hd) / 1000.0
+                    except Exception:
+                        pw = None
+                    self._nv_rows.append((sm, mx, tuple(n for n, b in bits if rs & b), rs, pw))
                 time.sleep(0.005)
         except Exception:
             pass
@@ -138,7 +143,9 @@ class ClockSampler:
             rows = list(self._nv_rows)
             reasons = sorted({r for row in rows for r in row[2]})
             out.update(sm_mhz=float(np.median([r[0] for r in rows])), sm_max_mhz=float(max(r[1] for r in rows)), reasons=reasons,
-                       samples=len(rows), source="nvml")
+                       samples=len(rows), source="nvml", sm_mhz_min=float(min(r[0] for r in rows)),
+                       reasons_mask="0x%x" % int(np.bitwise_or.reduce([r[3] for r in rows])),
+                       power_w=(float(np.median([r[4] for r in rows if r[4] is not None])) if any(r[4] is not None for r in rows) else None))
             return out
         if self.p is None:
             return out
