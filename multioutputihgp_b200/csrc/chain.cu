@@ -46,39 +46,41 @@ const Shape kShapes[] = {
 };
 }  // namespace
 
-// the instantiated shape that serves a model with p outputs and L latents: (p, L) itself, or the next larger
-// instantiated P with the same L (padded variant of k_filter_chain: zero columns, zero rows of U), else null
-static const Shape* find_shape(int p, int L) {
+// the instantiated shape that serves a model with p outputs, L latents and state dimension dim: (p, L) itself, or the
+// smallest instantiated (P >= p, Lt >= L) - padded variants of the kernels: zero columns of Y / zero rows of U for the
+// outputs, idle lanes / zero columns of U for the latents.  Padded latents need L * dim even (16-byte pieces of X) and
+// Lt >= 2; L = 1 with dim = 3 is not served (a sequence-round of X is 3 doubles).
+static const Shape* find_shape(int p, int L, int dim) {
+    if (L == 1 && dim == 3) return nullptr;
     const Shape* best = nullptr;
     for (const Shape& s : kShapes) {
-        if (s.L != L || s.p < p) continue;
-        if (s.p != p && p < L) continue;
-        if (!best || s.p < best->p) best = &s;
+        if (s.L < L || s.p < p || p < L) continue;
+        if (s.L != L && (s.L < 2 || L < 2 || (L * dim) % 2 != 0)) continue;
+        if (!best || s.L < best->L || (s.L == best->L && s.p < best->p)) best = &s;
     }
     return best;
 }
 
-// L = 1 with state dimension 3: a sequence-round of X is 3 doubles, which the 16-byte copy-out of the staging tile cannot
-// tile - Matern-5/2 models with a single latent take the chunked-scan path
 bool chain_supported(int p, int L, int dim) {
     if (dim != 2 && dim != 3) return false;
-    if (L == 1 && dim == 3) return false;
-    return find_shape(p, L) != nullptr;
+    return find_shape(p, L, dim) != nullptr;
 }
 
-// the automatic path choice: every served shape but (P = 32, L = 16), where the chunked-scan path ties or wins
-// (profiles/r02/chain_vs_scan_by_shape_v2_square_fix.txt, chain_vs_scan_padded_p.txt: 0.74 - 1.05x)
+// the automatic path choice: every served shape but (P = 32, L = 16) and padded latents under P = 32, where the chunked-scan
+// path ties or wins (profiles/r02/chain_vs_scan_by_shape_v2_square_fix.txt, chain_vs_scan_padded_p.txt,
+// chain_vs_scan_padded_L.txt: 0.69 - 1.05x)
 bool chain_preferred(int p, int L, int dim) {
-    if (!chain_supported(p, L, dim)) return false;
-    const Shape* s = find_shape(p, L);
-    return s != nullptr && !(s->p == 32 && s->L == 16);
+    if (dim != 2 && dim != 3) return false;
+    const Shape* s = find_shape(p, L, dim);
+    return s != nullptr && !(s->p == 32 && (s->L == 16 || s->L != L));
 }
 
 cudaError_t launch_chain(int p, int L, int dim, const ChainArgs& a, cudaStream_t st) {
-    const Shape* s = find_shape(p, L);
+    const Shape* s = find_shape(p, L, dim);
     if (!s) return cudaErrorInvalidValue;
     ChainArgs b = a;
     b.p = p;
+    b.L = L;
     return s->fn(dim, b, st);
 }
 

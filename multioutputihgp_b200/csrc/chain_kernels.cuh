@@ -153,12 +153,15 @@ struct FilterCfg {
 // P-column tile rows (16-byte copies when p is even, 8-byte copies when it is odd and the rows are only 8-byte aligned); the other columns are zeroed once and U has zero rows
 // there (run_chain_ns), so every later stage - tensor-pipe projection, squared norms, explicit residual, missing-data
 // projection - sees a P-output model whose extra outputs are identically zero and carry no weight.
+// The same variant serves L_real < L latents (L_real * D even): U has zero columns there, lanes (s, j >= L_real) own no
+// chain, and X keeps the CALLER'S layout [t][L_real][D] - a sequence-round is L steps of L_real * D doubles, staged and
+// copied out with run-time lengths.
 template <int P, int L, int D, int NS_, bool PADP>
 __global__ void __launch_bounds__(32, 14) k_filter_chain(const double* __restrict__ Y, const __grid_constant__ ProjConsts<P, L> pc,
                                                     const LatentConsts* __restrict__ consts, double sigma, double nll_const,
                                                     long long N, long long T, const double* __restrict__ x0,
                                                     double* __restrict__ X, double* __restrict__ nll, double* __restrict__ xT,
-                                                    int* __restrict__ nan_flag, int p_real) {
+                                                    int* __restrict__ nan_flag, int p_real, int L_real) {
     using C = FilterCfg<P, L, D, NS_>;
     constexpr int NS = C::NS, CH = C::CH, KB = C::KB, NB = C::NB, LD = C::LD, R = C::R, RB = C::RB;
     static_assert(P % 4 == 0 && (CH & (CH - 1)) == 0 && CH <= 32, "P must be 4, 8, 16, 32 or 64");
@@ -174,7 +177,9 @@ __global__ void __launch_bounds__(32, 14) k_filter_chain(const double* __restric
     const long long n0 = (long long)blockIdx.x * NS;
     const int nvalid = (int)(N - n0 < NS ? N - n0 : NS);                       // sequences of this warp that exist
     const long long n = n0 + s;
-    const bool active = lane < R;                                              // phase 2 lanes that own a chain
+    const int Lr = PADP ? L_real : L;                                          // latents of the model
+    const int LDr = PADP ? L_real * D : LD;                                    // doubles per time step of X (the caller's layout)
+    const bool active = lane < R && (!PADP || j < Lr);                         // phase 2 lanes that own a chain
     const bool seq_ok = s < nvalid;
     const long long rounds = (T + L - 1) / L;
 
@@ -194,7 +199,7 @@ __global__ void __launch_bounds__(32, 14) k_filter_chain(const double* __restric
     const int own_row = 8 * q4 + g4, own_s = own_row / L, own_i = own_row % L;
     // phase 2: the latent's filter constants
     const bool owner = q4 < RB;
-    const LatentConsts* lc = consts + j;
+    const LatentConsts* lc = consts + (PADP ? min(j, Lr - 1) : j);
     double M[D * D], K[D], HA[D];
 #pragma unroll
     for (int a = 0; a < D; ++a) {
@@ -205,7 +210,7 @@ __global__ void __launch_bounds__(32, 14) k_filter_chain(const double* __restric
     }
     double x[D];
 #pragma unroll
-    for (int a = 0; a < D; ++a) x[a] = (x0 && active && seq_ok) ? x0[((size_t)n * L + j) * D + a] : 0.0;
+    for (int a = 0; a < D; ++a) x[a] = (x0 && active && seq_ok) ? x0[((size_t)n * Lr + j) * D + a] : 0.0;
     const double rs_j = pc.rs[j];                                              // S_j^-1/2  (moihgp.h:181)
     double rho_acc = 0.0, vsq_acc = 0.0;
     bool saw_nan = false;
@@ -264,7 +269,7 @@ __global__ void __launch_bounds__(32, 14) k_filter_chain(const double* __restric
     double* const xw = xch + (g4 / L) * C::XSEQ + (g4 % L) * C::XROW + 2 * q4;   // + row-block offset below
     const double* const xc = xch + s * C::XSEQ + j;
     double* const oc = ost + s * C::OSEQ + j * D;
-    double* const Xcta = X ? X + (size_t)n0 * T * LD : nullptr;
+    double* const Xcta = X ? X + (size_t)n0 * T * LDr : nullptr;
 
     for (long long r = 0; r < rounds; ++r) {
         issue(r + STAGES - 1);
@@ -307,8 +312,9 @@ __global__ void __launch_bounds__(32, 14) k_filter_chain(const double* __restric
             double q = ysq - wsq;                                                 // || (I - U U') y ||^2
             // P == L: U is square and orthogonal, (I - U U') y vanishes identically and the explicit form would return
             // rounding noise for EVERY row: rho = 0 unless the row holds a NaN
-            if (P == L && ysq == ysq) q = 0.0;
-            const bool bad = owner && !(q >= 1e-4 * ysq) && !(P == L && ysq == ysq);   // cancellation (or NaN): evaluate explicitly
+            const bool square = PADP ? p_real == Lr : P == L;                     // of the MODEL, not of the instantiated shape
+            if (square && ysq == ysq) q = 0.0;
+            const bool bad = owner && !(q >= 1e-4 * ysq) && !(square && ysq == ysq);   // cancellation (or NaN): evaluate explicitly
             if (__any_sync(FULL, bad)) {
                 // explicit  || y - U (U' y) ||^2  of row `lane` (moihgp.h:651), w read back from the exchange tile
                 __syncwarp();
@@ -352,12 +358,12 @@ __global__ void __launch_bounds__(32, 14) k_filter_chain(const double* __restric
                 const unsigned char* yrow = tile + row * C::ROWB;
                 const int sw_ = C::swz(row);
                 double* sc = ost;
-                ls_solve_coop(P, L,
+                ls_solve_coop(P, Lr,
                               [&](int r) { return *reinterpret_cast<const double*>(yrow + (((r >> 1) ^ sw_) << 4) + ((r & 1) << 3)); },
                               [&](int r, int l) { return pc.U[r][l]; },
                               sc, sc + L * L, sc + 2 * L * L, sc + 2 * L * L + L, reinterpret_cast<int*>(sc + 2 * L * L + 2 * L),
                               lane, 32, [] { __syncwarp(); });
-                if (lane < L) xch[(row / L) * C::XSEQ + (row % L) * C::XROW + lane] = sc[2 * L * L + L + lane];   // z; phase 2 applies S^-1/2
+                if (lane < L) xch[(row / L) * C::XSEQ + (row % L) * C::XROW + lane] = lane < Lr ? sc[2 * L * L + L + lane] : 0.0;   // z; phase 2 applies S^-1/2
                 __syncwarp();
             }
         }
@@ -388,7 +394,7 @@ __global__ void __launch_bounds__(32, 14) k_filter_chain(const double* __restric
                 vsq_acc = fma(v, v, vsq_acc);
 #pragma unroll
                 for (int a = 0; a < D; ++a) x[a] = xn[a];
-                store_state<D>(oc + i * LD, xn);
+                store_state<D>(oc + i * LDr, xn);
             }
         } else {
 #pragma unroll
@@ -411,12 +417,23 @@ __global__ void __launch_bounds__(32, 14) k_filter_chain(const double* __restric
 #pragma unroll
                     for (int a = 0; a < D; ++a) x[a] = xn[a];
                 }
-                store_state<D>(oc + i * LD, x);
+                store_state<D>(oc + i * LDr, x);
             }
         }
         __syncwarp();
         // ---- store: NS contiguous runs of L rows ------------------------------------------------------
-        if (Xcta) {
+        if (Xcta && PADP && Lr != L) {
+            // padded latents: a sequence-round is L steps of LDr doubles (even), copied out in 16-byte pieces with run-time lengths
+            double* Xr = Xcta + (size_t)t0 * LDr;
+            const int PSr = L * LDr / 2;
+            const long long rows_left = T - t0;
+            const int valid16 = (int)(rows_left >= L ? PSr : rows_left * LDr / 2);
+            for (int q = lane; q < NS * PSr; q += 32) {
+                const int qs = q / PSr, qo = q - qs * PSr;
+                if (qs < nvalid && qo < valid16)
+                    *reinterpret_cast<double2*>(Xr + (size_t)qs * T * LDr + 2 * qo) = *reinterpret_cast<const double2*>(ost + qs * C::OSEQ + 2 * qo);
+            }
+        } else if (Xcta) {
             double* Xr = Xcta + (size_t)t0 * LD;
             if (fast) {
                 constexpr int NPASS = (NS * C::PS + 31) / 32;
@@ -455,7 +472,7 @@ __global__ void __launch_bounds__(32, 14) k_filter_chain(const double* __restric
     // ---- final state and NLL of each sequence ---------------------------------------------------------
     if (xT && active && seq_ok) {
 #pragma unroll
-        for (int a = 0; a < D; ++a) xT[((size_t)n * L + j) * D + a] = x[a];
+        for (int a = 0; a < D; ++a) xT[((size_t)n * Lr + j) * D + a] = x[a];
     }
     if (saw_nan) *nan_flag = 1;
     if (nll) {
@@ -473,7 +490,7 @@ __global__ void __launch_bounds__(32, 14) k_filter_chain(const double* __restric
             // come from the host (parameters), the innovation variances S_l from K-setup's records - read here so that the
             // host never has to wait for them
             double logs = 0.0;
-            for (int l = 0; l < L; ++l) logs += __ldg(&consts[l].logS);
+            for (int l = 0; l < Lr; ++l) logs += __ldg(&consts[l].logS);
             nll[n] = 0.5 * rho / sigma + part + (double)T * (nll_const + 0.5 * logs);
         }
     }
@@ -503,22 +520,26 @@ struct SmoothCfg {
 // grid: ceil(N / NS) CTAs of one warp; rounds of L steps from the end of the sequence.  Each sequence-round of X is one
 // contiguous run of L*L*D doubles: it is brought in by ONE TMA bulk copy (mbarrier-tracked), smoothed in place in
 // shared memory, and written out by ONE bulk store - no per-lane load/store instructions touch HBM.
-template <int L, int D, int MODE, int NS_, int RM_>
+// PADL: the model has L_real < L latents (L_real * D even): lanes (s, j >= L_real) own no chain and the runs keep the caller's
+// layout, RL steps of L_real * D doubles.
+template <int L, int D, int MODE, int NS_, int RM_, bool PADL>
 __global__ void __launch_bounds__(32, 14) k_smooth_chain(const double* __restrict__ X, const LatentConsts* __restrict__ consts,
-                                                        long long N, long long T, double* __restrict__ Xs) {
+                                                        long long N, long long T, double* __restrict__ Xs, int L_real) {
     using C = SmoothCfg<L, D, NS_, RM_>;
-    constexpr int NS = C::NS, LD = C::LD, RL = C::RL, RM = C::RM;
+    constexpr int NS = C::NS, RL = C::RL, RM = C::RM;
+    const int Lr = PADL ? L_real : L;
+    const int LD = PADL ? L_real * D : C::LD;      // doubles per time step (the caller's layout)
     constexpr int LOOK = SSTAGES - 2;                  // loads in flight ahead of the round being processed
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* tiles = reinterpret_cast<double*>(smem_raw);                                   // [SSTAGES][NS][OSEQ]
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(tiles + SSTAGES * NS * C::OSEQ);
     const int lane = threadIdx.x;
     const int s = lane / L, j = lane % L;
-    const bool active = lane < NS * L;
+    const bool active = lane < NS * L && (!PADL || j < Lr);
     const long long n0 = (long long)blockIdx.x * NS;
     const int nvalid = (int)(N - n0 < NS ? N - n0 : NS);
     const long long rounds = (T + RL - 1) / RL;
-    const LatentConsts* lc = consts + j;
+    const LatentConsts* lc = consts + (PADL ? min(j, Lr - 1) : j);
     double G[D * D], B[D * D];                     // B: I - A (literal, applied to X[j+1]) or I - G A (rts, applied to X[j])
 #pragma unroll
     for (int a = 0; a < D; ++a)
@@ -638,31 +659,39 @@ cudaError_t run_chain_ns(const ChainArgs& a, cudaStream_t st) {
     constexpr int SRM = (NS >= 2 && NS == 32 / L) ? 2 : 1;           // ... rounds twice as long: 2x longer contiguous runs per bulk copy
     using SS = SmoothCfg<L, D, SNS, SRM>;
     ProjConsts<P, L> pc;
-    const int p_real = a.p > 0 ? a.p : P;
-    for (int r = 0; r < P; ++r) for (int l = 0; l < L; ++l) pc.U[r][l] = r < p_real ? a.U_host[(size_t)r * L + l] : 0.0;
-    for (int l = 0; l < L; ++l) pc.rs[l] = 1.0 / std::sqrt(a.S_host[l]);
+    const int p_real = a.p > 0 ? a.p : P, L_real = a.L > 0 ? a.L : L;       // the model's own sizes (<= the instantiated ones)
+    for (int r = 0; r < P; ++r)
+        for (int l = 0; l < L; ++l) pc.U[r][l] = (r < p_real && l < L_real) ? a.U_host[(size_t)r * L_real + l] : 0.0;
+    for (int l = 0; l < L; ++l) pc.rs[l] = l < L_real ? 1.0 / std::sqrt(a.S_host[l]) : 0.0;
+    const bool padded = p_real != P || L_real != L, padL = L_real != L;
+    if (padL && (L_real * D) % 2 != 0) return cudaErrorInvalidValue;        // chain_supported() excludes it
     const unsigned grid = (unsigned)((a.N + NS - 1) / NS);
     static std::atomic<int> attr_done[64];          // per device: function attributes belong to the device's context
     if (AttrOnce once(attr_done); once) {
         cudaFuncSetAttribute(k_filter_chain<P, L, D, NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS::BYTES);
         cudaFuncSetAttribute(k_filter_chain<P, L, D, NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS::BYTES);
-        cudaFuncSetAttribute(k_smooth_chain<L, D, 0, SNS, SRM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS::BYTES);
-        cudaFuncSetAttribute(k_smooth_chain<L, D, 1, SNS, SRM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS::BYTES);
-        cudaFuncSetAttribute(k_smooth_chain<L, D, 0, NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmoothCfg<L, D, NS, 1>::BYTES);
-        cudaFuncSetAttribute(k_smooth_chain<L, D, 1, NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmoothCfg<L, D, NS, 1>::BYTES);
+        cudaFuncSetAttribute(k_smooth_chain<L, D, 0, SNS, SRM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS::BYTES);
+        cudaFuncSetAttribute(k_smooth_chain<L, D, 1, SNS, SRM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS::BYTES);
+        cudaFuncSetAttribute(k_smooth_chain<L, D, 0, SNS, SRM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS::BYTES);
+        cudaFuncSetAttribute(k_smooth_chain<L, D, 1, SNS, SRM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS::BYTES);
+        cudaFuncSetAttribute(k_smooth_chain<L, D, 0, NS, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmoothCfg<L, D, NS, 1>::BYTES);
+        cudaFuncSetAttribute(k_smooth_chain<L, D, 1, NS, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmoothCfg<L, D, NS, 1>::BYTES);
     }
-    if (p_real == P) k_filter_chain<P, L, D, NS, false><<<grid, 32, FS::BYTES, st>>>(a.Y, pc, a.consts, a.sigma, a.nll_const, a.N, a.T, a.x0, a.X, a.nll, a.xT, a.nan_flag, P);
-    else k_filter_chain<P, L, D, NS, true><<<grid, 32, FS::BYTES, st>>>(a.Y, pc, a.consts, a.sigma, a.nll_const, a.N, a.T, a.x0, a.X, a.nll, a.xT, a.nan_flag, p_real);
+    if (!padded) k_filter_chain<P, L, D, NS, false><<<grid, 32, FS::BYTES, st>>>(a.Y, pc, a.consts, a.sigma, a.nll_const, a.N, a.T, a.x0, a.X, a.nll, a.xT, a.nan_flag, P, L);
+    else k_filter_chain<P, L, D, NS, true><<<grid, 32, FS::BYTES, st>>>(a.Y, pc, a.consts, a.sigma, a.nll_const, a.N, a.T, a.x0, a.X, a.nll, a.xT, a.nan_flag, p_real, L_real);
     mark(a.mk, "k_filter_chain");
     if (a.Xs) {
         static const bool long_rounds = []() { const char* e = std::getenv("MOIHGP_SMOOTH_LONG_ROUNDS"); return !(e && e[0] == '0'); }();
-        if (long_rounds) {
-            const unsigned sgrid = (unsigned)((a.N + SNS - 1) / SNS);
-            if (a.mode == 0) k_smooth_chain<L, D, 0, SNS, SRM><<<sgrid, 32, SS::BYTES, st>>>(a.X, a.consts, a.N, a.T, a.Xs);
-            else k_smooth_chain<L, D, 1, SNS, SRM><<<sgrid, 32, SS::BYTES, st>>>(a.X, a.consts, a.N, a.T, a.Xs);
+        const unsigned sgrid = (unsigned)((a.N + SNS - 1) / SNS);
+        if (padL) {
+            if (a.mode == 0) k_smooth_chain<L, D, 0, SNS, SRM, true><<<sgrid, 32, SS::BYTES, st>>>(a.X, a.consts, a.N, a.T, a.Xs, L_real);
+            else k_smooth_chain<L, D, 1, SNS, SRM, true><<<sgrid, 32, SS::BYTES, st>>>(a.X, a.consts, a.N, a.T, a.Xs, L_real);
+        } else if (long_rounds) {
+            if (a.mode == 0) k_smooth_chain<L, D, 0, SNS, SRM, false><<<sgrid, 32, SS::BYTES, st>>>(a.X, a.consts, a.N, a.T, a.Xs, L);
+            else k_smooth_chain<L, D, 1, SNS, SRM, false><<<sgrid, 32, SS::BYTES, st>>>(a.X, a.consts, a.N, a.T, a.Xs, L);
         } else {
-            if (a.mode == 0) k_smooth_chain<L, D, 0, NS, 1><<<grid, 32, SmoothCfg<L, D, NS, 1>::BYTES, st>>>(a.X, a.consts, a.N, a.T, a.Xs);
-            else k_smooth_chain<L, D, 1, NS, 1><<<grid, 32, SmoothCfg<L, D, NS, 1>::BYTES, st>>>(a.X, a.consts, a.N, a.T, a.Xs);
+            if (a.mode == 0) k_smooth_chain<L, D, 0, NS, 1, false><<<grid, 32, SmoothCfg<L, D, NS, 1>::BYTES, st>>>(a.X, a.consts, a.N, a.T, a.Xs, L);
+            else k_smooth_chain<L, D, 1, NS, 1, false><<<grid, 32, SmoothCfg<L, D, NS, 1>::BYTES, st>>>(a.X, a.consts, a.N, a.T, a.Xs, L);
         }
         mark(a.mk, "k_smooth_chain");
     }

@@ -101,7 +101,7 @@ cudaError_t launch_nll_reduce(const double* rho_part, const double* vsq, const L
 // chain.cu  (many-chains path: thread per (sequence, latent), sequential in time)
 struct ChainArgs {
     const double* Y;              // [N][T][p], 16-byte aligned
-    int p = 0;                    // outputs of the model (0 = the instantiated P); p < P runs the padded variant (p even)
+    int p = 0, L = 0;             // outputs / latents of the model (0 = the instantiated P / L); smaller ones run the padded variants
     const double *U_host, *S_host;    // host copies (become constant-bank kernel parameters)
     const LatentConsts* consts;   // device
     double sigma, nll_const;      // nll_const = 1/2 log sum S + 1/2 m_n log sigma (per step; the kernel adds 1/2 sum_l log S_l from the device records)

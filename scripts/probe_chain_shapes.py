@@ -19,10 +19,14 @@ kernels = ("Matern32", "Matern52")
 if len(sys.argv) > 1 and sys.argv[1] == "one":         # one latent: Matern-3/2 only (chain.cu)
     shapes = [(2, 1), (4, 1), (7, 1), (8, 1), (16, 1), (32, 1)]
     kernels = ("Matern32",)
+if len(sys.argv) > 1 and sys.argv[1] == "padL":        # L between the instantiated widths (Matern-5/2: even L only)
+    shapes = [(8, 3), (12, 5), (8, 6), (16, 6), (16, 7), (16, 10), (16, 12), (24, 6), (30, 14)]
 T = 4096
 for kernel in kernels:
     for p, L in shapes:
         N = max(256, int(2.5e8 / (T * L)) // 32 * 32)
+        if (L * (3 if kernel == "Matern52" else 2)) % 2 and L not in (1, 2, 4, 8, 16):
+            continue
         params, Hmix = model_params(p, L, kernel, 4321)
         m = MOIHGPSequences(DT, p, L, kernel, threading=True, device=0)
         m.update(params)

@@ -293,6 +293,17 @@ CHAIN_CONFIGS = [
     ("Matern32", 7, 1, 33, 130, 61),
     ("Matern32", 16, 1, 37, 41, 62),
     ("Matern32", 29, 1, 65, 33, 63),
+    ("Matern32", 8, 3, 13, 91, 64),              # L between the instantiated widths: idle lanes, X in the caller's [t][L][d] layout
+    ("Matern32", 5, 3, 21, 64, 65),
+    ("Matern32", 12, 5, 7, 140, 66),
+    ("Matern32", 6, 6, 9, 77, 67),
+    ("Matern32", 16, 7, 5, 120, 68),
+    ("Matern32", 15, 11, 5, 66, 69),
+    ("Matern32", 24, 12, 3, 50, 70),
+    ("Matern52", 12, 6, 7, 85, 71),              # ... Matern-5/2: even L only (L * d even)
+    ("Matern52", 16, 10, 5, 70, 72),
+    ("Matern52", 9, 6, 9, 33, 73),
+    ("Matern52", 14, 14, 3, 90, 74),
 ]
 
 
@@ -559,6 +570,8 @@ NAN_CONFIGS = [
     ("Matern32", 6, 2, 19, 70, "chain"),
     ("Matern52", 11, 4, 9, 85, "chain"),      # ... with odd p
     ("Matern32", 3, 1, 40, 60, "chain"),      # one latent
+    ("Matern32", 10, 3, 11, 75, "chain"),     # padded latents
+    ("Matern52", 12, 6, 7, 66, "chain"),
     ("Matern32", 5, 3, 3, 280, "scan"),       # odd p: scalar projection kernel
     ("Matern32", 64, 32, 1, 600, "scan"),     # tensor-pipe projection kernel, large L
 ]
@@ -770,7 +783,7 @@ def test_bound_data_objective_equals_host_buffer_objective(cuda_lib):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("path,kernel,p,L,N,T", [("chain", "Matern52", 16, 8, 5, 203), ("chain", "Matern32", 8, 4, 9, 37),
-                                                 ("chain", "Matern52", 4, 2, 37, 45), ("chain", "Matern52", 10, 4, 11, 57), ("chain", "Matern32", 22, 8, 5, 43), ("chain", "Matern52", 7, 2, 19, 41), ("chain", "Matern32", 2, 1, 45, 50), ("chain", "Matern32", 32, 2, 19, 70), ("chain", "Matern52", 4, 4, 9, 66),
+                                                 ("chain", "Matern52", 4, 2, 37, 45), ("chain", "Matern52", 10, 4, 11, 57), ("chain", "Matern32", 22, 8, 5, 43), ("chain", "Matern52", 7, 2, 19, 41), ("chain", "Matern32", 2, 1, 45, 50), ("chain", "Matern32", 9, 5, 9, 47), ("chain", "Matern52", 12, 6, 7, 39), ("chain", "Matern32", 32, 2, 19, 70), ("chain", "Matern52", 4, 4, 9, 66),
                                                  ("scan", "Matern52", 16, 8, 3, 515), ("scan", "Matern32", 5, 3, 2, 257)])
 def test_outputs_stay_inside_their_buffers(cuda_lib, path, kernel, p, L, N, T):
     """Ragged N / T through the device entry points with every output placed between guard zones: the guards are intact
