@@ -570,10 +570,10 @@ int moihgp_cuda_filter_smoother_nll_dev(moihgp_handle* h, const double* Y, size_
     if (mk) { mk->st = h->stream; mk->mark("begin"); }
     auto aligned16 = [](const void* q) { return (reinterpret_cast<size_t>(q) & 15) == 0; };
     const size_t chain_warps = (N * (size_t)L + 31) / 32;
-    bool use_chain = chain_preferred(h->p, L, D) && aligned16(Y) && aligned16(X) && aligned16(Xs) && chain_warps >= 148;
+    bool use_chain = chain_preferred(h->p, L, D, (long long)T) && aligned16(Y) && aligned16(X) && aligned16(Xs) && chain_warps >= 148;
     if (h->path == 1) use_chain = false;
     if (h->path == 2) {
-        if (!(chain_supported(h->p, L, D) && aligned16(Y) && aligned16(X) && aligned16(Xs))) return fail(h, "many-chains path not available for this shape/alignment");
+        if (!(chain_supported(h->p, L, D, (long long)T) && aligned16(Y) && aligned16(X) && aligned16(Xs))) return fail(h, "many-chains path not available for this shape/alignment");
         use_chain = true;
     }
     if (use_chain) {

@@ -46,37 +46,39 @@ const Shape kShapes[] = {
 };
 }  // namespace
 
-// the instantiated shape that serves a model with p outputs, L latents and state dimension dim: (p, L) itself, or the
-// smallest instantiated (P >= p, Lt >= L) - padded variants of the kernels: zero columns of Y / zero rows of U for the
-// outputs, idle lanes / zero columns of U for the latents.  Padded latents need L * dim even (16-byte pieces of X) and
-// Lt >= 2; L = 1 with dim = 3 is not served (a sequence-round of X is 3 doubles).
-static const Shape* find_shape(int p, int L, int dim) {
+// the instantiated shape that serves a model with p outputs, L latents and state dimension dim on sequences of T steps:
+// (p, L) itself, or the smallest instantiated (P >= p, Lt >= L) - padded variants of the kernels: zero columns of Y / zero
+// rows of U for the outputs, idle lanes / zero columns of U for the latents.  Padded latents need Lt >= 2 and 16-byte
+// aligned runs of X: L * dim even, or - L * dim odd - an even T (then every sequence, round and ragged tail starts and ends
+// on a 16-byte boundary all the same).  L = 1 with dim = 3 is not served (a sequence-round of X is 3 doubles).
+static const Shape* find_shape(int p, int L, int dim, long long T) {
     if (L == 1 && dim == 3) return nullptr;
+    const bool runs_ok = (L * dim) % 2 == 0 || (T > 0 && T % 2 == 0);
     const Shape* best = nullptr;
     for (const Shape& s : kShapes) {
         if (s.L < L || s.p < p || p < L) continue;
-        if (s.L != L && (s.L < 2 || L < 2 || (L * dim) % 2 != 0)) continue;
+        if (s.L != L && (s.L < 2 || L < 2 || !runs_ok)) continue;
         if (!best || s.L < best->L || (s.L == best->L && s.p < best->p)) best = &s;
     }
     return best;
 }
 
-bool chain_supported(int p, int L, int dim) {
+bool chain_supported(int p, int L, int dim, long long T) {
     if (dim != 2 && dim != 3) return false;
-    return find_shape(p, L, dim) != nullptr;
+    return find_shape(p, L, dim, T) != nullptr;
 }
 
 // the automatic path choice: every served shape but (P = 32, L = 16) and padded latents under P = 32, where the chunked-scan
 // path ties or wins (profiles/r02/chain_vs_scan_by_shape_v2_square_fix.txt, chain_vs_scan_padded_p.txt,
 // chain_vs_scan_padded_L.txt: 0.69 - 1.05x)
-bool chain_preferred(int p, int L, int dim) {
+bool chain_preferred(int p, int L, int dim, long long T) {
     if (dim != 2 && dim != 3) return false;
-    const Shape* s = find_shape(p, L, dim);
+    const Shape* s = find_shape(p, L, dim, T);
     return s != nullptr && !(s->p == 32 && (s->L == 16 || s->L != L));
 }
 
 cudaError_t launch_chain(int p, int L, int dim, const ChainArgs& a, cudaStream_t st) {
-    const Shape* s = find_shape(p, L, dim);
+    const Shape* s = find_shape(p, L, dim, a.T);
     if (!s) return cudaErrorInvalidValue;
     ChainArgs b = a;
     b.p = p;

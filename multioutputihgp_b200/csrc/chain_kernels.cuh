@@ -153,7 +153,7 @@ struct FilterCfg {
 // P-column tile rows (16-byte copies when p is even, 8-byte copies when it is odd and the rows are only 8-byte aligned); the other columns are zeroed once and U has zero rows
 // there (run_chain_ns), so every later stage - tensor-pipe projection, squared norms, explicit residual, missing-data
 // projection - sees a P-output model whose extra outputs are identically zero and carry no weight.
-// The same variant serves L_real < L latents (L_real * D even): U has zero columns there, lanes (s, j >= L_real) own no
+// The same variant serves L_real < L latents (L_real * D even, or T even: 16-byte aligned runs of X either way): U has zero columns there, lanes (s, j >= L_real) own no
 // chain, and X keeps the CALLER'S layout [t][L_real][D] - a sequence-round is L steps of L_real * D doubles, staged and
 // copied out with run-time lengths.
 template <int P, int L, int D, int NS_, bool PADP>
@@ -520,7 +520,7 @@ struct SmoothCfg {
 // grid: ceil(N / NS) CTAs of one warp; rounds of L steps from the end of the sequence.  Each sequence-round of X is one
 // contiguous run of L*L*D doubles: it is brought in by ONE TMA bulk copy (mbarrier-tracked), smoothed in place in
 // shared memory, and written out by ONE bulk store - no per-lane load/store instructions touch HBM.
-// PADL: the model has L_real < L latents (L_real * D even): lanes (s, j >= L_real) own no chain and the runs keep the caller's
+// PADL: the model has L_real < L latents (L_real * D even, or T even): lanes (s, j >= L_real) own no chain and the runs keep the caller's
 // layout, RL steps of L_real * D doubles.
 template <int L, int D, int MODE, int NS_, int RM_, bool PADL>
 __global__ void __launch_bounds__(32, 14) k_smooth_chain(const double* __restrict__ X, const LatentConsts* __restrict__ consts,
@@ -664,7 +664,7 @@ cudaError_t run_chain_ns(const ChainArgs& a, cudaStream_t st) {
         for (int l = 0; l < L; ++l) pc.U[r][l] = (r < p_real && l < L_real) ? a.U_host[(size_t)r * L_real + l] : 0.0;
     for (int l = 0; l < L; ++l) pc.rs[l] = l < L_real ? 1.0 / std::sqrt(a.S_host[l]) : 0.0;
     const bool padded = p_real != P || L_real != L, padL = L_real != L;
-    if (padL && (L_real * D) % 2 != 0) return cudaErrorInvalidValue;        // chain_supported() excludes it
+    if (padL && (L_real * D) % 2 != 0 && a.T % 2 != 0) return cudaErrorInvalidValue;   // chain_supported() excludes it: runs of X would not be 16-byte aligned
     const unsigned grid = (unsigned)((a.N + NS - 1) / NS);
     static std::atomic<int> attr_done[64];          // per device: function attributes belong to the device's context
     if (AttrOnce once(attr_done); once) {

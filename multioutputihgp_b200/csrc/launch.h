@@ -113,8 +113,8 @@ struct ChainArgs {
     int seqs_per_warp = 0;        // 0 = automatic
     Marker* mk = nullptr;
 };
-bool chain_supported(int p, int L, int dim);     // a many-chains instantiation serves the shape (exactly, or p padded to the next width)
-bool chain_preferred(int p, int L, int dim);     // ... and it is the faster path for many sequences (automatic choice)
+bool chain_supported(int p, int L, int dim, long long T);     // a many-chains instantiation serves the shape (exactly, or padded to the next widths)
+bool chain_preferred(int p, int L, int dim, long long T);     // ... and it is the faster path for many sequences (automatic choice)
 cudaError_t launch_chain(int p, int L, int dim, const ChainArgs& a, cudaStream_t st);
 
 // objective.cu

@@ -304,7 +304,34 @@ CHAIN_CONFIGS = [
     ("Matern52", 16, 10, 5, 70, 72),
     ("Matern52", 9, 6, 9, 33, 73),
     ("Matern52", 14, 14, 3, 90, 74),
+    ("Matern52", 8, 3, 13, 64, 75),              # ... odd L with Matern-5/2: served when T is even (16-byte aligned runs of X)
+    ("Matern52", 12, 5, 7, 140, 76),
+    ("Matern52", 16, 7, 5, 90, 77),
+    ("Matern52", 15, 9, 5, 66, 78),
 ]
+
+
+def test_many_chains_path_refuses_runs_it_cannot_align(cuda_lib):
+    """Odd L with Matern-5/2 (L * d odd) and an odd T: the runs of X would not be 16-byte aligned - the many-chains path says so
+    (the automatic choice takes the chunked-scan path, which serves the shape)."""
+    from multioutputihgp_b200 import MOIHGPSequences
+    from oracle.binding import OracleMOIHGP
+    from oracle.gen_golden import make_data, make_params
+    rng = np.random.default_rng(5)
+    p, L, N, T = 8, 3, 200, 65
+    m = MOIHGPSequences(0.1, p, L, "Matern52", True)
+    params = make_params(rng, p, L, "Matern52")
+    m.update(params)
+    Y = np.stack([make_data(rng, p, L, T) for _ in range(N)])
+    m.set_path("chain")
+    with pytest.raises(RuntimeError):
+        m.filter_smoother_nll(Y, smoother_mode=1)
+    m.set_path("auto")
+    r = m.filter_smoother_nll(Y, smoother_mode=1)
+    o = OracleMOIHGP(0.1, p, L, "Matern52", True)
+    o.update(params)
+    ro = o.filter_smoother_nll(Y, smoother_mode=1)
+    assert rel_err(r["X"], ro["X"]) < TOL and rel_err(r["Xs"], ro["Xs"]) < TOL and rel_err(r["nll"], ro["nll"]) < TOL
 
 
 @pytest.mark.parametrize("kernel,p,L,N,T,seed", CHAIN_CONFIGS)
@@ -572,6 +599,7 @@ NAN_CONFIGS = [
     ("Matern32", 3, 1, 40, 60, "chain"),      # one latent
     ("Matern32", 10, 3, 11, 75, "chain"),     # padded latents
     ("Matern52", 12, 6, 7, 66, "chain"),
+    ("Matern52", 10, 5, 9, 70, "chain"),      # odd L * d, even T
     ("Matern32", 5, 3, 3, 280, "scan"),       # odd p: scalar projection kernel
     ("Matern32", 64, 32, 1, 600, "scan"),     # tensor-pipe projection kernel, large L
 ]
@@ -783,7 +811,7 @@ def test_bound_data_objective_equals_host_buffer_objective(cuda_lib):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("path,kernel,p,L,N,T", [("chain", "Matern52", 16, 8, 5, 203), ("chain", "Matern32", 8, 4, 9, 37),
-                                                 ("chain", "Matern52", 4, 2, 37, 45), ("chain", "Matern52", 10, 4, 11, 57), ("chain", "Matern32", 22, 8, 5, 43), ("chain", "Matern52", 7, 2, 19, 41), ("chain", "Matern32", 2, 1, 45, 50), ("chain", "Matern32", 9, 5, 9, 47), ("chain", "Matern52", 12, 6, 7, 39), ("chain", "Matern32", 32, 2, 19, 70), ("chain", "Matern52", 4, 4, 9, 66),
+                                                 ("chain", "Matern52", 4, 2, 37, 45), ("chain", "Matern52", 10, 4, 11, 57), ("chain", "Matern32", 22, 8, 5, 43), ("chain", "Matern52", 7, 2, 19, 41), ("chain", "Matern32", 2, 1, 45, 50), ("chain", "Matern32", 9, 5, 9, 47), ("chain", "Matern52", 12, 6, 7, 39), ("chain", "Matern52", 9, 3, 13, 46), ("chain", "Matern32", 32, 2, 19, 70), ("chain", "Matern52", 4, 4, 9, 66),
                                                  ("scan", "Matern52", 16, 8, 3, 515), ("scan", "Matern32", 5, 3, 2, 257)])
 def test_outputs_stay_inside_their_buffers(cuda_lib, path, kernel, p, L, N, T):
     """Ragged N / T through the device entry points with every output placed between guard zones: the guards are intact
