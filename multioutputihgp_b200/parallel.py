@@ -266,7 +266,10 @@ class TimeShardedDeviceObjective(object):
         last = rank == world - 1
         m.objective_begin_async(Y_block_dev, None if last else self.zend)
         if multi:
-            dist.all_gather_into_tensor(self.ends, self.zend, group=self.group)
+            if dist.get_backend(self.group) == "gloo":       # gloo (ranks sharing a GPU, CPU tests) takes the list form
+                dist.all_gather(list(self.ends.unbind(0)), self.zend, group=self.group)
+            else:
+                dist.all_gather_into_tensor(self.ends, self.zend, group=self.group)
         m.carry_in_device(self.ends, self.block_lengths, rank, self.xin, self.dxin, x0=x0, dx0=dx0)
         m.objective_finish_device(Y_block_dev, self.buf[0:1], self.buf[2:], x0=self.xin, dx0=self.dxin)
         if multi:

@@ -15,9 +15,16 @@ from multioutputihgp_b200 import MOIHGPSequences
 from multioutputihgp_b200.parallel import TimeShardedFilterSmoother, time_block_bounds_aligned
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+# TS_BACKEND=gloo: the ranks share the visible GPUs (rank r on device r % device_count) and exchange through gloo - lets a
+# ONE-GPU box run the whole protocol with two ranks (NCCL refuses two ranks on one device)
+backend = os.environ.get("TS_BACKEND", "nccl")
+local = local % torch.cuda.device_count() if backend == "gloo" else local
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
-dist.init_process_group("nccl", device_id=dev)
+if backend == "gloo":
+    dist.init_process_group("gloo")
+else:
+    dist.init_process_group("nccl", device_id=dev)
 p, L, T, kernel = int(os.environ.get("TS_P", 64)), int(os.environ.get("TS_L", 32)), int(os.environ.get("TS_T", 2000000)), "Matern32"
 params, Hmix = model_params(p, L, kernel, 4321)
 m = MOIHGPSequences(DT, p, L, kernel, threading=True, device=local)

@@ -753,6 +753,23 @@ def test_time_sharded_filter_smoother_device_side_exchange(cuda_lib, kernel, p, 
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("script,needle,env", [("gpu_time_shard.py", "time-sharded objective", {"TS_T": "60000", "TS_P": "16", "TS_L": "8"}),
+                                               ("gpu_time_shard_fsn.py", "block borders agree", {"TS_T": "70001", "TS_P": "16", "TS_L": "8"})])
+def test_time_sharded_passes_two_ranks_on_one_gpu(cuda_lib, script, needle, env):
+    """The two time-sharded protocols end to end with TWO ranks on whatever GPUs are visible (gloo exchange, ranks share a
+    device on a one-GPU box): blocks per rank, device-side carry kernels, all-gathers, all-reduce - against the whole-sequence
+    pass.  The NCCL twins (test_time_sharded_*_two_gpus) need two devices."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    e = dict(os.environ, TS_BACKEND="gloo", **env)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29547", os.path.join(ROOT, "scripts", script)], capture_output=True, text=True, env=e, timeout=600)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and needle in r.stdout
+
+
+@pytest.mark.gpu
 def test_time_sharded_filter_smoother_two_gpus(cuda_lib):
     """the fused filter + smoother + NLL pass of one long sequence split in time over two GPUs (forward and
     backward carry all-gathers + NCCL all-reduce of the NLL) equals the single-GPU pass.  Needs two devices."""
