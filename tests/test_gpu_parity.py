@@ -256,6 +256,34 @@ def test_device_pass_right_after_update_is_capturable_in_a_cuda_graph(cuda_lib, 
         assert rel_err(nll.cpu().numpy(), ro["nll"]) < TOL, rep
 
 
+def test_one_device_model_behind_both_python_interfaces(cuda_lib):
+    """MOIHGPSequences.adopt(pywrapper.MOIHGP): the whole-sequence interface on the SAME handle as the per-observation one
+     - an update through either object is seen by both, and the per-observation step equals the
+    first step of the whole-sequence pass."""
+    from multioutputihgp_b200 import MOIHGPSequences
+    from multioutputihgp_b200.pywrapper import MOIHGP
+    from oracle.gen_golden import make_data, make_params
+    rng = np.random.default_rng(11)
+    p, L, T = 8, 4, 40
+    legacy = MOIHGP(0.1, p, L, kernel="Matern32", threading=False)
+    seq = MOIHGPSequences.adopt(legacy)
+    assert (seq.num_output, seq.num_latent, seq.igp_dim, seq.num_param) == (p, L, 2, legacy.num_param)
+    params = make_params(rng, p, L, "Matern32")
+    seq.update(params)                                         # through the whole-sequence object ...
+    assert np.array_equal(legacy.params, seq.params)           # ... seen by the per-observation one (polar factor taken)
+    Y = make_data(rng, p, L, T)
+    r = seq.filter_smoother_nll(Y[None], smoother_mode=-1, want_yhat=True)
+    x = np.zeros((L, 2))
+    for t in range(3):
+        x, yhat = legacy.step(x, y=Y[t])[:2]
+        assert rel_err(x, r["X"][0, t]) < 1e-12 and rel_err(yhat, r["Yhat"][0, t]) < 1e-12, t
+    params2 = make_params(rng, p, L, "Matern32")
+    legacy.update(params2)                                     # ... and the other way round
+    assert np.array_equal(legacy.params, seq.params)
+    del seq                                                    # the adopted handle is not destroyed with the adopter
+    assert legacy.params.shape == (legacy.num_param,)
+
+
 CHAIN_CONFIGS = [
     # kernel, p, L, N, T, seed      shapes instantiated for the many-chains kernels (chain.cu); ragged N and T on purpose
     ("Matern52", 16, 8, 9, 1037, 21),
